@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- Metropolis site-updates/s of the cylinder_b200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...      # the reference algorithm on the host CPUs
+    torchrun --nproc-per-node N bench.py --gpus N ...                # one rank per GPU (weak scaling)
+
+One "step" = SWEEPS_PER_STEP full sweeps (site moves + Robbins-Monro + measurement + one global amplitude move per
+sweep) of the per-GPU share of config C5: 8192 independent replicas over C3's (alpha, C, k) grid x 2 seeds, 50 x 50
+base lattice (Z = round(50/k) in [40, 100], T = 50), fp32 psi, lattices resident in shared memory.
+Legs, all in one run and one JSON line:
+  value      device-resident state, CUDA events around K steps, max over ranks
+  e2e        same steps through ReplicaBatch with HOST (pinned) lattice + chain buffers: H2D of the state, the sweeps,
+             D2H of lattice + observable records, every step
+  roofline   config C4: one 4096 x 4096 fp32 lattice streamed from HBM by the TMA-tiled kernel, timed alone with
+             CUDA events; achieved = 24 B x site-updates / time against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's sequential restatement of the reference's per-site Python loop, one independent replica
+             per host core for a bounded wall time (rank 0, N = 1 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "metropolis_site_updates_per_s"
+UNIT = "site-updates/s"
+REPLICAS_PER_GPU = 8192
+SWEEPS_PER_STEP = 50
+DIMS = (50, 50)
+SEED = 0x5EED
+ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
+
+
+def grid_params(n_replicas, replica0=0):
+    """C3's grid: alpha in {-2..1.75} (16) x C in {.25..4} (16) x k in linspace(.5, 1.25, 16) = 4096 points; replica r
+    uses grid point r % 4096 (the seed copies of C5 differ only in their Philox replica index)."""
+    import numpy as np
+    alphas = -2.0 + 0.25 * np.arange(16)
+    Cs = 0.25 + 0.25 * np.arange(16)
+    ks = np.linspace(0.5, 1.25, 16)
+    idx = (replica0 + np.arange(n_replicas)) % 4096
+    ia, ic, ik = idx // 256, (idx // 16) % 16, idx % 16
+    return dict(wavenumber=ks[ik], radius=1.0, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=alphas[ia], u=1.0, C=Cs[ic],
+                n=6.0, temperature=0.01, amp_bound=0.8, amp_target_acceptance=0.3)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (sequential random-site Metropolis, per-proposal Robbins-Monro) as restated by
+# the oracle -- the only place bench.py executes oracle/ code, and only as the thing timed for the CPU baseline.
+# ------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    idx, seconds, warm = args
+    import random
+    from oracle import checkerboard_oracle as cb
+    from oracle import lattice_oracle as lo
+    psi = cb.random_initialize(50, 50, .1, SEED, idx)
+    st = lo.LatticeState(psi, 1.0, 1.0, -1.0, 1.0, 1.0, 6, .01)           # config C1: alpha=-1, C=1, u=1, n=6, k=1, T=.01
+    rng = random.Random(12345 + idx)
+    a = 0.3
+
+    def go(n):
+        for _ in range(n):
+            lo.step_lattice_loc(st, a, rng.randrange(-1, st.Z - 1), rng.randrange(-1, st.T_len - 1), rng.gauss(0, 1),
+                                rng.gauss(0, 1), rng.random)
+    go(warm)
+    n_done, t0 = 0, time.perf_counter()
+    while True:
+        go(2000)
+        n_done += 2000
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            return n_done, dt
+
+
+def cpu_reference_rate(seconds, cores=None, warm=2000):
+    """Aggregate site-updates/s of `cores` independent replicas (what scripts/taskarray.sh does with one process per
+    grid point).  Returns (rate, cores, total updates)."""
+    import multiprocessing as mp
+    cores = cores or (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(i, seconds, warm) for i in range(cores)])
+    total = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return total / wall, cores, total
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(min(per_step, 2.0))
+    rates, cores, total = [], 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, n = cpu_reference_rate(per_step)
+        rates.append(r)
+        total += n
+    wall = time.perf_counter() - t0
+    value = sum(rates) / len(rates)
+    sample = ("%d independent 50x50 replicas (config C1: alpha=-1,C=1,u=1,n=6,k=1,T=.01,a=.3), sequential random-site "
+              "Metropolis with per-proposal Robbins-Monro, %.1f s per step" % (cores, per_step))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "reference algorithm on host CPU cores: " + sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows]
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--replicas-per-gpu", type=int, default=REPLICAS_PER_GPU)
+    ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
+    ap.add_argument("--hbm-size", type=int, default=4096)
+    ap.add_argument("--hbm-sweeps", type=int, default=50)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-hbm", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from cylinder_b200 import _abi, ops
+    from cylinder_b200.replicas import ReplicaBatch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _abi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    Bg, nsw, K, W = args.replicas_per_gpu, args.sweeps_per_step, args.steps, max(args.warmup, 0)
+    replica0 = rank * Bg
+    batch = ReplicaBatch(grid_params(Bg, replica0), dims=DIMS, variant="simple", dtype=torch.complex64, device=dev, seed=SEED,
+                         replica0=replica0, amplitude=0.0)
+    sites_per_sweep = batch.sites
+    rec_buf = None
+
+    def step_device():
+        batch.run(nsw, amp_moves=True, measure=True, adapt=True)
+        if world > 1:                      # the path's one exchange: observable records of every replica on every rank
+            batch.gather_records()
+
+    # ---- value leg ----
+    for _ in range(W):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step_device()
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    updates_per_step_all = float(sites_per_sweep) * nsw
+    if world > 1:
+        t = torch.tensor([updates_per_step_all], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        updates_per_step_all = float(t.item())
+    value = updates_per_step_all * K / (ms_total * 1e-3)
+    acc = float(batch.observables()["site_acceptance"].mean().item())
+
+    # ---- e2e leg: host buffers in, host buffers out, every step ----
+    e2e = None
+    if not args.no_e2e:
+        psi_h = batch.psi.cpu().pin_memory()
+        chain_h = batch.chain.cpu().pin_memory()
+        rec = batch.record()
+        rec_h = torch.empty(rec.shape, dtype=rec.dtype).pin_memory()
+        psi_out_h = torch.empty_like(psi_h).pin_memory()
+
+        def step_e2e():
+            batch.load_host(psi_h, chain_h)                         # H2D: lattices + chain state
+            batch.run(nsw, amp_moves=True, measure=True, adapt=True)
+            if world > 1:
+                batch.gather_records()
+            rec_h.copy_(batch.record(), non_blocking=True)         # D2H: observable records
+            psi_out_h.copy_(batch.psi, non_blocking=True)          # D2H: lattices (what `.lattice` hands to the caller)
+            torch.cuda.current_stream().synchronize()              # the caller reads the host buffers
+        for _ in range(min(W, 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_e2e()
+        barrier()
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        h2d = psi_h.numel() * psi_h.element_size() + chain_h.numel() * 8
+        d2h = rec_h.numel() * 8 + psi_out_h.numel() * psi_out_h.element_size()
+        e2e = {"value": updates_per_step_all * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K,
+               "api": "ReplicaBatch.load_host -> .run -> .record()/.psi to pinned host, stream-synchronised per step"}
+
+    # ---- roofline leg: C4, one large lattice streamed from HBM ----
+    roofline = None
+    if not args.no_hbm:
+        n = args.hbm_size
+        par = ops.make_params(dev, wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=.01)
+        Zt = torch.tensor([n], dtype=torch.int32, device=dev)
+        psi = torch.zeros(1, n, n, dtype=torch.complex64, device=dev)
+        ops.lattice_init(psi, Zt, .1, SEED, 0)
+        ws = ops.HbmWorkspace(n, n, torch.complex64, dev)
+        ws.pack(psi[0])
+        del psi
+        chain = ops.new_chain(1, dev, amplitude=0.3)[0]
+        ws.sweep(par, chain, SEED, 0, 10, 0, _abi.SWEEP_ADAPT_SIGMA)          # warm-up (also adapts sigma)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        ws.sweep(par, chain, SEED, 10, args.hbm_sweeps, 0, _abi.SWEEP_ADAPT_SIGMA)
+        h1.record()
+        barrier()
+        ms_hbm = h0.elapsed_time(h1)
+        peak, peak_src = measured_peak_hbm()
+        upd = float(n) * n * args.hbm_sweeps
+        achieved = upd * ALG_BYTES_PER_UPDATE_F32 / (ms_hbm * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "kernel": "sweep_hbm_kernel<float,2> (TMA-tiled, ping-pong)",
+                    "workload": "C4: %dx%d fp32 lattice (%.0f MB > L2), a=0.3 fixed, %d sweeps" % (n, n, n * n * 8 / 1e6, args.hbm_sweeps),
+                    "algorithmic_bytes_per_update": ALG_BYTES_PER_UPDATE_F32, "site_updates_per_s": upd / (ms_hbm * 1e-3),
+                    "us_per_sweep": 1e3 * ms_hbm / args.hbm_sweeps,
+                    "note": "time = whole call / sweeps: includes the 1-thread post-sweep kernel (sigma update, buffer flip)"}
+        del ws
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, cores, total = cpu_reference_rate(args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d independent 50x50 replicas (config C1, a=.3), %.0f s wall, %d proposals: oracle restatement of the "
+                         "reference's sequential per-site Python loop" % (cores, args.cpu_seconds, total)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "C5 per-GPU share: %d replicas/GPU over C3's 16x16x16 (alpha, C, k) grid x seeds, dims (50,50) "
+                                       "=> Z=round(50/k) in [40,100] (odd Z: 3 colours), T=50, fp32 psi resident in shared memory" % Bg,
+                           "sweeps_per_step": nsw, "per_sweep": "site moves + Robbins-Monro + row moments/measure + 1 amplitude move",
+                           "site_updates_per_step": updates_per_step_all, "variant": "simple", "temperature": 0.01,
+                           "l2_policy": "state re-read from HBM once per step (%.0f MB/GPU > L2 not required: lattices live in "
+                                        "shared memory during a step)" % (Bg * batch.Zmax * batch.T * 8 / 1e6),
+                           "mean_site_acceptance": acc},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K,"roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

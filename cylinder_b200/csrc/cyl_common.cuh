@@ -1,0 +1,166 @@
+// Shared device/host helpers: error plumbing, surface geometry (system_cylinder.py:25-41), Philox4x32-10,
+// uniform/normal conversion, warp/CTA reductions.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/cylinder_b200.h"
+
+// ----------------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ----------------------------------------------------------------------------------------------------
+void cyl_set_error(const char* fmt, ...);
+
+#define CYL_CHECK_ARG(cond, ...)                                  \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      cyl_set_error(__VA_ARGS__);                                 \
+      return CYL_E_INVALID;                                       \
+    }                                                             \
+  } while (0)
+
+#define CYL_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      cyl_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+      return CYL_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+#define CYL_LAUNCH_CHECK()                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) {                                                                \
+      cyl_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__));      \
+      return CYL_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ----------------------------------------------------------------------------------------------------
+// real-type traits
+// ----------------------------------------------------------------------------------------------------
+template <typename R> struct Real;
+template <> struct Real<float> {
+  using complex_t = float2;
+  static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); }
+};
+template <> struct Real<double> {
+  using complex_t = double2;
+  static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); }
+};
+
+// ----------------------------------------------------------------------------------------------------
+// surface geometry r(z) = r(a)(1 + a sin kz)       system_cylinder.py:25-41
+// Always evaluated in fp64: it is O(Z) work per amplitude change, never per site.
+// ----------------------------------------------------------------------------------------------------
+struct Geo {
+  double gth;   // sqrt_g_theta   :28
+  double gz;    // sqrt_g_z       :34
+  double ath;   // A_theta        :40
+};
+
+__host__ __device__ __forceinline__ double geo_radius_rescaled(double r, double a) {   // :37
+  return r / sqrt(1.0 + a * a / 2.0);
+}
+
+__host__ __device__ __forceinline__ Geo geo_eval(double k, double r, double a, double z) {
+  Geo g;
+  const double ra = geo_radius_rescaled(r, a);
+  double s, c;
+  sincos(k * z, &s, &c);
+  g.gth = ra * (1.0 + a * s);                           // :28
+  const double t = ra * a * k * c;
+  g.gz = sqrt(1.0 + t * t);                             // :34
+  g.ath = k * ra * a * c / g.gz;                        // :40
+  return g;
+}
+
+// Same from cached sin(kz), cos(kz) -- these do not depend on the amplitude, so the sweep kernels tabulate them
+// once per launch and re-evaluate the metric after every accepted amplitude move without trigonometry.
+__host__ __device__ __forceinline__ Geo geo_from_sc(double k, double ra, double a, double s, double c) {
+  Geo g;
+  g.gth = ra * (1.0 + a * s);
+  const double t = ra * a * k * c;
+  g.gz = sqrt(1.0 + t * t);
+  g.ath = k * ra * a * c / g.gz;
+  return g;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: no state, any (counter, key) in O(1).
+// ----------------------------------------------------------------------------------------------------
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                                                      uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+  const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+  const uint32_t n1 = (uint32_t)p1;
+  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+  const uint32_t n3 = (uint32_t)p0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+template <int ROUNDS = 10>
+__host__ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < ROUNDS; ++i) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += PHILOX_W0;
+    k1 += PHILOX_W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Stream tags in counter word 3 (upper byte), so that site moves, amplitude moves and initialisation of the
+// same (site, replica, sweep) never share a counter.
+#define CYL_TAG_SITE 0u
+#define CYL_TAG_AMP  1u
+#define CYL_TAG_INIT 2u
+__host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t tag, uint64_t sweep) {
+  return (tag << 24) | (uint32_t)((sweep >> 32) & 0xFFFFFFu);
+}
+
+// uniforms strictly inside (0,1)
+__host__ __device__ __forceinline__ double u01_f64(uint32_t x) {            // 32 bits, midpoint
+  return ((double)x + 0.5) * (1.0 / 4294967296.0);
+}
+__device__ __forceinline__ float u01_f32_open0(uint32_t x) {                // (0,1], 23 bits, no I2F
+  return 2.0f - __uint_as_float(0x3F800000u | (x >> 9));
+}
+__device__ __forceinline__ float u01_f32_half(uint32_t x) {                 // [0,1), 23 bits, no I2F
+  return __uint_as_float(0x3F800000u | (x >> 9)) - 1.0f;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// reductions
+// ----------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA; result valid in every thread.  scratch: >= 32 elements of T in shared memory.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();                      // scratch may still be read from a previous call
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  T t = (lane < nwarp) ? scratch[lane] : T(0);
+  t = warp_sum(t);
+  return t;
+}

@@ -1,0 +1,66 @@
+// Whole-lattice field energy in row-moment form.
+//
+// Lattice.surface_field_energy (On_lattice_simple.py:185-213; 0th-order override
+// On_lattice_rescaled_0thorder.py:247-278) is linear in five amplitude-independent sums per z-row,
+//   S1 = sum_j |psi|^2   S2 = sum_j |psi|^4   S3 = sum_j |dz|^2   S4 = sum_j |dth|^2   S5 = sum_j Im(conj(psi) dth)
+// (left differences divided by the pixel lengths, :170-182), so one O(Z*T) reduction serves any number of
+// trial amplitudes at O(Z) each.  S6 = sum_j |psi|, S7 + i S8 = sum_j psi feed Lattice.measure (:121-131).
+#pragma once
+#include "cyl_common.cuh"
+
+#define CYL_NMOM 8
+
+// one site's contribution to the row moments; L = psi[i-1][j], W = psi[i][j-1]
+template <typename C>
+__device__ __forceinline__ void moments_accumulate(double (&m)[CYL_NMOM], C p, C L, C W, double inv_lz2, double inv_lth2,
+                                                   double inv_lth) {
+  const double pr = p.x, pi = p.y;
+  const double p2 = pr * pr + pi * pi;
+  const double zr = pr - (double)L.x, zi = pi - (double)L.y;
+  const double tr = pr - (double)W.x, ti = pi - (double)W.y;
+  m[0] += p2;
+  m[1] += p2 * p2;
+  m[2] += (zr * zr + zi * zi) * inv_lz2;
+  m[3] += (tr * tr + ti * ti) * inv_lth2;
+  m[4] += (pr * ti - pi * tr) * inv_lth;            // Im(conj(p) * dth)
+  m[5] += sqrt(p2);
+  m[6] += pr;
+  m[7] += pi;
+}
+
+// Energy of one row at trial amplitude a_eval given the metric reference amplitude a_ref (only the 0th-order
+// variant distinguishes them).  S = the row's moments; g0e / gme = metric at z_i / z_{i-1/2} for a_eval,
+// g0r = metric at z_i for a_ref.  Returns E_i WITHOUT the global lz*lth factor.
+__device__ __forceinline__ double field_energy_row(int variant, const CylParams& p, double lz, double lth, int T,
+                                                   const Geo& g0e, const Geo& gme, const Geo& g0r, const double* S) {
+  const double Cn2 = p.C * p.n * p.n;
+  if (variant == CYL_VARIANT_SIMPLE) {
+    const double zs = gme.gz;                                  // :191
+    const double w0 = zs * g0e.gth;                            // :193
+    const double wir = g0e.gz / gme.gth;                       // :194
+    const double A = gme.ath;                                  // :195
+    return (p.alpha * S[0] + p.u / 2 * S[1]) * w0              // :199
+           + p.C * S[2] / (zs * zs) * w0                       // :200-202
+           + p.C * S[3] * wir                                  // :206
+           + p.C * p.n * 2 * A * S[4] * wir                    // :208
+           + Cn2 * S[0] * (A * A) * wir;                       // :210
+  } else {
+    const double zs = g0r.gz, ths = g0r.gth;                   // 0th:253-254
+    const double w0 = g0r.gz * g0e.gth;                        // 0th:255
+    const double wir = w0 / (ths * ths);                       // 0th:256
+    const double A = g0e.ath;                                  // 0th:257
+    const double area = (lz * g0e.gz) * (lth * g0e.gth);       // 0th:261, :68
+    const double bg = -p.temperature / area + ((p.alpha < 0) ? .5 * p.alpha * p.alpha / p.u : 0.0);   // 0th:66-92
+    return (p.alpha * S[0] + p.u / 2 * S[1]) * w0 + p.C * S[2] / (zs * zs) * w0 + p.C * S[3] * wir +
+           p.C * p.n * 2 * A * S[4] * wir + Cn2 * S[0] * (A * A) * wir + T * bg * w0;                  // 0th:262-275
+  }
+}
+
+// convenience: evaluate the metric with sincos (standalone kernels; the sweep kernels use cached sin/cos tables)
+__device__ __forceinline__ double field_energy_row_eval(int variant, const CylParams& p, double lz, double lth, int T, int i,
+                                                        double a_eval, double a_ref, const double* S) {
+  const double k = p.wavenumber, r = p.radius;
+  const Geo g0e = geo_eval(k, r, a_eval, i * lz), gme = geo_eval(k, r, a_eval, (i - .5) * lz);
+  const Geo g0r = geo_eval(k, r, a_ref, i * lz);
+  return field_energy_row(variant, p, lz, lth, T, g0e, gme, g0r, S);
+}

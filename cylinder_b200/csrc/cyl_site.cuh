@@ -1,0 +1,144 @@
+// The single-site Metropolis move of Lattice.step_lattice_loc in the form the parallel kernels use.
+//
+// With d = psi' - psi, every term of the reference's dE (On_lattice_simple.py:620-669; 0th-order variant
+// On_lattice_rescaled_0thorder.py:142-192) is a polynomial in d whose coefficients depend only on the z-row:
+//
+//   dE = K [ mass*s + (u/2) s (2|p|^2 + s) + csum |d|^2 + Re(conj(d) H) ]
+//     s    = |p+d|^2 - |p|^2
+//     H    = 2 (csum p - clz L - crz Rz - clt W - crt E)  +  i xl W  -  i xr E        (complex)
+//     L,Rz = psi[i-1,j], psi[i+1,j]     W,E = psi[i,j-1], psi[i,j+1]
+//
+//   simple:   clz = C/(lz^2 Gz(z-)^2)        crz = C/(lz^2 Gz(z+)^2)             (:633,:643)
+//             clt = C/(lth^2 Gth(z-)^4)      crt = C/(lth^2 Gth(z+)^4)           (:634,:644)
+//             xl  = 2Cn A(z-)/(lth Gth(z-)^2) xr = 2Cn A(z+)/(lth Gth(z+)^2)     (:651-663)
+//             mass= alpha + C n^2 A(z-)^2/Gth(z-)^2                              (:621,:665)
+//   0thorder: clz = C/(lz^2 Gz(z-)^2) sg(z-)/sg(z)   crz likewise with z+        (0th:153,:163)
+//             clt = crt = C/(lth^2 Gth(z)^2)                                     (0th:154,:164)
+//             xl = xr = 2Cn A(z)/(lth Gth(z)^2); mass = alpha + C n^2 A(z)^2/Gth(z)^2 (0th:168-188)
+//             proposal width sigma*sg(z)                                         (0th:135-136)
+//   K = sg(z) lz lth (:668-669), z = lz*i, z-+ = lz*(i -+ 1/2).
+//
+// This is algebraically identical to the reference expression (verified against the oracle's verbatim
+// restatement in tests/test_oracle_checkerboard.py) and numerically better conditioned than differencing two
+// large energies, which matters for the fp32 instantiation.  The verbatim operation order lives in k_replay.cu.
+#pragma once
+#include "cyl_common.cuh"
+
+template <typename R>
+struct __align__(16) RowCoef {
+  R kacc;    // K * log2(e) / T  (accept test in log2 domain); +inf when T == 0
+  R mass;
+  R csum;    // clz + crz + clt + crt
+  R hu;      // u / 2
+  R clz, crz, clt, crt;
+  R xl, xr;
+  R sgmul;   // proposal width multiplier (1 or sg)
+  R kfull;   // K (for energy bookkeeping)
+};
+
+// Build the coefficients of a row from the metric at z = lz*i (g0) and z -+ lz/2 (gm, gp), all at the current
+// amplitude.  fp64 in, R out.
+template <typename R>
+__device__ __forceinline__ RowCoef<R> row_coef(const CylParams& p, int variant, double lz, double lth, const Geo& g0,
+                                               const Geo& gm, const Geo& gp) {
+  const double sg = g0.gth * g0.gz;
+  const double Cn2 = p.C * p.n * p.n;
+  double clz, crz, clt, crt, xl, xr, mass, sgmul;
+  if (variant == CYL_VARIANT_SIMPLE) {
+    const double Rm = 1.0 / (gm.gth * gm.gth), Rp = 1.0 / (gp.gth * gp.gth);
+    clz = p.C / (lz * lz * gm.gz * gm.gz);
+    crz = p.C / (lz * lz * gp.gz * gp.gz);
+    clt = p.C * Rm * Rm / (lth * lth);
+    crt = p.C * Rp * Rp / (lth * lth);
+    xl = 2 * p.C * p.n * Rm * gm.ath / lth;
+    xr = 2 * p.C * p.n * Rp * gp.ath / lth;
+    mass = p.alpha + Cn2 * Rm * gm.ath * gm.ath;
+    sgmul = 1.0;
+  } else {
+    const double R0 = 1.0 / (g0.gth * g0.gth);
+    clz = p.C / (lz * lz * gm.gz * gm.gz) * (gm.gth * gm.gz) / sg;
+    crz = p.C / (lz * lz * gp.gz * gp.gz) * (gp.gth * gp.gz) / sg;
+    clt = crt = p.C * R0 / (lth * lth);
+    xl = xr = 2 * p.C * p.n * R0 * g0.ath / lth;
+    mass = p.alpha + Cn2 * R0 * g0.ath * g0.ath;
+    sgmul = sg;
+  }
+  const double K = sg * lz * lth;
+  RowCoef<R> c;
+  c.kfull = (R)K;
+  c.kacc = (p.temperature > 0) ? (R)(K * 1.4426950408889634 / p.temperature) : (R)INFINITY;
+  c.mass = (R)mass;
+  c.csum = (R)(clz + crz + clt + crt);
+  c.hu = (R)(p.u / 2);
+  c.clz = (R)clz; c.crz = (R)crz; c.clt = (R)clt; c.crt = (R)crt;
+  c.xl = (R)xl; c.xr = (R)xr;
+  c.sgmul = (R)sgmul;
+  return c;
+}
+
+// dE / K for the move p -> p + d.
+template <typename R, typename C>
+__device__ __forceinline__ R site_delta_over_k(const RowCoef<R>& c, C p, C L, C Rz, C W, C E, R dre, R dim) {
+  const R gre = c.csum * p.x - (c.clz * L.x + c.crz * Rz.x + c.clt * W.x + c.crt * E.x);
+  const R gim = c.csum * p.y - (c.clz * L.y + c.crz * Rz.y + c.clt * W.y + c.crt * E.y);
+  const R hre = R(2) * gre - c.xl * W.y + c.xr * E.y;
+  const R him = R(2) * gim + c.xl * W.x - c.xr * E.x;
+  const R d2 = dre * dre + dim * dim;
+  const R p2 = p.x * p.x + p.y * p.y;
+  const R s = d2 + R(2) * (dre * p.x + dim * p.y);
+  return c.mass * s + c.hu * s * (R(2) * p2 + s) + c.csum * d2 + (dre * hre + dim * him);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// random draws for one proposal from one Philox block x = (x0, x1, x2, x3):
+//   x0, x1 -> Box-Muller pair (z_re, z_im);  x2 -> accept uniform.  x3 unused.
+// fp64: full-precision log / sincospi (the oracle restates exactly this, tests compare at 1e-12);
+// fp32: MUFU lg2 / sqrt / sin / cos, 23-bit uniforms built by bit tricks (no I2F).
+// ------------------------------------------------------------------------------------------------------
+template <typename R> struct Draw;
+
+template <> struct Draw<double> {
+  static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, double& zre, double& zim) {
+    const double rad = sqrt(-2.0 * log(u01_f64(x0)));
+    double s, c;
+    sincospi(2.0 * u01_f64(x1), &s, &c);
+    zre = rad * c;
+    zim = rad * s;
+  }
+  // accept iff dE <= 0, or T > 0 and u <= exp(-dE/T); den = dE/K, kacc = K log2(e)/T
+  static __device__ __forceinline__ bool accept(uint32_t x2, double den, double kacc) {
+    if (den <= 0.0) return true;
+    return log2(u01_f64(x2)) <= -(kacc * den);          // kacc = inf => -inf => false
+  }
+};
+
+template <> struct Draw<float> {
+  static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, float& zre, float& zim) {
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(u01_f32_open0(x0)));     // sqrt(-2 ln u)
+    float s, c;
+    __sincosf(6.283185307179586f * u01_f32_half(x1), &s, &c);
+    zre = rad * c;
+    zim = rad * s;
+  }
+  static __device__ __forceinline__ bool accept(uint32_t x2, float den, float kacc) {
+    if (den <= 0.0f) return true;
+    return __log2f(u01_f32_open0(x2)) <= -(kacc * den);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// colouring.  A periodic ring of even length is 2-colourable (parity); an odd ring needs a third colour for its
+// last site.  axis colour a(i) = i & 1, except a(len-1) = 2 when len is odd; site colour = (a(i) + a(j)) % ncol
+// with ncol = 2 if both lengths are even, else 3.  Neighbours differ in exactly one axis colour, so they never
+// share a site colour (Latin-square argument), including across the periodic seam.
+// ------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int axis_colour(int i, int len) { return ((len & 1) && i == len - 1) ? 2 : (i & 1); }
+__host__ __device__ __forceinline__ int num_colours(int Z, int T) { return ((Z | T) & 1) ? 3 : 2; }
+
+// Robbins-Monro width update applied once for a batch of n proposals with k accepts and a frozen step factor
+// f = max(step_counter, 200): the reference's per-proposal rule (On_lattice_simple.py:688-696, m = 1, p* = .5,
+// ratio = 4) is sigma *= (1 + 2/f) on accept, (1 - 2/f) on reject; the batch applies the product.
+__device__ __forceinline__ double rm_batch_update(double sigma, double step_counter, double n, double k) {
+  const double f = fmax(step_counter + 0.5 * n, 200.0);
+  return sigma * exp(k * log1p(2.0 / f) + (n - k) * log1p(-2.0 / f));
+}

@@ -1,0 +1,604 @@
+// One large lattice streamed from HBM: TMA-staged halo tiles, a full checkerboard sweep per pass.
+//
+// Storage (cyl_hbm_layout): ping-pong pair of buffers; each buffer is the halo-padded lattice
+//   padded (Rr, Q) = (i + HR, j + HC),  Rr in [0, Z + 2 HR),  Q in [0, pitch)
+// split into two column-parity planes: plane = Q & 1, plane column = Q >> 1.  Halo rows/columns are periodic
+// copies.  With both lattice lengths even the site colour is (i + j) & 1, so the sites of one colour in a row
+// are CONTIGUOUS in one plane: shared-memory accesses of a warp are unit-stride 8-byte (conflict-free) and the
+// global stores are fully coalesced.
+//
+// Kernel (one CTA per TH x TW tile):
+//   1. one elected thread arms an mbarrier with the byte count and issues two cp.async.bulk.tensor.2d loads
+//      (one box per plane) of the tile plus a halo of NCOL sites on every side;
+//   2. colour c = 0..NCOL-1 is updated in shared memory on the tile grown by (NCOL-1-c) sites: the halo sites
+//      are recomputed redundantly -- the Philox counter is the GLOBAL site index, so the redundant result is
+//      bit-identical to what the neighbouring tile computes for the same site;
+//   3. the interior is written to the other buffer (plus its periodic halo copies).
+// A sweep therefore reads each site once (+ halo overhead) and writes it once, whatever the number of colours.
+//
+// Reference semantics restated: Lattice.step_lattice_loc (On_lattice_simple.py:598-686) per site,
+// update_sigma (:688-696) batched per sweep, Lattice.measure (:121-131), amplitude move (:544-550).
+#include <cuda.h>
+
+#include "cyl_common.cuh"
+#include "cyl_energy.cuh"
+#include "cyl_site.cuh"
+#include "cyl_surface.cuh"
+
+#define HBM_NT 512
+#define HBM_HC 4          // column halo in the global layout (>= NCOL; 4 keeps plane columns 16-byte aligned)
+#define HBM_TW 128        // tile width (sites)
+
+template <typename R> struct HbmTile;
+template <> struct HbmTile<float>  { static constexpr int TH = 64; };
+template <> struct HbmTile<double> { static constexpr int TH = 32; };
+
+struct HbmGeom {
+  int Z, T, ncol, hr, hc;
+  int64_t pitch;          // padded row length in complex elements (even)
+  int64_t rows;           // Z + 2 hr
+  int64_t plane_elems;    // rows * pitch/2
+  int64_t buffer_elems;   // 2 planes
+};
+
+static HbmGeom hbm_geom(int Z, int T) {
+  HbmGeom g;
+  g.Z = Z; g.T = T;
+  g.ncol = num_colours(Z, T);
+  g.hr = g.ncol;
+  g.hc = HBM_HC;
+  g.pitch = ((int64_t)T + 2 * g.hc + 31) / 32 * 32;
+  g.rows = (int64_t)Z + 2 * g.hr;
+  g.plane_elems = g.rows * (g.pitch / 2);
+  g.buffer_elems = 2 * g.plane_elems;
+  return g;
+}
+
+// scratch: [0,64) counters | RowCoef[Z] | moments [Z][8]
+struct HbmCounters { unsigned long long accepted; unsigned long long pad[7]; };
+template <typename R>
+struct HbmScratch {
+  size_t off_coef, off_mom, total;
+  __host__ __device__ explicit HbmScratch(int Z) {
+    off_coef = 64;
+    off_mom = (off_coef + (size_t)Z * sizeof(RowCoef<R>) + 63) & ~(size_t)63;
+    total = off_mom + (size_t)Z * CYL_NMOM * sizeof(double);
+  }
+};
+
+extern "C" int cyl_hbm_layout(int Z, int T, int is_f64, int* halo_rows, int* halo_cols, int64_t* pitch_elems,
+                              int64_t* buffer_elems, int64_t* scratch_bytes) {
+  CYL_CHECK_ARG(Z >= 8 && T >= 8, "cyl_hbm_layout: the HBM path needs Z, T >= 8 (got %d x %d); use the shared-memory path", Z, T);
+  const HbmGeom g = hbm_geom(Z, T);
+  if (halo_rows) *halo_rows = g.hr;
+  if (halo_cols) *halo_cols = g.hc;
+  if (pitch_elems) *pitch_elems = g.pitch;
+  if (buffer_elems) *buffer_elems = g.buffer_elems;
+  if (scratch_bytes) *scratch_bytes = (int64_t)(is_f64 ? HbmScratch<double>(Z).total : HbmScratch<float>(Z).total);
+  return CYL_OK;
+}
+
+__device__ __forceinline__ int wrapi(int i, int n) {      // i in [-n, 2n)
+  if (i < 0) i += n;
+  if (i >= n) i -= n;
+  return i;
+}
+__device__ __forceinline__ int modi(int i, int n) {       // any i
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// pack / unpack
+// ----------------------------------------------------------------------------------------------------
+template <typename C>
+__global__ void hbm_pack_kernel(const C* __restrict__ psi, HbmGeom g, C* __restrict__ work, int32_t* __restrict__ cur) {
+  const int64_t Q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t Rr = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *cur = 0;
+  if (Q >= g.pitch) return;
+  C v; v.x = 0; v.y = 0;
+  if (Q < g.T + 2 * g.hc) {
+    int gi = (int)((Rr - g.hr) % g.Z); if (gi < 0) gi += g.Z;
+    int gj = (int)((Q - g.hc) % g.T);  if (gj < 0) gj += g.T;
+    v = psi[(size_t)gi * g.T + gj];
+  }
+  work[(Q & 1) * g.plane_elems + Rr * (g.pitch / 2) + (Q >> 1)] = v;
+}
+
+template <typename C>
+__global__ void hbm_unpack_kernel(const C* __restrict__ work, const int32_t* __restrict__ cur, HbmGeom g, C* __restrict__ psi) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= g.T) return;
+  const int64_t Q = j + g.hc, Rr = i + g.hr;
+  const C* buf = work + (size_t)(*cur) * g.buffer_elems;
+  psi[(size_t)i * g.T + j] = buf[(Q & 1) * g.plane_elems + Rr * (g.pitch / 2) + (Q >> 1)];
+}
+
+template <typename R>
+static int hbm_pack(const void* psi, int Z, int T, void* work, int32_t* cur, void* stream) {
+  using C = typename Real<R>::complex_t;
+  CYL_CHECK_ARG(psi && work && cur && Z >= 8 && T >= 8, "cyl_hbm_pack: bad arguments");
+  const HbmGeom g = hbm_geom(Z, T);
+  dim3 grid((unsigned)((g.pitch + 255) / 256), (unsigned)g.rows);
+  hbm_pack_kernel<C><<<grid, 256, 0, as_stream(stream)>>>((const C*)psi, g, (C*)work, cur);
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+template <typename R>
+static int hbm_unpack(const void* work, const int32_t* cur, int Z, int T, void* psi, void* stream) {
+  using C = typename Real<R>::complex_t;
+  CYL_CHECK_ARG(psi && work && cur && Z >= 8 && T >= 8, "cyl_hbm_unpack: bad arguments");
+  const HbmGeom g = hbm_geom(Z, T);
+  dim3 grid((unsigned)((T + 255) / 256), (unsigned)Z);
+  hbm_unpack_kernel<C><<<grid, 256, 0, as_stream(stream)>>>((const C*)work, cur, g, (C*)psi);
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+extern "C" int cyl_hbm_pack_f32(const void* psi, int Z, int T, void* work, int32_t* cur, void* s) { return hbm_pack<float>(psi, Z, T, work, cur, s); }
+extern "C" int cyl_hbm_pack_f64(const void* psi, int Z, int T, void* work, int32_t* cur, void* s) { return hbm_pack<double>(psi, Z, T, work, cur, s); }
+extern "C" int cyl_hbm_unpack_f32(const void* work, const int32_t* cur, int Z, int T, void* psi, void* s) { return hbm_unpack<float>(work, cur, Z, T, psi, s); }
+extern "C" int cyl_hbm_unpack_f64(const void* work, const int32_t* cur, int Z, int T, void* psi, void* s) { return hbm_unpack<double>(work, cur, Z, T, psi, s); }
+
+// ----------------------------------------------------------------------------------------------------
+// per-row coefficients for the current amplitude (chain[CYL_CH_AMPLITUDE]) -> scratch
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const double* __restrict__ chain, int Z, int T, int variant,
+                                RowCoef<R>* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Z) return;
+  const CylParams p = *params;
+  const double a = chain[CYL_CH_AMPLITUDE];
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
+  const Geo g0 = geo_eval(p.wavenumber, p.radius, a, lz * i), gm = geo_eval(p.wavenumber, p.radius, a, lz * (i - .5)),
+            gp = geo_eval(p.wavenumber, p.radius, a, lz * (i + .5));
+  coef[i] = row_coef<R>(p, variant, lz, lth, g0, gm, gp);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS)
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------------
+// the sweep kernel
+// ----------------------------------------------------------------------------------------------------
+template <typename R, int NCOL>
+struct HbmSmem {
+  using C = typename Real<R>::complex_t;
+  static constexpr int TH = HbmTile<R>::TH, TW = HBM_TW;
+  static constexpr int HS = (NCOL + 1) & ~1;      // column halo in shared memory: even, so a plane row is 16-byte granular
+  static constexpr int SH = TH + 2 * NCOL, SW = TW + 2 * HS, SWH = SW / 2;
+  static constexpr size_t plane_bytes = ((size_t)SH * SWH * sizeof(C) + 127) & ~(size_t)127;
+  static constexpr size_t off_coef = 2 * plane_bytes;
+  static constexpr size_t off_bar = off_coef + (size_t)SH * sizeof(RowCoef<R>);
+  static constexpr size_t total = off_bar + 64;
+};
+
+struct HbmMaps { CUtensorMap m[2][2]; };   // [buffer][plane]
+
+template <typename R, int NCOL>
+__global__ void __launch_bounds__(HBM_NT)
+sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
+                 const int32_t* __restrict__ cur_p, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
+                 const double* __restrict__ chain, HbmCounters* __restrict__ counters, uint64_t seed, uint32_t rep,
+                 uint64_t sweep) {
+  using C = typename Real<R>::complex_t;
+  using L = HbmSmem<R, NCOL>;
+  constexpr int TH = L::TH, TW = L::TW, SH = L::SH, SW = L::SW, SWH = L::SWH, HS = L::HS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* pl0 = reinterpret_cast<C*>(smem_raw);
+  C* pl1 = reinterpret_cast<C*>(smem_raw + L::plane_bytes);
+  RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + L::off_coef);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
+
+  const int tid = threadIdx.x;
+  const int cur = *cur_p;
+  const int ti0 = blockIdx.y * TH, tj0 = blockIdx.x * TW;          // interior origin (lattice coords)
+  // smem (r, q) <-> padded (ti0 + r, Q0 + q);  padded row of r = 0 is ti0 - hr + hr
+  const int Q0 = tj0 + g.hc - HS;
+  const int x0 = (Q0 + ((0 - Q0) & 1)) >> 1, x1 = (Q0 + ((1 - Q0) & 1)) >> 1;    // first plane column of each plane's box
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    constexpr uint32_t bytes = 2u * SH * SWH * sizeof(C);
+    constexpr int esz = sizeof(C) / 8;                              // f64 complex is two FLOAT64 elements
+    mbar_expect_tx(bar, bytes);
+    tma_load_2d(pl0, &maps.m[cur][0], x0 * esz, ti0, bar);
+    tma_load_2d(pl1, &maps.m[cur][1], x1 * esz, ti0, bar);
+  }
+  // overlap: row coefficients and scalars while the tile is in flight
+  for (int r = tid; r < SH; r += HBM_NT) coef[r] = coef_g[modi(ti0 - NCOL + r, g.Z)];
+  const R sigma = (R)chain[CYL_CH_SIGMA_SITE];
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  int nacc = 0;
+  const bool even = (NCOL == 2);
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) {
+    const int m = c + 1;                                           // row margin of this colour's region
+    const int mq = m + (HS - NCOL);                                // column margin
+    const int nrows = SH - 2 * m;
+    if (even) {
+      // colour of smem (r, q) is (r + q) & 1: the colour-c sites of row r are q = q0 + 2 cc, one plane, unit stride
+      const int npr = (SW - 2 * mq) / 2;
+      for (int idx = tid; idx < nrows * npr; idx += HBM_NT) {
+        const int rr = idx / npr, cc = idx - rr * npr;
+        const int r = m + rr;
+        const int q = mq + ((mq + r + c) & 1) + 2 * cc;
+        const int par = (Q0 + q) & 1;
+        C* own = par ? pl1 : pl0;
+        C* oth = par ? pl0 : pl1;
+        const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
+        const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
+        const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
+        const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
+        const RowCoef<R> rc = coef[r];
+        const int gi = wrapi(ti0 - NCOL + r, g.Z), gj = wrapi(tj0 - HS + q, g.T);
+        const uint4 x = philox4x32<10>((uint32_t)(gi * g.T + gj), rep, c2, c3, k0, k1);
+        R zre, zim;
+        Draw<R>::normals(x.x, x.y, zre, zim);
+        const R w = sigma * rc.sgmul;
+        const R dre = w * zre, dim = w * zim;
+        const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
+        if (Draw<R>::accept(x.z, den, rc.kacc)) {
+          own[r * SWH + col] = Real<R>::make(pv.x + dre, pv.y + dim);
+          const int li = r - NCOL, lj = q - HS;                   // interior (counted) vs halo (redundant)
+          nacc += (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
+        }
+      }
+    } else {
+      // odd periodic ring(s): 3 colours, general colour function; every region site is visited and filtered
+      const int ncl = SW - 2 * mq;
+      for (int idx = tid; idx < nrows * ncl; idx += HBM_NT) {
+        const int rr = idx / ncl, r = m + rr, q = mq + (idx - rr * ncl);
+        // lattice coordinates; tiles past the edge hold zero-filled padding that is never stored
+        const int ui = ti0 - NCOL + r, uj = tj0 - HS + q;
+        if (ui >= g.Z + NCOL || uj >= g.T + NCOL) continue;
+        const int gi = wrapi(ui, g.Z), gj = wrapi(uj, g.T);
+        if ((axis_colour(gi, g.Z) + axis_colour(gj, g.T)) % 3 != c) continue;
+        const int par = (Q0 + q) & 1;
+        C* own = par ? pl1 : pl0;
+        C* oth = par ? pl0 : pl1;
+        const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
+        const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
+        const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
+        const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
+        const RowCoef<R> rc = coef[r];
+        const uint4 x = philox4x32<10>((uint32_t)(gi * g.T + gj), rep, c2, c3, k0, k1);
+        R zre, zim;
+        Draw<R>::normals(x.x, x.y, zre, zim);
+        const R w = sigma * rc.sgmul;
+        const R dre = w * zre, dim = w * zim;
+        const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
+        if (Draw<R>::accept(x.z, den, rc.kacc)) {
+          own[r * SWH + col] = Real<R>::make(pv.x + dre, pv.y + dim);
+          const int li = r - NCOL, lj = q - HS;
+          nacc += (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write the interior (and its periodic halo copies) to the other buffer ----
+  C* out = work + (size_t)(cur ^ 1) * g.buffer_elems;
+  const int64_t ph = g.pitch / 2;
+  for (int idx = tid; idx < 2 * TH * (TW / 2); idx += HBM_NT) {
+    const int par_slot = idx / (TH * (TW / 2));                    // which smem plane
+    const int rem = idx - par_slot * (TH * (TW / 2));
+    const int li = rem / (TW / 2), cc = rem - li * (TW / 2);
+    // interior columns of smem plane `par_slot`: q = HS + lj with (Q0 + q) & 1 == par_slot
+    const int lj = 2 * cc + ((par_slot - (Q0 + HS)) & 1);
+    const int gi = ti0 + li, gj = tj0 + lj;
+    if (gi >= g.Z || gj >= g.T) continue;
+    const int r = li + NCOL, q = lj + HS;
+    const C* src = par_slot ? pl1 : pl0;
+    const C v = src[r * SWH + (((Q0 + q) >> 1) - (par_slot ? x1 : x0))];
+    const int64_t Rr = gi + g.hr, Q = gj + g.hc;
+    int64_t R2 = -1, Q2 = -1;
+    if (gi < g.hr) R2 = Rr + g.Z; else if (gi >= g.Z - g.hr) R2 = Rr - g.Z;
+    if (gj < g.hc) Q2 = Q + g.T; else if (gj >= g.T - g.hc) Q2 = Q - g.T;
+    out[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)] = v;
+    if (R2 >= 0) out[(Q & 1) * g.plane_elems + R2 * ph + (Q >> 1)] = v;
+    if (Q2 >= 0) {
+      out[(Q2 & 1) * g.plane_elems + Rr * ph + (Q2 >> 1)] = v;
+      if (R2 >= 0) out[(Q2 & 1) * g.plane_elems + R2 * ph + (Q2 >> 1)] = v;
+    }
+  }
+
+  // ---- accept count ----
+  nacc = warp_sum(nacc);
+  if ((tid & 31) == 0 && nacc) atomicAdd(&counters->accepted, (unsigned long long)nacc);
+}
+
+// after every sweep: Robbins-Monro on sigma_site, counters, flip the buffer index
+__global__ void hbm_post_sweep_kernel(double* __restrict__ chain, HbmCounters* __restrict__ counters, int32_t* __restrict__ cur,
+                                      double nsite, uint32_t flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double acc = (double)counters->accepted;
+  counters->accepted = 0ull;
+  if (flags & CYL_SWEEP_ADAPT_SIGMA)
+    chain[CYL_CH_SIGMA_SITE] = rm_batch_update(chain[CYL_CH_SIGMA_SITE], chain[CYL_CH_STEP_COUNTER], nsite, acc);
+  chain[CYL_CH_STEP_COUNTER] += nsite;
+  chain[CYL_CH_SITE_PROPOSED] += nsite;
+  chain[CYL_CH_SITE_ACCEPTED] += acc;
+  *cur ^= 1;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// row moments of the plane-split layout: one warp per row
+// ----------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void hbm_row_moments_kernel(const typename Real<R>::complex_t* __restrict__ work, const int32_t* __restrict__ cur_p,
+                                       HbmGeom g, const CylParams* __restrict__ params, double* __restrict__ S) {
+  using C = typename Real<R>::complex_t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= g.Z) return;
+  const CylParams p = *params;
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / g.Z, lth = (2 * pi * p.radius) / g.T;
+  const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
+  const C* buf = work + (size_t)(*cur_p) * g.buffer_elems;
+  const int64_t ph = g.pitch / 2;
+  const int64_t Rr = i + g.hr;
+  double m[CYL_NMOM];
+#pragma unroll
+  for (int q = 0; q < CYL_NMOM; ++q) m[q] = 0.0;
+  for (int j = lane; j < g.T; j += 32) {
+    const int64_t Q = j + g.hc;
+    const C pv = buf[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)];
+    const C Ln = buf[(Q & 1) * g.plane_elems + (Rr - 1) * ph + (Q >> 1)];          // halo rows make i-1 valid at i = 0
+    const C W = buf[((Q - 1) & 1) * g.plane_elems + Rr * ph + ((Q - 1) >> 1)];
+    moments_accumulate(m, pv, Ln, W, inv_lz2, inv_lth2, inv_lth);
+  }
+#pragma unroll
+  for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < CYL_NMOM; ++q) S[(size_t)i * CYL_NMOM + q] = m[q];
+  }
+}
+
+template <typename R>
+static int hbm_row_moments(const void* work, const int32_t* cur, int Z, int T, const CylParams* params, double* S, void* stream) {
+  CYL_CHECK_ARG(work && cur && params && S && Z >= 8 && T >= 8, "cyl_hbm_row_moments: bad arguments");
+  const HbmGeom g = hbm_geom(Z, T);
+  const int warps = 8;
+  hbm_row_moments_kernel<R><<<(Z + warps - 1) / warps, warps * 32, 0, as_stream(stream)>>>(
+      (const typename Real<R>::complex_t*)work, cur, g, params, S);
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+extern "C" int cyl_hbm_row_moments_f32(const void* work, const int32_t* cur, int Z, int T, const CylParams* params, double* S, void* s) {
+  return hbm_row_moments<float>(work, cur, Z, T, params, S, s);
+}
+extern "C" int cyl_hbm_row_moments_f64(const void* work, const int32_t* cur, int Z, int T, const CylParams* params, double* S, void* s) {
+  return hbm_row_moments<double>(work, cur, Z, T, params, S, s);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// measurement + amplitude move from the row moments (one CTA)
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hbm_amp_kernel(const double* __restrict__ S, int Z, int T, const CylParams* __restrict__ params, double* __restrict__ chain,
+               uint64_t seed, uint32_t rep, uint64_t sweep, int variant, uint32_t flags, double* __restrict__ obs,
+               double* __restrict__ prof) {
+  __shared__ double scr[64];
+  __shared__ double sh_es[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const CylParams p = *params;
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
+  const double a = chain[CYL_CH_AMPLITUDE], sigma_amp = chain[CYL_CH_SIGMA_AMP];
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint4 x = philox4x32<10>(0u, rep, (uint32_t)sweep, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
+  double zre, zim;
+  Draw<double>::normals(x.x, x.y, zre, zim);
+  const double a_new = a + sigma_amp * zre;
+  const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
+  double e_cur = 0.0, e_new = 0.0, s_p2 = 0.0, s_abs = 0.0;
+  for (int i = tid; i < Z; i += blockDim.x) {
+    const double* Sr = S + (size_t)i * CYL_NMOM;
+    const Geo g0 = geo_eval(p.wavenumber, p.radius, a, lz * i), gm = geo_eval(p.wavenumber, p.radius, a, lz * (i - .5));
+    e_cur += field_energy_row(variant, p, lz, lth, T, g0, gm, g0, Sr);
+    if (try_move) {
+      const Geo h0 = geo_eval(p.wavenumber, p.radius, a_new, lz * i), hm = geo_eval(p.wavenumber, p.radius, a_new, lz * (i - .5));
+      e_new += field_energy_row(variant, p, lz, lth, T, h0, hm, g0, Sr);
+    }
+    s_p2 += Sr[0];
+    s_abs += Sr[5];
+    if ((flags & CYL_SWEEP_MEASURE) && prof) {
+      prof[3 * i] += Sr[6]; prof[3 * i + 1] += Sr[7]; prof[3 * i + 2] += Sr[5];
+    }
+  }
+  e_cur = block_sum<double>(e_cur, scr) * lz * lth;
+  e_new = block_sum<double>(e_new, scr) * lz * lth;
+  s_p2 = block_sum<double>(s_p2, scr);
+  s_abs = block_sum<double>(s_abs, scr);
+  if (warp == 0) { const double es = surface_energy_warp(p, a, nullptr, nullptr, true); if (lane == 0) sh_es[0] = es; }
+  if (warp == 1 && try_move) { const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true); if (lane == 0) sh_es[1] = es; }
+  __syncthreads();
+  if (tid != 0) return;
+  const double nsite = (double)Z * T;
+  chain[CYL_CH_E_FIELD] = e_cur;
+  chain[CYL_CH_E_SURF] = sh_es[0];
+  if ((flags & CYL_SWEEP_MEASURE) && obs) {
+    obs[CYL_OB_COUNT] += 1.0;
+    obs[CYL_OB_ABS_A] += fabs(a);
+    obs[CYL_OB_A] += a;
+    obs[CYL_OB_A2] += a * a;
+    obs[CYL_OB_PSI2] += s_p2 / nsite;
+    obs[CYL_OB_ABSPSI] += s_abs / nsite;
+    obs[CYL_OB_E_FIELD] += e_cur;
+    obs[CYL_OB_E_SURF] += sh_es[0];
+    obs[CYL_OB_E_FIELD2] += e_cur * e_cur;
+    obs[CYL_OB_SIGMA] += chain[CYL_CH_SIGMA_SITE];
+  }
+  if (!(flags & CYL_SWEEP_AMP_MOVES)) return;
+  int accept = 0;
+  if (try_move) {
+    const double dE = (sh_es[1] + e_new) - (sh_es[0] + e_cur);
+    if (!isfinite(dE)) chain[CYL_CH_FLAGS] = (double)((unsigned)chain[CYL_CH_FLAGS] | 1u);
+    if (dE <= 0) accept = 1;
+    else if (p.temperature == 0) accept = 0;
+    else accept = (u01_f64(x.z) <= exp(-dE / p.temperature));
+  }
+  const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
+  const double ratio = 1.0 / (pt * (1.0 - pt));
+  chain[CYL_CH_AMP_COUNTER] += 1;
+  chain[CYL_CH_AMP_PROPOSED] += 1;
+  const double f = fmax(chain[CYL_CH_AMP_COUNTER], 200.0), c = sigma_amp * ratio;
+  if (flags & CYL_SWEEP_ADAPT_SIGMA) chain[CYL_CH_SIGMA_AMP] = accept ? sigma_amp + c * (1 - pt) / f : sigma_amp - c * pt / f;
+  if (accept) {
+    chain[CYL_CH_AMPLITUDE] = a_new;
+    chain[CYL_CH_E_SURF] = sh_es[1];
+    chain[CYL_CH_AMP_ACCEPTED] += 1;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host driver
+// ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CYL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    if (!f || qres != cudaDriverEntryPointSuccess) {
+      cyl_set_error("cuTensorMapEncodeTiled not available from the driver (query result %d)", (int)qres);
+      return CYL_E_CUDA;
+    }
+    cached = (EncodeTiledFn)f;
+  }
+  *fn = cached;
+  return CYL_OK;
+}
+
+template <typename R, int NCOL>
+static int make_maps(const HbmGeom& g, void* work, HbmMaps* maps) {
+  using C = typename Real<R>::complex_t;
+  using L = HbmSmem<R, NCOL>;
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  constexpr int esz = sizeof(C) / 8;          // 8-byte elements per complex
+  const CUtensorMapDataType dt = (sizeof(C) == 8) ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+  for (int b = 0; b < 2; ++b)
+    for (int pl = 0; pl < 2; ++pl) {
+      void* base = (C*)work + (size_t)b * g.buffer_elems + (size_t)pl * g.plane_elems;
+      const cuuint64_t dims[2] = {(cuuint64_t)(g.pitch / 2) * esz, (cuuint64_t)g.rows};
+      const cuuint64_t strides[1] = {(cuuint64_t)(g.pitch / 2) * sizeof(C)};
+      const cuuint32_t box[2] = {(cuuint32_t)(L::SWH * esz), (cuuint32_t)L::SH};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = enc(&maps->m[b][pl], dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        cyl_set_error("cuTensorMapEncodeTiled failed (%d): pitch %lld rows %lld box %u x %u", (int)r, (long long)g.pitch,
+                      (long long)g.rows, box[0], box[1]);
+        return CYL_E_CUDA;
+      }
+    }
+  return CYL_OK;
+}
+
+template <typename R, int NCOL>
+static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylParams* params, double* chain, uint64_t seed,
+                          int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch,
+                          double* obs, double* prof, cudaStream_t st) {
+  using C = typename Real<R>::complex_t;
+  using L = HbmSmem<R, NCOL>;
+  static_assert((L::SWH * sizeof(C)) % 16 == 0, "TMA box rows must be a multiple of 16 bytes");
+  HbmMaps maps;
+  int rc = make_maps<R, NCOL>(g, work, &maps);
+  if (rc) return rc;
+  const HbmScratch<R> sl(g.Z);
+  HbmCounters* counters = reinterpret_cast<HbmCounters*>(scratch);
+  RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>((char*)scratch + sl.off_coef);
+  double* S = reinterpret_cast<double*>((char*)scratch + sl.off_mom);
+  auto kern = sweep_hbm_kernel<R, NCOL>;
+  CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+  CYL_CUDA(cudaMemsetAsync(counters, 0, sizeof(HbmCounters), st));
+  const dim3 grid((g.T + L::TW - 1) / L::TW, (g.Z + L::TH - 1) / L::TH);
+  const bool amp = flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE);
+  hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
+  for (int s = 0; s < nsweeps; ++s) {
+    const uint64_t sweep = sweep0 + (uint64_t)s;
+    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, seed, (uint32_t)replica, sweep);
+    hbm_post_sweep_kernel<<<1, 32, 0, st>>>(chain, counters, cur, (double)g.Z * g.T, flags);
+    if (amp) {
+      hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, cur, g, params, S);
+      hbm_amp_kernel<<<1, 256, 0, st>>>(S, g.Z, g.T, params, chain, seed, (uint32_t)replica, sweep, variant, flags, obs, prof);
+      if (flags & CYL_SWEEP_AMP_MOVES) hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
+    }
+  }
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+
+template <typename R>
+static int sweep_hbm(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain, uint64_t seed,
+                     int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch, double* obs,
+                     double* prof, void* stream) {
+  CYL_CHECK_ARG(work && cur && params && chain && scratch && nsweeps >= 0, "cyl_sweep_hbm: bad arguments");
+  CYL_CHECK_ARG(Z >= 8 && T >= 8, "cyl_sweep_hbm: the HBM path needs Z, T >= 8 (got %d x %d)", Z, T);
+  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_sweep_hbm: unknown variant %d", variant);
+  CYL_CHECK_ARG(!(flags & CYL_SWEEP_MEASURE) || obs, "cyl_sweep_hbm: CYL_SWEEP_MEASURE needs obs");
+  CYL_CHECK_ARG(((uintptr_t)work & 127) == 0, "cyl_sweep_hbm: work must be 128-byte aligned");
+  const HbmGeom g = hbm_geom(Z, T);
+  if (nsweeps == 0) return CYL_OK;
+  if (g.ncol == 2)
+    return sweep_hbm_impl<R, 2>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, as_stream(stream));
+  return sweep_hbm_impl<R, 3>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, as_stream(stream));
+}
+
+extern "C" int cyl_sweep_hbm_f32(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain, uint64_t seed,
+                                 int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch,
+                                 double* obs, double* prof, void* stream) {
+  return sweep_hbm<float>(work, cur, Z, T, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, stream);
+}
+extern "C" int cyl_sweep_hbm_f64(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain, uint64_t seed,
+                                 int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch,
+                                 double* obs, double* prof, void* stream) {
+  return sweep_hbm<double>(work, cur, Z, T, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, stream);
+}

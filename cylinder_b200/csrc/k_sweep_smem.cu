@@ -1,0 +1,335 @@
+// Batched-replica checkerboard sweeps, lattice resident in shared memory.
+//
+// One CTA owns one replica for the whole launch (nsweeps sweeps): psi is read from HBM once, kept in shared
+// memory, written back once; the per-row metric coefficients, the amplitude-independent sin/cos tables and the
+// row moments live in shared memory too.  Per sweep:
+//   1. site moves  (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once;
+//      draws from Philox4x32-10 keyed by seed with counter (site, replica, sweep, tag) -- stateless, so a sweep can
+//      be re-run or resumed bit-identically;
+//   2. Robbins-Monro update of sigma_site from the sweep's accept count (:688-696, batched; cyl_site.cuh);
+//   3. row moments by warp-shuffle reduction -> E_field(a, a), profiles (Lattice.measure :121-131);
+//   4. global amplitude move a' = a + sigma_amp N(0,1) on E_surf(a') + E_field(a', a) (Lattice.run :544-550 through
+//      engine.step_real_group; accept rule B.2; Robbins-Monro on sigma_amp);
+//   5. on accept, rebuild the row coefficients from the sin/cos tables (no trigonometry).
+// The replicas are the (alpha, C, n, kappa, k) parameter grid that scripts/taskarray.sh farms out as separate CPU
+// jobs in the reference.
+#include "cyl_common.cuh"
+#include "cyl_energy.cuh"
+#include "cyl_site.cuh"
+#include "cyl_surface.cuh"
+
+#define SWEEP_NT 256
+
+struct SmemScalars {
+  double amp, amp_new, sigma_site, sigma_amp, e_field, e_surf, e_surf_new;
+  double step_counter, site_proposed, site_accepted, amp_proposed, amp_accepted, amp_counter, flags;
+  int amp_accept, amp_in_bounds;
+};
+
+// sin/cos(k z) at z_i and z_{i-1/2}
+struct RowTrig { double s0, c0, sm, cm; };
+
+template <typename R>
+struct SweepSmemLayout {
+  using C = typename Real<R>::complex_t;
+  size_t off_coef, off_trig, off_mom, off_scr, off_sc, total;
+  __host__ __device__ SweepSmemLayout(int Zmax, int T) {
+    size_t o = (size_t)Zmax * T * sizeof(C);
+    o = (o + 15) & ~(size_t)15;
+    off_coef = o; o += (size_t)Zmax * sizeof(RowCoef<R>);
+    o = (o + 15) & ~(size_t)15;
+    off_trig = o; o += (size_t)Zmax * sizeof(RowTrig);
+    off_mom = o;  o += (size_t)Zmax * CYL_NMOM * sizeof(double);
+    off_scr = o;  o += 64 * sizeof(double);
+    off_sc = o;   o += sizeof(SmemScalars);
+    total = (o + 15) & ~(size_t)15;
+  }
+};
+
+template <typename R>
+__device__ __forceinline__ void build_row_coefs(RowCoef<R>* coef, const RowTrig* trig, const CylParams& p, int variant,
+                                                double a, double lz, double lth, int Z) {
+  const double ra = geo_radius_rescaled(p.radius, a);
+  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
+    const RowTrig t = trig[i], tp = trig[i + 1 == Z ? 0 : i + 1];
+    const Geo g0 = geo_from_sc(p.wavenumber, ra, a, t.s0, t.c0);
+    const Geo gm = geo_from_sc(p.wavenumber, ra, a, t.sm, t.cm);
+    const Geo gp = geo_from_sc(p.wavenumber, ra, a, tp.sm, tp.cm);      // z_{i+1/2} = z_{(i+1)-1/2}, periodic
+    coef[i] = row_coef<R>(p, variant, lz, lth, g0, gm, gp);
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(SWEEP_NT)
+sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
+                  const CylParams* __restrict__ params, double* __restrict__ chain, uint64_t seed, int64_t replica0,
+                  uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
+                  double* __restrict__ prof) {
+  using C = typename Real<R>::complex_t;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SweepSmemLayout<R> lay(Zmax, T);
+  C* psi = reinterpret_cast<C*>(smem_raw);
+  RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
+  RowTrig* trig = reinterpret_cast<RowTrig*>(smem_raw + lay.off_trig);
+  double* mom = reinterpret_cast<double*>(smem_raw + lay.off_mom);
+  double* scr = reinterpret_cast<double*>(smem_raw + lay.off_scr);
+  SmemScalars* sc = reinterpret_cast<SmemScalars*>(smem_raw + lay.off_sc);
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Z = Zs[b];
+  const int nsite = Z * T;
+  const CylParams p = params[b];
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;     // On_lattice_simple.py:47,:49
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t rep = (uint32_t)(replica0 + b);
+  double* ch = chain + (size_t)b * CYL_CHAIN_DOUBLES;
+  C* psi_b = psi_g + (size_t)b * Zmax * T;
+
+  // ---- prologue: state, lattice, tables ----
+  if (tid == 0) {
+    sc->amp = ch[CYL_CH_AMPLITUDE];
+    sc->sigma_site = ch[CYL_CH_SIGMA_SITE];
+    sc->sigma_amp = ch[CYL_CH_SIGMA_AMP];
+    sc->step_counter = ch[CYL_CH_STEP_COUNTER];
+    sc->site_proposed = ch[CYL_CH_SITE_PROPOSED];
+    sc->site_accepted = ch[CYL_CH_SITE_ACCEPTED];
+    sc->amp_proposed = ch[CYL_CH_AMP_PROPOSED];
+    sc->amp_accepted = ch[CYL_CH_AMP_ACCEPTED];
+    sc->amp_counter = ch[CYL_CH_AMP_COUNTER];
+    sc->flags = ch[CYL_CH_FLAGS];
+    sc->e_field = ch[CYL_CH_E_FIELD];
+  }
+  for (int s = tid; s < nsite; s += SWEEP_NT) psi[s] = psi_b[s];
+  for (int i = tid; i < Z; i += SWEEP_NT) {
+    RowTrig t;
+    sincos(p.wavenumber * (lz * i), &t.s0, &t.c0);
+    sincos(p.wavenumber * (lz * (i - .5)), &t.sm, &t.cm);
+    trig[i] = t;
+  }
+  __syncthreads();
+  build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
+  if ((flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) && warp == 0) {
+    const double es = surface_energy_warp(p, sc->amp, nullptr, nullptr, true);
+    if (lane == 0) sc->e_surf = es;
+  }
+  __syncthreads();
+
+  const int ncol = num_colours(Z, T);
+  const int Th = (T + 1) >> 1, Teven = T & ~1;
+  const int di = SWEEP_NT / Th, dj = SWEEP_NT % Th;
+
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    const uint64_t sweep = sweep0 + (uint64_t)sw;
+    const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
+    const R sigma = (R)sc->sigma_site;
+    int nacc = 0;
+    // ---- 1. site moves ----
+    for (int colour = 0; colour < ncol; ++colour) {
+      int i = tid / Th, jj = tid - i * Th;
+      while (i < Z) {
+        int beta = colour - axis_colour(i, Z);
+        if (beta < 0) beta += ncol;
+        int j;
+        bool valid;
+        if (beta < 2) { j = beta + 2 * jj; valid = j < Teven; }
+        else          { j = T - 1;         valid = (T & 1) && jj == 0; }
+        if (valid) {
+          const int row = i * T;
+          const int rm = (i == 0 ? Z - 1 : i - 1) * T, rp = (i == Z - 1 ? 0 : i + 1) * T;
+          const int jm = (j == 0 ? T - 1 : j - 1), jp = (j == T - 1 ? 0 : j + 1);
+          const C pv = psi[row + j], L = psi[rm + j], Rz = psi[rp + j], W = psi[row + jm], E = psi[row + jp];
+          const RowCoef<R> rc = coef[i];
+          const uint4 x = philox4x32<10>((uint32_t)(row + j), rep, c2, c3, k0, k1);
+          R zre, zim;
+          Draw<R>::normals(x.x, x.y, zre, zim);
+          const R w = sigma * rc.sgmul;
+          const R dre = w * zre, dim = w * zim;
+          const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
+          if (Draw<R>::accept(x.z, den, rc.kacc)) {
+            psi[row + j] = Real<R>::make(pv.x + dre, pv.y + dim);
+            ++nacc;
+          }
+        }
+        jj += dj; i += di;
+        if (jj >= Th) { jj -= Th; ++i; }
+      }
+      __syncthreads();
+    }
+    // ---- 2. Robbins-Monro on sigma_site ----
+    const double acc_total = block_sum<double>((double)nacc, scr);
+    if (tid == 0) {
+      if (flags & CYL_SWEEP_ADAPT_SIGMA)
+        sc->sigma_site = rm_batch_update(sc->sigma_site, sc->step_counter, (double)nsite, acc_total);
+      sc->step_counter += nsite;
+      sc->site_proposed += nsite;
+      sc->site_accepted += acc_total;
+    }
+    if (!(flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE))) { __syncthreads(); continue; }
+
+    // ---- 3. row moments ----
+    {
+      const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
+      for (int i = warp; i < Z; i += SWEEP_NT / 32) {
+        const int row = i * T, rm = (i == 0 ? Z - 1 : i - 1) * T;
+        double m[CYL_NMOM];
+#pragma unroll
+        for (int q = 0; q < CYL_NMOM; ++q) m[q] = 0.0;
+        for (int j = lane; j < T; j += 32)
+          moments_accumulate(m, psi[row + j], psi[rm + j], psi[row + (j == 0 ? T - 1 : j - 1)], inv_lz2, inv_lth2, inv_lth);
+#pragma unroll
+        for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < CYL_NMOM; ++q) mom[i * CYL_NMOM + q] = m[q];
+        }
+      }
+    }
+    // ---- 4. amplitude proposal (thread 0 draws), energies (all threads) ----
+    if (tid == 0) {
+      const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
+      double zre, zim;
+      Draw<double>::normals(x.x, x.y, zre, zim);
+      sc->amp_new = sc->amp + sc->sigma_amp * zre;
+      sc->amp_in_bounds = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(sc->amp_new) < p.amp_bound);
+    }
+    __syncthreads();
+    const double a = sc->amp, a_new = sc->amp_new;
+    const bool try_move = sc->amp_in_bounds != 0;
+    double e_cur = 0.0, e_new = 0.0, s_p2 = 0.0, s_abs = 0.0;
+    {
+      const double ra = geo_radius_rescaled(p.radius, a), ran = geo_radius_rescaled(p.radius, a_new);
+      for (int i = tid; i < Z; i += SWEEP_NT) {
+        const RowTrig t = trig[i];
+        const double* S = mom + i * CYL_NMOM;
+        const Geo g0 = geo_from_sc(p.wavenumber, ra, a, t.s0, t.c0), gm = geo_from_sc(p.wavenumber, ra, a, t.sm, t.cm);
+        e_cur += field_energy_row(variant, p, lz, lth, T, g0, gm, g0, S);
+        if (try_move) {
+          const Geo h0 = geo_from_sc(p.wavenumber, ran, a_new, t.s0, t.c0), hm = geo_from_sc(p.wavenumber, ran, a_new, t.sm, t.cm);
+          e_new += field_energy_row(variant, p, lz, lth, T, h0, hm, g0, S);       // a_ref = current amplitude (:75)
+        }
+        s_p2 += S[0];
+        s_abs += S[5];
+        if ((flags & CYL_SWEEP_MEASURE) && prof) {                               // Lattice.measure :121-131
+          double* pr = prof + ((size_t)b * Zmax + i) * 3;
+          pr[0] += S[6]; pr[1] += S[7]; pr[2] += S[5];
+        }
+      }
+    }
+    e_cur = block_sum<double>(e_cur, scr) * lz * lth;
+    e_new = block_sum<double>(e_new, scr) * lz * lth;
+    if (flags & CYL_SWEEP_MEASURE) {
+      s_p2 = block_sum<double>(s_p2, scr);
+      s_abs = block_sum<double>(s_abs, scr);
+    }
+    if (try_move && warp == 0) {
+      const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
+      if (lane == 0) sc->e_surf_new = es;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sc->e_field = e_cur;
+      if ((flags & CYL_SWEEP_MEASURE) && obs) {                                   // measure_avgs :135-156 + engine record
+        double* o = obs + (size_t)b * CYL_OBS_DOUBLES;
+        o[CYL_OB_COUNT] += 1.0;
+        o[CYL_OB_ABS_A] += fabs(a);
+        o[CYL_OB_A] += a;
+        o[CYL_OB_A2] += a * a;
+        o[CYL_OB_PSI2] += s_p2 / nsite;
+        o[CYL_OB_ABSPSI] += s_abs / nsite;
+        o[CYL_OB_E_FIELD] += e_cur;
+        o[CYL_OB_E_SURF] += sc->e_surf;
+        o[CYL_OB_E_FIELD2] += e_cur * e_cur;
+        o[CYL_OB_SIGMA] += sc->sigma_site;
+      }
+      int accept = 0;
+      if (flags & CYL_SWEEP_AMP_MOVES) {
+        if (try_move) {
+          const double dE = (sc->e_surf_new + e_new) - (sc->e_surf + e_cur);
+          if (!isfinite(dE)) sc->flags = (double)((unsigned)sc->flags | 1u);
+          const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
+          if (dE <= 0) accept = 1;                                                // accept rule B.2
+          else if (p.temperature == 0) accept = 0;
+          else accept = (u01_f64(x.z) <= exp(-dE / p.temperature));
+        }
+        // Robbins-Monro on sigma_amp (engine, SURVEY.md B.3: m = 1, target p*)
+        const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
+        const double ratio = 1.0 / (pt * (1.0 - pt));
+        sc->amp_counter += 1;
+        sc->amp_proposed += 1;
+        const double f = fmax(sc->amp_counter, 200.0), c = sc->sigma_amp * ratio;
+        if (flags & CYL_SWEEP_ADAPT_SIGMA) {
+          if (accept) sc->sigma_amp += c * (1 - pt) / f;
+          else sc->sigma_amp -= c * pt / f;
+        }
+        if (accept) {
+          sc->amp = a_new;
+          sc->e_surf = sc->e_surf_new;
+          sc->amp_accepted += 1;
+        }
+      }
+      sc->amp_accept = accept;
+    }
+    __syncthreads();
+    // ---- 5. metric tables follow the amplitude ----
+    if (sc->amp_accept) {
+      build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  __syncthreads();
+  for (int s = tid; s < nsite; s += SWEEP_NT) psi_b[s] = psi[s];
+  if (tid == 0) {
+    ch[CYL_CH_AMPLITUDE] = sc->amp;
+    ch[CYL_CH_SIGMA_SITE] = sc->sigma_site;
+    ch[CYL_CH_SIGMA_AMP] = sc->sigma_amp;
+    ch[CYL_CH_E_FIELD] = sc->e_field;
+    if (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) ch[CYL_CH_E_SURF] = sc->e_surf;
+    ch[CYL_CH_STEP_COUNTER] = sc->step_counter;
+    ch[CYL_CH_SITE_PROPOSED] = sc->site_proposed;
+    ch[CYL_CH_SITE_ACCEPTED] = sc->site_accepted;
+    ch[CYL_CH_AMP_PROPOSED] = sc->amp_proposed;
+    ch[CYL_CH_AMP_ACCEPTED] = sc->amp_accepted;
+    ch[CYL_CH_AMP_COUNTER] = sc->amp_counter;
+    ch[CYL_CH_FLAGS] = sc->flags;
+  }
+}
+
+template <typename R>
+static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params, double* chain,
+                      uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags,
+                      double* obs, double* prof, void* stream) {
+  CYL_CHECK_ARG(psi && Z && params && chain && B > 0 && Zmax > 0 && T > 1 && nsweeps >= 0, "cyl_sweep_smem: bad arguments");
+  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_sweep_smem: unknown variant %d", variant);
+  CYL_CHECK_ARG(!(flags & CYL_SWEEP_MEASURE) || obs, "cyl_sweep_smem: CYL_SWEEP_MEASURE needs obs");
+  if (nsweeps == 0) return CYL_OK;
+  const SweepSmemLayout<R> lay(Zmax, T);
+  int dev = 0, max_optin = 0;
+  CYL_CUDA(cudaGetDevice(&dev));
+  CYL_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (lay.total > (size_t)max_optin) {
+    cyl_set_error("cyl_sweep_smem: lattice %d x %d needs %zu B of shared memory (> %d); use the HBM path", Zmax, T,
+                  lay.total, max_optin);
+    return CYL_E_UNSUPPORTED;
+  }
+  auto kern = sweep_smem_kernel<R>;
+  CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+  kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, seed,
+                                                      replica0, sweep0, nsweeps, variant, flags, obs, prof);
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+
+extern "C" int cyl_sweep_smem_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                                  double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                                  int variant, uint32_t flags, double* obs, double* prof, void* stream) {
+  return sweep_smem<float>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, stream);
+}
+extern "C" int cyl_sweep_smem_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                                  double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                                  int variant, uint32_t flags, double* obs, double* prof, void* stream) {
+  return sweep_smem<double>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, stream);
+}

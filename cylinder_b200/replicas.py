@@ -1,0 +1,147 @@
+"""Batched replicas: the (alpha, C, n, kappa, k, ...) parameter grid that the reference farms out as one OS process
+per grid point (scripts/taskarray.sh -> scripts/cylinder_array.sh:10-15 -> parallel_single_run.py) runs here as
+ONE launch: replica b of the batch = task b of the SGE array.  Replicas never interact, so across GPUs they shard
+by contiguous index range, one process per GPU, with a single NCCL all-gather of the observable records standing
+in for the reference's `glob("*_mean.csv")` join (parallel_postprocessing.py:8-29).
+"""
+import numpy as np
+import torch
+
+from . import _abi, ops
+from ._abi import SWEEP_ADAPT_SIGMA, SWEEP_AMP_MOVES, SWEEP_MEASURE
+
+OBS_NAMES = ("abs_amplitude", "amplitude", "amplitude_squared", "psi_squared", "abs_psi", "field_energy", "surface_energy",
+             "field_energy_squared", "sampling_width")
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous replica index range [lo, hi) owned by `rank` (balanced to within one replica)."""
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def parameter_grid(**axes):
+    """Cartesian product of named 1-D axes -> dict of flat arrays (first axis slowest), like the reference's
+    varfile.txt written by parallel_preprocessing.py:22-46."""
+    names = list(axes)
+    grids = np.meshgrid(*[np.asarray(axes[n], dtype=np.float64) for n in names], indexing="ij")
+    return {n: g.ravel() for n, g in zip(names, grids)}
+
+
+class ReplicaBatch:
+    """B independent Lattice chains on one GPU, lattices resident in shared memory during a launch.
+
+    params: dict name -> scalar or array[B] with the reference's constructor names (wavenumber, radius, gamma, kappa,
+    intrinsic_curvature, alpha, u, C, n, temperature) plus amp_bound / amp_target_acceptance.
+    `replica0` is the global index of local replica 0 (the Philox stream of a replica depends only on its global
+    index and the seed, so results do not depend on how the batch is sharded)."""
+
+    def __init__(self, params, dims=(50, 50), variant="simple", dtype=torch.complex64, device=None, seed=0, replica0=0,
+                 amplitude=0.0, sigma_site=.005, sigma_amp=.005, init_magnitude=.1, initialize=True):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        _abi.lib()                                           # fail loudly if the CUDA library is missing
+        self.params = ops.make_params(self.device, **params)
+        self.B = self.params.shape[0]
+        k = self.params[:, 0].cpu().numpy()
+        zs = np.array([ops.lattice_dims(dims, kk)[0] for kk in k], dtype=np.int32)      # On_lattice_simple.py:41
+        self.T = int(dims[1])
+        self.Zmax = int(zs.max())
+        self.Z_host = zs
+        self.Z = torch.from_numpy(zs).to(self.device)
+        self.variant = ops.variant_id(variant)
+        self.dtype = dtype
+        self.seed, self.replica0 = int(seed), int(replica0)
+        self.psi = torch.zeros(self.B, self.Zmax, self.T, dtype=dtype, device=self.device)
+        if initialize:
+            ops.lattice_init(self.psi, self.Z, init_magnitude, self.seed, self.replica0)
+        self.chain = ops.new_chain(self.B, self.device, amplitude, sigma_site, sigma_amp)
+        self.obs, self.prof = ops.new_obs(self.B, self.Zmax, self.device)
+        self.sweeps_done = 0
+
+    # ---- hot path --------------------------------------------------------------------------------------
+    @property
+    def sites(self):
+        """Site-updates per sweep summed over the batch."""
+        return int(self.Z_host.astype(np.int64).sum()) * self.T
+
+    def run(self, nsweeps, amp_moves=True, measure=True, adapt=True):
+        flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
+        ops.sweep_smem(self.psi, self.Z, self.params, self.chain, self.seed, self.sweeps_done, nsweeps, self.variant, flags,
+                       self.replica0, self.obs, self.prof)
+        self.sweeps_done += int(nsweeps)
+        return self
+
+    def reset_observables(self):
+        self.obs.zero_()
+        self.prof.zero_()
+
+    # ---- observables -----------------------------------------------------------------------------------
+    def observables(self):
+        """Per-replica means over the measurements so far: dict name -> tensor[B] (device)."""
+        n = self.obs[:, _abi.OB_COUNT].clamp(min=1.0)
+        out = {name: self.obs[:, 1 + i] / n for i, name in enumerate(OBS_NAMES)}
+        ch = self.chain
+        out["site_acceptance"] = ch[:, _abi.CH_SITE_ACCEPTED] / ch[:, _abi.CH_SITE_PROPOSED].clamp(min=1.0)
+        out["amplitude_acceptance"] = ch[:, _abi.CH_AMP_ACCEPTED] / ch[:, _abi.CH_AMP_PROPOSED].clamp(min=1.0)
+        out["n_measurements"] = self.obs[:, _abi.OB_COUNT]
+        return out
+
+    def profiles(self):
+        """(<Psi>(z), <|Psi|>(z)) per replica, theta- and time-averaged: Lattice.get_profiles_df (On_lattice_simple.py:109-118)."""
+        n = self.obs[:, _abi.OB_COUNT].clamp(min=1.0)[:, None] * self.T
+        return torch.complex(self.prof[..., 0], self.prof[..., 1]) / n, self.prof[..., 2] / n
+
+    def record(self):
+        """Fixed-size per-replica record [B, 16 + 16 + 3*Zmax] (obs | chain | profiles) -- the gather payload."""
+        return torch.cat([self.obs, self.chain, self.prof.reshape(self.B, -1)], dim=1).contiguous()
+
+    def gather_records(self, group=None):
+        """All ranks' records, concatenated in replica order, on every rank (one NCCL all-gather; gloo on CPU tests)."""
+        import torch.distributed as dist
+        rec = self.record()
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return rec
+        return gather_ragged(rec, group)
+
+    # ---- host round trips ------------------------------------------------------------------------------
+    @property
+    def lattice(self):
+        """numpy [B, Zmax, T] complex (rows >= Z[b] are zero)."""
+        return self.psi.cpu().numpy()
+
+    def load_host(self, psi_host, chain_host=None, non_blocking=True):
+        """Upload lattices (and chain state) from host tensors (pinned for async copies)."""
+        self.psi.copy_(psi_host, non_blocking=non_blocking)
+        if chain_host is not None:
+            self.chain.copy_(chain_host, non_blocking=non_blocking)
+
+    def state_dict(self):
+        return dict(psi=self.psi.cpu(), chain=self.chain.cpu(), obs=self.obs.cpu(), prof=self.prof.cpu(), seed=self.seed,
+                    replica0=self.replica0, sweeps_done=self.sweeps_done, variant=self.variant)
+
+    def load_state_dict(self, sd):
+        """Exact resume: the counter-based RNG has no state beyond (seed, replica, sweep index)."""
+        self.psi.copy_(sd["psi"])
+        self.chain.copy_(sd["chain"])
+        self.obs.copy_(sd["obs"])
+        self.prof.copy_(sd["prof"])
+        self.seed, self.replica0, self.sweeps_done = int(sd["seed"]), int(sd["replica0"]), int(sd["sweeps_done"])
+
+
+def gather_ragged(rec, group=None):
+    """all_gather of [B_r, W] tensors whose B_r (and W) may differ by rank: pad to the max, gather, trim."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    shape = torch.tensor(list(rec.shape), dtype=torch.int64, device=rec.device)
+    shapes = [torch.zeros_like(shape) for _ in range(world)]
+    dist.all_gather(shapes, shape, group=group)
+    bmax = max(int(s[0]) for s in shapes)
+    wmax = max(int(s[1]) for s in shapes)
+    pad = torch.zeros(bmax, wmax, dtype=rec.dtype, device=rec.device)
+    pad[: rec.shape[0], : rec.shape[1]] = rec
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[: int(s[0])] for o, s in zip(outs, shapes)], dim=0)

@@ -1,0 +1,213 @@
+/* cylinder_b200.h -- C-ABI of the B200-native Metropolis engine for the jklebes/cylinder hot path.
+ *
+ * The reference (pure Python, /root/reference) has no FFI boundary of its own; its boundary is the
+ * Python object API.  Each entry point below replaces the inner loop of one reference
+ * function, cited as <file>:<line> relative to /root/reference/surfaces_and_fields/ unless noted.  The
+ * Python mirror of the reference API (cylinder_b200/*.py) binds these through ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every buffer is a CALLER-OWNED DEVICE pointer (a torch tensor's data_ptr()); the library allocates
+ *     nothing that outlives a call and never frees caller memory;
+ *   - work is enqueued on the caller's stream (`stream` = cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no host synchronisation inside unless the function says so;
+ *   - return 0 on success, negative CYL_E_* on error, text in cyl_last_error() (thread-local);
+ *   - no C++ exceptions cross the boundary; no global mutable state besides the per-thread error text;
+ *   - complex numbers are interleaved (re, im), row-major [z][theta], theta fastest -- the memory layout
+ *     of numpy complex64 / complex128, so `.lattice` round-trips without repacking.
+ */
+#ifndef CYLINDER_B200_H
+#define CYLINDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYL_ABI_VERSION 3
+
+/* error codes */
+#define CYL_OK             0
+#define CYL_E_INVALID     (-1)   /* bad argument */
+#define CYL_E_CUDA        (-2)   /* CUDA runtime / driver error (text has the CUDA string) */
+#define CYL_E_UNSUPPORTED (-3)   /* shape or option outside what the kernel was built for */
+
+/* dE variants: which reference class the single-site move restates */
+#define CYL_VARIANT_SIMPLE        0   /* On_lattice_simple.py:598-686            */
+#define CYL_VARIANT_RESCALED_0TH  1   /* On_lattice_rescaled_0thorder.py:116-209 */
+
+/* flags of the sweep entry points */
+#define CYL_SWEEP_ADAPT_SIGMA   1u    /* Robbins-Monro width adaptation (On_lattice_simple.py:688-696) */
+#define CYL_SWEEP_AMP_MOVES     2u    /* one global amplitude move per sweep (run_lattice.py:72-90)     */
+#define CYL_SWEEP_MEASURE       4u    /* accumulate observables after every sweep (:121-156)            */
+
+/* Physical parameters of one replica = constructor arguments of the reference's
+ * Cylinder (system_cylinder.py:15) and Lattice (On_lattice_simple.py:18-19). 12 doubles. */
+typedef struct CylParams {
+  double wavenumber;            /* k                                                  */
+  double radius;                /* r                                                  */
+  double gamma;                 /* surface tension                                    */
+  double kappa;                 /* bending rigidity                                   */
+  double intrinsic_curvature;   /* H0                                                 */
+  double alpha, u, C, n;        /* field couplings                                    */
+  double temperature;           /* T of both the site moves and the amplitude move    */
+  double amp_bound;             /* reject |a'| >= amp_bound (.8 On_lattice_simple.py:83, .99 run.py:281) */
+  double amp_target_acceptance; /* Robbins-Monro target of the amplitude move (engine default .3); 0 = .3 */
+} CylParams;
+
+/* Mutable per-replica chain state, CYL_CHAIN_DOUBLES doubles per replica (counters are stored as
+ * doubles: exact to 2^53). */
+#define CYL_CHAIN_DOUBLES 16
+#define CYL_CH_AMPLITUDE     0   /* a                         Lattice.amplitude                         */
+#define CYL_CH_SIGMA_SITE    1   /* sampling_width            On_lattice_simple.py:101                  */
+#define CYL_CH_SIGMA_AMP     2   /* real_group_sampling_width engine                                    */
+#define CYL_CH_E_FIELD       3   /* last surface_field_energy(a, a)                                     */
+#define CYL_CH_E_SURF        4   /* last calc_surface_energy(a)                                         */
+#define CYL_CH_STEP_COUNTER  5   /* Robbins-Monro step counter of the site moves (:689)                 */
+#define CYL_CH_SITE_PROPOSED 6
+#define CYL_CH_SITE_ACCEPTED 7   /* acceptance_counter                                                  */
+#define CYL_CH_AMP_PROPOSED  8
+#define CYL_CH_AMP_ACCEPTED  9
+#define CYL_CH_AMP_COUNTER  10   /* Robbins-Monro step counter of the amplitude moves                   */
+#define CYL_CH_FLAGS        11   /* bit0: non-finite energy seen                                         */
+
+/* Per-replica observable accumulators (sums over measurements), CYL_OBS_DOUBLES doubles. */
+#define CYL_OBS_DOUBLES 16
+#define CYL_OB_COUNT     0
+#define CYL_OB_ABS_A     1   /* sum |a|         measure_avgs :137-138 */
+#define CYL_OB_A         2   /* sum a                                 */
+#define CYL_OB_A2        3   /* sum a^2                               */
+#define CYL_OB_PSI2      4   /* sum of lattice-mean |psi|^2           */
+#define CYL_OB_ABSPSI    5   /* sum of lattice-mean |psi|             */
+#define CYL_OB_E_FIELD   6
+#define CYL_OB_E_SURF    7
+#define CYL_OB_E_FIELD2  8
+#define CYL_OB_SIGMA     9   /* sum of sigma_site                     */
+
+/* ---------------------------------------------------------------- library ---------------------------- */
+int         cyl_abi_version(void);
+const char* cyl_last_error(void);                 /* thread-local; valid until the next call on this thread */
+int         cyl_set_device(int device);           /* cudaSetDevice for this thread's calls                  */
+int         cyl_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
+
+/* ---------------------------------------------------------------- surface geometry ------------------- */
+/* system_cylinder.py:25-41 evaluated on the device: out[i] = {radius_rescaled, sqrt_g_theta, g_theta,
+ * sqrt_g_z, g_z, A_theta}(a[i], z[i]).  Parity hook for tests/golden/geometry.npz. */
+int cyl_geometry_eval_f64(double wavenumber, double radius, const double* a, const double* z, int64_t n,
+                          double* out /*[n][6]*/, void* stream);
+
+/* Cylinder.calc_surface_energy (system_cylinder.py:119-124): E(m) by AGM, the two bending integrals by a
+ * 256-node periodic trapezoid.  out_terms (may be NULL) = {A_integral_0, bending} per replica. */
+int cyl_surface_energy_f64(const CylParams* params /*[B]*/, const double* amp /*[B]*/, int B,
+                           double* E_out /*[B]*/, double* out_terms /*[B][2] or NULL*/, void* stream);
+
+/* ---------------------------------------------------------------- counter-based RNG ------------------ */
+/* Philox4x32-10 known-answer hook: out[i] = philox(ctr[i], key[i]). */
+int cyl_philox4x32_10(const uint32_t* ctr /*[n][4]*/, const uint32_t* key /*[n][2]*/, int64_t n,
+                      uint32_t* out /*[n][4]*/, void* stream);
+
+/* Lattice.random_initialize (On_lattice_simple.py:159-182): psi = rect(U(0,mag_max), U(0,2pi)), drawn from
+ * Philox keyed (seed; site, replica0+b).  psi is [B][Zmax][T]; rows >= Z[b] are zeroed. */
+int cyl_lattice_init_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, double mag_max,
+                         uint64_t seed, int64_t replica0, void* stream);
+int cyl_lattice_init_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, double mag_max,
+                         uint64_t seed, int64_t replica0, void* stream);
+
+/* ---------------------------------------------------------------- sequential replay (parity mode) ---- */
+/* n proposals of Lattice.step_lattice_loc (On_lattice_simple.py:598-686 / 0th-order :116-209) replayed
+ * strictly in order from a recorded random tape: site (iz, ith) in the reference's [-1, len-2] convention,
+ * unit normals (zre drawn first), uniform u (NaN where the reference drew none).  fp64, arithmetic in the
+ * reference's operation order, no FMA contraction.  rm_state = {sigma, step_counter} is read and written.
+ * Outputs (each may be NULL): accept[n], dE[n], sigma_after[n]. */
+int cyl_replay_f64(double* psi /*[Z][T] complex128*/, int Z, int T, const CylParams* params /*[1]*/,
+                   double amp, int variant, const int32_t* iz, const int32_t* ith,
+                   const double* zre, const double* zim, const double* u, int64_t n,
+                   double* rm_state /*[2]*/, uint8_t* accept_out, double* dE_out, double* sigma_out,
+                   void* stream);
+
+/* One proposal with a supplied increment (d_re, d_im): out = {dE, new_re, new_im}.  Does not write psi.
+ * Serves Lattice.step_lattice_loc when the host draws from Python's `random` like the reference. */
+int cyl_site_delta_f64(const double* psi, int Z, int T, const CylParams* params, double amp, int variant,
+                       int iz, int ith, double d_re, double d_im, double* out /*[3]*/, void* stream);
+
+/* ---------------------------------------------------------------- field energy ----------------------- */
+/* Row moments S1..S5 of psi[B][Zmax][T]: sum_j |psi|^2, |psi|^4, |dz|^2, |dth|^2,
+ * Im(conj(psi) dth), left differences divided by the pixel lengths; plus S6 = sum_j |psi|, S7/S8 = sum_j psi.
+ * out is [B][Zmax][8] doubles (fp64 accumulation for both storage types). */
+int cyl_row_moments_f32(const void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                        double* S, void* stream);
+int cyl_row_moments_f64(const void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                        double* S, void* stream);
+
+/* Lattice.surface_field_energy(a_eval, a_ref, ...) (On_lattice_simple.py:185-213; 0th-order :247-278)
+ * from row moments: E_out[b]. */
+int cyl_field_energy_f64(const double* S /*[B][Zmax][8]*/, int B, const int32_t* Z, int Zmax, int T,
+                         const CylParams* params, const double* amp_eval, const double* amp_ref,
+                         int variant, double* E_out, void* stream);
+
+/* ---------------------------------------------------------------- batched replica sweeps ------------- */
+/* nsweeps checkerboard sweeps of B independent replicas, one CTA per replica, lattice resident in shared
+ * memory for the whole launch.  Per sweep: every site proposed once (2 colours, 3 when Z or T is odd),
+ * then, per flags, Robbins-Monro update of sigma_site, one amplitude move a' = a + sigma_amp*N(0,1)
+ * accepted on E_surf + E_field(a', a) (On_lattice_simple.py:544-550 via engine.step_real_group), and
+ * observable accumulation.  Philox counter = (site, replica0+b, sweep0+s, stream tag); key = seed.
+ * psi [B][Zmax][T]; chain [B][CYL_CHAIN_DOUBLES]; obs [B][CYL_OBS_DOUBLES] and prof [B][Zmax][3]
+ * (sum_theta Re psi, Im psi, |psi| summed over measurements) may be NULL when CYL_SWEEP_MEASURE is off. */
+int cyl_sweep_smem_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                       double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                       int variant, uint32_t flags, double* obs, double* prof, void* stream);
+int cyl_sweep_smem_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                       double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                       int variant, uint32_t flags, double* obs, double* prof, void* stream);
+
+/* ---------------------------------------------------------------- one large lattice ------------------ */
+/* Workspace of the HBM path.  The lattice lives in a ping-pong pair of halo-padded buffers, each split into
+ * two column-parity planes (even / odd padded column) so that one checkerboard colour of a row is contiguous:
+ *   work[buf][plane][Z + 2*halo_rows][pitch/2] complex,   padded (row, col) = (i + halo_rows, j + halo_cols),
+ * halo rows / columns hold periodic copies.  cyl_hbm_layout reports the geometry; work must hold
+ * 2*buffer_elems complex elements, scratch scratch_bytes bytes (row coefficients, row moments, counters). */
+int cyl_hbm_layout(int Z, int T, int is_f64, int* halo_rows, int* halo_cols, int64_t* pitch_elems,
+                   int64_t* buffer_elems, int64_t* scratch_bytes);
+/* psi [Z][T] (numpy layout) -> work buffer 0 incl. halos; sets *cur = 0.  unpack reads buffer *cur. */
+int cyl_hbm_pack_f32(const void* psi, int Z, int T, void* work, int32_t* cur, void* stream);
+int cyl_hbm_pack_f64(const void* psi, int Z, int T, void* work, int32_t* cur, void* stream);
+int cyl_hbm_unpack_f32(const void* work, const int32_t* cur, int Z, int T, void* psi, void* stream);
+int cyl_hbm_unpack_f64(const void* work, const int32_t* cur, int Z, int T, void* psi, void* stream);
+
+/* nsweeps checkerboard sweeps of one Z x T lattice streamed from HBM.  One CTA per 2-D tile; the tile plus a
+ * halo of one site per colour is staged into shared memory by TMA (cp.async.bulk.tensor.2d, one box per
+ * parity plane, completion on an mbarrier); ALL colours of the sweep are then updated in shared memory (halo
+ * sites are recomputed redundantly -- the counter-based RNG makes that bit-identical to the neighbour tile's
+ * own result) and the interior is written to the other buffer, so a sweep moves 8 B read + 8 B written per
+ * site (fp32) instead of one read + one write per colour.  `cur` (device int32) is flipped per sweep.
+ * chain [CYL_CHAIN_DOUBLES] device.  Accept counts feed the Robbins-Monro sigma update once per sweep; with
+ * CYL_SWEEP_AMP_MOVES / CYL_SWEEP_MEASURE a row-moment pass and an amplitude move / measurement follow every
+ * sweep.  obs [CYL_OBS_DOUBLES], prof [Z][3] may be NULL without CYL_SWEEP_MEASURE. */
+int cyl_sweep_hbm_f32(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain,
+                      uint64_t seed, int64_t replica, uint64_t sweep0, int nsweeps, int variant,
+                      uint32_t flags, void* scratch, double* obs, double* prof, void* stream);
+int cyl_sweep_hbm_f64(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain,
+                      uint64_t seed, int64_t replica, uint64_t sweep0, int nsweeps, int variant,
+                      uint32_t flags, void* scratch, double* obs, double* prof, void* stream);
+/* Row moments of the lattice held in work[*cur] -> S [Z][8] (same columns as cyl_row_moments_*). */
+int cyl_hbm_row_moments_f32(const void* work, const int32_t* cur, int Z, int T, const CylParams* params,
+                            double* S, void* stream);
+int cyl_hbm_row_moments_f64(const void* work, const int32_t* cur, int Z, int T, const CylParams* params,
+                            double* S, void* stream);
+
+/* ---------------------------------------------------------------- Fourier-mode model ----------------- */
+/* Cylinder2D.calc_field_energy / calc_field_energy_amplitude_change (system_cylinder2D.py:151-198) by the
+ * real-space quadrature of SURVEY.md A.7: E[b] for coefficient sets c[b][(2*nth+1)][(2*nz+1)] complex128
+ * at amplitudes a[b].  One warp per chain. */
+int cyl_fourier_energy_f64(const CylParams* params /*[B]*/, int nz, int nth, const double* amp /*[B]*/,
+                           const double* coeffs /*[B][ncoef] complex128*/, int B, double* E_out, void* stream);
+
+/* Cylinder1D.calc_surface_energy (system_cylinder1D.py:189-194): gamma_eff*int(G_th G_z) + kappa*bending. */
+int cyl_fourier_surface_energy_f64(const CylParams* params, const double* amp, int B, double* E_out,
+                                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYLINDER_B200_H */

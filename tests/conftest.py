@@ -26,3 +26,25 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Path of libcylinder_b200.so; (re)built incrementally when nvcc is present, else the shipped file."""
+    from cylinder_b200 import build as b
+    try:
+        return b.build()
+    except RuntimeError:
+        if os.path.exists(b.lib_path()):
+            return b.lib_path()
+        raise
+
+
+@pytest.fixture(scope="session")
+def cuda(built_lib):
+    """torch CUDA device for -m gpu tests; fails (not skips) when the extension cannot load."""
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    from cylinder_b200 import _abi
+    _abi.lib()
+    return torch.device("cuda", 0)

@@ -1,0 +1,336 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the golden vectors recorded from the reference
+and against the oracle on the same seeded inputs.  Bars: accept/reject sequences exact; fp64 energies within
+1e-10 relative (BASELINE.json north_star); the fp32 kernels within the tolerances written at each test."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import checkerboard_oracle as cb
+from oracle import lattice_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LATTICE_CASES = sorted(os.path.basename(p)[len("lattice_"):-4] for p in glob.glob(os.path.join(HERE, "golden", "lattice_*.npz")))
+
+
+def _load_case(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "lattice_%s.npz" % tag))
+    P = dict(zip(g["params_names"].tolist(), g["params"].tolist()))
+    variant = lo.SIMPLE if str(g["variant"]) == "On_lattice_simple" else lo.RESCALED_0TH
+    return g, P, variant
+
+
+def _params(ops, dev, P, **over):
+    kw = dict(P)
+    kw.update(over)
+    return ops.make_params(dev, **kw)
+
+
+def test_geometry_matches_reference(cuda, golden_dir):
+    import torch
+    from cylinder_b200 import ops
+    t = np.load(os.path.join(golden_dir, "geometry.npz"))["table"]
+    for k, r in sorted(set(map(tuple, t[:, :2]))):
+        rows = t[(t[:, 0] == k) & (t[:, 1] == r)]
+        out = ops.geometry_eval(k, r, torch.tensor(rows[:, 2], device=cuda), torch.tensor(rows[:, 3], device=cuda)).cpu().numpy()
+        np.testing.assert_allclose(out, rows[:, 4:10], rtol=2e-15, atol=1e-16)
+
+
+def test_surface_energy_matches_reference(cuda, golden_dir):
+    """Cylinder.calc_surface_energy incl. the reference's own tables surfenergy_H0.csv / curvenergy_H0.csv."""
+    import torch
+    from cylinder_b200 import ops
+    g = np.load(os.path.join(golden_dir, "surface_energy.npz"))
+    d = g["direct"]
+    par = ops.make_params(cuda, wavenumber=d[:, 0], radius=d[:, 1], gamma=d[:, 2], kappa=d[:, 3], intrinsic_curvature=d[:, 4],
+                          alpha=-1, u=1, C=1, n=1, temperature=.01)
+    E, terms = ops.surface_energy(par, torch.tensor(d[:, 5], device=cuda), return_terms=True)
+    np.testing.assert_allclose(terms[:, 0].cpu().numpy(), d[:, 6], rtol=1e-12)
+    np.testing.assert_allclose(terms[:, 1].cpu().numpy(), d[:, 7], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(E.cpu().numpy(), d[:, 8], rtol=1e-10)
+    A, K = np.meshgrid(g["a_vals"], g["k_vals"], indexing="ij")
+    par = ops.make_params(cuda, wavenumber=K.ravel(), radius=1.0, gamma=1.0, kappa=1.0, intrinsic_curvature=0.0, alpha=-1, u=1,
+                          C=1, n=1, temperature=.01)
+    _, terms = ops.surface_energy(par, torch.tensor(A.ravel(), device=cuda), return_terms=True)
+    np.testing.assert_allclose(terms[:, 0].cpu().numpy().reshape(A.shape), g["surfenergy_H0"], rtol=1e-12)
+    np.testing.assert_allclose(terms[:, 1].cpu().numpy().reshape(A.shape), g["curvenergy_H0"], rtol=1e-10)
+
+
+def test_philox_known_answers(cuda):
+    import torch
+    from cylinder_b200 import ops
+    ctr = torch.from_numpy(np.array([k[0] for k in cb.PHILOX_KAT], dtype=np.uint32).view(np.int32)).to(cuda)
+    key = torch.from_numpy(np.array([k[1] for k in cb.PHILOX_KAT], dtype=np.uint32).view(np.int32)).to(cuda)
+    out = ops.philox4x32_10(ctr.contiguous(), key.contiguous()).cpu().numpy().view(np.uint32)
+    assert out.tolist() == [list(k[2]) for k in cb.PHILOX_KAT]
+
+
+@pytest.mark.parametrize("tag", LATTICE_CASES)
+def test_replay_reproduces_reference_chain(cuda, golden_dir, tag):
+    """A chain fed the reference's recorded random stream reproduces its accept/reject sequence exactly; dE within
+    1e-10 relative; sigma trajectory and final lattice to rounding."""
+    import torch
+    from cylinder_b200 import ops
+    g, P, variant = _load_case(golden_dir, tag)
+    par = _params(ops, cuda, P)
+    psi = torch.tensor(g["psi0"], dtype=torch.complex128, device=cuda).contiguous()
+    rm = torch.tensor([.005, 0.0], dtype=torch.float64, device=cuda)
+    u = np.where(np.isfinite(g["u"]), g["u"], 2.0)          # never consulted where the reference drew none
+    acc, dE, sig = ops.replay(psi, par, float(g["amp"]), variant, torch.tensor(g["iz"], device=cuda), torch.tensor(g["ith"], device=cuda),
+                              torch.tensor(g["zre"], device=cuda), torch.tensor(g["zim"], device=cuda), torch.tensor(u, device=cuda), rm)
+    assert np.array_equal(acc.cpu().numpy(), g["accept"])
+    np.testing.assert_allclose(dE.cpu().numpy(), g["dE"], rtol=1e-10, atol=1e-18)
+    np.testing.assert_allclose(sig.cpu().numpy(), g["sigma"], rtol=1e-12)
+    np.testing.assert_allclose(psi.cpu().numpy(), g["psi_final"], rtol=0, atol=1e-14)
+    assert rm[1].item() == int(g["step_counter"])
+    # the drawn uniforms were consulted exactly where the reference drew them
+    drew = np.isfinite(g["u"])
+    assert np.all((g["dE"] > 0)[drew]) and (P["temperature"] == 0 or np.all(drew[g["dE"] > 0]))
+
+
+@pytest.mark.parametrize("tag", LATTICE_CASES)
+def test_field_energy_matches_reference(cuda, golden_dir, tag):
+    """surface_field_energy(a', a_ref) of the reference's initial and final configurations, fp64, <= 1e-10 relative;
+    profiles of Lattice.measure."""
+    import torch
+    from cylinder_b200 import ops
+    g, P, variant = _load_case(golden_dir, tag)
+    par = _params(ops, cuda, P)
+    for key_psi, key_e in (("psi0", "field_energy_initial"), ("psi_final", "field_energy_final")):
+        psi = torch.tensor(g[key_psi], dtype=torch.complex128, device=cuda)[None].contiguous()
+        Z = torch.tensor([psi.shape[1]], dtype=torch.int32, device=cuda)
+        S = ops.row_moments(psi, Z, par)
+        for a2, ar, e in g[key_e]:
+            E = ops.field_energy(S, Z, psi.shape[2], par, torch.tensor([a2], device=cuda), torch.tensor([ar], device=cuda), variant)
+            assert E.item() == pytest.approx(e, rel=1e-10)
+    np.testing.assert_allclose(S[0, :, 6].cpu().numpy() + 1j * S[0, :, 7].cpu().numpy(), g["profile_sum"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(S[0, :, 5].cpu().numpy(), g["profile_abs_sum"], rtol=1e-12)
+    # fp32 storage: same energies within 2e-6 relative (fp32 rounding of psi, fp64 accumulation)
+    psi32 = psi.to(torch.complex64)
+    S32 = ops.row_moments(psi32, Z, par)
+    a2, ar, e = g["field_energy_final"][1]
+    E32 = ops.field_energy(S32, Z, psi.shape[2], par, torch.tensor([a2], device=cuda), torch.tensor([ar], device=cuda), variant)
+    assert E32.item() == pytest.approx(e, rel=2e-6)
+
+
+def test_known_answer_uniform_field(cuda):
+    """tests/test_On_lattice.py:75-88 of the reference: psi == 1, alpha=-1, u=1, a=0  =>  E = -2 pi^2 on (500,250) and (50,25)."""
+    import torch
+    from cylinder_b200 import ops
+    par = ops.make_params(cuda, wavenumber=1, radius=1, alpha=-1, u=1, C=1, n=1, temperature=.01)
+    for dims in ((500, 250), (50, 25)):
+        Zl, T = ops.lattice_dims(dims, 1.0)
+        psi = torch.ones(1, Zl, T, dtype=torch.complex128, device=cuda)
+        Z = torch.tensor([Zl], dtype=torch.int32, device=cuda)
+        E = ops.field_energy(ops.row_moments(psi, Z, par), Z, T, par, torch.zeros(1, device=cuda), None, 0)
+        assert E.item() == pytest.approx(-.5 * 4 * math.pi ** 2, rel=1e-12)
+
+
+def _oracle_state(psi, P, variant, sigma):
+    st = lo.LatticeState(psi, P["wavenumber"], P["radius"], P["alpha"], P["u"], P["C"], P["n"], P["temperature"], variant=variant)
+    st.sigma = sigma
+    return st
+
+
+CHECKER_CASES = [  # (Z, T, variant, a, temperature)
+    (12, 10, lo.SIMPLE, 0.3, .05), (12, 10, lo.RESCALED_0TH, -0.45, .05), (11, 10, lo.SIMPLE, 0.3, .05),
+    (12, 9, lo.RESCALED_0TH, 0.2, .05), (7, 5, lo.SIMPLE, -0.6, .2), (10, 8, lo.SIMPLE, 0.5, 0.0),
+]
+
+
+@pytest.mark.parametrize("Z,T,variant,a,temp", CHECKER_CASES)
+def test_smem_sweep_f64_matches_oracle(cuda, Z, T, variant, a, temp):
+    """fp64 shared-memory checkerboard kernel vs the numpy restatement, same Philox stream, several sweeps incl. odd
+    rings (3 colours): lattice to 1e-11, identical accept counts and Robbins-Monro sigma."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-.8, u=1.2, C=.9, n=3, temperature=temp)
+    rng = np.random.RandomState(Z * 100 + T)
+    psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
+    st = _oracle_state(psi0.copy(), P, variant, .05)
+    par = _params(ops, cuda, P)
+    psi = torch.tensor(psi0, dtype=torch.complex128, device=cuda)[None].contiguous()
+    Zt = torch.tensor([Z], dtype=torch.int32, device=cuda)
+    chain = ops.new_chain(1, cuda, amplitude=a, sigma_site=.05)
+    seed, rep, nsw = 0xC0FFEE1234, 17, 4
+    ops.sweep_smem(psi, Zt, par, chain, seed, 100, nsw, variant, _abi.SWEEP_ADAPT_SIGMA, replica0=rep)
+    for s in range(nsw):
+        cb.sweep(st, a, seed, rep, 100 + s)
+    np.testing.assert_allclose(psi[0].cpu().numpy(), st.psi, rtol=0, atol=1e-11)
+    ch = chain[0].cpu().numpy()
+    assert ch[_abi.CH_SITE_ACCEPTED] == st.accepted and ch[_abi.CH_STEP_COUNTER] == st.step_counter
+    assert ch[_abi.CH_SIGMA_SITE] == pytest.approx(st.sigma, rel=1e-12)
+
+
+@pytest.mark.parametrize("variant", [lo.SIMPLE, lo.RESCALED_0TH])
+def test_smem_sweep_with_amplitude_moves_matches_oracle(cuda, variant):
+    """Sweeps + global amplitude moves + measurement, fp64, vs the oracle: same amplitude trajectory end point,
+    same accept counts, energies within 1e-10."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    Z, T = 12, 10
+    P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.3, intrinsic_curvature=0.2, alpha=-.8, u=1.2, C=.9, n=3, temperature=.3)
+    rng = np.random.RandomState(5)
+    psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
+    st = _oracle_state(psi0.copy(), P, variant, .05)
+    am = cb.AmpState(amplitude=.1, sigma_amp=.05, target=.3, bound=.8)
+    par = _params(ops, cuda, P, amp_bound=.8, amp_target_acceptance=.3)
+    psi = torch.tensor(psi0, dtype=torch.complex128, device=cuda)[None].contiguous()
+    Zt = torch.tensor([Z], dtype=torch.int32, device=cuda)
+    chain = ops.new_chain(1, cuda, amplitude=.1, sigma_site=.05, sigma_amp=.05)
+    obs, prof = ops.new_obs(1, Z, cuda)
+    seed, rep, nsw = 77, 3, 12
+    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
+    ops.sweep_smem(psi, Zt, par, chain, seed, 0, nsw, variant, flags, replica0=rep, obs=obs, prof=prof)
+    sum_abs_a = sum_ef = 0.0
+    prof_o = np.zeros((Z, 3))
+    for s in range(nsw):
+        cb.sweep(st, am.a, seed, rep, s)
+        sum_abs_a += abs(am.a)
+        sum_ef += lo.surface_field_energy(st, am.a, am.a)
+        ps, pa = lo.measure_profiles(st.psi)
+        prof_o += np.stack([ps.real, ps.imag, pa], 1)
+        cb.amplitude_move(st, am, P, seed, rep, s)
+    ch = chain[0].cpu().numpy()
+    assert ch[_abi.CH_AMP_ACCEPTED] == am.accepted and ch[_abi.CH_AMP_PROPOSED] == am.proposed
+    assert am.accepted >= 1, "test should exercise an accepted amplitude move"
+    assert ch[_abi.CH_AMPLITUDE] == pytest.approx(am.a, rel=1e-12)
+    assert ch[_abi.CH_SIGMA_AMP] == pytest.approx(am.sigma, rel=1e-12)
+    np.testing.assert_allclose(psi[0].cpu().numpy(), st.psi, rtol=0, atol=1e-11)
+    o = obs[0].cpu().numpy()
+    assert o[_abi.OB_COUNT] == nsw
+    assert o[_abi.OB_ABS_A] == pytest.approx(sum_abs_a, rel=1e-12)
+    assert o[_abi.OB_E_FIELD] == pytest.approx(sum_ef, rel=1e-10)
+    np.testing.assert_allclose(prof[0].cpu().numpy(), prof_o, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("Z,T,variant", [(64, 128, lo.SIMPLE), (40, 24, lo.RESCALED_0TH), (71, 25, lo.SIMPLE), (70, 131, lo.SIMPLE),
+                                         (130, 260, lo.SIMPLE)])
+def test_hbm_sweep_f64_matches_oracle(cuda, Z, T, variant):
+    """TMA-tiled HBM kernel (fp64) vs the oracle: tiles with halos, partial tiles, multi-tile lattices and odd rings
+    reproduce the oracle's checkerboard sweep on the whole lattice."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    a = 0.3
+    P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-.8, u=1.2, C=.9, n=3, temperature=.05)
+    rng = np.random.RandomState(Z + T)
+    psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
+    st = _oracle_state(psi0.copy(), P, variant, .05)
+    par = _params(ops, cuda, P)
+    ws = ops.HbmWorkspace(Z, T, torch.complex128, cuda)
+    ws.pack(torch.tensor(psi0, dtype=torch.complex128, device=cuda))
+    np.testing.assert_array_equal(ws.unpack().cpu().numpy(), psi0)
+    chain = ops.new_chain(1, cuda, amplitude=a, sigma_site=.05)
+    seed, rep, nsw = 991, 2, 3
+    ws.sweep(par, chain[0], seed, 5, nsw, variant, _abi.SWEEP_ADAPT_SIGMA, replica=rep)
+    for s in range(nsw):
+        cb.sweep(st, a, seed, rep, 5 + s)
+    np.testing.assert_allclose(ws.unpack().cpu().numpy(), st.psi, rtol=0, atol=1e-11)
+    ch = chain[0].cpu().numpy()
+    assert ch[_abi.CH_SITE_ACCEPTED] == st.accepted
+    assert ch[_abi.CH_SIGMA_SITE] == pytest.approx(st.sigma, rel=1e-12)
+    # row moments of the plane-split layout == packed-layout kernel
+    S1 = ws.row_moments(par).cpu().numpy()
+    S2 = ops.row_moments(ws.unpack()[None].contiguous(), torch.tensor([Z], dtype=torch.int32, device=cuda), par)[0].cpu().numpy()
+    np.testing.assert_allclose(S1, S2, rtol=1e-12, atol=1e-13)
+
+
+def test_hbm_and_smem_paths_agree_f32(cuda):
+    """The two fp32 kernels run the same arithmetic on the same Philox stream: identical lattices after a sweep."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    Z, T = 64, 48
+    P = dict(wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6, temperature=.01)
+    par = ops.make_params(cuda, **P)
+    Zt = torch.tensor([Z], dtype=torch.int32, device=cuda)
+    psi = torch.zeros(1, Z, T, dtype=torch.complex64, device=cuda)
+    ops.lattice_init(psi, Zt, .1, seed=5)
+    ws = ops.HbmWorkspace(Z, T, torch.complex64, cuda)
+    ws.pack(psi[0])
+    c1, c2 = ops.new_chain(1, cuda, amplitude=.3), ops.new_chain(1, cuda, amplitude=.3)
+    ops.sweep_smem(psi, Zt, par, c1, 42, 0, 3, 0, _abi.SWEEP_ADAPT_SIGMA)
+    ws.sweep(par, c2[0], 42, 0, 3, 0, _abi.SWEEP_ADAPT_SIGMA)
+    assert torch.equal(ws.unpack(), psi[0])
+    assert torch.equal(c1, c2)
+
+
+def test_f32_sweep_tracks_f64(cuda):
+    """fp32 kernel vs fp64 kernel on the same stream: after one sweep from the same start, <= 0.5 % of the sites may
+    differ in their accept decision (borderline exp comparisons); the others agree to 2e-6 absolute."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    Z, T = 60, 50
+    P = dict(wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6, temperature=.01)
+    par = ops.make_params(cuda, **P)
+    Zt = torch.tensor([Z], dtype=torch.int32, device=cuda)
+    psi64 = torch.zeros(1, Z, T, dtype=torch.complex128, device=cuda)
+    ops.lattice_init(psi64, Zt, .1, seed=9)
+    psi32 = psi64.to(torch.complex64)
+    start = psi32.to(torch.complex128)
+    psi64 = start.clone()
+    c32, c64 = ops.new_chain(1, cuda, amplitude=.3), ops.new_chain(1, cuda, amplitude=.3)
+    ops.sweep_smem(psi32, Zt, par, c32, 1, 0, 1, 0, 0)
+    ops.sweep_smem(psi64, Zt, par, c64, 1, 0, 1, 0, 0)
+    diff = (psi32.to(torch.complex128) - psi64).abs()[0]
+    mism = (diff > 2e-6).float().mean().item()
+    assert mism < 5e-3, mism
+    assert abs(c32[0, _abi.CH_SITE_ACCEPTED].item() - c64[0, _abi.CH_SITE_ACCEPTED].item()) <= 0.005 * Z * T
+
+
+def test_lattice_init_matches_oracle(cuda):
+    import torch
+    from cylinder_b200 import ops
+    Zs = [7, 12]
+    psi = torch.zeros(2, 12, 10, dtype=torch.complex128, device=cuda)
+    ops.lattice_init(psi, torch.tensor(Zs, dtype=torch.int32, device=cuda), .1, seed=123456789012, replica0=40)
+    for b, Z in enumerate(Zs):
+        ref = cb.random_initialize(12, 10, .1, 123456789012, 40 + b)
+        np.testing.assert_allclose(psi[b, :Z].cpu().numpy(), ref[:Z], rtol=0, atol=1e-16)
+        assert torch.all(psi[b, Z:] == 0)
+    assert psi.abs().max().item() <= .1
+
+
+def test_batched_replicas_are_independent_and_ragged(cuda):
+    """B replicas with different Z (ragged, incl. odd) and parameters in one launch == each run alone."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    ks = np.array([.5, .55, .8, 1.0, 1.25])
+    Zs = [ops.lattice_dims((50, 50), k)[0] for k in ks]
+    assert any(z % 2 for z in Zs)
+    B, Zmax, T = len(ks), max(Zs), 50
+    par = ops.make_params(cuda, wavenumber=ks, radius=1.0, alpha=[-2, -1, -.5, 0.5, 1.0], u=1.0, C=[.5, 1, 2, 1, 1], n=6, temperature=.01)
+    Zt = torch.tensor(Zs, dtype=torch.int32, device=cuda)
+    psi = torch.zeros(B, Zmax, T, dtype=torch.complex64, device=cuda)
+    ops.lattice_init(psi, Zt, .1, seed=3)
+    start = psi.clone()
+    chain = ops.new_chain(B, cuda, amplitude=.2)
+    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES
+    ops.sweep_smem(psi, Zt, par, chain, 11, 0, 5, 0, flags)
+    for b in range(B):
+        p1 = start[b:b + 1].clone()
+        c1 = ops.new_chain(1, cuda, amplitude=.2)
+        ops.sweep_smem(p1, Zt[b:b + 1].contiguous(), par[b:b + 1].contiguous(), c1, 11, 0, 5, 0, flags, replica0=b)
+        assert torch.equal(p1[0], psi[b])
+        assert torch.equal(c1[0], chain[b])
+    assert torch.all(psi[0, Zs[0]:] == 0) or Zs[0] == Zmax
+
+
+def test_invalid_arguments_fail_loudly(cuda):
+    import torch
+    from cylinder_b200 import ops, _abi
+    par = ops.make_params(cuda, wavenumber=1, radius=1, alpha=-1, u=1, C=1, n=1, temperature=.01)
+    psi = torch.zeros(1, 8, 8, dtype=torch.complex64, device=cuda)
+    Zt = torch.tensor([8], dtype=torch.int32, device=cuda)
+    with pytest.raises(_abi.CylinderB200Error):
+        ops.sweep_smem(psi, Zt, par, ops.new_chain(1, cuda), 0, 0, 1, variant=7)
+    with pytest.raises(_abi.CylinderB200Error):
+        ops.sweep_smem(psi.cpu(), Zt, par, ops.new_chain(1, cuda), 0, 0, 1)
+    big = torch.zeros(1, 400, 400, dtype=torch.complex64, device=cuda)
+    with pytest.raises(_abi.CylinderB200Error, match="shared memory"):
+        ops.sweep_smem(big, torch.tensor([400], dtype=torch.int32, device=cuda), par, ops.new_chain(1, cuda), 0, 0, 1)
+    with pytest.raises(_abi.CylinderB200Error):
+        ops.HbmWorkspace(4, 4, torch.complex64, cuda)
