@@ -135,11 +135,10 @@ __host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t tag, uint64_t sw
 __host__ __device__ __forceinline__ double u01_f64(uint32_t x) {            // 32 bits, midpoint
   return ((double)x + 0.5) * (1.0 / 4294967296.0);
 }
-__device__ __forceinline__ float u01_f32_open0(uint32_t x) {                // (0,1], 23 bits, no I2F
-  return 2.0f - __uint_as_float(0x3F800000u | (x >> 9));
-}
-__device__ __forceinline__ float u01_f32_half(uint32_t x) {                 // [0,1), 23 bits, no I2F
-  return __uint_as_float(0x3F800000u | (x >> 9)) - 1.0f;
+// fp32: the top 23 bits at the midpoint of their cell, (m + 1/2) 2^-23 in (0,1), built without an int->float
+// conversion: [1,2) mantissa trick, then an exact subtraction of 1 - 2^-24.  Tracks u01_f64 to 2^-24.
+__device__ __forceinline__ float u01_f32(uint32_t x) {
+  return __uint_as_float(0x3F800000u | (x >> 9)) - 0.99999994f;
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -114,15 +114,15 @@ template <> struct Draw<double> {
 
 template <> struct Draw<float> {
   static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, float& zre, float& zim) {
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u01_f32_open0(x0)));     // sqrt(-2 ln u)
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(u01_f32(x0)));     // sqrt(-2 ln u)
     float s, c;
-    __sincosf(6.283185307179586f * u01_f32_half(x1), &s, &c);
+    __sincosf(6.283185307179586f * u01_f32(x1), &s, &c);
     zre = rad * c;
     zim = rad * s;
   }
   static __device__ __forceinline__ bool accept(uint32_t x2, float den, float kacc) {
     if (den <= 0.0f) return true;
-    return __log2f(u01_f32_open0(x2)) <= -(kacc * den);
+    return __log2f(u01_f32(x2)) <= -(kacc * den);
   }
 };
 

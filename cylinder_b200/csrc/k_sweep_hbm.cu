@@ -193,7 +193,9 @@ template <typename R, int NCOL>
 struct HbmSmem {
   using C = typename Real<R>::complex_t;
   static constexpr int TH = HbmTile<R>::TH, TW = HBM_TW;
-  static constexpr int HS = (NCOL + 1) & ~1;      // column halo in shared memory: even, so a plane row is 16-byte granular
+  // Column halo in shared memory.  4 (not NCOL) so that every TMA box starts on a 16-byte boundary of its plane
+  // row: box start = (tj0 + HBM_HC - HS)/2 plane columns = tj0/2, a multiple of 64 complex elements.
+  static constexpr int HS = HBM_HC;
   static constexpr int SH = TH + 2 * NCOL, SW = TW + 2 * HS, SWH = SW / 2;
   static constexpr size_t plane_bytes = ((size_t)SH * SWH * sizeof(C) + 127) & ~(size_t)127;
   static constexpr size_t off_coef = 2 * plane_bytes;
@@ -201,7 +203,7 @@ struct HbmSmem {
   static constexpr size_t total = off_bar + 64;
 };
 
-struct HbmMaps { CUtensorMap m[2][2]; };   // [buffer][plane]
+struct HbmMaps { CUtensorMap m[2][2]; int esz; };   // [buffer][plane]; esz = TMA elements per complex value
 
 template <typename R, int NCOL>
 __global__ void __launch_bounds__(HBM_NT)
@@ -233,10 +235,9 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   __syncthreads();
   if (tid == 0) {
     constexpr uint32_t bytes = 2u * SH * SWH * sizeof(C);
-    constexpr int esz = sizeof(C) / 8;                              // f64 complex is two FLOAT64 elements
     mbar_expect_tx(bar, bytes);
-    tma_load_2d(pl0, &maps.m[cur][0], x0 * esz, ti0, bar);
-    tma_load_2d(pl1, &maps.m[cur][1], x1 * esz, ti0, bar);
+    tma_load_2d(pl0, &maps.m[cur][0], x0 * maps.esz, ti0, bar);    // esz: TMA elements per complex value
+    tma_load_2d(pl1, &maps.m[cur][1], x1 * maps.esz, ti0, bar);
   }
   // overlap: row coefficients and scalars while the tile is in flight
   for (int r = tid; r < SH; r += HBM_NT) coef[r] = coef_g[modi(ti0 - NCOL + r, g.Z)];
@@ -522,7 +523,9 @@ static int make_maps(const HbmGeom& g, void* work, HbmMaps* maps) {
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
-  constexpr int esz = sizeof(C) / 8;          // 8-byte elements per complex
+  // one complex64 = one UINT64 element; one complex128 = two FLOAT64 elements (TMA has no 16-byte type)
+  // (the box start along the contiguous dimension must fall on a 16-byte boundary, else the load traps)
+  const int esz = sizeof(C) / 8;
   const CUtensorMapDataType dt = (sizeof(C) == 8) ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
   for (int b = 0; b < 2; ++b)
     for (int pl = 0; pl < 2; ++pl) {
@@ -539,6 +542,7 @@ static int make_maps(const HbmGeom& g, void* work, HbmMaps* maps) {
         return CYL_E_CUDA;
       }
     }
+  maps->esz = esz;
   return CYL_OK;
 }
 

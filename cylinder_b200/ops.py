@@ -128,8 +128,8 @@ def row_moments(psi, Z, params):
 
 def field_energy(S, Z, T, params, amp_eval, amp_ref=None, variant=0):
     B, Zmax, _ = S.shape
-    amp_eval = amp_eval.to(F64).contiguous()
-    amp_ref = None if amp_ref is None else amp_ref.to(F64).contiguous()
+    amp_eval = torch.as_tensor(amp_eval, dtype=F64, device=S.device).reshape(-1).contiguous()
+    amp_ref = None if amp_ref is None else torch.as_tensor(amp_ref, dtype=F64, device=S.device).reshape(-1).contiguous()
     E = torch.empty(B, dtype=F64, device=S.device)
     call("cyl_field_energy_f64", _dev(S), ptr(S), B, ptr(Z), Zmax, int(T), ptr(params), ptr(amp_eval), ptr(amp_ref),
          variant_id(variant), ptr(E), stream())
