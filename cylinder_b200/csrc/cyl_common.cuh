@@ -99,15 +99,26 @@ __host__ __device__ __forceinline__ Geo geo_from_sc(double k, double ra, double 
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
 
+__host__ __device__ __forceinline__ void philox_mulhilo(uint32_t m, uint32_t c, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  uint64_t p;                                   // one IMAD.WIDE.U32; hi/lo are the register pair
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(m), "r"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+#else
+  const uint64_t p = (uint64_t)m * c;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+#endif
+}
+
 __host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
                                                       uint32_t k0, uint32_t k1) {
-  const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
-  const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
-  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-  const uint32_t n1 = (uint32_t)p1;
-  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-  const uint32_t n3 = (uint32_t)p0;
-  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  uint32_t h0, l0, h1, l1;
+  philox_mulhilo(PHILOX_M0, c0, h0, l0);
+  philox_mulhilo(PHILOX_M1, c2, h1, l1);
+  const uint32_t n0 = h1 ^ c1 ^ k0;
+  const uint32_t n2 = h0 ^ c3 ^ k1;
+  c0 = n0; c1 = l1; c2 = n2; c3 = l0;
 }
 
 template <int ROUNDS = 10>
@@ -119,6 +130,22 @@ __host__ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, u
     k0 += PHILOX_W0;
     k1 += PHILOX_W1;
   }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// The ten round keys of one 64-bit seed, expanded once on the host and passed BY VALUE as a kernel parameter: the hot
+// loops then read them as constant-bank operands of the XOR (LOP3 ..., c[0x0][..]) instead of recomputing the Weyl
+// sequence for every site.
+struct PhiloxKeys { uint32_t k[20]; };
+static inline PhiloxKeys philox_expand(uint64_t seed) {
+  PhiloxKeys ks;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; ++i) { ks.k[2 * i] = k0; ks.k[2 * i + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+  return ks;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& ks) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) philox_round(c0, c1, c2, c3, ks.k[2 * i], ks.k[2 * i + 1]);
   return make_uint4(c0, c1, c2, c3);
 }
 

@@ -28,32 +28,40 @@ __device__ __forceinline__ void moments_accumulate(double (&m)[CYL_NMOM], C p, C
   m[7] += pi;
 }
 
-// Energy of one row at trial amplitude a_eval given the metric reference amplitude a_ref (only the 0th-order
-// variant distinguishes them).  S = the row's moments; g0e / gme = metric at z_i / z_{i-1/2} for a_eval,
-// g0r = metric at z_i for a_ref.  Returns E_i WITHOUT the global lz*lth factor.
-__device__ __forceinline__ double field_energy_row(int variant, const CylParams& p, double lz, double lth, int T,
-                                                   const Geo& g0e, const Geo& gme, const Geo& g0r, const double* S) {
+// Row weights of the energy: E_i = W[0] S1 + W[1] S2 + W[2] S3 + W[3] S4 + W[4] S5 + W[5], at trial amplitude a_eval
+// given the metric reference amplitude a_ref (only the 0th-order variant distinguishes them).  g0e / gme = metric at
+// z_i / z_{i-1/2} for a_eval, g0r = metric at z_i for a_ref.  WITHOUT the global lz*lth factor.
+__device__ __forceinline__ void field_energy_weights(int variant, const CylParams& p, double lz, double lth, int T,
+                                                     const Geo& g0e, const Geo& gme, const Geo& g0r, double (&W)[6]) {
   const double Cn2 = p.C * p.n * p.n;
+  double w0, wir, zs, A;
+  W[5] = 0.0;
   if (variant == CYL_VARIANT_SIMPLE) {
-    const double zs = gme.gz;                                  // :191
-    const double w0 = zs * g0e.gth;                            // :193
-    const double wir = g0e.gz / gme.gth;                       // :194
-    const double A = gme.ath;                                  // :195
-    return (p.alpha * S[0] + p.u / 2 * S[1]) * w0              // :199
-           + p.C * S[2] / (zs * zs) * w0                       // :200-202
-           + p.C * S[3] * wir                                  // :206
-           + p.C * p.n * 2 * A * S[4] * wir                    // :208
-           + Cn2 * S[0] * (A * A) * wir;                       // :210
+    zs = gme.gz;                                               // :191
+    w0 = zs * g0e.gth;                                         // :193
+    wir = g0e.gz / gme.gth;                                    // :194
+    A = gme.ath;                                               // :195
   } else {
-    const double zs = g0r.gz, ths = g0r.gth;                   // 0th:253-254
-    const double w0 = g0r.gz * g0e.gth;                        // 0th:255
-    const double wir = w0 / (ths * ths);                       // 0th:256
-    const double A = g0e.ath;                                  // 0th:257
+    zs = g0r.gz;                                               // 0th:253
+    w0 = g0r.gz * g0e.gth;                                     // 0th:255
+    wir = w0 / (g0r.gth * g0r.gth);                            // 0th:254,256
+    A = g0e.ath;                                               // 0th:257
     const double area = (lz * g0e.gz) * (lth * g0e.gth);       // 0th:261, :68
     const double bg = -p.temperature / area + ((p.alpha < 0) ? .5 * p.alpha * p.alpha / p.u : 0.0);   // 0th:66-92
-    return (p.alpha * S[0] + p.u / 2 * S[1]) * w0 + p.C * S[2] / (zs * zs) * w0 + p.C * S[3] * wir +
-           p.C * p.n * 2 * A * S[4] * wir + Cn2 * S[0] * (A * A) * wir + T * bg * w0;                  // 0th:262-275
+    W[5] = T * bg * w0;                                        // 0th:275
   }
+  W[0] = p.alpha * w0 + Cn2 * (A * A) * wir;                   // :199 (alpha part) + :210
+  W[1] = p.u / 2 * w0;                                         // :199
+  W[2] = p.C / (zs * zs) * w0;                                 // :200-202
+  W[3] = p.C * wir;                                            // :206
+  W[4] = p.C * p.n * 2 * A * wir;                              // :208
+}
+
+__device__ __forceinline__ double field_energy_row(int variant, const CylParams& p, double lz, double lth, int T,
+                                                   const Geo& g0e, const Geo& gme, const Geo& g0r, const double* S) {
+  double W[6];
+  field_energy_weights(variant, p, lz, lth, T, g0e, gme, g0r, W);
+  return W[0] * S[0] + W[1] * S[1] + W[2] * S[2] + W[3] * S[3] + W[4] * S[4] + W[5];
 }
 
 // convenience: evaluate the metric with sincos (standalone kernels; the sweep kernels use cached sin/cos tables)

@@ -112,17 +112,24 @@ template <> struct Draw<double> {
   }
 };
 
+// u01_f32 never returns a denormal, so the flush-to-zero MUFU form needs no range fix-up
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <> struct Draw<float> {
   static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, float& zre, float& zim) {
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u01_f32(x0)));     // sqrt(-2 ln u)
+    float rad;                                                                // sqrt(-2 ln u): MUFU.LG2, MUFU.SQRT
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg2_fast(u01_f32(x0))));
     float s, c;
     __sincosf(6.283185307179586f * u01_f32(x1), &s, &c);
     zre = rad * c;
     zim = rad * s;
   }
   static __device__ __forceinline__ bool accept(uint32_t x2, float den, float kacc) {
-    if (den <= 0.0f) return true;
-    return __log2f(u01_f32(x2)) <= -(kacc * den);
+    return (den <= 0.0f) | (lg2_fast(u01_f32(x2)) <= -(kacc * den));           // branch-free; kacc = inf when T = 0
   }
 };
 

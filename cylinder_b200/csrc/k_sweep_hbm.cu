@@ -209,8 +209,8 @@ template <typename R, int NCOL>
 __global__ void __launch_bounds__(HBM_NT)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
                  const int32_t* __restrict__ cur_p, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
-                 const double* __restrict__ chain, HbmCounters* __restrict__ counters, uint64_t seed, uint32_t rep,
-                 uint64_t sweep) {
+                 const double* __restrict__ chain, HbmCounters* __restrict__ counters, const __grid_constant__ PhiloxKeys keys,
+                 uint32_t rep, uint64_t sweep) {
   using C = typename Real<R>::complex_t;
   using L = HbmSmem<R, NCOL>;
   constexpr int TH = L::TH, TW = L::TW, SH = L::SH, SW = L::SW, SWH = L::SWH, HS = L::HS;
@@ -242,49 +242,62 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // overlap: row coefficients and scalars while the tile is in flight
   for (int r = tid; r < SH; r += HBM_NT) coef[r] = coef_g[modi(ti0 - NCOL + r, g.Z)];
   const R sigma = (R)chain[CYL_CH_SIGMA_SITE];
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
   __syncthreads();
   mbar_wait(bar, 0);
 
   int nacc = 0;
-  const bool even = (NCOL == 2);
+  // tiles on the lattice boundary wrap their global coordinates, may be partial, and own periodic halo copies
+  const bool border = (blockIdx.x == 0) | (blockIdx.y == 0) | (blockIdx.x == gridDim.x - 1) | (blockIdx.y == gridDim.y - 1);
+  constexpr int PS = (int)(L::plane_bytes / sizeof(C));             // plane stride in shared memory (elements)
+  C* out = work + (size_t)(cur ^ 1) * g.buffer_elems;
+  const int64_t ph = g.pitch / 2;
+
+  if constexpr (NCOL == 2) {
+    // Both lengths even: colour of smem (r, q) is (r + q) & 1, so the colour-c sites of row r are q = qb + 2 cc in
+    // ONE parity plane at unit stride.  Index arithmetic per site is a handful of adds; neighbours are immediates.
 #pragma unroll
-  for (int c = 0; c < NCOL; ++c) {
-    const int m = c + 1;                                           // row margin of this colour's region
-    const int mq = m + (HS - NCOL);                                // column margin
-    const int nrows = SH - 2 * m;
-    if (even) {
-      // colour of smem (r, q) is (r + q) & 1: the colour-c sites of row r are q = q0 + 2 cc, one plane, unit stride
-      const int npr = (SW - 2 * mq) / 2;
-      for (int idx = tid; idx < nrows * npr; idx += HBM_NT) {
-        const int rr = idx / npr, cc = idx - rr * npr;
+    for (int c = 0; c < 2; ++c) {
+      const int m = c + 1, mq = m + (HS - 2);
+      const int npr = (SW - 2 * mq) / 2, nrows = SH - 2 * m;
+      const int drr = HBM_NT / npr, dcc = HBM_NT % npr;
+      int rr = tid / npr, cc = tid - rr * npr;
+      while (rr < nrows) {
         const int r = m + rr;
-        const int q = mq + ((mq + r + c) & 1) + 2 * cc;
-        const int par = (Q0 + q) & 1;
-        C* own = par ? pl1 : pl0;
-        C* oth = par ? pl0 : pl1;
-        const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
-        const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
-        const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
-        const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
+        const int qb = mq + ((mq + r + c) & 1);                       // first column of colour c in row r
+        const int par = qb & 1;
+        const int q = qb + 2 * cc;
+        C* own = pl0 + par * PS + r * SWH + (qb >> 1) + cc;
+        const C* oth = pl0 + (par ^ 1) * PS + r * SWH + (qb >> 1) + cc - 1 + par;
+        const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
         const RowCoef<R> rc = coef[r];
-        const int gi = wrapi(ti0 - NCOL + r, g.Z), gj = wrapi(tj0 - HS + q, g.T);
-        const uint4 x = philox4x32<10>((uint32_t)(gi * g.T + gj), rep, c2, c3, k0, k1);
+        int gi = ti0 - 2 + r, gj = tj0 - HS + q;
+        bool counted = (c == 1) || ((unsigned)(r - 2) < (unsigned)TH && (unsigned)(q - HS) < (unsigned)TW);
+        if (border) {
+          counted = counted && gi < g.Z && gj < g.T;
+          gi = modi(gi, g.Z);
+          gj = modi(gj, g.T);
+        }
+        const uint4 x = philox4x32_10((uint32_t)(gi * g.T + gj), rep, c2, c3, keys);
         R zre, zim;
         Draw<R>::normals(x.x, x.y, zre, zim);
         const R w = sigma * rc.sgmul;
         const R dre = w * zre, dim = w * zim;
         const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-        if (Draw<R>::accept(x.z, den, rc.kacc)) {
-          own[r * SWH + col] = Real<R>::make(pv.x + dre, pv.y + dim);
-          const int li = r - NCOL, lj = q - HS;                   // interior (counted) vs halo (redundant)
-          nacc += (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
-        }
+        const bool acc = Draw<R>::accept(x.z, den, rc.kacc);
+        if (acc) own[0] = Real<R>::make(pv.x + dre, pv.y + dim);
+        nacc += (acc && counted);
+        rr += drr;
+        cc += dcc;
+        if (dcc != 0 && cc >= npr) { cc -= npr; ++rr; }
       }
-    } else {
-      // odd periodic ring(s): 3 colours, general colour function; every region site is visited and filtered
-      const int ncl = SW - 2 * mq;
+      __syncthreads();
+    }
+  } else {
+    // odd periodic ring(s): 3 colours, general colour function; every region site is visited and filtered
+    for (int c = 0; c < NCOL; ++c) {
+      const int m = c + 1, mq = m + (HS - NCOL);
+      const int nrows = SH - 2 * m, ncl = SW - 2 * mq;
       for (int idx = tid; idx < nrows * ncl; idx += HBM_NT) {
         const int rr = idx / ncl, r = m + rr, q = mq + (idx - rr * ncl);
         // lattice coordinates; tiles past the edge hold zero-filled padding that is never stored
@@ -300,7 +313,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
         const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
         const RowCoef<R> rc = coef[r];
-        const uint4 x = philox4x32<10>((uint32_t)(gi * g.T + gj), rep, c2, c3, k0, k1);
+        const uint4 x = philox4x32_10((uint32_t)(gi * g.T + gj), rep, c2, c3, keys);
         R zre, zim;
         Draw<R>::normals(x.x, x.y, zre, zim);
         const R w = sigma * rc.sgmul;
@@ -312,33 +325,44 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
           nacc += (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // ---- write the interior (and its periodic halo copies) to the other buffer ----
-  C* out = work + (size_t)(cur ^ 1) * g.buffer_elems;
-  const int64_t ph = g.pitch / 2;
-  for (int idx = tid; idx < 2 * TH * (TW / 2); idx += HBM_NT) {
-    const int par_slot = idx / (TH * (TW / 2));                    // which smem plane
-    const int rem = idx - par_slot * (TH * (TW / 2));
-    const int li = rem / (TW / 2), cc = rem - li * (TW / 2);
-    // interior columns of smem plane `par_slot`: q = HS + lj with (Q0 + q) & 1 == par_slot
-    const int lj = 2 * cc + ((par_slot - (Q0 + HS)) & 1);
-    const int gi = ti0 + li, gj = tj0 + lj;
-    if (gi >= g.Z || gj >= g.T) continue;
-    const int r = li + NCOL, q = lj + HS;
-    const C* src = par_slot ? pl1 : pl0;
-    const C v = src[r * SWH + (((Q0 + q) >> 1) - (par_slot ? x1 : x0))];
-    const int64_t Rr = gi + g.hr, Q = gj + g.hc;
-    int64_t R2 = -1, Q2 = -1;
-    if (gi < g.hr) R2 = Rr + g.Z; else if (gi >= g.Z - g.hr) R2 = Rr - g.Z;
-    if (gj < g.hc) Q2 = Q + g.T; else if (gj >= g.T - g.hc) Q2 = Q - g.T;
-    out[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)] = v;
-    if (R2 >= 0) out[(Q & 1) * g.plane_elems + R2 * ph + (Q >> 1)] = v;
-    if (Q2 >= 0) {
-      out[(Q2 & 1) * g.plane_elems + Rr * ph + (Q2 >> 1)] = v;
-      if (R2 >= 0) out[(Q2 & 1) * g.plane_elems + R2 * ph + (Q2 >> 1)] = v;
+  if (NCOL == 2 && !border) {
+    // interior tile: every (row, plane) is 64 contiguous complex values on both sides, 16-byte aligned
+    constexpr int NV = (TW / 2) * (int)sizeof(C) / 16;              // 16-byte vectors per plane row
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int pr = warp; pr < 2 * TH; pr += HBM_NT / 32) {
+      const int li = pr >> 1, p = pr & 1;
+      const int4* src = reinterpret_cast<const int4*>(pl0 + p * PS + (li + NCOL) * SWH + HS / 2);
+      int4* dst = reinterpret_cast<int4*>(out + p * g.plane_elems + (int64_t)(ti0 + li + g.hr) * ph + ((tj0 + g.hc) >> 1));
+#pragma unroll
+      for (int v = lane; v < NV; v += 32) dst[v] = src[v];
+    }
+  } else {
+    for (int idx = tid; idx < 2 * TH * (TW / 2); idx += HBM_NT) {
+      const int par_slot = idx / (TH * (TW / 2));                    // which smem plane
+      const int rem = idx - par_slot * (TH * (TW / 2));
+      const int li = rem / (TW / 2), cc = rem - li * (TW / 2);
+      // interior columns of smem plane `par_slot`: q = HS + lj with (Q0 + q) & 1 == par_slot
+      const int lj = 2 * cc + ((par_slot - (Q0 + HS)) & 1);
+      const int gi = ti0 + li, gj = tj0 + lj;
+      if (gi >= g.Z || gj >= g.T) continue;
+      const int r = li + NCOL, q = lj + HS;
+      const C* src = par_slot ? pl1 : pl0;
+      const C v = src[r * SWH + (((Q0 + q) >> 1) - (par_slot ? x1 : x0))];
+      const int64_t Rr = gi + g.hr, Q = gj + g.hc;
+      int64_t R2 = -1, Q2 = -1;
+      if (gi < g.hr) R2 = Rr + g.Z; else if (gi >= g.Z - g.hr) R2 = Rr - g.Z;
+      if (gj < g.hc) Q2 = Q + g.T; else if (gj >= g.T - g.hc) Q2 = Q - g.T;
+      out[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)] = v;
+      if (R2 >= 0) out[(Q & 1) * g.plane_elems + R2 * ph + (Q >> 1)] = v;
+      if (Q2 >= 0) {
+        out[(Q2 & 1) * g.plane_elems + Rr * ph + (Q2 >> 1)] = v;
+        if (R2 >= 0) out[(Q2 & 1) * g.plane_elems + R2 * ph + (Q2 >> 1)] = v;
+      }
     }
   }
 
@@ -565,10 +589,11 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   CYL_CUDA(cudaMemsetAsync(counters, 0, sizeof(HbmCounters), st));
   const dim3 grid((g.T + L::TW - 1) / L::TW, (g.Z + L::TH - 1) / L::TH);
   const bool amp = flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE);
+  const PhiloxKeys keys = philox_expand(seed);
   hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
-    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, seed, (uint32_t)replica, sweep);
+    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, keys, (uint32_t)replica, sweep);
     hbm_post_sweep_kernel<<<1, 32, 0, st>>>(chain, counters, cur, (double)g.Z * g.T, flags);
     if (amp) {
       hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, cur, g, params, S);

@@ -2,12 +2,15 @@
 //
 // One CTA owns one replica for the whole launch (nsweeps sweeps): psi is read from HBM once, kept in shared
 // memory, written back once; the per-row metric coefficients, the amplitude-independent sin/cos tables and the
-// row moments live in shared memory too.  Per sweep:
+// per-row energy weights live in shared memory too.  Per sweep:
 //   1. site moves  (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once;
 //      draws from Philox4x32-10 keyed by seed with counter (site, replica, sweep, tag) -- stateless, so a sweep can
 //      be re-run or resumed bit-identically;
 //   2. Robbins-Monro update of sigma_site from the sweep's accept count (:688-696, batched; cyl_site.cuh);
-//   3. row moments by warp-shuffle reduction -> E_field(a, a), profiles (Lattice.measure :121-131);
+//   3. energy pass: every thread forms the five energy densities of its sites and dots them with the
+//      row weights of the current amplitude and of the PROPOSED amplitude (weight difference, so the energy change of
+//      the amplitude move is accumulated directly, not as a difference of two large sums); one CTA tree reduction.
+//      The same pass accumulates the profiles of Lattice.measure (:121-131) by warp shuffles;
 //   4. global amplitude move a' = a + sigma_amp N(0,1) on E_surf(a') + E_field(a', a) (Lattice.run :544-550 through
 //      engine.step_real_group; accept rule B.2; Robbins-Monro on sigma_amp);
 //   5. on accept, rebuild the row coefficients from the sin/cos tables (no trigonometry).
@@ -19,6 +22,7 @@
 #include "cyl_surface.cuh"
 
 #define SWEEP_NT 256
+#define SWEEP_NWARP (SWEEP_NT / 32)
 
 struct SmemScalars {
   double amp, amp_new, sigma_site, sigma_amp, e_field, e_surf, e_surf_new;
@@ -29,18 +33,21 @@ struct SmemScalars {
 // sin/cos(k z) at z_i and z_{i-1/2}
 struct RowTrig { double s0, c0, sm, cm; };
 
+// energy weights of a row: current amplitude, and (proposed - current); pixel-length factors folded in
+template <typename R>
+struct __align__(16) RowW { R cur[5]; R dif[5]; R pad[2]; };
+
 template <typename R>
 struct SweepSmemLayout {
   using C = typename Real<R>::complex_t;
-  size_t off_coef, off_trig, off_mom, off_scr, off_sc, total;
+  size_t off_coef, off_trig, off_w, off_scr, off_sc, total;
   __host__ __device__ SweepSmemLayout(int Zmax, int T) {
     size_t o = (size_t)Zmax * T * sizeof(C);
     o = (o + 15) & ~(size_t)15;
     off_coef = o; o += (size_t)Zmax * sizeof(RowCoef<R>);
-    o = (o + 15) & ~(size_t)15;
     off_trig = o; o += (size_t)Zmax * sizeof(RowTrig);
-    off_mom = o;  o += (size_t)Zmax * CYL_NMOM * sizeof(double);
-    off_scr = o;  o += 64 * sizeof(double);
+    off_w = o;    o += (size_t)Zmax * sizeof(RowW<R>);
+    off_scr = o;  o += 8 * SWEEP_NWARP * sizeof(double);
     off_sc = o;   o += sizeof(SmemScalars);
     total = (o + 15) & ~(size_t)15;
   }
@@ -59,11 +66,48 @@ __device__ __forceinline__ void build_row_coefs(RowCoef<R>* coef, const RowTrig*
   }
 }
 
+// Sum N doubles over the CTA (result in every thread).  scratch: N * SWEEP_NWARP doubles.
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < N; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) scratch[q * SWEEP_NWARP + warp] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < SWEEP_NWARP; ++w) t += scratch[q * SWEEP_NWARP + w];
+    v[q] = t;
+  }
+}
+
+// one site move; returns 1 when accepted
+template <typename R, typename C>
+__device__ __forceinline__ int site_move(C* psi, int idx, int im, int ip, int jm, int jp, const RowCoef<R>& rc, R sigma,
+                                         uint32_t site, uint32_t rep, uint32_t c2, uint32_t c3, const PhiloxKeys& keys) {
+  const C pv = psi[idx], L = psi[im], Rz = psi[ip], W = psi[jm], E = psi[jp];
+  const uint4 x = philox4x32_10(site, rep, c2, c3, keys);
+  R zre, zim;
+  Draw<R>::normals(x.x, x.y, zre, zim);
+  const R w = sigma * rc.sgmul;
+  const R dre = w * zre, dim = w * zim;
+  const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
+  const bool acc = Draw<R>::accept(x.z, den, rc.kacc);
+  if (acc) psi[idx] = Real<R>::make(pv.x + dre, pv.y + dim);
+  return acc ? 1 : 0;
+}
+
 template <typename R>
-__global__ void __launch_bounds__(SWEEP_NT)
+__global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? 4 : 2))
 sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
-                  const CylParams* __restrict__ params, double* __restrict__ chain, uint64_t seed, int64_t replica0,
-                  uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
+                  const CylParams* __restrict__ params, double* __restrict__ chain, const __grid_constant__ PhiloxKeys keys,
+                  int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
                   double* __restrict__ prof) {
   using C = typename Real<R>::complex_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,7 +115,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   C* psi = reinterpret_cast<C*>(smem_raw);
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
   RowTrig* trig = reinterpret_cast<RowTrig*>(smem_raw + lay.off_trig);
-  double* mom = reinterpret_cast<double*>(smem_raw + lay.off_mom);
+  RowW<R>* roww = reinterpret_cast<RowW<R>*>(smem_raw + lay.off_w);
   double* scr = reinterpret_cast<double*>(smem_raw + lay.off_scr);
   SmemScalars* sc = reinterpret_cast<SmemScalars*>(smem_raw + lay.off_sc);
 
@@ -82,10 +126,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const CylParams p = params[b];
   const double pi = 3.14159265358979323846;
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;     // On_lattice_simple.py:47,:49
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint32_t rep = (uint32_t)(replica0 + b);
   double* ch = chain + (size_t)b * CYL_CHAIN_DOUBLES;
   C* psi_b = psi_g + (size_t)b * Zmax * T;
+  const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
+  const bool measure = (flags & CYL_SWEEP_MEASURE) != 0;
 
   // ---- prologue: state, lattice, tables ----
   if (tid == 0) {
@@ -100,6 +145,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     sc->amp_counter = ch[CYL_CH_AMP_COUNTER];
     sc->flags = ch[CYL_CH_FLAGS];
     sc->e_field = ch[CYL_CH_E_FIELD];
+    sc->amp_accept = 0;
   }
   for (int s = tid; s < nsite; s += SWEEP_NT) psi[s] = psi_b[s];
   for (int i = tid; i < Z; i += SWEEP_NT) {
@@ -110,7 +156,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   }
   __syncthreads();
   build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
-  if ((flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) && warp == 0) {
+  if (extras && warp == 0) {
     const double es = surface_energy_warp(p, sc->amp, nullptr, nullptr, true);
     if (lane == 0) sc->e_surf = es;
   }
@@ -119,6 +165,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const int ncol = num_colours(Z, T);
   const int Th = (T + 1) >> 1, Teven = T & ~1;
   const int di = SWEEP_NT / Th, dj = SWEEP_NT % Th;
+  const R inv_lz2 = (R)(1.0 / (lz * lz)), inv_lth2 = (R)(1.0 / (lth * lth)), inv_lth = (R)(1.0 / lth);
 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
@@ -126,38 +173,47 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     const R sigma = (R)sc->sigma_site;
     int nacc = 0;
     // ---- 1. site moves ----
-    for (int colour = 0; colour < ncol; ++colour) {
-      int i = tid / Th, jj = tid - i * Th;
-      while (i < Z) {
-        int beta = colour - axis_colour(i, Z);
-        if (beta < 0) beta += ncol;
-        int j;
-        bool valid;
-        if (beta < 2) { j = beta + 2 * jj; valid = j < Teven; }
-        else          { j = T - 1;         valid = (T & 1) && jj == 0; }
-        if (valid) {
+    if (ncol == 2) {
+      // both lengths even: colour = (i + j) & 1, T/2 sites of each colour in every row
+      for (int colour = 0; colour < 2; ++colour) {
+        int i = tid / Th, jj = tid - i * Th;
+        while (i < Z) {
+          const int j = 2 * jj + ((colour + i) & 1);
           const int row = i * T;
-          const int rm = (i == 0 ? Z - 1 : i - 1) * T, rp = (i == Z - 1 ? 0 : i + 1) * T;
-          const int jm = (j == 0 ? T - 1 : j - 1), jp = (j == T - 1 ? 0 : j + 1);
-          const C pv = psi[row + j], L = psi[rm + j], Rz = psi[rp + j], W = psi[row + jm], E = psi[row + jp];
-          const RowCoef<R> rc = coef[i];
-          const uint4 x = philox4x32<10>((uint32_t)(row + j), rep, c2, c3, k0, k1);
-          R zre, zim;
-          Draw<R>::normals(x.x, x.y, zre, zim);
-          const R w = sigma * rc.sgmul;
-          const R dre = w * zre, dim = w * zim;
-          const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
-          if (Draw<R>::accept(x.z, den, rc.kacc)) {
-            psi[row + j] = Real<R>::make(pv.x + dre, pv.y + dim);
-            ++nacc;
-          }
+          const int im = (i == 0 ? nsite : row) - T, ip = (i == Z - 1 ? 0 : row + T);
+          const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
+          nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), rep,
+                                  c2, c3, keys);
+          jj += dj; i += di;
+          if (jj >= Th) { jj -= Th; ++i; }
         }
-        jj += dj; i += di;
-        if (jj >= Th) { jj -= Th; ++i; }
+        __syncthreads();
       }
-      __syncthreads();
+    } else {
+      // an odd ring: 3 colours, colour = (axis_colour(i) + axis_colour(j)) % 3
+      for (int colour = 0; colour < 3; ++colour) {
+        int i = tid / Th, jj = tid - i * Th;
+        while (i < Z) {
+          int beta = colour - axis_colour(i, Z);
+          if (beta < 0) beta += 3;
+          int j;
+          bool valid;
+          if (beta < 2) { j = beta + 2 * jj; valid = j < Teven; }
+          else          { j = T - 1;         valid = (T & 1) && jj == 0; }
+          if (valid) {
+            const int row = i * T;
+            const int im = (i == 0 ? nsite : row) - T, ip = (i == Z - 1 ? 0 : row + T);
+            const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
+            nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), rep,
+                                    c2, c3, keys);
+          }
+          jj += dj; i += di;
+          if (jj >= Th) { jj -= Th; ++i; }
+        }
+        __syncthreads();
+      }
     }
-    // ---- 2. Robbins-Monro on sigma_site ----
+    // ---- 2. Robbins-Monro on sigma_site; amplitude proposal ----
     const double acc_total = block_sum<double>((double)nacc, scr);
     if (tid == 0) {
       if (flags & CYL_SWEEP_ADAPT_SIGMA)
@@ -165,79 +221,93 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       sc->step_counter += nsite;
       sc->site_proposed += nsite;
       sc->site_accepted += acc_total;
-    }
-    if (!(flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE))) { __syncthreads(); continue; }
-
-    // ---- 3. row moments ----
-    {
-      const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
-      for (int i = warp; i < Z; i += SWEEP_NT / 32) {
-        const int row = i * T, rm = (i == 0 ? Z - 1 : i - 1) * T;
-        double m[CYL_NMOM];
-#pragma unroll
-        for (int q = 0; q < CYL_NMOM; ++q) m[q] = 0.0;
-        for (int j = lane; j < T; j += 32)
-          moments_accumulate(m, psi[row + j], psi[rm + j], psi[row + (j == 0 ? T - 1 : j - 1)], inv_lz2, inv_lth2, inv_lth);
-#pragma unroll
-        for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
-        if (lane == 0) {
-#pragma unroll
-          for (int q = 0; q < CYL_NMOM; ++q) mom[i * CYL_NMOM + q] = m[q];
-        }
+      if (extras) {
+        const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), keys.k[0], keys.k[1]);
+        double zre, zim;
+        Draw<double>::normals(x.x, x.y, zre, zim);
+        sc->amp_new = sc->amp + sc->sigma_amp * zre;
+        sc->amp_in_bounds = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(sc->amp_new) < p.amp_bound);
       }
     }
-    // ---- 4. amplitude proposal (thread 0 draws), energies (all threads) ----
-    if (tid == 0) {
-      const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
-      double zre, zim;
-      Draw<double>::normals(x.x, x.y, zre, zim);
-      sc->amp_new = sc->amp + sc->sigma_amp * zre;
-      sc->amp_in_bounds = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(sc->amp_new) < p.amp_bound);
-    }
     __syncthreads();
+    if (!extras) continue;
+
+    // ---- 3a. row weights for the current and the proposed amplitude ----
     const double a = sc->amp, a_new = sc->amp_new;
     const bool try_move = sc->amp_in_bounds != 0;
-    double e_cur = 0.0, e_new = 0.0, s_p2 = 0.0, s_abs = 0.0;
+    double red[6] = {0, 0, 0, 0, 0, 0};       // e_cur, e_dif, const_cur, const_dif, sum |psi|^2, sum |psi|
     {
       const double ra = geo_radius_rescaled(p.radius, a), ran = geo_radius_rescaled(p.radius, a_new);
       for (int i = tid; i < Z; i += SWEEP_NT) {
         const RowTrig t = trig[i];
-        const double* S = mom + i * CYL_NMOM;
         const Geo g0 = geo_from_sc(p.wavenumber, ra, a, t.s0, t.c0), gm = geo_from_sc(p.wavenumber, ra, a, t.sm, t.cm);
-        e_cur += field_energy_row(variant, p, lz, lth, T, g0, gm, g0, S);
+        double Wc[6], Wn[6];
+        field_energy_weights(variant, p, lz, lth, T, g0, gm, g0, Wc);
         if (try_move) {
           const Geo h0 = geo_from_sc(p.wavenumber, ran, a_new, t.s0, t.c0), hm = geo_from_sc(p.wavenumber, ran, a_new, t.sm, t.cm);
-          e_new += field_energy_row(variant, p, lz, lth, T, h0, hm, g0, S);       // a_ref = current amplitude (:75)
+          field_energy_weights(variant, p, lz, lth, T, h0, hm, g0, Wn);          // a_ref = current amplitude (:75)
+        } else {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) Wn[q] = Wc[q];
         }
-        s_p2 += S[0];
-        s_abs += S[5];
-        if ((flags & CYL_SWEEP_MEASURE) && prof) {                               // Lattice.measure :121-131
-          double* pr = prof + ((size_t)b * Zmax + i) * 3;
-          pr[0] += S[6]; pr[1] += S[7]; pr[2] += S[5];
-        }
+        RowW<R> w;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { w.cur[q] = (R)Wc[q]; w.dif[q] = (R)(Wn[q] - Wc[q]); }
+        roww[i] = w;
+        red[2] += Wc[5];
+        red[3] += Wn[5] - Wc[5];
       }
     }
-    e_cur = block_sum<double>(e_cur, scr) * lz * lth;
-    e_new = block_sum<double>(e_new, scr) * lz * lth;
-    if (flags & CYL_SWEEP_MEASURE) {
-      s_p2 = block_sum<double>(s_p2, scr);
-      s_abs = block_sum<double>(s_abs, scr);
-    }
-    if (try_move && warp == 0) {
+    if (try_move && warp == SWEEP_NWARP - 1) {
       const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
       if (lane == 0) sc->e_surf_new = es;
     }
     __syncthreads();
+    // ---- 3b. energy pass: one warp per row, lanes over theta ----
+    for (int i = warp; i < Z; i += SWEEP_NWARP) {
+      const int row = i * T, rm = (i == 0 ? nsite : row) - T;
+      const RowW<R> w = roww[i];
+      R ec = 0, ed = 0, s2 = 0, sa = 0, sre = 0, sim = 0;
+      for (int j = lane; j < T; j += 32) {
+        const C pv = psi[row + j], L = psi[rm + j], W = psi[row + (j == 0 ? T : j) - 1];
+        const R p2 = pv.x * pv.x + pv.y * pv.y;
+        const R zr = pv.x - L.x, zi = pv.y - L.y, tr = pv.x - W.x, ti = pv.y - W.y;
+        const R m2 = p2 * p2;
+        const R m3 = (zr * zr + zi * zi) * inv_lz2;
+        const R m4 = (tr * tr + ti * ti) * inv_lth2;
+        const R m5 = (pv.x * ti - pv.y * tr) * inv_lth;                 // Im(conj(p) dth)
+        ec += w.cur[0] * p2 + w.cur[1] * m2 + w.cur[2] * m3 + w.cur[3] * m4 + w.cur[4] * m5;
+        ed += w.dif[0] * p2 + w.dif[1] * m2 + w.dif[2] * m3 + w.dif[3] * m4 + w.dif[4] * m5;
+        if (measure) { s2 += p2; sa += sqrt(p2); sre += pv.x; sim += pv.y; }
+      }
+      red[0] += (double)ec;
+      red[1] += (double)ed;
+      if (measure) {
+        red[4] += (double)s2;
+        red[5] += (double)sa;
+        if (prof) {                                                      // Lattice.measure :121-131
+          const R rsa = warp_sum(sa), rre = warp_sum(sre), rim = warp_sum(sim);
+          if (lane == 0) {
+            double* pr = prof + ((size_t)b * Zmax + i) * 3;
+            pr[0] += (double)rre; pr[1] += (double)rim; pr[2] += (double)rsa;
+          }
+        }
+      }
+    }
+    block_sum_n<6>(red, scr);
+    // ---- 4. measurement + amplitude decision (thread 0) ----
     if (tid == 0) {
+      const double e_cur = (red[0] + red[2]) * lz * lth;                 // :213
+      const double e_dif = (red[1] + red[3]) * lz * lth;
       sc->e_field = e_cur;
-      if ((flags & CYL_SWEEP_MEASURE) && obs) {                                   // measure_avgs :135-156 + engine record
+      if (measure && obs) {                                              // measure_avgs :135-156 + engine record
         double* o = obs + (size_t)b * CYL_OBS_DOUBLES;
         o[CYL_OB_COUNT] += 1.0;
         o[CYL_OB_ABS_A] += fabs(a);
         o[CYL_OB_A] += a;
         o[CYL_OB_A2] += a * a;
-        o[CYL_OB_PSI2] += s_p2 / nsite;
-        o[CYL_OB_ABSPSI] += s_abs / nsite;
+        o[CYL_OB_PSI2] += red[4] / nsite;
+        o[CYL_OB_ABSPSI] += red[5] / nsite;
         o[CYL_OB_E_FIELD] += e_cur;
         o[CYL_OB_E_SURF] += sc->e_surf;
         o[CYL_OB_E_FIELD2] += e_cur * e_cur;
@@ -246,10 +316,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       int accept = 0;
       if (flags & CYL_SWEEP_AMP_MOVES) {
         if (try_move) {
-          const double dE = (sc->e_surf_new + e_new) - (sc->e_surf + e_cur);
+          const double dE = (sc->e_surf_new - sc->e_surf) + e_dif;
           if (!isfinite(dE)) sc->flags = (double)((unsigned)sc->flags | 1u);
-          const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
-          if (dE <= 0) accept = 1;                                                // accept rule B.2
+          const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), keys.k[0], keys.k[1]);
+          if (dE <= 0) accept = 1;                                       // accept rule B.2
           else if (p.temperature == 0) accept = 0;
           else accept = (u01_f64(x.z) <= exp(-dE / p.temperature));
         }
@@ -287,7 +357,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     ch[CYL_CH_SIGMA_SITE] = sc->sigma_site;
     ch[CYL_CH_SIGMA_AMP] = sc->sigma_amp;
     ch[CYL_CH_E_FIELD] = sc->e_field;
-    if (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) ch[CYL_CH_E_SURF] = sc->e_surf;
+    if (extras) ch[CYL_CH_E_SURF] = sc->e_surf;
     ch[CYL_CH_STEP_COUNTER] = sc->step_counter;
     ch[CYL_CH_SITE_PROPOSED] = sc->site_proposed;
     ch[CYL_CH_SITE_ACCEPTED] = sc->site_accepted;
@@ -317,7 +387,8 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
   }
   auto kern = sweep_smem_kernel<R>;
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-  kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, seed,
+  const PhiloxKeys keys = philox_expand(seed);
+  kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,
                                                       replica0, sweep0, nsweeps, variant, flags, obs, prof);
   CYL_LAUNCH_CHECK();
   return CYL_OK;

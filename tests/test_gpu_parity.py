@@ -334,3 +334,28 @@ def test_invalid_arguments_fail_loudly(cuda):
         ops.sweep_smem(big, torch.tensor([400], dtype=torch.int32, device=cuda), par, ops.new_chain(1, cuda), 0, 0, 1)
     with pytest.raises(_abi.CylinderB200Error):
         ops.HbmWorkspace(4, 4, torch.complex64, cuda)
+
+
+FOURIER_CASES = ["k05_n6_21", "k1_n1_11", "k08_n2_30", "k12_n3_02"]
+FOURIER_NAMES = ("wavenumber", "radius", "alpha", "C", "u", "n", "kappa", "gamma", "intrinsic_curvature")
+
+
+@pytest.mark.parametrize("tag", FOURIER_CASES)
+def test_fourier_energy_matches_reference(cuda, golden_dir, tag):
+    """Cylinder2D.calc_field_energy_amplitude_change / calc_field_energy and Cylinder1D.calc_surface_energy recorded
+    from the reference (tensor form, scipy quad) vs the single-integral CUDA kernel: <= 1e-10 relative."""
+    import torch
+    from cylinder_b200 import ops
+    g = np.load(os.path.join(golden_dir, "fourier.npz"))
+    P = dict(zip(FOURIER_NAMES, g[tag + "_params"].tolist()))
+    nz, nth = (int(x) for x in g[tag + "_nfc"])
+    amps = g[tag + "_amps"]
+    B = len(amps)
+    par = ops.make_params(cuda, temperature=.1, **P)
+    par = par.repeat(B, 1).contiguous()
+    c = torch.tensor(g[tag + "_coeffs"], dtype=torch.complex128, device=cuda)[None].repeat(B, 1, 1).contiguous()
+    E = ops.fourier_energy(par, nz, nth, torch.tensor(amps, device=cuda), c).cpu().numpy()
+    np.testing.assert_allclose(E, g[tag + "_E_change"], rtol=1e-10)
+    np.testing.assert_allclose(E, g[tag + "_E_stored"], rtol=1e-10)
+    Es = ops.fourier_surface_energy(par, torch.tensor(amps, device=cuda)).cpu().numpy()
+    np.testing.assert_allclose(Es, g[tag + "_E_surf"].real, rtol=1e-10)
