@@ -80,14 +80,38 @@ __host__ __device__ __forceinline__ Geo geo_eval(double k, double r, double a, d
   return g;
 }
 
+// fp64 reciprocal / reciprocal square root from the fp32 MUFU seed + two Newton steps (relative error ~2e-16 for
+// arguments well inside the fp32 range, which every metric factor is).  The sweep kernels rebuild O(Z) metric
+// coefficients per amplitude proposal on a handful of threads: that phase is latency-bound, and the IEEE division
+// and square-root sequences are its critical path.  The parity-critical entry points (geometry_eval, replay) keep
+// the IEEE operations.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = r * fma(-x, r, 2.0);
+  r = r * fma(-x, r, 2.0);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  r = r * fma(-hx * r, r, 1.5);
+  r = r * fma(-hx * r, r, 1.5);
+  return r;
+}
+__device__ __forceinline__ double fast_radius_rescaled(double r, double a) {             // :37
+  return r * fast_rsqrt(fma(0.5 * a, a, 1.0));
+}
+
 // Same from cached sin(kz), cos(kz) -- these do not depend on the amplitude, so the sweep kernels tabulate them
 // once per launch and re-evaluate the metric after every accepted amplitude move without trigonometry.
-__host__ __device__ __forceinline__ Geo geo_from_sc(double k, double ra, double a, double s, double c) {
+__device__ __forceinline__ Geo geo_from_sc(double k, double ra, double a, double s, double c) {
   Geo g;
   g.gth = ra * (1.0 + a * s);
   const double t = ra * a * k * c;
-  g.gz = sqrt(1.0 + t * t);
-  g.ath = k * ra * a * c / g.gz;
+  const double x = fma(t, t, 1.0);
+  const double rs = fast_rsqrt(x);
+  g.gz = x * rs;
+  g.ath = k * ra * a * c * rs;
   return g;
 }
 

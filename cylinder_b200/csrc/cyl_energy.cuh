@@ -39,20 +39,20 @@ __device__ __forceinline__ void field_energy_weights(int variant, const CylParam
   if (variant == CYL_VARIANT_SIMPLE) {
     zs = gme.gz;                                               // :191
     w0 = zs * g0e.gth;                                         // :193
-    wir = g0e.gz / gme.gth;                                    // :194
+    wir = g0e.gz * fast_rcp(gme.gth);                          // :194
     A = gme.ath;                                               // :195
   } else {
     zs = g0r.gz;                                               // 0th:253
     w0 = g0r.gz * g0e.gth;                                     // 0th:255
-    wir = w0 / (g0r.gth * g0r.gth);                            // 0th:254,256
+    wir = w0 * fast_rcp(g0r.gth * g0r.gth);                    // 0th:254,256
     A = g0e.ath;                                               // 0th:257
     const double area = (lz * g0e.gz) * (lth * g0e.gth);       // 0th:261, :68
-    const double bg = -p.temperature / area + ((p.alpha < 0) ? .5 * p.alpha * p.alpha / p.u : 0.0);   // 0th:66-92
+    const double bg = -p.temperature * fast_rcp(area) + ((p.alpha < 0) ? .5 * p.alpha * p.alpha * fast_rcp(p.u) : 0.0);   // 0th:66-92
     W[5] = T * bg * w0;                                        // 0th:275
   }
   W[0] = p.alpha * w0 + Cn2 * (A * A) * wir;                   // :199 (alpha part) + :210
   W[1] = p.u / 2 * w0;                                         // :199
-  W[2] = p.C / (zs * zs) * w0;                                 // :200-202
+  W[2] = p.C * fast_rcp(zs * zs) * w0;                         // :200-202
   W[3] = p.C * wir;                                            // :206
   W[4] = p.C * p.n * 2 * A * wir;                              // :208
 }

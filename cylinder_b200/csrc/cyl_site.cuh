@@ -43,30 +43,34 @@ __device__ __forceinline__ RowCoef<R> row_coef(const CylParams& p, int variant, 
                                                const Geo& gm, const Geo& gp) {
   const double sg = g0.gth * g0.gz;
   const double Cn2 = p.C * p.n * p.n;
+  const double ilz2 = fast_rcp(lz * lz), ilth = fast_rcp(lth);
+  const double igzm = fast_rcp(gm.gz), igzp = fast_rcp(gp.gz);
   double clz, crz, clt, crt, xl, xr, mass, sgmul;
   if (variant == CYL_VARIANT_SIMPLE) {
-    const double Rm = 1.0 / (gm.gth * gm.gth), Rp = 1.0 / (gp.gth * gp.gth);
-    clz = p.C / (lz * lz * gm.gz * gm.gz);
-    crz = p.C / (lz * lz * gp.gz * gp.gz);
-    clt = p.C * Rm * Rm / (lth * lth);
-    crt = p.C * Rp * Rp / (lth * lth);
-    xl = 2 * p.C * p.n * Rm * gm.ath / lth;
-    xr = 2 * p.C * p.n * Rp * gp.ath / lth;
+    const double igtm = fast_rcp(gm.gth), igtp = fast_rcp(gp.gth);
+    const double Rm = igtm * igtm, Rp = igtp * igtp;
+    clz = p.C * ilz2 * igzm * igzm;
+    crz = p.C * ilz2 * igzp * igzp;
+    clt = p.C * Rm * Rm * ilth * ilth;
+    crt = p.C * Rp * Rp * ilth * ilth;
+    xl = 2 * p.C * p.n * Rm * gm.ath * ilth;
+    xr = 2 * p.C * p.n * Rp * gp.ath * ilth;
     mass = p.alpha + Cn2 * Rm * gm.ath * gm.ath;
     sgmul = 1.0;
   } else {
-    const double R0 = 1.0 / (g0.gth * g0.gth);
-    clz = p.C / (lz * lz * gm.gz * gm.gz) * (gm.gth * gm.gz) / sg;
-    crz = p.C / (lz * lz * gp.gz * gp.gz) * (gp.gth * gp.gz) / sg;
-    clt = crt = p.C * R0 / (lth * lth);
-    xl = xr = 2 * p.C * p.n * R0 * g0.ath / lth;
+    const double igt0 = fast_rcp(g0.gth);
+    const double R0 = igt0 * igt0, isg = igt0 * fast_rcp(g0.gz);
+    clz = p.C * ilz2 * igzm * gm.gth * isg;                 // C/(lz^2 Gz(z-)^2) * sg(z-)/sg(z)
+    crz = p.C * ilz2 * igzp * gp.gth * isg;
+    clt = crt = p.C * R0 * ilth * ilth;
+    xl = xr = 2 * p.C * p.n * R0 * g0.ath * ilth;
     mass = p.alpha + Cn2 * R0 * g0.ath * g0.ath;
     sgmul = sg;
   }
   const double K = sg * lz * lth;
   RowCoef<R> c;
   c.kfull = (R)K;
-  c.kacc = (p.temperature > 0) ? (R)(K * 1.4426950408889634 / p.temperature) : (R)INFINITY;
+  c.kacc = (p.temperature > 0) ? (R)(K * 1.4426950408889634 * fast_rcp(p.temperature)) : (R)INFINITY;
   c.mass = (R)mass;
   c.csum = (R)(clz + crz + clt + crt);
   c.hu = (R)(p.u / 2);
@@ -143,9 +147,16 @@ __host__ __device__ __forceinline__ int axis_colour(int i, int len) { return ((l
 __host__ __device__ __forceinline__ int num_colours(int Z, int T) { return ((Z | T) & 1) ? 3 : 2; }
 
 // Robbins-Monro width update applied once for a batch of n proposals with k accepts and a frozen step factor
-// f = max(step_counter, 200): the reference's per-proposal rule (On_lattice_simple.py:688-696, m = 1, p* = .5,
-// ratio = 4) is sigma *= (1 + 2/f) on accept, (1 - 2/f) on reject; the batch applies the product.
-__device__ __forceinline__ double rm_batch_update(double sigma, double step_counter, double n, double k) {
+// f = max(step_counter + n/2, 200): the reference's per-proposal rule (On_lattice_simple.py:688-696, m = 1, p* = .5,
+// ratio = 4) is sigma *= (1 + 2/f) on accept, (1 - 2/f) on reject; the batch applies the product.  The fp32 kernels
+// evaluate the exponent in fp32 (sigma is a tuning width, and both fp32 kernels share this code so they stay
+// bit-identical to each other); the fp64 kernels in fp64 (the oracle restates exactly that).
+template <typename R> __device__ __forceinline__ double rm_batch_update(double sigma, double step_counter, double n, double k);
+template <> __device__ __forceinline__ double rm_batch_update<double>(double sigma, double step_counter, double n, double k) {
   const double f = fmax(step_counter + 0.5 * n, 200.0);
   return sigma * exp(k * log1p(2.0 / f) + (n - k) * log1p(-2.0 / f));
+}
+template <> __device__ __forceinline__ double rm_batch_update<float>(double sigma, double step_counter, double n, double k) {
+  const float x = 2.0f / fmaxf((float)step_counter + 0.5f * (float)n, 200.0f);
+  return sigma * (double)expf((float)k * log1pf(x) + (float)(n - k) * log1pf(-x));
 }

@@ -25,12 +25,12 @@
 #include "cyl_site.cuh"
 #include "cyl_surface.cuh"
 
-#define HBM_NT 512
+#define HBM_NT 256
 #define HBM_HC 4          // column halo in the global layout (>= NCOL; 4 keeps plane columns 16-byte aligned)
 #define HBM_TW 128        // tile width (sites)
 
 template <typename R> struct HbmTile;
-template <> struct HbmTile<float>  { static constexpr int TH = 64; };
+template <> struct HbmTile<float>  { static constexpr int TH = 32; };
 template <> struct HbmTile<double> { static constexpr int TH = 32; };
 
 struct HbmGeom {
@@ -153,8 +153,15 @@ __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const doub
   const double a = chain[CYL_CH_AMPLITUDE];
   const double pi = 3.14159265358979323846;
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
-  const Geo g0 = geo_eval(p.wavenumber, p.radius, a, lz * i), gm = geo_eval(p.wavenumber, p.radius, a, lz * (i - .5)),
-            gp = geo_eval(p.wavenumber, p.radius, a, lz * (i + .5));
+  // same arithmetic as the shared-memory kernel's tables (the two fp32 paths stay bit-identical)
+  const double ra = fast_radius_rescaled(p.radius, a);
+  const int ip = (i + 1 == Z) ? 0 : i + 1;
+  double s0, c0, sm, cm, sp, cp;
+  sincos(p.wavenumber * (lz * i), &s0, &c0);
+  sincos(p.wavenumber * (lz * (i - .5)), &sm, &cm);
+  sincos(p.wavenumber * (lz * (ip - .5)), &sp, &cp);
+  const Geo g0 = geo_from_sc(p.wavenumber, ra, a, s0, c0), gm = geo_from_sc(p.wavenumber, ra, a, sm, cm),
+            gp = geo_from_sc(p.wavenumber, ra, a, sp, cp);
   coef[i] = row_coef<R>(p, variant, lz, lth, g0, gm, gp);
 }
 
@@ -275,8 +282,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         bool counted = (c == 1) || ((unsigned)(r - 2) < (unsigned)TH && (unsigned)(q - HS) < (unsigned)TW);
         if (border) {
           counted = counted && gi < g.Z && gj < g.T;
-          gi = modi(gi, g.Z);
-          gj = modi(gj, g.T);
+          gi = wrapi(gi, g.Z);       // rows / columns past Z + halo only exist in partial tiles and are never stored
+          gj = wrapi(gj, g.T);
         }
         const uint4 x = philox4x32_10((uint32_t)(gi * g.T + gj), rep, c2, c3, keys);
         R zre, zim;
@@ -372,13 +379,14 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
 }
 
 // after every sweep: Robbins-Monro on sigma_site, counters, flip the buffer index
+template <typename R>
 __global__ void hbm_post_sweep_kernel(double* __restrict__ chain, HbmCounters* __restrict__ counters, int32_t* __restrict__ cur,
                                       double nsite, uint32_t flags) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double acc = (double)counters->accepted;
   counters->accepted = 0ull;
   if (flags & CYL_SWEEP_ADAPT_SIGMA)
-    chain[CYL_CH_SIGMA_SITE] = rm_batch_update(chain[CYL_CH_SIGMA_SITE], chain[CYL_CH_STEP_COUNTER], nsite, acc);
+    chain[CYL_CH_SIGMA_SITE] = rm_batch_update<R>(chain[CYL_CH_SIGMA_SITE], chain[CYL_CH_STEP_COUNTER], nsite, acc);
   chain[CYL_CH_STEP_COUNTER] += nsite;
   chain[CYL_CH_SITE_PROPOSED] += nsite;
   chain[CYL_CH_SITE_ACCEPTED] += acc;
@@ -594,7 +602,7 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
     kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, keys, (uint32_t)replica, sweep);
-    hbm_post_sweep_kernel<<<1, 32, 0, st>>>(chain, counters, cur, (double)g.Z * g.T, flags);
+    hbm_post_sweep_kernel<R><<<1, 32, 0, st>>>(chain, counters, cur, (double)g.Z * g.T, flags);
     if (amp) {
       hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, cur, g, params, S);
       hbm_amp_kernel<<<1, 256, 0, st>>>(S, g.Z, g.T, params, chain, seed, (uint32_t)replica, sweep, variant, flags, obs, prof);

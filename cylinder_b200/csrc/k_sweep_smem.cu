@@ -27,8 +27,11 @@
 struct SmemScalars {
   double amp, amp_new, sigma_site, sigma_amp, e_field, e_surf, e_surf_new;
   double step_counter, site_proposed, site_accepted, amp_proposed, amp_accepted, amp_counter, flags;
-  int amp_accept, amp_in_bounds;
+  double obs[CYL_OBS_DOUBLES];      // observable sums of this launch, flushed once at the end
+  int amp_accept;
 };
+
+#define AMP_CHUNK 64                // amplitude-move draws are precomputed for this many sweeps at a time
 
 // sin/cos(k z) at z_i and z_{i-1/2}
 struct RowTrig { double s0, c0, sm, cm; };
@@ -40,13 +43,16 @@ struct __align__(16) RowW { R cur[5]; R dif[5]; R pad[2]; };
 template <typename R>
 struct SweepSmemLayout {
   using C = typename Real<R>::complex_t;
-  size_t off_coef, off_trig, off_w, off_scr, off_sc, total;
+  size_t off_coef, off_trig, off_w, off_prof, off_amp, off_scr, off_sc, total;
   __host__ __device__ SweepSmemLayout(int Zmax, int T) {
     size_t o = (size_t)Zmax * T * sizeof(C);
     o = (o + 15) & ~(size_t)15;
     off_coef = o; o += (size_t)Zmax * sizeof(RowCoef<R>);
     off_trig = o; o += (size_t)Zmax * sizeof(RowTrig);
     off_w = o;    o += (size_t)Zmax * sizeof(RowW<R>);
+    off_prof = o; o += (size_t)Zmax * 3 * sizeof(R);          // per-launch profile sums, flushed once at the end
+    o = (o + 15) & ~(size_t)15;
+    off_amp = o;  o += 2 * AMP_CHUNK * sizeof(double);          // unit normal + accept uniform per sweep
     off_scr = o;  o += 8 * SWEEP_NWARP * sizeof(double);
     off_sc = o;   o += sizeof(SmemScalars);
     total = (o + 15) & ~(size_t)15;
@@ -56,7 +62,7 @@ struct SweepSmemLayout {
 template <typename R>
 __device__ __forceinline__ void build_row_coefs(RowCoef<R>* coef, const RowTrig* trig, const CylParams& p, int variant,
                                                 double a, double lz, double lth, int Z) {
-  const double ra = geo_radius_rescaled(p.radius, a);
+  const double ra = fast_radius_rescaled(p.radius, a);
   for (int i = threadIdx.x; i < Z; i += blockDim.x) {
     const RowTrig t = trig[i], tp = trig[i + 1 == Z ? 0 : i + 1];
     const Geo g0 = geo_from_sc(p.wavenumber, ra, a, t.s0, t.c0);
@@ -116,6 +122,9 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
   RowTrig* trig = reinterpret_cast<RowTrig*>(smem_raw + lay.off_trig);
   RowW<R>* roww = reinterpret_cast<RowW<R>*>(smem_raw + lay.off_w);
+  R* prof_s = reinterpret_cast<R*>(smem_raw + lay.off_prof);
+  double* ampz = reinterpret_cast<double*>(smem_raw + lay.off_amp);
+  double* ampu = ampz + AMP_CHUNK;
   double* scr = reinterpret_cast<double*>(smem_raw + lay.off_scr);
   SmemScalars* sc = reinterpret_cast<SmemScalars*>(smem_raw + lay.off_sc);
 
@@ -146,8 +155,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     sc->flags = ch[CYL_CH_FLAGS];
     sc->e_field = ch[CYL_CH_E_FIELD];
     sc->amp_accept = 0;
+    for (int q = 0; q < CYL_OBS_DOUBLES; ++q) sc->obs[q] = 0.0;
   }
   for (int s = tid; s < nsite; s += SWEEP_NT) psi[s] = psi_b[s];
+  for (int s = tid; s < 3 * Z; s += SWEEP_NT) prof_s[s] = R(0);
   for (int i = tid; i < Z; i += SWEEP_NT) {
     RowTrig t;
     sincos(p.wavenumber * (lz * i), &t.s0, &t.c0);
@@ -162,6 +173,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   }
   __syncthreads();
 
+  const double amp_pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
+  const double amp_ratio = 1.0 / (amp_pt * (1.0 - amp_pt));
   const int ncol = num_colours(Z, T);
   const int Th = (T + 1) >> 1, Teven = T & ~1;
   const int di = SWEEP_NT / Th, dj = SWEEP_NT % Th;
@@ -169,6 +182,18 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
+    if (extras && (sw & (AMP_CHUNK - 1)) == 0) {
+      // draws of the next AMP_CHUNK amplitude moves, one sweep per thread (counter-based: any order, any thread)
+      if (tid < AMP_CHUNK && sw + tid < nsweeps) {
+        const uint64_t s2 = sweep + (uint64_t)tid;
+        const uint4 x = philox4x32_10(0u, rep, (uint32_t)s2, philox_c3(CYL_TAG_AMP, s2), keys);
+        double zre, zim;
+        Draw<double>::normals(x.x, x.y, zre, zim);
+        ampz[tid] = zre;
+        ampu[tid] = u01_f64(x.z);
+      }
+      __syncthreads();
+    }
     const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
     const R sigma = (R)sc->sigma_site;
     int nacc = 0;
@@ -190,10 +215,15 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         __syncthreads();
       }
     } else {
-      // an odd ring: 3 colours, colour = (axis_colour(i) + axis_colour(j)) % 3
+      // an odd ring: 3 colours, colour = (axis_colour(i) + axis_colour(j)) % 3.  With T even (Z odd) the rows that hold
+      // sites of a colour are enumerable (pass 0: even rows incl. the last, pass 1: all rows, pass 2: odd rows + the
+      // last), so no thread iterates over empty rows; with T odd every row is visited and filtered.
+      const bool t_even = (T & 1) == 0;
       for (int colour = 0; colour < 3; ++colour) {
-        int i = tid / Th, jj = tid - i * Th;
-        while (i < Z) {
+        const int nrow_pass = (t_even && colour != 1) ? (Z + 1) >> 1 : Z;
+        int ii = tid / Th, jj = tid - ii * Th;
+        while (ii < nrow_pass) {
+          const int i = !t_even || colour == 1 ? ii : (colour == 0 ? 2 * ii : min(2 * ii + 1, Z - 1));
           int beta = colour - axis_colour(i, Z);
           if (beta < 0) beta += 3;
           int j;
@@ -207,78 +237,97 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), rep,
                                     c2, c3, keys);
           }
-          jj += dj; i += di;
-          if (jj >= Th) { jj -= Th; ++i; }
+          jj += dj; ii += di;
+          if (jj >= Th) { jj -= Th; ++ii; }
         }
         __syncthreads();
       }
     }
-    // ---- 2. Robbins-Monro on sigma_site; amplitude proposal ----
+    // ---- 2. accept count; Robbins-Monro on sigma_site (one thread, overlapped with the weights phase) ----
     const double acc_total = block_sum<double>((double)nacc, scr);
-    if (tid == 0) {
+    if (tid == SWEEP_NT - 1) {
       if (flags & CYL_SWEEP_ADAPT_SIGMA)
-        sc->sigma_site = rm_batch_update(sc->sigma_site, sc->step_counter, (double)nsite, acc_total);
+        sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, acc_total);
       sc->step_counter += nsite;
       sc->site_proposed += nsite;
       sc->site_accepted += acc_total;
-      if (extras) {
-        const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), keys.k[0], keys.k[1]);
-        double zre, zim;
-        Draw<double>::normals(x.x, x.y, zre, zim);
-        sc->amp_new = sc->amp + sc->sigma_amp * zre;
-        sc->amp_in_bounds = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(sc->amp_new) < p.amp_bound);
-      }
     }
-    __syncthreads();
-    if (!extras) continue;
+    if (!extras) { __syncthreads(); continue; }
 
-    // ---- 3a. row weights for the current and the proposed amplitude ----
-    const double a = sc->amp, a_new = sc->amp_new;
-    const bool try_move = sc->amp_in_bounds != 0;
+    // The proposal a' = a + sigma_amp N(0,1) is known to every thread: the unit normal was drawn ahead of time, a and
+    // sigma_amp were fixed by the previous sweep's decision.
+    const double a = sc->amp;
+    const double a_new = a + sc->sigma_amp * ampz[sw & (AMP_CHUNK - 1)];
+    const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
     double red[6] = {0, 0, 0, 0, 0, 0};       // e_cur, e_dif, const_cur, const_dif, sum |psi|^2, sum |psi|
-    {
-      const double ra = geo_radius_rescaled(p.radius, a), ran = geo_radius_rescaled(p.radius, a_new);
-      for (int i = tid; i < Z; i += SWEEP_NT) {
-        const RowTrig t = trig[i];
-        const Geo g0 = geo_from_sc(p.wavenumber, ra, a, t.s0, t.c0), gm = geo_from_sc(p.wavenumber, ra, a, t.sm, t.cm);
-        double Wc[6], Wn[6];
-        field_energy_weights(variant, p, lz, lth, T, g0, gm, g0, Wc);
-        if (try_move) {
-          const Geo h0 = geo_from_sc(p.wavenumber, ran, a_new, t.s0, t.c0), hm = geo_from_sc(p.wavenumber, ran, a_new, t.sm, t.cm);
-          field_energy_weights(variant, p, lz, lth, T, h0, hm, g0, Wn);          // a_ref = current amplitude (:75)
-        } else {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) Wn[q] = Wc[q];
-        }
+
+    // ---- 3a. row weights on warps 0..6: lane pair (2i, 2i+1) = (current, proposed amplitude) of row i;
+    //          warp 7 meanwhile evaluates the surface energy of the proposal ----
+    if (warp == SWEEP_NWARP - 1) {
+      if (try_move) {
+        const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
+        if (lane == 0) sc->e_surf_new = es;
+      }
+    } else {
+      const double ae = (try_move && (tid & 1)) ? a_new : a;
+      const double ra = fast_radius_rescaled(p.radius, a), rae = (tid & 1) ? fast_radius_rescaled(p.radius, ae) : ra;
+      for (int base = 0; base < 2 * Z; base += SWEEP_NT - 32) {
+        const int t = base + tid;
+        const int i = min(t >> 1, Z - 1);
+        const RowTrig tr = trig[i];
+        const Geo g0e = geo_from_sc(p.wavenumber, rae, ae, tr.s0, tr.c0), gme = geo_from_sc(p.wavenumber, rae, ae, tr.sm, tr.cm);
+        Geo g0r = g0e;                                                   // a_ref = current amplitude (:75); 0th order only
+        if (variant != CYL_VARIANT_SIMPLE && (tid & 1)) g0r = geo_from_sc(p.wavenumber, ra, a, tr.s0, tr.c0);
+        double W[6];
+        field_energy_weights(variant, p, lz, lth, T, g0e, gme, g0r, W);
         RowW<R> w;
+        double dif5 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) { w.cur[q] = (R)Wc[q]; w.dif[q] = (R)(Wn[q] - Wc[q]); }
-        roww[i] = w;
-        red[2] += Wc[5];
-        red[3] += Wn[5] - Wc[5];
+        for (int q = 0; q < 6; ++q) {
+          const double other = __shfl_xor_sync(0xffffffffu, W[q], 1);    // even lane receives W(a')
+          if (q < 5) { w.cur[q] = (R)W[q]; w.dif[q] = (R)(other - W[q]); }
+          else dif5 = other - W[q];
+        }
+        if (t < 2 * Z && !(tid & 1)) {
+          roww[i] = w;
+          red[2] += W[5];
+          red[3] += dif5;
+        }
       }
     }
-    if (try_move && warp == SWEEP_NWARP - 1) {
-      const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
-      if (lane == 0) sc->e_surf_new = es;
-    }
     __syncthreads();
-    // ---- 3b. energy pass: one warp per row, lanes over theta ----
+
+    // ---- 3b. energy pass: one warp per row ----
+    auto site_terms = [&](const C pv, const C L, const C W, const RowW<R>& w, R& ec, R& ed, R& s2, R& sa, R& sre, R& sim) {
+      const R p2 = pv.x * pv.x + pv.y * pv.y;
+      const R zr = pv.x - L.x, zi = pv.y - L.y, tr = pv.x - W.x, ti = pv.y - W.y;
+      const R m2 = p2 * p2;
+      const R m3 = (zr * zr + zi * zi) * inv_lz2;
+      const R m4 = (tr * tr + ti * ti) * inv_lth2;
+      const R m5 = (pv.x * ti - pv.y * tr) * inv_lth;                   // Im(conj(p) dth)
+      ed += w.dif[0] * p2 + w.dif[1] * m2 + w.dif[2] * m3 + w.dif[3] * m4 + w.dif[4] * m5;
+      if (measure) {
+        ec += w.cur[0] * p2 + w.cur[1] * m2 + w.cur[2] * m3 + w.cur[3] * m4 + w.cur[4] * m5;
+        s2 += p2; sa += sqrt(p2); sre += pv.x; sim += pv.y;
+      }
+    };
+    struct __align__(16) Pair { C a, b; };
     for (int i = warp; i < Z; i += SWEEP_NWARP) {
       const int row = i * T, rm = (i == 0 ? nsite : row) - T;
       const RowW<R> w = roww[i];
       R ec = 0, ed = 0, s2 = 0, sa = 0, sre = 0, sim = 0;
-      for (int j = lane; j < T; j += 32) {
-        const C pv = psi[row + j], L = psi[rm + j], W = psi[row + (j == 0 ? T : j) - 1];
-        const R p2 = pv.x * pv.x + pv.y * pv.y;
-        const R zr = pv.x - L.x, zi = pv.y - L.y, tr = pv.x - W.x, ti = pv.y - W.y;
-        const R m2 = p2 * p2;
-        const R m3 = (zr * zr + zi * zi) * inv_lz2;
-        const R m4 = (tr * tr + ti * ti) * inv_lth2;
-        const R m5 = (pv.x * ti - pv.y * tr) * inv_lth;                 // Im(conj(p) dth)
-        ec += w.cur[0] * p2 + w.cur[1] * m2 + w.cur[2] * m3 + w.cur[3] * m4 + w.cur[4] * m5;
-        ed += w.dif[0] * p2 + w.dif[1] * m2 + w.dif[2] * m3 + w.dif[3] * m4 + w.dif[4] * m5;
-        if (measure) { s2 += p2; sa += sqrt(p2); sre += pv.x; sim += pv.y; }
+      if ((T & 1) == 0) {
+        for (int pp = lane; 2 * pp < T; pp += 32) {                      // two adjacent sites per lane, 16-byte loads
+          const int j = 2 * pp;
+          const Pair own = *reinterpret_cast<const Pair*>(psi + row + j);
+          const Pair up = *reinterpret_cast<const Pair*>(psi + rm + j);
+          const C Wc = psi[row + (j == 0 ? T : j) - 1];
+          site_terms(own.a, up.a, Wc, w, ec, ed, s2, sa, sre, sim);
+          site_terms(own.b, up.b, own.a, w, ec, ed, s2, sa, sre, sim);
+        }
+      } else {
+        for (int j = lane; j < T; j += 32)
+          site_terms(psi[row + j], psi[rm + j], psi[row + (j == 0 ? T : j) - 1], w, ec, ed, s2, sa, sre, sim);
       }
       red[0] += (double)ec;
       red[1] += (double)ed;
@@ -286,22 +335,37 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         red[4] += (double)s2;
         red[5] += (double)sa;
         if (prof) {                                                      // Lattice.measure :121-131
-          const R rsa = warp_sum(sa), rre = warp_sum(sre), rim = warp_sum(sim);
-          if (lane == 0) {
-            double* pr = prof + ((size_t)b * Zmax + i) * 3;
-            pr[0] += (double)rre; pr[1] += (double)rim; pr[2] += (double)rsa;
+          // three row sums by one transposed butterfly: 6 shuffles instead of 15
+          R v0 = sre, v1 = sim, v2 = sa, v3 = R(0);
+          {
+            const bool hi = lane & 16;                                   // xor 16: upper half keeps (v2, v3)
+            const R s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
+            const R r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+            v0 = (hi ? v2 : v0) + r0;
+            v1 = (hi ? v3 : v1) + r1;
           }
+          {
+            const bool hi = lane & 8;                                    // xor 8: keeps one of the two
+            const R s0 = hi ? v0 : v1;
+            const R r0 = __shfl_xor_sync(0xffffffffu, s0, 8);
+            v0 = (hi ? v1 : v0) + r0;
+          }
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 4);
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+          v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+          // lane 0: sum re, lane 8: sum im, lane 16: sum |psi|, (lane 24: 0)
+          if ((lane & 7) == 0 && lane < 24) prof_s[3 * i + (lane >> 3)] += v0;
         }
       }
     }
     block_sum_n<6>(red, scr);
     // ---- 4. measurement + amplitude decision (thread 0) ----
     if (tid == 0) {
-      const double e_cur = (red[0] + red[2]) * lz * lth;                 // :213
       const double e_dif = (red[1] + red[3]) * lz * lth;
-      sc->e_field = e_cur;
-      if (measure && obs) {                                              // measure_avgs :135-156 + engine record
-        double* o = obs + (size_t)b * CYL_OBS_DOUBLES;
+      if (measure) {                                                     // measure_avgs :135-156 + engine record
+        const double e_cur = (red[0] + red[2]) * lz * lth;               // :213
+        sc->e_field = e_cur;
+        double* o = sc->obs;
         o[CYL_OB_COUNT] += 1.0;
         o[CYL_OB_ABS_A] += fabs(a);
         o[CYL_OB_A] += a;
@@ -318,20 +382,17 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         if (try_move) {
           const double dE = (sc->e_surf_new - sc->e_surf) + e_dif;
           if (!isfinite(dE)) sc->flags = (double)((unsigned)sc->flags | 1u);
-          const uint4 x = philox4x32<10>(0u, rep, c2, philox_c3(CYL_TAG_AMP, sweep), keys.k[0], keys.k[1]);
           if (dE <= 0) accept = 1;                                       // accept rule B.2
           else if (p.temperature == 0) accept = 0;
-          else accept = (u01_f64(x.z) <= exp(-dE / p.temperature));
+          else accept = (ampu[sw & (AMP_CHUNK - 1)] <= exp(-dE / p.temperature));
         }
         // Robbins-Monro on sigma_amp (engine, SURVEY.md B.3: m = 1, target p*)
-        const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
-        const double ratio = 1.0 / (pt * (1.0 - pt));
         sc->amp_counter += 1;
         sc->amp_proposed += 1;
-        const double f = fmax(sc->amp_counter, 200.0), c = sc->sigma_amp * ratio;
         if (flags & CYL_SWEEP_ADAPT_SIGMA) {
-          if (accept) sc->sigma_amp += c * (1 - pt) / f;
-          else sc->sigma_amp -= c * pt / f;
+          const double cf = sc->sigma_amp * amp_ratio / fmax(sc->amp_counter, 200.0);
+          if (accept) sc->sigma_amp += cf * (1 - amp_pt);
+          else sc->sigma_amp -= cf * amp_pt;
         }
         if (accept) {
           sc->amp = a_new;
@@ -352,6 +413,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   // ---- epilogue ----
   __syncthreads();
   for (int s = tid; s < nsite; s += SWEEP_NT) psi_b[s] = psi[s];
+  if (measure && prof) {
+    double* pr = prof + (size_t)b * Zmax * 3;
+    for (int s = tid; s < 3 * Z; s += SWEEP_NT) pr[s] += (double)prof_s[s];
+  }
+  if (measure && obs && tid < CYL_OBS_DOUBLES) obs[(size_t)b * CYL_OBS_DOUBLES + tid] += sc->obs[tid];
   if (tid == 0) {
     ch[CYL_CH_AMPLITUDE] = sc->amp;
     ch[CYL_CH_SIGMA_SITE] = sc->sigma_site;
