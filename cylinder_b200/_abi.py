@@ -39,7 +39,7 @@ _SIGNATURES = {
     "cyl_lattice_init_f32": [_vp, _i, _vp, _i, _i, _d, _u64, _i64, _vp],
     "cyl_lattice_init_f64": [_vp, _i, _vp, _i, _i, _d, _u64, _i64, _vp],
     "cyl_replay_f64": [_vp, _i, _i, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
-    "cyl_site_delta_f64": [_vp, _i, _i, _vp, _d, _i, _i, _i, _d, _d, _vp, _vp],
+    "cyl_site_delta_f64": [_vp, _i, _i, _vp, _d, _i, _i, _i, _d, _d, _d, _vp, _vp],
     "cyl_row_moments_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp],
     "cyl_row_moments_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp],
     "cyl_field_energy_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],

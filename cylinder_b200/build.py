@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJDIR, src[:-3] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
-            cmd = [nvcc] + ARCH + COMMON + EXTRA.get(src, []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + EXTRA.get(src, []) + os.environ.get("CYL_EXTRA_NVCC_FLAGS", "").split() + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -155,7 +155,7 @@ extern "C" int cyl_replay_f64(double* psi, int Z, int T, const CylParams* params
 }
 
 __global__ void site_delta_kernel(const double2* __restrict__ psi, int Z, int T, const CylParams* __restrict__ params,
-                                  double amp, int variant, int iz, int ith, double d_re, double d_im,
+                                  double amp, int variant, int iz, int ith, double zre, double zim, double sigma,
                                   double* __restrict__ out) {
   if (threadIdx.x != 0) return;
   const CylParams p = *params;
@@ -163,7 +163,8 @@ __global__ void site_delta_kernel(const double2* __restrict__ psi, int Z, int T,
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
   const SiteGeo g = site_geo(p, amp, lz, iz, variant);
   const double2 v = psi[(size_t)wrap(iz, Z) * T + wrap(ith, T)];
-  const Cplx nv = {v.x + d_re, v.y + d_im};
+  const double sw = (variant == CYL_VARIANT_SIMPLE) ? sigma : sigma * g.sg;       // :613 / 0th:135-136
+  const Cplx nv = {v.x + (0.0 + zre * sw), v.y + (0.0 + zim * sw)};               // :617  gauss = mu + z*sigma
   out[0] = delta_energy(psi, Z, T, p, lz, lth, g, variant, iz, ith, nv);
   out[1] = nv.re;
   out[2] = nv.im;
@@ -171,10 +172,10 @@ __global__ void site_delta_kernel(const double2* __restrict__ psi, int Z, int T,
 }
 
 extern "C" int cyl_site_delta_f64(const double* psi, int Z, int T, const CylParams* params, double amp, int variant,
-                                  int iz, int ith, double d_re, double d_im, double* out, void* stream) {
+                                  int iz, int ith, double zre, double zim, double sigma, double* out, void* stream) {
   CYL_CHECK_ARG(psi && params && out && Z > 0 && T > 0, "cyl_site_delta_f64: bad arguments");
   CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_site_delta_f64: unknown variant %d", variant);
-  site_delta_kernel<<<1, 32, 0, as_stream(stream)>>>((const double2*)psi, Z, T, params, amp, variant, iz, ith, d_re, d_im, out);
+  site_delta_kernel<<<1, 32, 0, as_stream(stream)>>>((const double2*)psi, Z, T, params, amp, variant, iz, ith, zre, zim, sigma, out);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

@@ -31,6 +31,14 @@ struct SmemScalars {
   int amp_accept;
 };
 
+// Optional per-phase cycle accounting (build with CYL_EXTRA_NVCC_FLAGS=-DCYL_PHASE_TIMING): thread 0 accumulates
+// clock64() deltas into obs slots 10..15 = site moves, accept count, weights/surface, energy pass, decision, rebuild.
+#ifdef CYL_PHASE_TIMING
+#define PHASE_MARK(k) do { if (tid == 0) { const long long t__ = clock64(); sc->obs[10 + (k)] += (double)(t__ - t_phase); t_phase = t__; } } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
 #define AMP_CHUNK 64                // amplitude-move draws are precomputed for this many sweeps at a time
 
 // sin/cos(k z) at z_i and z_{i-1/2}
@@ -197,6 +205,9 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
     const R sigma = (R)sc->sigma_site;
     int nacc = 0;
+#ifdef CYL_PHASE_TIMING
+    long long t_phase = clock64();
+#endif
     // ---- 1. site moves ----
     if (ncol == 2) {
       // both lengths even: colour = (i + j) & 1, T/2 sites of each colour in every row
@@ -243,8 +254,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         __syncthreads();
       }
     }
+    PHASE_MARK(0);
     // ---- 2. accept count; Robbins-Monro on sigma_site (one thread, overlapped with the weights phase) ----
     const double acc_total = block_sum<double>((double)nacc, scr);
+    PHASE_MARK(1);
     if (tid == SWEEP_NT - 1) {
       if (flags & CYL_SWEEP_ADAPT_SIGMA)
         sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, acc_total);
@@ -296,6 +309,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       }
     }
     __syncthreads();
+    PHASE_MARK(2);
 
     // ---- 3b. energy pass: one warp per row ----
     auto site_terms = [&](const C pv, const C L, const C W, const RowW<R>& w, R& ec, R& ed, R& s2, R& sa, R& sre, R& sim) {
@@ -358,6 +372,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         }
       }
     }
+    PHASE_MARK(3);
     block_sum_n<6>(red, scr);
     // ---- 4. measurement + amplitude decision (thread 0) ----
     if (tid == 0) {
@@ -403,11 +418,13 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       sc->amp_accept = accept;
     }
     __syncthreads();
+    PHASE_MARK(4);
     // ---- 5. metric tables follow the amplitude ----
     if (sc->amp_accept) {
       build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
       __syncthreads();
     }
+    PHASE_MARK(5);
   }
 
   // ---- epilogue ----

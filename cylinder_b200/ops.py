@@ -108,13 +108,13 @@ def replay(psi, params, amp, variant, iz, ith, zre, zim, u, rm_state):
     return acc, dE, sig
 
 
-def site_delta(psi, params, amp, variant, iz, ith, d_re, d_im, out=None):
-    """dE and proposed value of one move psi[iz, ith] += d.  Returns tensor [4] = (dE, new_re, new_im, sqrt_g)."""
+def site_delta(psi, params, amp, variant, iz, ith, zre, zim, sigma, out=None):
+    """dE and proposed value of the move psi[iz, ith] += sigma_eff (zre + i zim).  Returns [4] = (dE, new_re, new_im, sqrt_g)."""
     Z, T = psi.shape
     if out is None:
         out = torch.empty(4, dtype=F64, device=psi.device)
     call("cyl_site_delta_f64", _dev(psi), ptr(psi), Z, T, ptr(params), float(amp), variant_id(variant), int(iz), int(ith),
-         float(d_re), float(d_im), ptr(out), stream())
+         float(zre), float(zim), float(sigma), ptr(out), stream())
     return out
 
 

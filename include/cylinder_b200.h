@@ -126,10 +126,11 @@ int cyl_replay_f64(double* psi /*[Z][T] complex128*/, int Z, int T, const CylPar
                    double* rm_state /*[2]*/, uint8_t* accept_out, double* dE_out, double* sigma_out,
                    void* stream);
 
-/* One proposal with a supplied increment (d_re, d_im): out = {dE, new_re, new_im}.  Does not write psi.
- * Serves Lattice.step_lattice_loc when the host draws from Python's `random` like the reference. */
+/* One proposal psi' = psi + sigma_eff * (zre + i zim) with supplied unit normals (sigma_eff = sigma, or
+ * sigma*sqrt(g) for the 0th-order variant): out = {dE, new_re, new_im, sqrt_g}.  Does not write psi.  Serves
+ * Lattice.step_lattice_loc when the host draws from Python's `random` exactly like the reference. */
 int cyl_site_delta_f64(const double* psi, int Z, int T, const CylParams* params, double amp, int variant,
-                       int iz, int ith, double d_re, double d_im, double* out /*[3]*/, void* stream);
+                       int iz, int ith, double zre, double zim, double sigma, double* out /*[4]*/, void* stream);
 
 /* ---------------------------------------------------------------- field energy ----------------------- */
 /* Row moments S1..S5 of psi[B][Zmax][T]: sum_j |psi|^2, |psi|^4, |dz|^2, |dth|^2,

@@ -1,0 +1,149 @@
+"""GPU tests of the reference-facing Python API (the drop-in boundary): Cylinder, Lattice (both variants),
+Cylinder2D, MetropolisEngine wiring, run.single_run -- against golden vectors recorded from the reference."""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BASE = dict(amplitude=0, wavenumber=1, radius=1, gamma=1, kappa=0, intrinsic_curvature=0, alpha=-1, u=1, C=1, n=6,
+            temperature=.01, temperature_final=.01, dims=(50, 50))
+
+
+def _case(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "lattice_%s.npz" % tag))
+    P = dict(zip(g["params_names"].tolist(), g["params"].tolist()))
+    kw = dict(amplitude=0, wavenumber=P["wavenumber"], radius=P["radius"], gamma=P["gamma"], kappa=P["kappa"],
+              intrinsic_curvature=P["intrinsic_curvature"], alpha=P["alpha"], u=P["u"], C=P["C"], n=P["n"],
+              temperature=P["temperature"], temperature_final=P["temperature"], dims=tuple(int(x) for x in g["dims"]))
+    return g, kw
+
+
+@pytest.mark.parametrize("tag,cls", [("simple_c1_a03", "Lattice"), ("rescaled0_odd_am06", "LatticeRescaled0thOrder"),
+                                     ("simple_T0", "Lattice")])
+def test_lattice_sequential_path_reproduces_reference_stream(cuda, golden_dir, tag, cls):
+    """random.seed(s); Lattice(...); step_lattice(a) x N consumes Python's generator exactly like the reference: same
+    initial field, same accept/reject sequence, same adaptive width, same final field."""
+    import cylinder_b200
+    g, kw = _case(golden_dir, tag)
+    random.seed(int(g["seed"]))
+    lat = getattr(cylinder_b200, cls)(**kw)
+    assert (lat.z_len, lat.th_len) == tuple(g["shape"])
+    assert lat.z_pixel_len == float(g["z_pixel_len"]) and lat.th_pixel_len == float(g["th_pixel_len"])
+    np.testing.assert_allclose(lat.lattice, g["psi0"], rtol=0, atol=1e-17)
+    for a2, ar, e in g["field_energy_initial"]:
+        assert lat.surface_field_energy(a2, ar, lat.lattice, lat.psi_squared, lat.dz, lat.dth) == pytest.approx(e, rel=1e-10)
+    amp, n = float(g["amp"]), 400
+    acc = []
+    for i in range(n):
+        before = lat.acceptance_counter
+        lat.step_lattice(amp)
+        acc.append(lat.acceptance_counter - before)
+        assert lat.sampling_width == pytest.approx(float(g["sigma"][i]), rel=1e-12)
+    assert acc == g["accept"][:n].tolist()
+    assert lat.step_counter == n
+    # caches are derived from psi
+    assert np.allclose(lat.dz, (lat.lattice - np.roll(lat.lattice, 1, 0)) / lat.z_pixel_len)
+    assert np.allclose(lat.psi_squared, np.abs(lat.lattice) ** 2)
+
+
+def test_known_answer_through_lattice_api(cuda):
+    """tests/test_On_lattice.py:75-88 of the reference, with the current signature."""
+    import cylinder_b200
+    random.seed(1)
+    lat = cylinder_b200.Lattice(radius=1, wavenumber=1, amplitude=0, gamma=1, kappa=0, intrinsic_curvature=0, alpha=-1, u=1,
+                                C=1, n=1, temperature=0.01, temperature_final=0.01, dims=(50, 25))
+    ones = np.ones((lat.z_len, lat.th_len), dtype=complex)
+    zeros = np.zeros_like(ones)
+    e = lat.surface_field_energy(0, 0, ones, np.ones(ones.shape), zeros, zeros)
+    assert e == pytest.approx(-.5 * 4 * math.pi ** 2, rel=1e-12)
+    assert lat.z_pixel_len * lat.th_pixel_len * lat.z_len * lat.th_len == pytest.approx(4 * math.pi ** 2)   # pixel x count
+
+
+def test_cylinder_api(cuda, golden_dir):
+    import cylinder_b200
+    t = np.load(os.path.join(golden_dir, "geometry.npz"))["table"]
+    for k, r, a, z, rr, sgt, gt, sgz, gz, ath in t[::37]:
+        c = cylinder_b200.Cylinder(wavenumber=k, radius=r, kappa=0)
+        assert c.radius_rescaled(a) == pytest.approx(rr, rel=1e-15)
+        assert c.sqrt_g_theta(a, z) == pytest.approx(sgt, rel=2e-15, abs=1e-16)
+        assert c.g_theta(a, z) == pytest.approx(gt, rel=4e-15, abs=1e-16)
+        assert c.sqrt_g_z(a, z) == pytest.approx(sgz, rel=2e-15)
+        assert c.g_z(a, z) == pytest.approx(gz, rel=4e-15)
+        assert c.A_theta(a, z) == pytest.approx(ath, rel=4e-15, abs=1e-16)
+    # reference tests/test_system.py:22-68
+    c = cylinder_b200.Cylinder(wavenumber=1.0, radius=1.0, kappa=1.0, gamma=1.0)
+    assert c.sqrt_g_theta(0, .3) == 1 and c.sqrt_g_z(0, .3) == 1 and c.sqrt_g_z(.3, .2) > 1 and c.radius_rescaled(.4) <= 1
+    g = np.load(os.path.join(golden_dir, "surface_energy.npz"))
+    for k, r, gam, kap, H0, a, A0, bend, E in g["direct"][::5]:
+        c = cylinder_b200.Cylinder(wavenumber=k, radius=r, kappa=kap, gamma=gam, intrinsic_curvature=H0)
+        assert c.calc_surface_energy(a) == pytest.approx(E, rel=1e-10)
+        assert c.evaluate_A_integral_0(a) == pytest.approx(A0, rel=1e-12)
+    with pytest.raises(AssertionError):
+        cylinder_b200.Cylinder(wavenumber=-1, radius=1, kappa=0)
+
+
+def test_cylinder2d_api(cuda, golden_dir):
+    import cylinder_b200
+    g = np.load(os.path.join(golden_dir, "fourier.npz"))
+    names = ("wavenumber", "radius", "alpha", "C", "u", "n", "kappa", "gamma", "intrinsic_curvature")
+    tag = "k05_n6_21"
+    P = dict(zip(names, g[tag + "_params"].tolist()))
+    se = cylinder_b200.Cylinder2D(num_field_coeffs=tuple(int(x) for x in g[tag + "_nfc"]), **P)
+    c = g[tag + "_coeffs"]
+    for ia, a in enumerate(g[tag + "_amps"]):
+        assert se.calc_field_energy_amplitude_change(float(a), c) == pytest.approx(float(g[tag + "_E_change"][ia]), rel=1e-10)
+        se.save_temporary_matrices()
+        assert se.calc_field_energy(c) == pytest.approx(float(g[tag + "_E_stored"][ia]), rel=1e-10)
+        assert se.calc_surface_energy(float(a)) == pytest.approx(g[tag + "_E_surf"][ia].real, rel=1e-10)
+    Eb = se.calc_field_energy_batch(g[tag + "_amps"], np.broadcast_to(c, (len(g[tag + "_amps"]),) + c.shape)).cpu().numpy()
+    np.testing.assert_allclose(Eb, g[tag + "_E_change"], rtol=1e-10)
+
+
+def test_lattice_run_and_engine_wiring(cuda, tmp_path):
+    import cylinder_b200
+    random.seed(7)
+    lat = cylinder_b200.LatticeRescaled0thOrder(**dict(BASE, dims=(20, 16), temperature=.05, fieldsteps_per_ampstep=10))
+    # host-driven engine move evaluates its energies on the device
+    e0 = dict(lat.me.energy)
+    assert e0["field"] == pytest.approx(lat.surface_field_energy(0, 0), rel=1e-12)
+    assert e0["surface"] == pytest.approx(lat.surface.calc_surface_energy(0), rel=1e-12)
+    lat.me.step_real_group()
+    lat.run(30, 50)
+    assert len(lat.field_profile_history) == 30 and lat.field_profile_history[0].shape == (lat.z_len,)
+    assert abs(lat.amplitude) < .8 and lat.amplitude == lat.me.real_params[0]
+    assert 0.3 < lat.acceptance_counter / lat.step_counter < 0.7         # Robbins-Monro drives towards 50 %
+    lat.me.save_time_series()
+    assert len(lat.me.df) == 30 and {"amplitude", "field_energy", "surface_energy"} <= set(lat.me.df.columns)
+    prof, prof_abs = lat.get_profiles_df()
+    assert prof.shape == (30, lat.z_len)
+    lat.plot_save(str(tmp_path), "t")
+    assert os.path.exists(tmp_path / "t_snapshot.csv")
+    assert lat.me.energy["field"] == pytest.approx(lat.surface_field_energy(lat.amplitude, lat.amplitude), rel=1e-9)
+
+
+def test_single_run_lattice_and_fourier(cuda, tmp_path, monkeypatch):
+    from cylinder_b200 import run
+    monkeypatch.chdir(tmp_path)
+    random.seed(11)
+    np.random.seed(11)
+    out = tmp_path / "out"
+    out.mkdir()
+    names, obs, means, cov = run.single_run(temp=.05, temp_final=.05, n_steps=20, field_type="lattice", method="sequential",
+                                            num_field_coeffs=(0, 0), fieldsteps_per_ampstep=10, measure_every=1, alpha=-1, C=1, n=6, u=1,
+                                            gamma=1, kappa=0, radius=1, intrinsic_curvature=0, n_substeps=None, dims=(20, 16),
+                                            wavenumber=1, amplitude=0, outdir=str(out), title="lat")
+    assert names == ["amplitude"] and obs == ["abs_amplitude", "amplitude_squared"]
+    assert {"abs_amplitude", "amplitude_squared", "field_energy"} <= set(means)
+    for f in ("lat.csv", "lat_profile.csv", "lat_profile_abs.csv", "lat_snapshot.csv", "lat_avglattice.csv"):
+        assert (out / f).exists(), f
+    assert (tmp_path / "last_sigma.pickle").exists()
+    names, obs, means, cov = run.single_run(temp=.1, temp_final=.1, n_steps=15, field_type="fourier", method="sequential",
+                                            num_field_coeffs=(1, 1), fieldsteps_per_ampstep=3, measure_every=2, alpha=-1, C=1, n=6, u=1,
+                                            gamma=1, kappa=0, radius=1, intrinsic_curvature=0, n_substeps=None, dims=(20, 16),
+                                            wavenumber=.5, amplitude=0, outdir=str(out), title="four")
+    assert len(names) == 1 + 9 and names[1] == "coeff_-1_-1" and cov.shape == (9, 9)
+    assert (out / "four.csv").exists() and (tmp_path / "last_cov.pickle").exists()
