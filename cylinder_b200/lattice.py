@@ -278,8 +278,9 @@ class Lattice:
                 self.sweep(per_step - 1)
             c = self.sweep(1, amp_moves=True, measure=True)               # sweep, measurement record, amplitude move
             self.update_rescale_params(self.amplitude)
-            self.energy = c[_abi.CH_E_FIELD]
-            self.me.energy["field"] = c[_abi.CH_E_FIELD]
+            # energy resync at the amplitude the step ended with (:550,:560-562)
+            self.energy = self.surface_field_energy(self.amplitude, self.amplitude)
+            self.me.energy["field"] = self.energy
             self.me.energy["surface"] = c[_abi.CH_E_SURF]
             self.me.measure_real_system()
 

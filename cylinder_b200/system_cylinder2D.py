@@ -58,6 +58,6 @@ class Cylinder2D(Cylinder):
     def calc_field_energy_batch(self, amplitudes, field_coeffs):
         """amplitudes [B], field_coeffs [B, 2*nth+1, 2*nz+1] (numpy or torch) -> energies [B] (torch, device)."""
         amps = torch.as_tensor(amplitudes, dtype=torch.float64, device=self.device).reshape(-1)
-        c = torch.as_tensor(field_coeffs, device=self.device).to(torch.complex128).reshape(amps.numel(), self.len_arrays_theta, self.len_arrays_z)
+        c = torch.as_tensor(np.array(field_coeffs, dtype=complex), device=self.device).reshape(amps.numel(), self.len_arrays_theta, self.len_arrays_z)
         return ops.fourier_energy(self._params.expand(amps.numel(), -1).contiguous(), self.num_field_coeffs_z,
                                   self.num_field_coeffs_theta, amps, c.contiguous())
