@@ -226,10 +226,10 @@ def main():
             batch.gather_records()
 
     # ---- value leg ----
+    sampler = ClockSampler(local) if rank == 0 else None      # started before warm-up so that samples exist from the first timed ms
     for _ in range(W):
         step_device()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

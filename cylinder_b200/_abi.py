@@ -36,6 +36,7 @@ _SIGNATURES = {
     "cyl_geometry_eval_f64": [_d, _d, _vp, _vp, _i64, _vp, _vp],
     "cyl_surface_energy_f64": [_vp, _vp, _i, _vp, _vp, _vp],
     "cyl_philox4x32_10": [_vp, _vp, _i64, _vp, _vp],
+    "cyl_philox2x32_10": [_vp, _vp, _i64, _vp, _vp],
     "cyl_lattice_init_f32": [_vp, _i, _vp, _i, _i, _d, _u64, _i64, _vp],
     "cyl_lattice_init_f64": [_vp, _i, _vp, _i, _i, _d, _u64, _i64, _vp],
     "cyl_replay_f64": [_vp, _i, _i, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],

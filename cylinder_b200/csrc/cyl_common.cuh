@@ -173,6 +173,42 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Philox2x32-10 for the site moves.  A proposal needs 64 random bits (23-bit Box-Muller radius, 16-bit angle, 23-bit
+// acceptance uniform -- cyl_site.cuh), so the hot loops run the two-word generator: 10 multiplies instead of 20, and
+// the 32x32->64 multiply is the instruction that loads the busiest pipe of these kernels.
+//   counter = (global site index, sweep + off),  key = key
+// where (key, off) identify the replica's stream: two words of Philox4x32-10(replica; seed), so that streams of
+// different replicas / seeds differ in 64 pseudo-random bits (a bare 32-bit key would collide among 65536 replicas
+// with probability ~1/2).
+// ----------------------------------------------------------------------------------------------------
+#define PHILOX2_M 0xD256D193u
+
+__host__ __device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi, lo;
+    philox_mulhilo(PHILOX2_M, c0, hi, lo);
+    c0 = hi ^ key ^ c1;
+    c1 = lo;
+    key += PHILOX_W0;
+  }
+  return make_uint2(c0, c1);
+}
+
+// round keys expanded on the host for single-replica kernels (constant-bank operands of the XOR)
+struct SiteKeys { uint32_t k[10]; uint32_t off; uint32_t pad; };
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, const SiteKeys& ks) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi, lo;
+    philox_mulhilo(PHILOX2_M, c0, hi, lo);
+    c0 = hi ^ ks.k[i] ^ c1;
+    c1 = lo;
+  }
+  return make_uint2(c0, c1);
+}
+
 // Stream tags in counter word 3 (upper byte), so that site moves, amplitude moves and initialisation of the
 // same (site, replica, sweep) never share a counter.
 #define CYL_TAG_SITE 0u
@@ -182,14 +218,44 @@ __host__ __device__ __forceinline__ uint32_t philox_c3(uint32_t tag, uint64_t sw
   return (tag << 24) | (uint32_t)((sweep >> 32) & 0xFFFFFFu);
 }
 
+// identity of one replica's site-move stream
+struct SiteStream { uint32_t key, off; };
+__host__ __device__ __forceinline__ SiteStream site_stream(uint64_t seed, uint64_t replica) {
+  const uint4 x = philox4x32<10>((uint32_t)replica, (uint32_t)(replica >> 32), 0u, philox_c3(CYL_TAG_SITE, 0), (uint32_t)seed,
+                                 (uint32_t)(seed >> 32));
+  SiteStream s;
+  s.key = x.x;
+  s.off = x.y;
+  return s;
+}
+static inline SiteKeys site_keys_expand(uint64_t seed, uint64_t replica) {
+  const SiteStream st = site_stream(seed, replica);
+  SiteKeys ks;
+  uint32_t k = st.key;
+  for (int i = 0; i < 10; ++i) { ks.k[i] = k; k += PHILOX_W0; }
+  ks.off = st.off;
+  ks.pad = 0;
+  return ks;
+}
+
 // uniforms strictly inside (0,1)
 __host__ __device__ __forceinline__ double u01_f64(uint32_t x) {            // 32 bits, midpoint
   return ((double)x + 0.5) * (1.0 / 4294967296.0);
 }
+// bit fields of a site draw (x0, x1): x0[31:9] radius, x1[31:9] acceptance, angle = x0[7:0] : x1[7:0]
+__host__ __device__ __forceinline__ double u23_f64(uint32_t x) {            // top 23 bits, midpoint
+  return ((double)(x >> 9) + 0.5) * (1.0 / 8388608.0);
+}
+__host__ __device__ __forceinline__ uint32_t angle16(uint32_t x0, uint32_t x1) { return ((x0 & 0xFFu) << 8) | (x1 & 0xFFu); }
+__host__ __device__ __forceinline__ double u16_f64(uint32_t k) { return ((double)k + 0.5) * (1.0 / 65536.0); }
 // fp32: the top 23 bits at the midpoint of their cell, (m + 1/2) 2^-23 in (0,1), built without an int->float
 // conversion: [1,2) mantissa trick, then an exact subtraction of 1 - 2^-24.  Tracks u01_f64 to 2^-24.
 __device__ __forceinline__ float u01_f32(uint32_t x) {
   return __uint_as_float(0x3F800000u | (x >> 9)) - 0.99999994f;
+}
+// 16-bit field at the midpoint of its cell, (k + 1/2) 2^-16, same trick (exact)
+__device__ __forceinline__ float u16_f32(uint32_t k) {
+  return __uint_as_float(0x3F800000u | (k << 7)) - 0.99999237060546875f;     // 1 - 2^-17
 }
 
 // ----------------------------------------------------------------------------------------------------

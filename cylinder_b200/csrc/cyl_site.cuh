@@ -94,25 +94,27 @@ __device__ __forceinline__ R site_delta_over_k(const RowCoef<R>& c, C p, C L, C 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// random draws for one proposal from one Philox block x = (x0, x1, x2, x3):
-//   x0, x1 -> Box-Muller pair (z_re, z_im);  x2 -> accept uniform.  x3 unused.
-// fp64: full-precision log / sincospi (the oracle restates exactly this, tests compare at 1e-12);
-// fp32: MUFU lg2 / sqrt / sin / cos, 23-bit uniforms built by bit tricks (no I2F).
+// random draws for one proposal from one Philox2x32-10 block (x0, x1)  [bit fields: cyl_common.cuh]:
+//   x0[31:9] -> Box-Muller radius, (x0[7:0] : x1[7:0]) -> Box-Muller angle (65536 directions, symmetric under
+//   theta -> theta + pi, so the proposal stays symmetric), x1[31:9] -> acceptance uniform.
+// Both precisions see the SAME uniforms (they are exactly representable in fp32).
+// fp64: full-precision log / sincospi (the oracle restates exactly this, tests compare at 1e-11);
+// fp32: MUFU lg2 / sqrt / sin / cos; uniforms built by bit tricks (no I2F).
 // ------------------------------------------------------------------------------------------------------
 template <typename R> struct Draw;
 
 template <> struct Draw<double> {
   static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, double& zre, double& zim) {
-    const double rad = sqrt(-2.0 * log(u01_f64(x0)));
+    const double rad = sqrt(-2.0 * log(u23_f64(x0)));
     double s, c;
-    sincospi(2.0 * u01_f64(x1), &s, &c);
+    sincospi(2.0 * u16_f64(angle16(x0, x1)), &s, &c);
     zre = rad * c;
     zim = rad * s;
   }
   // accept iff dE <= 0, or T > 0 and u <= exp(-dE/T); den = dE/K, kacc = K log2(e)/T
-  static __device__ __forceinline__ bool accept(uint32_t x2, double den, double kacc) {
+  static __device__ __forceinline__ bool accept(uint32_t x1, double den, double kacc) {
     if (den <= 0.0) return true;
-    return log2(u01_f64(x2)) <= -(kacc * den);          // kacc = inf => -inf => false
+    return log2(u23_f64(x1)) <= -(kacc * den);          // kacc = inf => -inf => false
   }
 };
 
@@ -128,14 +130,22 @@ template <> struct Draw<float> {
     float rad;                                                                // sqrt(-2 ln u): MUFU.LG2, MUFU.SQRT
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg2_fast(u01_f32(x0))));
     float s, c;
-    __sincosf(6.283185307179586f * u01_f32(x1), &s, &c);
+    __sincosf(6.283185307179586f * u16_f32(__byte_perm(x0, x1, 0x0004) & 0xFFFFu), &s, &c);   // = angle16(x0, x1)
     zre = rad * c;
     zim = rad * s;
   }
-  static __device__ __forceinline__ bool accept(uint32_t x2, float den, float kacc) {
-    return (den <= 0.0f) | (lg2_fast(u01_f32(x2)) <= -(kacc * den));           // branch-free; kacc = inf when T = 0
+  static __device__ __forceinline__ bool accept(uint32_t x1, float den, float kacc) {
+    return (den <= 0.0f) | (lg2_fast(u01_f32(x1)) <= -(kacc * den));          // branch-free; kacc = inf when T = 0
   }
 };
+
+// draws of one global amplitude move from one Philox4x32-10 block: (x.x, x.y) -> unit normal, x.z -> acceptance uniform
+__device__ __forceinline__ void amp_draw(uint4 x, double& z, double& u) {
+  double s, c;
+  sincospi(2.0 * u01_f64(x.y), &s, &c);
+  z = sqrt(-2.0 * log(u01_f64(x.x))) * c;
+  u = u01_f64(x.z);
+}
 
 // ------------------------------------------------------------------------------------------------------
 // colouring.  A periodic ring of even length is 2-colourable (parity); an odd ring needs a third colour for its

@@ -81,8 +81,24 @@ extern "C" int cyl_philox4x32_10(const uint32_t* ctr, const uint32_t* key, int64
   return CYL_OK;
 }
 
+__global__ void philox2_kat_kernel(const uint32_t* __restrict__ ctr, const uint32_t* __restrict__ key, int64_t n,
+                                   uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 r = philox2x32_10(ctr[2 * i], ctr[2 * i + 1], key[i]);
+  out[2 * i] = r.x; out[2 * i + 1] = r.y;
+}
+
+extern "C" int cyl_philox2x32_10(const uint32_t* ctr, const uint32_t* key, int64_t n, uint32_t* out, void* stream) {
+  CYL_CHECK_ARG(n >= 0 && ctr && key && out, "cyl_philox2x32_10: null buffer or n<0");
+  if (n == 0) return CYL_OK;
+  philox2_kat_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(ctr, key, n, out);
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+
 // ----------------------------------------------------------------------------------------------------
-// Lattice.random_initialize   On_lattice_simple.py:159-182 : psi = rect(U(0,mag_max), U(0,2pi))
+// Lattice.random_initialize  On_lattice_simple.py:159-182 : psi = rect(U(0,mag_max), U(0,2pi))
 // counter = (site, replica, 0, INIT tag); x0 -> magnitude, x1 -> phase
 // ----------------------------------------------------------------------------------------------------
 template <typename R>

@@ -216,8 +216,8 @@ template <typename R, int NCOL>
 __global__ void __launch_bounds__(HBM_NT)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
                  const int32_t* __restrict__ cur_p, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
-                 const double* __restrict__ chain, HbmCounters* __restrict__ counters, const __grid_constant__ PhiloxKeys keys,
-                 uint32_t rep, uint64_t sweep) {
+                 const double* __restrict__ chain, HbmCounters* __restrict__ counters, const __grid_constant__ SiteKeys keys,
+                 uint64_t sweep) {
   using C = typename Real<R>::complex_t;
   using L = HbmSmem<R, NCOL>;
   constexpr int TH = L::TH, TW = L::TW, SH = L::SH, SW = L::SW, SWH = L::SWH, HS = L::HS;
@@ -249,7 +249,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // overlap: row coefficients and scalars while the tile is in flight
   for (int r = tid; r < SH; r += HBM_NT) coef[r] = coef_g[modi(ti0 - NCOL + r, g.Z)];
   const R sigma = (R)chain[CYL_CH_SIGMA_SITE];
-  const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
+  const uint32_t c1 = (uint32_t)sweep + keys.off;
   __syncthreads();
   mbar_wait(bar, 0);
 
@@ -285,13 +285,13 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
           gi = wrapi(gi, g.Z);       // rows / columns past Z + halo only exist in partial tiles and are never stored
           gj = wrapi(gj, g.T);
         }
-        const uint4 x = philox4x32_10((uint32_t)(gi * g.T + gj), rep, c2, c3, keys);
+        const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, keys);
         R zre, zim;
         Draw<R>::normals(x.x, x.y, zre, zim);
         const R w = sigma * rc.sgmul;
         const R dre = w * zre, dim = w * zim;
         const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-        const bool acc = Draw<R>::accept(x.z, den, rc.kacc);
+        const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
         if (acc) own[0] = Real<R>::make(pv.x + dre, pv.y + dim);
         nacc += (acc && counted);
         rr += drr;
@@ -320,13 +320,13 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
         const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
         const RowCoef<R> rc = coef[r];
-        const uint4 x = philox4x32_10((uint32_t)(gi * g.T + gj), rep, c2, c3, keys);
+        const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, keys);
         R zre, zim;
         Draw<R>::normals(x.x, x.y, zre, zim);
         const R w = sigma * rc.sgmul;
         const R dre = w * zre, dim = w * zim;
         const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-        if (Draw<R>::accept(x.z, den, rc.kacc)) {
+        if (Draw<R>::accept(x.y, den, rc.kacc)) {
           own[r * SWH + col] = Real<R>::make(pv.x + dre, pv.y + dim);
           const int li = r - NCOL, lj = q - HS;
           nacc += (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
@@ -461,8 +461,8 @@ hbm_amp_kernel(const double* __restrict__ S, int Z, int T, const CylParams* __re
   const double a = chain[CYL_CH_AMPLITUDE], sigma_amp = chain[CYL_CH_SIGMA_AMP];
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const uint4 x = philox4x32<10>(0u, rep, (uint32_t)sweep, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
-  double zre, zim;
-  Draw<double>::normals(x.x, x.y, zre, zim);
+  double zre, u_acc;
+  amp_draw(x, zre, u_acc);
   const double a_new = a + sigma_amp * zre;
   const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
   double e_cur = 0.0, e_new = 0.0, s_p2 = 0.0, s_abs = 0.0;
@@ -510,7 +510,7 @@ hbm_amp_kernel(const double* __restrict__ S, int Z, int T, const CylParams* __re
     if (!isfinite(dE)) chain[CYL_CH_FLAGS] = (double)((unsigned)chain[CYL_CH_FLAGS] | 1u);
     if (dE <= 0) accept = 1;
     else if (p.temperature == 0) accept = 0;
-    else accept = (u01_f64(x.z) <= exp(-dE / p.temperature));
+    else accept = (u_acc <= exp(-dE / p.temperature));
   }
   const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
   const double ratio = 1.0 / (pt * (1.0 - pt));
@@ -597,11 +597,11 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   CYL_CUDA(cudaMemsetAsync(counters, 0, sizeof(HbmCounters), st));
   const dim3 grid((g.T + L::TW - 1) / L::TW, (g.Z + L::TH - 1) / L::TH);
   const bool amp = flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE);
-  const PhiloxKeys keys = philox_expand(seed);
+  const SiteKeys keys = site_keys_expand(seed, (uint64_t)replica);
   hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
-    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, keys, (uint32_t)replica, sweep);
+    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, keys, sweep);
     hbm_post_sweep_kernel<R><<<1, 32, 0, st>>>(chain, counters, cur, (double)g.Z * g.T, flags);
     if (amp) {
       hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, cur, g, params, S);

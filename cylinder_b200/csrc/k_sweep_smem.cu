@@ -104,15 +104,15 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
 // one site move; returns 1 when accepted
 template <typename R, typename C>
 __device__ __forceinline__ int site_move(C* psi, int idx, int im, int ip, int jm, int jp, const RowCoef<R>& rc, R sigma,
-                                         uint32_t site, uint32_t rep, uint32_t c2, uint32_t c3, const PhiloxKeys& keys) {
+                                         uint32_t site, uint32_t c1, uint32_t key) {
   const C pv = psi[idx], L = psi[im], Rz = psi[ip], W = psi[jm], E = psi[jp];
-  const uint4 x = philox4x32_10(site, rep, c2, c3, keys);
+  const uint2 x = philox2x32_10(site, c1, key);
   R zre, zim;
   Draw<R>::normals(x.x, x.y, zre, zim);
   const R w = sigma * rc.sgmul;
   const R dre = w * zre, dim = w * zim;
   const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
-  const bool acc = Draw<R>::accept(x.z, den, rc.kacc);
+  const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
   if (acc) psi[idx] = Real<R>::make(pv.x + dre, pv.y + dim);
   return acc ? 1 : 0;
 }
@@ -121,7 +121,7 @@ template <typename R>
 __global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? 4 : 2))
 sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
                   const CylParams* __restrict__ params, double* __restrict__ chain, const __grid_constant__ PhiloxKeys keys,
-                  int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
+                  uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
                   double* __restrict__ prof) {
   using C = typename Real<R>::complex_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,6 +144,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const double pi = 3.14159265358979323846;
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;     // On_lattice_simple.py:47,:49
   const uint32_t rep = (uint32_t)(replica0 + b);
+  const SiteStream stream = site_stream(seed, (uint64_t)(replica0 + b));
   double* ch = chain + (size_t)b * CYL_CHAIN_DOUBLES;
   C* psi_b = psi_g + (size_t)b * Zmax * T;
   const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
@@ -194,15 +195,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       // draws of the next AMP_CHUNK amplitude moves, one sweep per thread (counter-based: any order, any thread)
       if (tid < AMP_CHUNK && sw + tid < nsweeps) {
         const uint64_t s2 = sweep + (uint64_t)tid;
-        const uint4 x = philox4x32_10(0u, rep, (uint32_t)s2, philox_c3(CYL_TAG_AMP, s2), keys);
-        double zre, zim;
-        Draw<double>::normals(x.x, x.y, zre, zim);
-        ampz[tid] = zre;
-        ampu[tid] = u01_f64(x.z);
+        amp_draw(philox4x32_10(0u, rep, (uint32_t)s2, philox_c3(CYL_TAG_AMP, s2), keys), ampz[tid], ampu[tid]);
       }
       __syncthreads();
     }
-    const uint32_t c2 = (uint32_t)sweep, c3 = philox_c3(CYL_TAG_SITE, sweep);
+    const uint32_t c1 = (uint32_t)sweep + stream.off;
     const R sigma = (R)sc->sigma_site;
     int nacc = 0;
 #ifdef CYL_PHASE_TIMING
@@ -218,8 +215,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const int row = i * T;
           const int im = (i == 0 ? nsite : row) - T, ip = (i == Z - 1 ? 0 : row + T);
           const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-          nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), rep,
-                                  c2, c3, keys);
+          nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), c1,
+                                  stream.key);
           jj += dj; i += di;
           if (jj >= Th) { jj -= Th; ++i; }
         }
@@ -245,8 +242,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             const int row = i * T;
             const int im = (i == 0 ? nsite : row) - T, ip = (i == Z - 1 ? 0 : row + T);
             const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-            nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), rep,
-                                    c2, c3, keys);
+            nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), c1,
+                                    stream.key);
           }
           jj += dj; ii += di;
           if (jj >= Th) { jj -= Th; ++ii; }
@@ -472,7 +469,7 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const PhiloxKeys keys = philox_expand(seed);
   kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,
-                                                      replica0, sweep0, nsweeps, variant, flags, obs, prof);
+                                                      seed, replica0, sweep0, nsweeps, variant, flags, obs, prof);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

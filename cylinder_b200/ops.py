@@ -79,6 +79,13 @@ def philox4x32_10(ctr, key):
     return out
 
 
+def philox2x32_10(ctr, key):
+    n = ctr.shape[0]
+    out = torch.empty_like(ctr)
+    call("cyl_philox2x32_10", _dev(ctr), ptr(ctr), ptr(key), n, ptr(out), stream())
+    return out
+
+
 def _suffix(psi):
     if psi.dtype == torch.complex64:
         return "f32"

@@ -107,6 +107,10 @@ int cyl_surface_energy_f64(const CylParams* params /*[B]*/, const double* amp /*
 int cyl_philox4x32_10(const uint32_t* ctr /*[n][4]*/, const uint32_t* key /*[n][2]*/, int64_t n,
                       uint32_t* out /*[n][4]*/, void* stream);
 
+/* Philox2x32-10 (the per-proposal generator of the sweep kernels): out[i] = philox(ctr[i], key[i]). */
+int cyl_philox2x32_10(const uint32_t* ctr /*[n][2]*/, const uint32_t* key /*[n]*/, int64_t n,
+                      uint32_t* out /*[n][2]*/, void* stream);
+
 /* Lattice.random_initialize (On_lattice_simple.py:159-182): psi = rect(U(0,mag_max), U(0,2pi)), drawn from
  * Philox keyed (seed; site, replica0+b).  psi is [B][Zmax][T]; rows >= Z[b] are zeroed. */
 int cyl_lattice_init_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, double mag_max,

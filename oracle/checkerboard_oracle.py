@@ -52,6 +52,41 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(x.astype(np.uint32) for x in (c0, c1, c2, c3))
 
 
+M2 = np.uint64(0xD256D193)
+# Random123 kat_vectors, philox2x32-10:  (counter, key, expected)
+PHILOX2_KAT = [
+    ((0x00000000, 0x00000000), 0x00000000, (0xff1dae59, 0x6cd10df2)),
+    ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+    ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12)),
+]
+
+
+def philox2x32_10(c0, c1, key):
+    """Vectorised Philox2x32-10 (the site-move generator, cyl_common.cuh).  Returns 2 uint32 arrays."""
+    c0, c1 = (np.asarray(x).astype(np.uint64) & MASK for x in np.broadcast_arrays(c0, c1))
+    key = int(key) & 0xFFFFFFFF
+    for _ in range(10):
+        p = M2 * c0
+        c0, c1 = (p >> np.uint64(32)) ^ np.uint64(key) ^ c1, p & MASK
+        key = (key + W0) & 0xFFFFFFFF
+    return c0.astype(np.uint32), c1.astype(np.uint32)
+
+
+def site_stream(seed, replica):
+    """(key, off) of a replica's site-move stream: two words of Philox4x32-10(replica; seed)  (cyl_common.cuh:site_stream)."""
+    x0, x1, _, _ = philox4x32_10(replica & 0xFFFFFFFF, replica >> 32, 0, philox_c3(TAG_SITE, 0), seed & 0xFFFFFFFF, seed >> 32)
+    return int(x0), int(x1)
+
+
+def site_draws(x0, x1):
+    """Bit fields of one site draw: x0[31:9] radius, (x0[7:0]:x1[7:0]) angle, x1[31:9] acceptance -> (z_re, z_im, u)."""
+    u_rad = ((x0 >> np.uint32(9)).astype(np.float64) + 0.5) / 8388608.0
+    ang = ((((x0 & np.uint32(0xFF)).astype(np.uint32) << np.uint32(8)) | (x1 & np.uint32(0xFF))).astype(np.float64) + 0.5) / 65536.0
+    u_acc = ((x1 >> np.uint32(9)).astype(np.float64) + 0.5) / 8388608.0
+    rad = np.sqrt(-2.0 * np.log(u_rad))
+    return rad * np.cos(2.0 * np.pi * ang), rad * np.sin(2.0 * np.pi * ang), u_acc
+
+
 def philox_c3(tag, sweep):
     return (tag << 24) | ((int(sweep) >> 32) & 0xFFFFFF)
 
@@ -169,14 +204,14 @@ def sweep(st, a, seed, replica, sweep_index, adapt=True, return_details=False):
     """One checkerboard sweep of `st` (lattice_oracle.LatticeState) in place.  Returns the accept count."""
     Z, T = st.Z, st.T_len
     cmap = colour_map(Z, T)
+    key, off = site_stream(seed, replica)
     nacc = 0
     details = {"dE": np.zeros((Z, T)), "accept": np.zeros((Z, T), bool), "u": np.zeros((Z, T))}
     for colour in range(num_colours(Z, T)):
         I, J = np.nonzero(cmap == colour)
         site = (I * T + J).astype(np.uint64)
-        x0, x1, x2, _ = philox4x32_10(site, replica & 0xFFFFFFFF, sweep_index & 0xFFFFFFFF, philox_c3(TAG_SITE, sweep_index),
-                                      seed & 0xFFFFFFFF, seed >> 32)
-        zre, zim = box_muller(x0, x1)
+        x0, x1 = philox2x32_10(site, (sweep_index + off) & 0xFFFFFFFF, key)
+        zre, zim, u = site_draws(x0, x1)
         v = st.psi[I, J]
         if st.variant == lo.SIMPLE:
             w = st.sigma
@@ -185,7 +220,6 @@ def sweep(st, a, seed, replica, sweep_index, adapt=True, return_details=False):
             w = st.sigma * (gth0 * gz0)
         new_values = (v.real + w * zre) + 1j * (v.imag + w * zim)
         dE, _ = delta_energy_vec(st, a, I, J, new_values)
-        u = u01(x2)
         if st.temperature > 0:
             with np.errstate(over="ignore"):
                 acc = (dE <= 0) | (u <= np.exp(-dE / st.temperature))

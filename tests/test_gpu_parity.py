@@ -67,6 +67,10 @@ def test_philox_known_answers(cuda):
     key = torch.from_numpy(np.array([k[1] for k in cb.PHILOX_KAT], dtype=np.uint32).view(np.int32)).to(cuda)
     out = ops.philox4x32_10(ctr.contiguous(), key.contiguous()).cpu().numpy().view(np.uint32)
     assert out.tolist() == [list(k[2]) for k in cb.PHILOX_KAT]
+    ctr = torch.from_numpy(np.array([k[0] for k in cb.PHILOX2_KAT], dtype=np.uint32).view(np.int32)).to(cuda)
+    key = torch.from_numpy(np.array([k[1] for k in cb.PHILOX2_KAT], dtype=np.uint32).view(np.int32)).to(cuda)
+    out = ops.philox2x32_10(ctr.contiguous(), key.contiguous()).cpu().numpy().view(np.uint32)
+    assert out.tolist() == [list(k[2]) for k in cb.PHILOX2_KAT]
 
 
 @pytest.mark.parametrize("tag", LATTICE_CASES)

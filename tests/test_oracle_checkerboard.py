@@ -15,6 +15,18 @@ def test_philox_known_answers():
     for ctr, key, exp in cb.PHILOX_KAT:
         out = cb.philox4x32_10(*[np.array([c]) for c in ctr], key[0], key[1])
         assert tuple(int(x[0]) for x in out) == exp
+    for ctr, key, exp in cb.PHILOX2_KAT:
+        out = cb.philox2x32_10(np.array([ctr[0]]), np.array([ctr[1]]), key)
+        assert tuple(int(x[0]) for x in out) == exp
+
+
+def test_site_draw_bit_fields_are_independent_and_uniform():
+    x0, x1 = cb.philox2x32_10(np.arange(200000), 7, 0xABCDEF)
+    zre, zim, u = cb.site_draws(x0, x1)
+    assert abs(zre.mean()) < 0.01 and abs(zim.mean()) < 0.01
+    assert zre.std() == pytest.approx(1.0, abs=0.01) and zim.std() == pytest.approx(1.0, abs=0.01)
+    assert abs(np.mean(zre * zim)) < 0.01 and abs(np.corrcoef(zre ** 2 + zim ** 2, u)[0, 1]) < 0.01
+    assert u.min() > 0 and u.max() < 1 and u.mean() == pytest.approx(.5, abs=.005)
 
 
 @pytest.mark.parametrize("Z,T", [(4, 4), (6, 8), (5, 4), (4, 7), (5, 7), (71, 25), (91, 50), (3, 3), (2, 2)])
