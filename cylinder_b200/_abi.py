@@ -47,14 +47,14 @@ _SIGNATURES = {
     "cyl_sweep_smem_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
     "cyl_sweep_smem_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
     "cyl_hbm_layout": [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)],
-    "cyl_hbm_pack_f32": [_vp, _i, _i, _vp, _vp, _vp],
-    "cyl_hbm_pack_f64": [_vp, _i, _i, _vp, _vp, _vp],
-    "cyl_hbm_unpack_f32": [_vp, _vp, _i, _i, _vp, _vp],
-    "cyl_hbm_unpack_f64": [_vp, _vp, _i, _i, _vp, _vp],
-    "cyl_sweep_hbm_f32": [_vp, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
-    "cyl_sweep_hbm_f64": [_vp, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
-    "cyl_hbm_row_moments_f32": [_vp, _vp, _i, _i, _vp, _vp, _vp],
-    "cyl_hbm_row_moments_f64": [_vp, _vp, _i, _i, _vp, _vp, _vp],
+    "cyl_hbm_pack_f32": [_vp, _i, _i, _vp, C.POINTER(C.c_int32), _vp],
+    "cyl_hbm_pack_f64": [_vp, _i, _i, _vp, C.POINTER(C.c_int32), _vp],
+    "cyl_hbm_unpack_f32": [_vp, _i, _i, _i, _vp, _vp],
+    "cyl_hbm_unpack_f64": [_vp, _i, _i, _i, _vp, _vp],
+    "cyl_sweep_hbm_f32": [_vp, C.POINTER(C.c_int32), _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
+    "cyl_sweep_hbm_f64": [_vp, C.POINTER(C.c_int32), _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
+    "cyl_hbm_row_moments_f32": [_vp, _i, _i, _i, _vp, _vp, _vp],
+    "cyl_hbm_row_moments_f64": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "cyl_fourier_energy_f64": [_vp, _i, _i, _vp, _vp, _i, _vp, _vp],
     "cyl_fourier_surface_energy_f64": [_vp, _vp, _i, _vp, _vp],
 }

@@ -92,10 +92,9 @@ __device__ __forceinline__ int modi(int i, int n) {       // any i
 // pack / unpack
 // ----------------------------------------------------------------------------------------------------
 template <typename C>
-__global__ void hbm_pack_kernel(const C* __restrict__ psi, HbmGeom g, C* __restrict__ work, int32_t* __restrict__ cur) {
+__global__ void hbm_pack_kernel(const C* __restrict__ psi, HbmGeom g, C* __restrict__ work) {
   const int64_t Q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t Rr = blockIdx.y;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *cur = 0;
   if (Q >= g.pitch) return;
   C v; v.x = 0; v.y = 0;
   if (Q < g.T + 2 * g.hc) {
@@ -107,12 +106,12 @@ __global__ void hbm_pack_kernel(const C* __restrict__ psi, HbmGeom g, C* __restr
 }
 
 template <typename C>
-__global__ void hbm_unpack_kernel(const C* __restrict__ work, const int32_t* __restrict__ cur, HbmGeom g, C* __restrict__ psi) {
+__global__ void hbm_unpack_kernel(const C* __restrict__ work, int cur, HbmGeom g, C* __restrict__ psi) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (j >= g.T) return;
   const int64_t Q = j + g.hc, Rr = i + g.hr;
-  const C* buf = work + (size_t)(*cur) * g.buffer_elems;
+  const C* buf = work + (size_t)cur * g.buffer_elems;
   psi[(size_t)i * g.T + j] = buf[(Q & 1) * g.plane_elems + Rr * (g.pitch / 2) + (Q >> 1)];
 }
 
@@ -122,14 +121,15 @@ static int hbm_pack(const void* psi, int Z, int T, void* work, int32_t* cur, voi
   CYL_CHECK_ARG(psi && work && cur && Z >= 8 && T >= 8, "cyl_hbm_pack: bad arguments");
   const HbmGeom g = hbm_geom(Z, T);
   dim3 grid((unsigned)((g.pitch + 255) / 256), (unsigned)g.rows);
-  hbm_pack_kernel<C><<<grid, 256, 0, as_stream(stream)>>>((const C*)psi, g, (C*)work, cur);
+  hbm_pack_kernel<C><<<grid, 256, 0, as_stream(stream)>>>((const C*)psi, g, (C*)work);
+  *cur = 0;
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }
 template <typename R>
-static int hbm_unpack(const void* work, const int32_t* cur, int Z, int T, void* psi, void* stream) {
+static int hbm_unpack(const void* work, int cur, int Z, int T, void* psi, void* stream) {
   using C = typename Real<R>::complex_t;
-  CYL_CHECK_ARG(psi && work && cur && Z >= 8 && T >= 8, "cyl_hbm_unpack: bad arguments");
+  CYL_CHECK_ARG(psi && work && (cur == 0 || cur == 1) && Z >= 8 && T >= 8, "cyl_hbm_unpack: bad arguments");
   const HbmGeom g = hbm_geom(Z, T);
   dim3 grid((unsigned)((T + 255) / 256), (unsigned)Z);
   hbm_unpack_kernel<C><<<grid, 256, 0, as_stream(stream)>>>((const C*)work, cur, g, (C*)psi);
@@ -138,8 +138,8 @@ static int hbm_unpack(const void* work, const int32_t* cur, int Z, int T, void* 
 }
 extern "C" int cyl_hbm_pack_f32(const void* psi, int Z, int T, void* work, int32_t* cur, void* s) { return hbm_pack<float>(psi, Z, T, work, cur, s); }
 extern "C" int cyl_hbm_pack_f64(const void* psi, int Z, int T, void* work, int32_t* cur, void* s) { return hbm_pack<double>(psi, Z, T, work, cur, s); }
-extern "C" int cyl_hbm_unpack_f32(const void* work, const int32_t* cur, int Z, int T, void* psi, void* s) { return hbm_unpack<float>(work, cur, Z, T, psi, s); }
-extern "C" int cyl_hbm_unpack_f64(const void* work, const int32_t* cur, int Z, int T, void* psi, void* s) { return hbm_unpack<double>(work, cur, Z, T, psi, s); }
+extern "C" int cyl_hbm_unpack_f32(const void* work, int cur, int Z, int T, void* psi, void* s) { return hbm_unpack<float>(work, cur, Z, T, psi, s); }
+extern "C" int cyl_hbm_unpack_f64(const void* work, int cur, int Z, int T, void* psi, void* s) { return hbm_unpack<double>(work, cur, Z, T, psi, s); }
 
 // ----------------------------------------------------------------------------------------------------
 // per-row coefficients for the current amplitude (chain[CYL_CH_AMPLITUDE]) -> scratch
@@ -168,6 +168,12 @@ __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const doub
 // ----------------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS)
 // ----------------------------------------------------------------------------------------------------
+// a load the compiler may not sink to its first use
+__device__ __forceinline__ double ld_early_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -215,7 +221,7 @@ struct HbmMaps { CUtensorMap m[2][2]; int esz; };   // [buffer][plane]; esz = TM
 template <typename R, int NCOL>
 __global__ void __launch_bounds__(HBM_NT)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
-                 const int32_t* __restrict__ cur_p, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
+                 int cur, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
                  const double* __restrict__ chain, HbmCounters* __restrict__ counters, const __grid_constant__ SiteKeys keys,
                  uint64_t sweep) {
   using C = typename Real<R>::complex_t;
@@ -228,30 +234,36 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
 
   const int tid = threadIdx.x;
-  const int cur = *cur_p;
+#ifdef HBM_PHASE_TIMING
+  long long t_ph = clock64();
+#define HBM_MARK(k) do { if (tid == 0) { const long long t__ = clock64(); atomicAdd(&counters->pad[k], (unsigned long long)(t__ - t_ph)); t_ph = t__; } } while (0)
+#else
+#define HBM_MARK(k) do { } while (0)
+#endif
   const int ti0 = blockIdx.y * TH, tj0 = blockIdx.x * TW;          // interior origin (lattice coords)
   // smem (r, q) <-> padded (ti0 + r, Q0 + q);  padded row of r = 0 is ti0 - hr + hr
   const int Q0 = tj0 + g.hc - HS;
   const int x0 = (Q0 + ((0 - Q0) & 1)) >> 1, x1 = (Q0 + ((1 - Q0) & 1)) >> 1;    // first plane column of each plane's box
 
+  // Prologue.  Global-memory latency under the bulk traffic of this kernel is several microseconds, so everything that
+  // comes from global memory is requested up front and in parallel: the tile (TMA, issued by thread 0 as soon as it has
+  // initialised the mbarrier), the row coefficients and the proposal width.
+  const R sigma = (R)ld_early_f64(chain + CYL_CH_SIGMA_SITE);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {
     constexpr uint32_t bytes = 2u * SH * SWH * sizeof(C);
     mbar_expect_tx(bar, bytes);
     tma_load_2d(pl0, &maps.m[cur][0], x0 * maps.esz, ti0, bar);    // esz: TMA elements per complex value
     tma_load_2d(pl1, &maps.m[cur][1], x1 * maps.esz, ti0, bar);
   }
-  // overlap: row coefficients and scalars while the tile is in flight
   for (int r = tid; r < SH; r += HBM_NT) coef[r] = coef_g[modi(ti0 - NCOL + r, g.Z)];
-  const R sigma = (R)chain[CYL_CH_SIGMA_SITE];
   const uint32_t c1 = (uint32_t)sweep + keys.off;
-  __syncthreads();
+  __syncthreads();                                                  // mbarrier initialised, coefficient rows staged
+  HBM_MARK(0);
   mbar_wait(bar, 0);
+  HBM_MARK(1);
 
   int nacc = 0;
   // tiles on the lattice boundary wrap their global coordinates, may be partial, and own periodic halo copies
@@ -261,44 +273,55 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   const int64_t ph = g.pitch / 2;
 
   if constexpr (NCOL == 2) {
-    // Both lengths even: colour of smem (r, q) is (r + q) & 1, so the colour-c sites of row r are q = qb + 2 cc in
-    // ONE parity plane at unit stride.  Index arithmetic per site is a handful of adds; neighbours are immediates.
+    // Both lengths even: colour of smem (r, q) is (r + q) & 1, so the colour-c sites of row r sit in ONE parity plane
+    // at unit stride.  Thread t owns plane column 2 + (t & 63) and rows (t >> 6) + 4 k: the row parity, hence the plane,
+    // is fixed per thread, and every address (tile, coefficient row, Philox counter) advances by a constant.
+    static_assert(TW == 128 && HBM_NT % 64 == 0 && ((HBM_NT / 64) & 1) == 0, "thread mapping assumes 64 columns per plane row");
+    constexpr int RSTEP = HBM_NT / 64;
+    auto move = [&](C* own, const C* oth, const RowCoef<R>& rc, uint32_t site, bool counted) {
+      const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
+      const uint2 x = philox2x32_10(site, c1, keys);
+      R zre, zim;
+      Draw<R>::normals(x.x, x.y, zre, zim);
+      const R w = sigma * rc.sgmul;
+      const R dre = w * zre, dim = w * zim;
+      const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
+      const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
+      if (acc) own[0] = Real<R>::make(pv.x + dre, pv.y + dim);
+      nacc += (acc && counted);
+    };
+    auto site_id = [&](int r, int q) -> uint32_t {             // Philox counter word 0 = global site index
+      int gi = ti0 - 2 + r, gj = tj0 - HS + q;
+      if (border) { gi = wrapi(gi, g.Z); gj = wrapi(gj, g.T); }  // past Z + halo only in partial tiles: never stored
+      return (uint32_t)(gi * g.T + gj);
+    };
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const int m = c + 1, mq = m + (HS - 2);
-      const int npr = (SW - 2 * mq) / 2, nrows = SH - 2 * m;
-      const int drr = HBM_NT / npr, dcc = HBM_NT % npr;
-      int rr = tid / npr, cc = tid - rr * npr;
-      while (rr < nrows) {
-        const int r = m + rr;
-        const int qb = mq + ((mq + r + c) & 1);                       // first column of colour c in row r
-        const int par = qb & 1;
-        const int q = qb + 2 * cc;
-        C* own = pl0 + par * PS + r * SWH + (qb >> 1) + cc;
-        const C* oth = pl0 + (par ^ 1) * PS + r * SWH + (qb >> 1) + cc - 1 + par;
-        const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
-        const RowCoef<R> rc = coef[r];
-        int gi = ti0 - 2 + r, gj = tj0 - HS + q;
-        bool counted = (c == 1) || ((unsigned)(r - 2) < (unsigned)TH && (unsigned)(q - HS) < (unsigned)TW);
-        if (border) {
-          counted = counted && gi < g.Z && gj < g.T;
-          gi = wrapi(gi, g.Z);       // rows / columns past Z + halo only exist in partial tiles and are never stored
-          gj = wrapi(gj, g.T);
-        }
-        const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, keys);
-        R zre, zim;
-        Draw<R>::normals(x.x, x.y, zre, zim);
-        const R w = sigma * rc.sgmul;
-        const R dre = w * zre, dim = w * zim;
-        const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-        const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-        if (acc) own[0] = Real<R>::make(pv.x + dre, pv.y + dim);
-        nacc += (acc && counted);
-        rr += drr;
-        cc += dcc;
-        if (dcc != 0 && cc >= npr) { cc -= npr; ++rr; }
+      const int m = c + 1;                                       // rows [m, SH - m)
+      const int col = HS / 2 + (tid & 63);                       // interior plane columns [HS/2, HS/2 + 64)
+      int r = m + (RSTEP - 1) - (tid >> 6);      // the longer row groups go to the higher warps (scheduler priority)
+      const int par = (r + c) & 1, q = 2 * col + par;
+      C* own = pl0 + par * PS + r * SWH + col;
+      const C* oth = pl0 + (par ^ 1) * PS + r * SWH + col - 1 + par;
+      const RowCoef<R>* rcp = coef + r;
+      if (!border) {
+        uint32_t site = site_id(r, q);
+        for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, rcp += RSTEP, site += RSTEP * g.T)
+          move(own, oth, *rcp, site, c == 1 || (r != 1 && r != SH - 2));
+      } else {
+        for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, rcp += RSTEP)
+          move(own, oth, *rcp, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T);
       }
+      if (c == 0) HBM_MARK(2);
+      if (c == 0 && tid >= HBM_NT - (SH - 2)) {
+        // the 65th colour-0 site of each row of the grown region: halo column q = HS - 1 (odd rows) or HS + TW (even rows)
+        const int r1 = 1 + (tid - (HBM_NT - (SH - 2))), q1 = (r1 & 1) ? HS - 1 : HS + TW;
+        const int p1 = q1 & 1;
+        move(pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), coef[r1], site_id(r1, q1), false);
+      }
+      if (c == 0) HBM_MARK(3);
       __syncthreads();
+      HBM_MARK(4 + c);
     }
   } else {
     // odd periodic ring(s): 3 colours, general colour function; every region site is visited and filtered
@@ -373,6 +396,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     }
   }
 
+  HBM_MARK(6);
   // ---- accept count ----
   nacc = warp_sum(nacc);
   if ((tid & 31) == 0 && nacc) atomicAdd(&counters->accepted, (unsigned long long)nacc);
@@ -380,7 +404,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
 
 // after every sweep: Robbins-Monro on sigma_site, counters, flip the buffer index
 template <typename R>
-__global__ void hbm_post_sweep_kernel(double* __restrict__ chain, HbmCounters* __restrict__ counters, int32_t* __restrict__ cur,
+__global__ void hbm_post_sweep_kernel(double* __restrict__ chain, HbmCounters* __restrict__ counters,
                                       double nsite, uint32_t flags) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double acc = (double)counters->accepted;
@@ -390,14 +414,13 @@ __global__ void hbm_post_sweep_kernel(double* __restrict__ chain, HbmCounters* _
   chain[CYL_CH_STEP_COUNTER] += nsite;
   chain[CYL_CH_SITE_PROPOSED] += nsite;
   chain[CYL_CH_SITE_ACCEPTED] += acc;
-  *cur ^= 1;
 }
 
 // ----------------------------------------------------------------------------------------------------
 // row moments of the plane-split layout: one warp per row
 // ----------------------------------------------------------------------------------------------------
 template <typename R>
-__global__ void hbm_row_moments_kernel(const typename Real<R>::complex_t* __restrict__ work, const int32_t* __restrict__ cur_p,
+__global__ void hbm_row_moments_kernel(const typename Real<R>::complex_t* __restrict__ work, int cur,
                                        HbmGeom g, const CylParams* __restrict__ params, double* __restrict__ S) {
   using C = typename Real<R>::complex_t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -407,7 +430,7 @@ __global__ void hbm_row_moments_kernel(const typename Real<R>::complex_t* __rest
   const double pi = 3.14159265358979323846;
   const double lz = (2 * pi / p.wavenumber) / g.Z, lth = (2 * pi * p.radius) / g.T;
   const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
-  const C* buf = work + (size_t)(*cur_p) * g.buffer_elems;
+  const C* buf = work + (size_t)cur * g.buffer_elems;
   const int64_t ph = g.pitch / 2;
   const int64_t Rr = i + g.hr;
   double m[CYL_NMOM];
@@ -429,8 +452,8 @@ __global__ void hbm_row_moments_kernel(const typename Real<R>::complex_t* __rest
 }
 
 template <typename R>
-static int hbm_row_moments(const void* work, const int32_t* cur, int Z, int T, const CylParams* params, double* S, void* stream) {
-  CYL_CHECK_ARG(work && cur && params && S && Z >= 8 && T >= 8, "cyl_hbm_row_moments: bad arguments");
+static int hbm_row_moments(const void* work, int cur, int Z, int T, const CylParams* params, double* S, void* stream) {
+  CYL_CHECK_ARG(work && (cur == 0 || cur == 1) && params && S && Z >= 8 && T >= 8, "cyl_hbm_row_moments: bad arguments");
   const HbmGeom g = hbm_geom(Z, T);
   const int warps = 8;
   hbm_row_moments_kernel<R><<<(Z + warps - 1) / warps, warps * 32, 0, as_stream(stream)>>>(
@@ -438,10 +461,10 @@ static int hbm_row_moments(const void* work, const int32_t* cur, int Z, int T, c
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }
-extern "C" int cyl_hbm_row_moments_f32(const void* work, const int32_t* cur, int Z, int T, const CylParams* params, double* S, void* s) {
+extern "C" int cyl_hbm_row_moments_f32(const void* work, int cur, int Z, int T, const CylParams* params, double* S, void* s) {
   return hbm_row_moments<float>(work, cur, Z, T, params, S, s);
 }
-extern "C" int cyl_hbm_row_moments_f64(const void* work, const int32_t* cur, int Z, int T, const CylParams* params, double* S, void* s) {
+extern "C" int cyl_hbm_row_moments_f64(const void* work, int cur, int Z, int T, const CylParams* params, double* S, void* s) {
   return hbm_row_moments<double>(work, cur, Z, T, params, S, s);
 }
 
@@ -601,10 +624,11 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
-    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, cur, g, coef, chain, counters, keys, sweep);
-    hbm_post_sweep_kernel<R><<<1, 32, 0, st>>>(chain, counters, cur, (double)g.Z * g.T, flags);
+    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, *cur, g, coef, chain, counters, keys, sweep);
+    *cur ^= 1;                                                      // host-side ping-pong index
+    hbm_post_sweep_kernel<R><<<1, 32, 0, st>>>(chain, counters, (double)g.Z * g.T, flags);
     if (amp) {
-      hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, cur, g, params, S);
+      hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, *cur, g, params, S);
       hbm_amp_kernel<<<1, 256, 0, st>>>(S, g.Z, g.T, params, chain, seed, (uint32_t)replica, sweep, variant, flags, obs, prof);
       if (flags & CYL_SWEEP_AMP_MOVES) hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
     }
@@ -617,7 +641,7 @@ template <typename R>
 static int sweep_hbm(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain, uint64_t seed,
                      int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch, double* obs,
                      double* prof, void* stream) {
-  CYL_CHECK_ARG(work && cur && params && chain && scratch && nsweeps >= 0, "cyl_sweep_hbm: bad arguments");
+  CYL_CHECK_ARG(work && cur && (*cur == 0 || *cur == 1) && params && chain && scratch && nsweeps >= 0, "cyl_sweep_hbm: bad arguments");
   CYL_CHECK_ARG(Z >= 8 && T >= 8, "cyl_sweep_hbm: the HBM path needs Z, T >= 8 (got %d x %d)", Z, T);
   CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_sweep_hbm: unknown variant %d", variant);
   CYL_CHECK_ARG(!(flags & CYL_SWEEP_MEASURE) || obs, "cyl_sweep_hbm: CYL_SWEEP_MEASURE needs obs");

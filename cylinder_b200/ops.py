@@ -175,28 +175,29 @@ class HbmWorkspace:
         self.suffix = "f32" if dtype == torch.complex64 else "f64"
         self.layout = hbm_layout(Z, T, dtype == torch.complex128)
         self.work = torch.zeros(2 * self.layout["buffer_elems"], dtype=dtype, device=device)
-        self.cur = torch.zeros(1, dtype=torch.int32, device=device)
+        import ctypes
+        self.cur = ctypes.c_int32(0)          # host-side index of the buffer that holds the lattice
         self.scratch = torch.zeros((self.layout["scratch_bytes"] + 7) // 8, dtype=torch.int64, device=device)
 
     def pack(self, psi):
         psi = psi.to(self.dtype).contiguous()
         assert psi.shape == (self.Z, self.T)
-        call("cyl_hbm_pack_" + self.suffix, _dev(psi), ptr(psi), self.Z, self.T, ptr(self.work), ptr(self.cur), stream())
+        call("cyl_hbm_pack_" + self.suffix, _dev(psi), ptr(psi), self.Z, self.T, ptr(self.work), self.cur, stream())
 
     def unpack(self, out=None):
         if out is None:
             out = torch.empty(self.Z, self.T, dtype=self.dtype, device=self.device)
-        call("cyl_hbm_unpack_" + self.suffix, _dev(out), ptr(self.work), ptr(self.cur), self.Z, self.T, ptr(out), stream())
+        call("cyl_hbm_unpack_" + self.suffix, _dev(out), ptr(self.work), int(self.cur.value), self.Z, self.T, ptr(out), stream())
         return out
 
     def sweep(self, params, chain, seed, sweep0, nsweeps, variant=0, flags=SWEEP_ADAPT_SIGMA, replica=0, obs=None, prof=None):
-        call("cyl_sweep_hbm_" + self.suffix, _dev(self.work), ptr(self.work), ptr(self.cur), self.Z, self.T, ptr(params),
+        call("cyl_sweep_hbm_" + self.suffix, _dev(self.work), ptr(self.work), self.cur, self.Z, self.T, ptr(params),
              ptr(chain), int(seed), int(replica), int(sweep0), int(nsweeps), variant_id(variant), int(flags),
              ptr(self.scratch), ptr(obs), ptr(prof), stream())
 
     def row_moments(self, params):
         S = torch.empty(self.Z, NMOM, dtype=F64, device=self.device)
-        call("cyl_hbm_row_moments_" + self.suffix, _dev(self.work), ptr(self.work), ptr(self.cur), self.Z, self.T,
+        call("cyl_hbm_row_moments_" + self.suffix, _dev(self.work), ptr(self.work), int(self.cur.value), self.Z, self.T,
              ptr(params), ptr(S), stream())
         return S
 

@@ -174,18 +174,19 @@ int cyl_sweep_smem_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, cons
  * 2*buffer_elems complex elements, scratch scratch_bytes bytes (row coefficients, row moments, counters). */
 int cyl_hbm_layout(int Z, int T, int is_f64, int* halo_rows, int* halo_cols, int64_t* pitch_elems,
                    int64_t* buffer_elems, int64_t* scratch_bytes);
-/* psi [Z][T] (numpy layout) -> work buffer 0 incl. halos; sets *cur = 0.  unpack reads buffer *cur. */
+/* psi [Z][T] (numpy layout) -> work buffer 0 incl. halos; sets *cur = 0.  `cur` is a HOST integer owned by the
+ * caller: the index (0/1) of the buffer that holds the lattice.  unpack reads buffer `cur`. */
 int cyl_hbm_pack_f32(const void* psi, int Z, int T, void* work, int32_t* cur, void* stream);
 int cyl_hbm_pack_f64(const void* psi, int Z, int T, void* work, int32_t* cur, void* stream);
-int cyl_hbm_unpack_f32(const void* work, const int32_t* cur, int Z, int T, void* psi, void* stream);
-int cyl_hbm_unpack_f64(const void* work, const int32_t* cur, int Z, int T, void* psi, void* stream);
+int cyl_hbm_unpack_f32(const void* work, int cur, int Z, int T, void* psi, void* stream);
+int cyl_hbm_unpack_f64(const void* work, int cur, int Z, int T, void* psi, void* stream);
 
 /* nsweeps checkerboard sweeps of one Z x T lattice streamed from HBM.  One CTA per 2-D tile; the tile plus a
  * halo of one site per colour is staged into shared memory by TMA (cp.async.bulk.tensor.2d, one box per
  * parity plane, completion on an mbarrier); ALL colours of the sweep are then updated in shared memory (halo
  * sites are recomputed redundantly -- the counter-based RNG makes that bit-identical to the neighbour tile's
  * own result) and the interior is written to the other buffer, so a sweep moves 8 B read + 8 B written per
- * site (fp32) instead of one read + one write per colour.  `cur` (device int32) is flipped per sweep.
+ * site (fp32) instead of one read + one write per colour.  `cur` (HOST int32, in/out) is flipped per sweep.
  * chain [CYL_CHAIN_DOUBLES] device.  Accept counts feed the Robbins-Monro sigma update once per sweep; with
  * CYL_SWEEP_AMP_MOVES / CYL_SWEEP_MEASURE a row-moment pass and an amplitude move / measurement follow every
  * sweep.  obs [CYL_OBS_DOUBLES], prof [Z][3] may be NULL without CYL_SWEEP_MEASURE. */
@@ -195,10 +196,10 @@ int cyl_sweep_hbm_f32(void* work, int32_t* cur, int Z, int T, const CylParams* p
 int cyl_sweep_hbm_f64(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain,
                       uint64_t seed, int64_t replica, uint64_t sweep0, int nsweeps, int variant,
                       uint32_t flags, void* scratch, double* obs, double* prof, void* stream);
-/* Row moments of the lattice held in work[*cur] -> S [Z][8] (same columns as cyl_row_moments_*). */
-int cyl_hbm_row_moments_f32(const void* work, const int32_t* cur, int Z, int T, const CylParams* params,
+/* Row moments of the lattice held in work[cur] -> S [Z][8] (same columns as cyl_row_moments_*). */
+int cyl_hbm_row_moments_f32(const void* work, int cur, int Z, int T, const CylParams* params,
                             double* S, void* stream);
-int cyl_hbm_row_moments_f64(const void* work, const int32_t* cur, int Z, int T, const CylParams* params,
+int cyl_hbm_row_moments_f64(const void* work, int cur, int Z, int T, const CylParams* params,
                             double* S, void* stream);
 
 /* ---------------------------------------------------------------- Fourier-mode model ----------------- */
