@@ -19,6 +19,7 @@
 // Reference semantics restated: Lattice.step_lattice_loc (On_lattice_simple.py:598-686) per site,
 // update_sigma (:688-696) batched per sweep, Lattice.measure (:121-131), amplitude move (:544-550).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "cyl_common.cuh"
 #include "cyl_energy.cuh"
@@ -29,9 +30,9 @@
 #define HBM_HC 4          // column halo in the global layout (>= NCOL; 4 keeps plane columns 16-byte aligned)
 #define HBM_TW 128        // tile width (sites)
 
-template <typename R> struct HbmTile;
-template <> struct HbmTile<float>  { static constexpr int TH = 32; };
-template <> struct HbmTile<double> { static constexpr int TH = 32; };
+// Tile height is a template parameter chosen per launch (see pick_tile_height): co-resident CTAs run in waves, and the
+// last, partially filled wave costs as much as a full one, so the height that makes the wave count of THIS lattice on
+// THIS device (almost) integral wins -- 4096 x 4096 on 148 SMs x 5 CTAs: 32 rows -> 5.53 waves, 30 rows -> 5.92.
 
 struct HbmGeom {
   int Z, T, ncol, hr, hc;
@@ -202,10 +203,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // ----------------------------------------------------------------------------------------------------
 // the sweep kernel
 // ----------------------------------------------------------------------------------------------------
-template <typename R, int NCOL>
+template <typename R, int NCOL, int TH_>
 struct HbmSmem {
   using C = typename Real<R>::complex_t;
-  static constexpr int TH = HbmTile<R>::TH, TW = HBM_TW;
+  static constexpr int TH = TH_, TW = HBM_TW;
   // Column halo in shared memory.  4 (not NCOL) so that every TMA box starts on a 16-byte boundary of its plane
   // row: box start = (tj0 + HBM_HC - HS)/2 plane columns = tj0/2, a multiple of 64 complex elements.
   static constexpr int HS = HBM_HC;
@@ -218,14 +219,14 @@ struct HbmSmem {
 
 struct HbmMaps { CUtensorMap m[2][2]; int esz; };   // [buffer][plane]; esz = TMA elements per complex value
 
-template <typename R, int NCOL>
+template <typename R, int NCOL, int TH_>
 __global__ void __launch_bounds__(HBM_NT)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
                  int cur, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
                  const double* __restrict__ chain, HbmCounters* __restrict__ counters, const __grid_constant__ SiteKeys keys,
                  uint64_t sweep) {
   using C = typename Real<R>::complex_t;
-  using L = HbmSmem<R, NCOL>;
+  using L = HbmSmem<R, NCOL, TH_>;
   constexpr int TH = L::TH, TW = L::TW, SH = L::SH, SW = L::SW, SWH = L::SWH, HS = L::HS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* pl0 = reinterpret_cast<C*>(smem_raw);
@@ -305,9 +306,32 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const C* oth = pl0 + (par ^ 1) * PS + r * SWH + col - 1 + par;
       const RowCoef<R>* rcp = coef + r;
       if (!border) {
+        // two rows per trip (same column and plane, RSTEP rows apart: never neighbours): two independent dependency chains
+        // -- Philox of one site overlaps the arithmetic of the other, and the warps of a CTA stop marching through the
+        // same pipe at the same time
         uint32_t site = site_id(r, q);
-        for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, rcp += RSTEP, site += RSTEP * g.T)
-          move(own, oth, *rcp, site, c == 1 || (r != 1 && r != SH - 2));
+        const uint32_t dsite = RSTEP * g.T;
+        for (; r + RSTEP < SH - m; r += 2 * RSTEP, own += 2 * RSTEP * SWH, oth += 2 * RSTEP * SWH, rcp += 2 * RSTEP, site += 2 * dsite) {
+          // all loads first (the compiler must assume the first store aliases the second site's loads), then the two chains
+          C* ownB = own + RSTEP * SWH;
+          const C* othB = oth + RSTEP * SWH;
+          const C pA = own[0], LA = own[-SWH], RA = own[SWH], WA = oth[0], EA = oth[1];
+          const C pB = ownB[0], LB = ownB[-SWH], RB = ownB[SWH], WB = othB[0], EB = othB[1];
+          const RowCoef<R> rcA = rcp[0], rcB = rcp[RSTEP];
+          const uint2 xA = philox2x32_10(site, c1, keys), xB = philox2x32_10(site + dsite, c1, keys);
+          R zA, yA, zB, yB;
+          Draw<R>::normals(xA.x, xA.y, zA, yA);
+          Draw<R>::normals(xB.x, xB.y, zB, yB);
+          const R wA = sigma * rcA.sgmul, wB = sigma * rcB.sgmul;
+          const R dAr = wA * zA, dAi = wA * yA, dBr = wB * zB, dBi = wB * yB;
+          const R denA = site_delta_over_k<R, C>(rcA, pA, LA, RA, WA, EA, dAr, dAi);
+          const R denB = site_delta_over_k<R, C>(rcB, pB, LB, RB, WB, EB, dBr, dBi);
+          const bool accA = Draw<R>::accept(xA.y, denA, rcA.kacc), accB = Draw<R>::accept(xB.y, denB, rcB.kacc);
+          if (accA) own[0] = Real<R>::make(pA.x + dAr, pA.y + dAi);
+          if (accB) ownB[0] = Real<R>::make(pB.x + dBr, pB.y + dBi);
+          nacc += (accA && (c == 1 || r != 1)) + (accB && (c == 1 || r + RSTEP != SH - 2));
+        }
+        if (r < SH - m) move(own, oth, *rcp, site, c == 1 || (r != 1 && r != SH - 2));
       } else {
         for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, rcp += RSTEP)
           move(own, oth, *rcp, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T);
@@ -571,10 +595,9 @@ static int get_encode_fn(EncodeTiledFn* fn) {
   return CYL_OK;
 }
 
-template <typename R, int NCOL>
-static int make_maps(const HbmGeom& g, void* work, HbmMaps* maps) {
+template <typename R>
+static int make_maps(const HbmGeom& g, void* work, int box_cols, int box_rows, HbmMaps* maps) {
   using C = typename Real<R>::complex_t;
-  using L = HbmSmem<R, NCOL>;
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
@@ -587,7 +610,7 @@ static int make_maps(const HbmGeom& g, void* work, HbmMaps* maps) {
       void* base = (C*)work + (size_t)b * g.buffer_elems + (size_t)pl * g.plane_elems;
       const cuuint64_t dims[2] = {(cuuint64_t)(g.pitch / 2) * esz, (cuuint64_t)g.rows};
       const cuuint64_t strides[1] = {(cuuint64_t)(g.pitch / 2) * sizeof(C)};
-      const cuuint32_t box[2] = {(cuuint32_t)(L::SWH * esz), (cuuint32_t)L::SH};
+      const cuuint32_t box[2] = {(cuuint32_t)(box_cols * esz), (cuuint32_t)box_rows};
       const cuuint32_t estr[2] = {1, 1};
       const CUresult r = enc(&maps->m[b][pl], dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -601,21 +624,21 @@ static int make_maps(const HbmGeom& g, void* work, HbmMaps* maps) {
   return CYL_OK;
 }
 
-template <typename R, int NCOL>
+template <typename R, int NCOL, int TH_>
 static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylParams* params, double* chain, uint64_t seed,
                           int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch,
                           double* obs, double* prof, cudaStream_t st) {
   using C = typename Real<R>::complex_t;
-  using L = HbmSmem<R, NCOL>;
+  using L = HbmSmem<R, NCOL, TH_>;
   static_assert((L::SWH * sizeof(C)) % 16 == 0, "TMA box rows must be a multiple of 16 bytes");
   HbmMaps maps;
-  int rc = make_maps<R, NCOL>(g, work, &maps);
+  int rc = make_maps<R>(g, work, L::SWH, L::SH, &maps);
   if (rc) return rc;
   const HbmScratch<R> sl(g.Z);
   HbmCounters* counters = reinterpret_cast<HbmCounters*>(scratch);
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>((char*)scratch + sl.off_coef);
   double* S = reinterpret_cast<double*>((char*)scratch + sl.off_mom);
-  auto kern = sweep_hbm_kernel<R, NCOL>;
+  auto kern = sweep_hbm_kernel<R, NCOL, TH_>;
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
   CYL_CUDA(cudaMemsetAsync(counters, 0, sizeof(HbmCounters), st));
   const dim3 grid((g.T + L::TW - 1) / L::TW, (g.Z + L::TH - 1) / L::TH);
@@ -637,6 +660,56 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   return CYL_OK;
 }
 
+// Relative cost of one sweep with tile height TH: waves of co-resident CTAs x site moves per tile (incl. the redundant halo).
+template <typename R, int NCOL, int TH_>
+static double tile_cost(const HbmGeom& g, int sms) {
+  using L = HbmSmem<R, NCOL, TH_>;
+  int occ = 0;
+  auto kern = sweep_hbm_kernel<R, NCOL, TH_>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HBM_NT, L::total) != cudaSuccess || occ <= 0) {
+    cudaGetLastError();
+    return 1e300;
+  }
+  const double tiles = (double)((g.T + L::TW - 1) / L::TW) * ((g.Z + TH_ - 1) / TH_);
+  const double waves = ceil(tiles / ((double)sms * occ));
+  double moves = 0;
+  for (int c = 0; c < NCOL; ++c) moves += (double)(TH_ + 2 * (NCOL - 1 - c)) * (L::TW / NCOL + 2);
+  return waves * moves * (1.0 + 600.0 / (moves * 8));        // + fixed per-tile cost (load wait, barriers) ~ 600 moves' worth
+}
+
+#define HBM_TRY_TH(TH_)                                                                                                   \
+  do {                                                                                                                    \
+    const double c__ = tile_cost<R, NCOL, TH_>(g, sms);                                                                   \
+    if (c__ < best_cost) { best_cost = c__; best = TH_; }                                                                 \
+  } while (0)
+#define HBM_RUN_TH(TH_)                                                                                                   \
+  case TH_:                                                                                                               \
+    return sweep_hbm_impl<R, NCOL, TH_>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, st)
+
+template <typename R, int NCOL>
+static int sweep_hbm_dispatch(const HbmGeom& g, void* work, int32_t* cur, const CylParams* params, double* chain, uint64_t seed,
+                              int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch,
+                              double* obs, double* prof, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  CYL_CUDA(cudaGetDevice(&dev));
+  CYL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int best = 32;
+  double best_cost = 1e300;
+  const char* force = getenv("CYL_HBM_TILE_ROWS");                  // tuning / debugging override
+  if (force) best = atoi(force);
+  else { HBM_TRY_TH(32); HBM_TRY_TH(30); HBM_TRY_TH(28); HBM_TRY_TH(24); }
+  switch (best) {
+    HBM_RUN_TH(32);
+    HBM_RUN_TH(30);
+    HBM_RUN_TH(28);
+    HBM_RUN_TH(24);
+    default:
+      cyl_set_error("cyl_sweep_hbm: unsupported tile height %d (32, 30, 28, 24)", best);
+      return CYL_E_UNSUPPORTED;
+  }
+}
+
 template <typename R>
 static int sweep_hbm(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain, uint64_t seed,
                      int64_t replica, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, void* scratch, double* obs,
@@ -649,8 +722,8 @@ static int sweep_hbm(void* work, int32_t* cur, int Z, int T, const CylParams* pa
   const HbmGeom g = hbm_geom(Z, T);
   if (nsweeps == 0) return CYL_OK;
   if (g.ncol == 2)
-    return sweep_hbm_impl<R, 2>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, as_stream(stream));
-  return sweep_hbm_impl<R, 3>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, as_stream(stream));
+    return sweep_hbm_dispatch<R, 2>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, as_stream(stream));
+  return sweep_hbm_dispatch<R, 3>(g, work, cur, params, chain, seed, replica, sweep0, nsweeps, variant, flags, scratch, obs, prof, as_stream(stream));
 }
 
 extern "C" int cyl_sweep_hbm_f32(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain, uint64_t seed,
