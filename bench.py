@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 METRIC = "metropolis_site_updates_per_s"
 UNIT = "site-updates/s"
 REPLICAS_PER_GPU = 8192
-SWEEPS_PER_STEP = 50
+SWEEPS_PER_STEP = 200
 DIMS = (50, 50)
 SEED = 0x5EED
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
@@ -170,7 +170,7 @@ def measured_peak_hbm():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--replicas-per-gpu", type=int, default=REPLICAS_PER_GPU)
@@ -258,13 +258,12 @@ def main():
         psi_out_h = torch.empty_like(psi_h).pin_memory()
 
         def step_e2e():
-            batch.load_host(psi_h, chain_h)                         # H2D: lattices + chain state
-            batch.run(nsw, amp_moves=True, measure=True, adapt=True)
+            # H2D: lattices + chain state; the sweeps; D2H: lattices (what `.lattice` hands to the caller) + records;
+            # pipelined over 4 slices of the batch, returns when the host buffers are complete
+            batch.step_host(psi_h, chain_h, psi_out_h, rec_h, nsw, nchunks=4)
             if world > 1:
                 batch.gather_records()
-            rec_h.copy_(batch.record(), non_blocking=True)         # D2H: observable records
-            psi_out_h.copy_(batch.psi, non_blocking=True)          # D2H: lattices (what `.lattice` hands to the caller)
-            torch.cuda.current_stream().synchronize()              # the caller reads the host buffers
+                torch.cuda.current_stream().synchronize()
         for _ in range(min(W, 2)):
             step_e2e()
         barrier()
@@ -277,7 +276,7 @@ def main():
         d2h = rec_h.numel() * 8 + psi_out_h.numel() * psi_out_h.element_size()
         e2e = {"value": updates_per_step_all * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K,
-               "api": "ReplicaBatch.load_host -> .run -> .record()/.psi to pinned host, stream-synchronised per step"}
+               "api": "ReplicaBatch.step_host: pinned host lattices + chain in, sweeps, lattices + records out, 4-slice stream pipeline, host-synchronised per step"}
 
     # ---- roofline leg: C4, one large lattice streamed from HBM ----
     roofline = None

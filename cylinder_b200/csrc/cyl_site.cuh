@@ -37,40 +37,51 @@ struct __align__(16) RowCoef {
 };
 
 // Build the coefficients of a row from the metric at z = lz*i (g0) and z -+ lz/2 (gm, gp), all at the current
-// amplitude.  fp64 in, R out.
+// amplitude.  The metric comes in fp64; the coefficient arithmetic runs in A = double for the fp64 kernels and in
+// A = float for the fp32 kernels (the results are stored as fp32 anyway; both fp32 kernels share this code, so their
+// tables are bit-identical) -- the rebuild after an accepted amplitude move is a latency-bound phase on Z threads.
+template <typename A> __device__ __forceinline__ A coef_rcp(A x);
+template <> __device__ __forceinline__ double coef_rcp<double>(double x) { return fast_rcp(x); }
+template <> __device__ __forceinline__ float coef_rcp<float>(float x) { return __frcp_rn(x); }
+
 template <typename R>
 __device__ __forceinline__ RowCoef<R> row_coef(const CylParams& p, int variant, double lz, double lth, const Geo& g0,
                                                const Geo& gm, const Geo& gp) {
-  const double sg = g0.gth * g0.gz;
-  const double Cn2 = p.C * p.n * p.n;
-  const double ilz2 = fast_rcp(lz * lz), ilth = fast_rcp(lth);
-  const double igzm = fast_rcp(gm.gz), igzp = fast_rcp(gp.gz);
-  double clz, crz, clt, crt, xl, xr, mass, sgmul;
+  using A = R;
+  const A g0t = (A)g0.gth, g0z = (A)g0.gz, g0a = (A)g0.ath;
+  const A gmt = (A)gm.gth, gmz = (A)gm.gz, gma = (A)gm.ath;
+  const A gpt = (A)gp.gth, gpz = (A)gp.gz, gpa = (A)gp.ath;
+  const A C = (A)p.C, n = (A)p.n, alpha = (A)p.alpha;
+  const A sg = g0t * g0z;
+  const A Cn2 = C * n * n;
+  const A ilz2 = (A)(1.0 / (lz * lz)), ilth = (A)(1.0 / lth);
+  const A igzm = coef_rcp<A>(gmz), igzp = coef_rcp<A>(gpz);
+  A clz, crz, clt, crt, xl, xr, mass, sgmul;
   if (variant == CYL_VARIANT_SIMPLE) {
-    const double igtm = fast_rcp(gm.gth), igtp = fast_rcp(gp.gth);
-    const double Rm = igtm * igtm, Rp = igtp * igtp;
-    clz = p.C * ilz2 * igzm * igzm;
-    crz = p.C * ilz2 * igzp * igzp;
-    clt = p.C * Rm * Rm * ilth * ilth;
-    crt = p.C * Rp * Rp * ilth * ilth;
-    xl = 2 * p.C * p.n * Rm * gm.ath * ilth;
-    xr = 2 * p.C * p.n * Rp * gp.ath * ilth;
-    mass = p.alpha + Cn2 * Rm * gm.ath * gm.ath;
-    sgmul = 1.0;
+    const A igtm = coef_rcp<A>(gmt), igtp = coef_rcp<A>(gpt);
+    const A Rm = igtm * igtm, Rp = igtp * igtp;
+    clz = C * ilz2 * igzm * igzm;
+    crz = C * ilz2 * igzp * igzp;
+    clt = C * Rm * Rm * ilth * ilth;
+    crt = C * Rp * Rp * ilth * ilth;
+    xl = 2 * C * n * Rm * gma * ilth;
+    xr = 2 * C * n * Rp * gpa * ilth;
+    mass = alpha + Cn2 * Rm * gma * gma;
+    sgmul = A(1);
   } else {
-    const double igt0 = fast_rcp(g0.gth);
-    const double R0 = igt0 * igt0, isg = igt0 * fast_rcp(g0.gz);
-    clz = p.C * ilz2 * igzm * gm.gth * isg;                 // C/(lz^2 Gz(z-)^2) * sg(z-)/sg(z)
-    crz = p.C * ilz2 * igzp * gp.gth * isg;
-    clt = crt = p.C * R0 * ilth * ilth;
-    xl = xr = 2 * p.C * p.n * R0 * g0.ath * ilth;
-    mass = p.alpha + Cn2 * R0 * g0.ath * g0.ath;
+    const A igt0 = coef_rcp<A>(g0t);
+    const A R0 = igt0 * igt0, isg = igt0 * coef_rcp<A>(g0z);
+    clz = C * ilz2 * igzm * gmt * isg;                      // C/(lz^2 Gz(z-)^2) * sg(z-)/sg(z)
+    crz = C * ilz2 * igzp * gpt * isg;
+    clt = crt = C * R0 * ilth * ilth;
+    xl = xr = 2 * C * n * R0 * g0a * ilth;
+    mass = alpha + Cn2 * R0 * g0a * g0a;
     sgmul = sg;
   }
-  const double K = sg * lz * lth;
+  const A K = sg * (A)(lz * lth);
   RowCoef<R> c;
   c.kfull = (R)K;
-  c.kacc = (p.temperature > 0) ? (R)(K * 1.4426950408889634 * fast_rcp(p.temperature)) : (R)INFINITY;
+  c.kacc = (p.temperature > 0) ? (R)(K * (A)(1.4426950408889634 / p.temperature)) : (R)INFINITY;
   c.mass = (R)mass;
   c.csum = (R)(clz + crz + clt + crt);
   c.hu = (R)(p.u / 2);

@@ -3,17 +3,21 @@
 // One CTA owns one replica for the whole launch (nsweeps sweeps): psi is read from HBM once, kept in shared
 // memory, written back once; the per-row metric coefficients, the amplitude-independent sin/cos tables and the
 // per-row energy weights live in shared memory too.  Per sweep:
-//   1. site moves  (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once;
-//      draws from Philox4x32-10 keyed by seed with counter (site, replica, sweep, tag) -- stateless, so a sweep can
-//      be re-run or resumed bit-identically;
-//   2. Robbins-Monro update of sigma_site from the sweep's accept count (:688-696, batched; cyl_site.cuh);
-//   3. energy pass: every thread forms the five energy densities of its sites and dots them with the
-//      row weights of the current amplitude and of the PROPOSED amplitude (weight difference, so the energy change of
-//      the amplitude move is accumulated directly, not as a difference of two large sums); one CTA tree reduction.
-//      The same pass accumulates the profiles of Lattice.measure (:121-131) by warp shuffles;
-//   4. global amplitude move a' = a + sigma_amp N(0,1) on E_surf(a') + E_field(a', a) (Lattice.run :544-550 through
-//      engine.step_real_group; accept rule B.2; Robbins-Monro on sigma_amp);
-//   5. on accept, rebuild the row coefficients from the sin/cos tables (no trigonometry).
+//   0. the amplitude proposal a' = a + sigma_amp N(0,1) is known up front (its draws are precomputed, counter-based);
+//      row weights of the field energy for the current amplitude and for (a' - a) are built by lane pairs on warps
+//      0..6 (fp64, fast reciprocals) while warp 7 evaluates E_surf(a');
+//   1. site moves (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once; draws from
+//      Philox2x32-10 at counter (site, sweep) -- stateless, so a sweep can be re-run or resumed bit-identically.  The
+//      ENERGY is accumulated in the same pass: a site adds its own |psi|^2, |psi|^4 terms when it is finalised, and a
+//      bond (|dz|^2, |dth|^2, Im(conj(psi) dth)) is added by whichever endpoint is finalised LATER
+//      (its neighbour has the lower colour), dotted with the row weights for a and for (a' - a): the energy change of
+//      the amplitude move is accumulated directly, not as a difference of two large sums, and no second pass over the
+//      lattice is needed;
+//   2. one CTA tree reduction of {accepts, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|};
+//   3. Robbins-Monro on sigma_site (On_lattice_simple.py:688-696, batched; cyl_site.cuh) and the amplitude decision
+//      (Lattice.run :544-550 through engine.step_real_group; accept rule B.2; Robbins-Monro on sigma_amp);
+//   4. on accept, rebuild the row coefficients from the sin/cos tables (no trigonometry);
+//   5. with CYL_SWEEP_MEASURE and a profile buffer: row sums of Lattice.measure (:121-131), one warp per row.
 // The replicas are the (alpha, C, n, kappa, k) parameter grid that scripts/taskarray.sh farms out as separate CPU
 // jobs in the reference.
 #include "cyl_common.cuh"
@@ -32,7 +36,7 @@ struct SmemScalars {
 };
 
 // Optional per-phase cycle accounting (build with CYL_EXTRA_NVCC_FLAGS=-DCYL_PHASE_TIMING): thread 0 accumulates
-// clock64() deltas into obs slots 10..15 = site moves, accept count, weights/surface, energy pass, decision, rebuild.
+// clock64() deltas into obs slots 10..15 = weights/surface, site moves + energy, reduction, decision, rebuild, profiles.
 #ifdef CYL_PHASE_TIMING
 #define PHASE_MARK(k) do { if (tid == 0) { const long long t__ = clock64(); sc->obs[10 + (k)] += (double)(t__ - t_phase); t_phase = t__; } } while (0)
 #else
@@ -101,11 +105,11 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
   }
 }
 
-// one site move; returns 1 when accepted
+// one site move; returns the accept flag, `q` = the site's value after the move
 template <typename R, typename C>
-__device__ __forceinline__ int site_move(C* psi, int idx, int im, int ip, int jm, int jp, const RowCoef<R>& rc, R sigma,
-                                         uint32_t site, uint32_t c1, uint32_t key) {
-  const C pv = psi[idx], L = psi[im], Rz = psi[ip], W = psi[jm], E = psi[jp];
+__device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz, const C W, const C E, const RowCoef<R>& rc,
+                                          R sigma, uint32_t site, uint32_t c1, uint32_t key, C& q) {
+  const C pv = psi[idx];
   const uint2 x = philox2x32_10(site, c1, key);
   R zre, zim;
   Draw<R>::normals(x.x, x.y, zre, zim);
@@ -113,11 +117,41 @@ __device__ __forceinline__ int site_move(C* psi, int idx, int im, int ip, int jm
   const R dre = w * zre, dim = w * zim;
   const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
   const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-  if (acc) psi[idx] = Real<R>::make(pv.x + dre, pv.y + dim);
-  return acc ? 1 : 0;
+  q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+  if (acc) psi[idx] = q;
+  return acc;
 }
 
-template <typename R>
+// energy accumulators of one thread: E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|
+template <typename R> struct EAcc { R ec, ed, s2, sa; };
+__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
+
+template <typename R, typename C>
+__device__ __forceinline__ void energy_own(EAcc<R>& e, const RowW<R>& w, C q, bool measure) {
+  const R p2 = q.x * q.x + q.y * q.y, p4 = p2 * p2;
+  e.ed += w.dif[0] * p2 + w.dif[1] * p4;
+  if (measure) { e.ec += w.cur[0] * p2 + w.cur[1] * p4; e.s2 += p2; e.sa += sqrt_fast(p2); }
+}
+// z-bond between the site `hi` of a row and the site `lo` of the row above it; (wc, wd) = that row's |dz|^2 weights
+template <typename R, typename C>
+__device__ __forceinline__ void energy_zbond(EAcc<R>& e, R wc, R wd, C hi, C lo, bool measure) {
+  const R dr = hi.x - lo.x, di = hi.y - lo.y, m = dr * dr + di * di;
+  e.ed += wd * m;
+  if (measure) e.ec += wc * m;
+}
+// theta-bond between the site `hi` (column j) and `lo` (column j-1) of one row
+template <typename R, typename C>
+__device__ __forceinline__ void energy_tbond(EAcc<R>& e, const RowW<R>& w, C hi, C lo, bool measure) {
+  const R tr = hi.x - lo.x, ti = hi.y - lo.y;
+  const R m4 = tr * tr + ti * ti, m5 = hi.x * ti - hi.y * tr;        // |dth|^2, Im(conj(psi) dth)
+  e.ed += w.dif[3] * m4 + w.dif[4] * m5;
+  if (measure) e.ec += w.cur[3] * m4 + w.cur[4] * m5;
+}
+
+// EXTRAS = amplitude moves and/or measurement requested: a compile-time switch so that the plain-sweep instantiation
+// does not carry the registers of the energy accumulation.
+template <typename R, bool EXTRAS>
 __global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? 4 : 2))
 sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
                   const CylParams* __restrict__ params, double* __restrict__ chain, const __grid_constant__ PhiloxKeys keys,
@@ -147,7 +181,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const SiteStream stream = site_stream(seed, (uint64_t)(replica0 + b));
   double* ch = chain + (size_t)b * CYL_CHAIN_DOUBLES;
   C* psi_b = psi_g + (size_t)b * Zmax * T;
-  const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
+  constexpr bool extras = EXTRAS;
   const bool measure = (flags & CYL_SWEEP_MEASURE) != 0;
 
   // ---- prologue: state, lattice, tables ----
@@ -184,10 +218,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 
   const double amp_pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
   const double amp_ratio = 1.0 / (amp_pt * (1.0 - amp_pt));
+  const double inv_nsite = 1.0 / nsite;
   const int ncol = num_colours(Z, T);
   const int Th = (T + 1) >> 1, Teven = T & ~1;
   const int di = SWEEP_NT / Th, dj = SWEEP_NT % Th;
-  const R inv_lz2 = (R)(1.0 / (lz * lz)), inv_lth2 = (R)(1.0 / (lth * lth)), inv_lth = (R)(1.0 / lth);
 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
@@ -201,11 +235,59 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     const uint32_t c1 = (uint32_t)sweep + stream.off;
     const R sigma = (R)sc->sigma_site;
-    int nacc = 0;
 #ifdef CYL_PHASE_TIMING
     long long t_phase = clock64();
 #endif
-    // ---- 1. site moves ----
+    // The proposal a' = a + sigma_amp N(0,1) is known to every thread: the unit normal was drawn ahead of time, a and
+    // sigma_amp were fixed by the previous sweep's decision.
+    const double a = sc->amp;
+    const double a_new = extras ? a + sc->sigma_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
+    const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
+    double cst_cur = 0.0, cst_dif = 0.0;
+
+    // ---- 0. row weights on warps 0..6: lane pair (2i, 2i+1) = (current, proposed amplitude) of row i;
+    //         warp 7 meanwhile evaluates the surface energy of the proposal ----
+    if (extras) {
+      if (warp == SWEEP_NWARP - 1) {
+        if (try_move) {
+          const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
+          if (lane == 0) sc->e_surf_new = es;
+        }
+      } else {
+        const double ae = (try_move && (tid & 1)) ? a_new : a;
+        const double ra = fast_radius_rescaled(p.radius, a), rae = (tid & 1) ? fast_radius_rescaled(p.radius, ae) : ra;
+        const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
+        for (int base = 0; base < 2 * Z; base += SWEEP_NT - 32) {
+          const int t = base + tid;
+          const int i = min(t >> 1, Z - 1);
+          const RowTrig tr = trig[i];
+          const Geo g0e = geo_from_sc(p.wavenumber, rae, ae, tr.s0, tr.c0), gme = geo_from_sc(p.wavenumber, rae, ae, tr.sm, tr.cm);
+          Geo g0r = g0e;                                                 // a_ref = current amplitude (:75); 0th order only
+          if (variant != CYL_VARIANT_SIMPLE && (tid & 1)) g0r = geo_from_sc(p.wavenumber, ra, a, tr.s0, tr.c0);
+          double W[6];
+          field_energy_weights(variant, p, lz, lth, T, g0e, gme, g0r, W);
+          RowW<R> w;
+          double dif5 = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const double other = __shfl_xor_sync(0xffffffffu, W[q], 1);  // even lane receives W(a')
+            if (q < 5) { w.cur[q] = (R)(W[q] * fold[q]); w.dif[q] = (R)((other - W[q]) * fold[q]); }
+            else dif5 = other - W[q];
+          }
+          if (t < 2 * Z && !(tid & 1)) {
+            roww[i] = w;
+            cst_cur += W[5];
+            cst_dif += dif5;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    PHASE_MARK(0);
+
+    // ---- 1. site moves, energy accumulated as bonds become final ----
+    int nacc = 0;
+    EAcc<R> e = {R(0), R(0), R(0), R(0)};
     if (ncol == 2) {
       // both lengths even: colour = (i + j) & 1, T/2 sites of each colour in every row
       for (int colour = 0; colour < 2; ++colour) {
@@ -215,8 +297,20 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const int row = i * T;
           const int im = (i == 0 ? nsite : row) - T, ip = (i == Z - 1 ? 0 : row + T);
           const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-          nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), c1,
-                                  stream.key);
+          const C L = psi[im + j], Rz = psi[ip + j], W = psi[row + jm], E = psi[row + jp];
+          C q;
+          nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
+          if (extras) {
+            const RowW<R> w = roww[i];
+            energy_own<R, C>(e, w, q, measure);
+            if (colour == 1) {                                             // all four neighbours are final
+              const int inext = (i == Z - 1 ? 0 : i + 1);
+              energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, L, measure);
+              energy_zbond<R, C>(e, roww[inext].cur[2], roww[inext].dif[2], Rz, q, measure);
+              energy_tbond<R, C>(e, w, q, W, measure);
+              energy_tbond<R, C>(e, w, E, q, measure);
+            }
+          }
           jj += dj; i += di;
           if (jj >= Th) { jj -= Th; ++i; }
         }
@@ -232,7 +326,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         int ii = tid / Th, jj = tid - ii * Th;
         while (ii < nrow_pass) {
           const int i = !t_even || colour == 1 ? ii : (colour == 0 ? 2 * ii : min(2 * ii + 1, Z - 1));
-          int beta = colour - axis_colour(i, Z);
+          const int ai = axis_colour(i, Z);
+          int beta = colour - ai;
           if (beta < 0) beta += 3;
           int j;
           bool valid;
@@ -240,10 +335,21 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           else          { j = T - 1;         valid = (T & 1) && jj == 0; }
           if (valid) {
             const int row = i * T;
-            const int im = (i == 0 ? nsite : row) - T, ip = (i == Z - 1 ? 0 : row + T);
+            const int iprev = (i == 0 ? Z - 1 : i - 1), inext = (i == Z - 1 ? 0 : i + 1);
             const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-            nacc += site_move<R, C>(psi, row + j, im + j, ip + j, row + jm, row + jp, coef[i], sigma, (uint32_t)(row + j), c1,
-                                    stream.key);
+            const C L = psi[iprev * T + j], Rz = psi[inext * T + j], W = psi[row + jm], E = psi[row + jp];
+            C q;
+            nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
+            if (extras) {
+              const RowW<R> w = roww[i];
+              energy_own<R, C>(e, w, q, measure);
+              // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
+              auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
+              if (col3(axis_colour(iprev, Z) + beta) < colour) energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, L, measure);
+              if (col3(axis_colour(inext, Z) + beta) < colour) energy_zbond<R, C>(e, roww[inext].cur[2], roww[inext].dif[2], Rz, q, measure);
+              if (col3(ai + axis_colour(jm, T)) < colour) energy_tbond<R, C>(e, w, q, W, measure);
+              if (col3(ai + axis_colour(jp, T)) < colour) energy_tbond<R, C>(e, w, E, q, measure);
+            }
           }
           jj += dj; ii += di;
           if (jj >= Th) { jj -= Th; ++ii; }
@@ -251,143 +357,37 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         __syncthreads();
       }
     }
-    PHASE_MARK(0);
-    // ---- 2. accept count; Robbins-Monro on sigma_site (one thread, overlapped with the weights phase) ----
-    const double acc_total = block_sum<double>((double)nacc, scr);
     PHASE_MARK(1);
-    if (tid == SWEEP_NT - 1) {
-      if (flags & CYL_SWEEP_ADAPT_SIGMA)
-        sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, acc_total);
-      sc->step_counter += nsite;
-      sc->site_proposed += nsite;
-      sc->site_accepted += acc_total;
-    }
-    if (!extras) { __syncthreads(); continue; }
 
-    // The proposal a' = a + sigma_amp N(0,1) is known to every thread: the unit normal was drawn ahead of time, a and
-    // sigma_amp were fixed by the previous sweep's decision.
-    const double a = sc->amp;
-    const double a_new = a + sc->sigma_amp * ampz[sw & (AMP_CHUNK - 1)];
-    const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
-    double red[6] = {0, 0, 0, 0, 0, 0};       // e_cur, e_dif, const_cur, const_dif, sum |psi|^2, sum |psi|
-
-    // ---- 3a. row weights on warps 0..6: lane pair (2i, 2i+1) = (current, proposed amplitude) of row i;
-    //          warp 7 meanwhile evaluates the surface energy of the proposal ----
-    if (warp == SWEEP_NWARP - 1) {
-      if (try_move) {
-        const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
-        if (lane == 0) sc->e_surf_new = es;
-      }
-    } else {
-      const double ae = (try_move && (tid & 1)) ? a_new : a;
-      const double ra = fast_radius_rescaled(p.radius, a), rae = (tid & 1) ? fast_radius_rescaled(p.radius, ae) : ra;
-      for (int base = 0; base < 2 * Z; base += SWEEP_NT - 32) {
-        const int t = base + tid;
-        const int i = min(t >> 1, Z - 1);
-        const RowTrig tr = trig[i];
-        const Geo g0e = geo_from_sc(p.wavenumber, rae, ae, tr.s0, tr.c0), gme = geo_from_sc(p.wavenumber, rae, ae, tr.sm, tr.cm);
-        Geo g0r = g0e;                                                   // a_ref = current amplitude (:75); 0th order only
-        if (variant != CYL_VARIANT_SIMPLE && (tid & 1)) g0r = geo_from_sc(p.wavenumber, ra, a, tr.s0, tr.c0);
-        double W[6];
-        field_energy_weights(variant, p, lz, lth, T, g0e, gme, g0r, W);
-        RowW<R> w;
-        double dif5 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const double other = __shfl_xor_sync(0xffffffffu, W[q], 1);    // even lane receives W(a')
-          if (q < 5) { w.cur[q] = (R)W[q]; w.dif[q] = (R)(other - W[q]); }
-          else dif5 = other - W[q];
-        }
-        if (t < 2 * Z && !(tid & 1)) {
-          roww[i] = w;
-          red[2] += W[5];
-          red[3] += dif5;
-        }
-      }
-    }
-    __syncthreads();
+    // ---- 2. one reduction: accepts, energies, moments ----
+    double red[7] = {(double)nacc, (double)e.ec, (double)e.ed, cst_cur, cst_dif, (double)e.s2, (double)e.sa};
+    block_sum_n<7>(red, scr);
     PHASE_MARK(2);
 
-    // ---- 3b. energy pass: one warp per row ----
-    auto site_terms = [&](const C pv, const C L, const C W, const RowW<R>& w, R& ec, R& ed, R& s2, R& sa, R& sre, R& sim) {
-      const R p2 = pv.x * pv.x + pv.y * pv.y;
-      const R zr = pv.x - L.x, zi = pv.y - L.y, tr = pv.x - W.x, ti = pv.y - W.y;
-      const R m2 = p2 * p2;
-      const R m3 = (zr * zr + zi * zi) * inv_lz2;
-      const R m4 = (tr * tr + ti * ti) * inv_lth2;
-      const R m5 = (pv.x * ti - pv.y * tr) * inv_lth;                   // Im(conj(p) dth)
-      ed += w.dif[0] * p2 + w.dif[1] * m2 + w.dif[2] * m3 + w.dif[3] * m4 + w.dif[4] * m5;
-      if (measure) {
-        ec += w.cur[0] * p2 + w.cur[1] * m2 + w.cur[2] * m3 + w.cur[3] * m4 + w.cur[4] * m5;
-        s2 += p2; sa += sqrt(p2); sre += pv.x; sim += pv.y;
-      }
-    };
-    struct __align__(16) Pair { C a, b; };
-    for (int i = warp; i < Z; i += SWEEP_NWARP) {
-      const int row = i * T, rm = (i == 0 ? nsite : row) - T;
-      const RowW<R> w = roww[i];
-      R ec = 0, ed = 0, s2 = 0, sa = 0, sre = 0, sim = 0;
-      if ((T & 1) == 0) {
-        for (int pp = lane; 2 * pp < T; pp += 32) {                      // two adjacent sites per lane, 16-byte loads
-          const int j = 2 * pp;
-          const Pair own = *reinterpret_cast<const Pair*>(psi + row + j);
-          const Pair up = *reinterpret_cast<const Pair*>(psi + rm + j);
-          const C Wc = psi[row + (j == 0 ? T : j) - 1];
-          site_terms(own.a, up.a, Wc, w, ec, ed, s2, sa, sre, sim);
-          site_terms(own.b, up.b, own.a, w, ec, ed, s2, sa, sre, sim);
-        }
-      } else {
-        for (int j = lane; j < T; j += 32)
-          site_terms(psi[row + j], psi[rm + j], psi[row + (j == 0 ? T : j) - 1], w, ec, ed, s2, sa, sre, sim);
-      }
-      red[0] += (double)ec;
-      red[1] += (double)ed;
-      if (measure) {
-        red[4] += (double)s2;
-        red[5] += (double)sa;
-        if (prof) {                                                      // Lattice.measure :121-131
-          // three row sums by one transposed butterfly: 6 shuffles instead of 15
-          R v0 = sre, v1 = sim, v2 = sa, v3 = R(0);
-          {
-            const bool hi = lane & 16;                                   // xor 16: upper half keeps (v2, v3)
-            const R s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
-            const R r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-            v0 = (hi ? v2 : v0) + r0;
-            v1 = (hi ? v3 : v1) + r1;
-          }
-          {
-            const bool hi = lane & 8;                                    // xor 8: keeps one of the two
-            const R s0 = hi ? v0 : v1;
-            const R r0 = __shfl_xor_sync(0xffffffffu, s0, 8);
-            v0 = (hi ? v1 : v0) + r0;
-          }
-          v0 += __shfl_xor_sync(0xffffffffu, v0, 4);
-          v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
-          v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
-          // lane 0: sum re, lane 8: sum im, lane 16: sum |psi|, (lane 24: 0)
-          if ((lane & 7) == 0 && lane < 24) prof_s[3 * i + (lane >> 3)] += v0;
-        }
-      }
+    // ---- 3. Robbins-Monro on sigma_site (last thread) and the amplitude decision (thread 0), concurrently ----
+    if (tid == SWEEP_NT - 1) {
+      if (flags & CYL_SWEEP_ADAPT_SIGMA)
+        sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, red[0]);
+      sc->step_counter += nsite;
+      sc->site_proposed += nsite;
+      sc->site_accepted += red[0];
     }
-    PHASE_MARK(3);
-    block_sum_n<6>(red, scr);
-    // ---- 4. measurement + amplitude decision (thread 0) ----
-    if (tid == 0) {
-      const double e_dif = (red[1] + red[3]) * lz * lth;
+    if (extras && tid == 0) {
+      const double e_dif = (red[2] + red[4]) * lz * lth;
       if (measure) {                                                     // measure_avgs :135-156 + engine record
-        const double e_cur = (red[0] + red[2]) * lz * lth;               // :213
+        const double e_cur = (red[1] + red[3]) * lz * lth;               // :213
         sc->e_field = e_cur;
         double* o = sc->obs;
         o[CYL_OB_COUNT] += 1.0;
         o[CYL_OB_ABS_A] += fabs(a);
         o[CYL_OB_A] += a;
         o[CYL_OB_A2] += a * a;
-        o[CYL_OB_PSI2] += red[4] / nsite;
-        o[CYL_OB_ABSPSI] += red[5] / nsite;
+        o[CYL_OB_PSI2] += red[5] * inv_nsite;
+        o[CYL_OB_ABSPSI] += red[6] * inv_nsite;
         o[CYL_OB_E_FIELD] += e_cur;
         o[CYL_OB_E_SURF] += sc->e_surf;
         o[CYL_OB_E_FIELD2] += e_cur * e_cur;
-        o[CYL_OB_SIGMA] += sc->sigma_site;
+        o[CYL_OB_SIGMA] += (double)sigma;
       }
       int accept = 0;
       if (flags & CYL_SWEEP_AMP_MOVES) {
@@ -402,7 +402,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         sc->amp_counter += 1;
         sc->amp_proposed += 1;
         if (flags & CYL_SWEEP_ADAPT_SIGMA) {
-          const double cf = sc->sigma_amp * amp_ratio / fmax(sc->amp_counter, 200.0);
+          const double cf = sc->sigma_amp * amp_ratio * fast_rcp(fmax(sc->amp_counter, 200.0));
           if (accept) sc->sigma_amp += cf * (1 - amp_pt);
           else sc->sigma_amp -= cf * amp_pt;
         }
@@ -415,11 +415,36 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       sc->amp_accept = accept;
     }
     __syncthreads();
-    PHASE_MARK(4);
-    // ---- 5. metric tables follow the amplitude ----
-    if (sc->amp_accept) {
+    PHASE_MARK(3);
+    // ---- 4. metric tables follow the amplitude ----
+    if (extras && sc->amp_accept) {
       build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
       __syncthreads();
+    }
+    PHASE_MARK(4);
+    // ---- 5. profiles of Lattice.measure (:121-131): one THREAD per row, taken from the top of the CTA so that they run
+    //         beside the next sweep's weight phase (threads from the bottom); that phase ends with a barrier before any
+    //         site is written again ----
+    if (measure && prof) {
+      struct __align__(16) Pair { C a, b; };
+      for (int i = (SWEEP_NT - 33) - tid; i >= 0 && i < Z; i += SWEEP_NT - 32) {
+        const int row = i * T;
+        R sa = 0, sre = 0, sim = 0;
+        int j = 0;
+        if ((T & 1) == 0) {
+          for (; j < T; j += 2) {
+            const Pair v = *reinterpret_cast<const Pair*>(psi + row + j);
+            sre += v.a.x + v.b.x; sim += v.a.y + v.b.y;
+            sa += sqrt_fast(v.a.x * v.a.x + v.a.y * v.a.y) + sqrt_fast(v.b.x * v.b.x + v.b.y * v.b.y);
+          }
+        } else {
+          for (; j < T; ++j) {
+            const C v = psi[row + j];
+            sre += v.x; sim += v.y; sa += sqrt_fast(v.x * v.x + v.y * v.y);
+          }
+        }
+        prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa;
+      }
     }
     PHASE_MARK(5);
   }
@@ -465,7 +490,8 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
                   lay.total, max_optin);
     return CYL_E_UNSUPPORTED;
   }
-  auto kern = sweep_smem_kernel<R>;
+  const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
+  auto kern = extras ? sweep_smem_kernel<R, true> : sweep_smem_kernel<R, false>;
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const PhiloxKeys keys = philox_expand(seed);
   kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,

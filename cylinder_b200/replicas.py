@@ -118,6 +118,34 @@ class ReplicaBatch:
         if chain_host is not None:
             self.chain.copy_(chain_host, non_blocking=non_blocking)
 
+    def step_host(self, psi_host, chain_host, psi_out_host, rec_out_host, nsweeps, nchunks=4, amp_moves=True, measure=True,
+                  adapt=True):
+        """One step with HOST buffers in and out (pinned tensors): upload lattices + chain state, run nsweeps, download
+        lattices + per-replica records.  The batch is cut into `nchunks` slices, each on its own stream, so the H2D copy of
+        one slice, the sweeps of another and the D2H copy of a third overlap (PCIe is full duplex; replicas are
+        independent).  Returns after everything has landed in the host buffers."""
+        flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
+        if not hasattr(self, "_streams") or len(self._streams) != nchunks:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(nchunks)]
+        main = torch.cuda.current_stream(self.device)
+        bounds = [shard_range(self.B, c, nchunks) for c in range(nchunks)]
+        for st, (b0, b1) in zip(self._streams, bounds):
+            if b1 <= b0:
+                continue
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self.psi[b0:b1].copy_(psi_host[b0:b1], non_blocking=True)
+                self.chain[b0:b1].copy_(chain_host[b0:b1], non_blocking=True)
+                ops.sweep_smem(self.psi[b0:b1], self.Z[b0:b1], self.params[b0:b1], self.chain[b0:b1], self.seed, self.sweeps_done,
+                               nsweeps, self.variant, flags, self.replica0 + b0, self.obs[b0:b1], self.prof[b0:b1])
+                psi_out_host[b0:b1].copy_(self.psi[b0:b1], non_blocking=True)
+                rec = torch.cat([self.obs[b0:b1], self.chain[b0:b1], self.prof[b0:b1].reshape(b1 - b0, -1)], dim=1)
+                rec_out_host[b0:b1].copy_(rec, non_blocking=True)
+        for st in self._streams:
+            main.wait_stream(st)
+        self.sweeps_done += int(nsweeps)
+        main.synchronize()
+
     def state_dict(self):
         return dict(psi=self.psi.cpu(), chain=self.chain.cpu(), obs=self.obs.cpu(), prof=self.prof.cpu(), seed=self.seed,
                     replica0=self.replica0, sweeps_done=self.sweeps_done, variant=self.variant)
