@@ -36,6 +36,7 @@ SWEEPS_PER_STEP = 200
 DIMS = (50, 50)
 SEED = 0x5EED
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
+NCU_HBM_TRAFFIC_BYTES = 135.776e6 + 82.401e6   # sweep_hbm_kernel<float,2,30>, 4096x4096, one launch (profiles/r01_ncu_full.md)
 
 
 def grid_params(n_replicas, replica0=0):
@@ -121,7 +122,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -129,7 +130,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -301,7 +302,12 @@ def main():
         peak, peak_src = measured_peak_hbm()
         upd = float(n) * n * args.hbm_sweeps
         achieved = upd * ALG_BYTES_PER_UPDATE_F32 / (ms_hbm * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic = NCU_HBM_TRAFFIC_BYTES if (n == 4096) else None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_ncu_full.md "
+                                      "(below the 24 B/update algorithmic figure: the kernel updates all colours per pass, 8.1 B read + "
+                                      "8 B written per site; part of the writes is still dirty in the 126 MB L2 when the kernel ends)",
+                    "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE_F32 * n * n,
                     "peak_source": peak_src, "kernel": "sweep_hbm_kernel<float,2> (TMA-tiled, ping-pong)",
                     "workload": "C4: %dx%d fp32 lattice (%.0f MB > L2), a=0.3 fixed, %d sweeps" % (n, n, n * n * 8 / 1e6, args.hbm_sweeps),
                     "algorithmic_bytes_per_update": ALG_BYTES_PER_UPDATE_F32, "site_updates_per_s": upd / (ms_hbm * 1e-3),

@@ -363,3 +363,50 @@ def test_fourier_energy_matches_reference(cuda, golden_dir, tag):
     np.testing.assert_allclose(E, g[tag + "_E_stored"], rtol=1e-10)
     Es = ops.fourier_surface_energy(par, torch.tensor(amps, device=cuda)).cpu().numpy()
     np.testing.assert_allclose(Es, g[tag + "_E_surf"].real, rtol=1e-10)
+
+
+def test_hbm_path_with_amplitude_moves_tracks_smem_path(cuda):
+    """fp64: the HBM path (row-moment kernel + one-CTA amplitude kernel) and the shared-memory path (energy fused into the
+    colour passes) see the same Philox streams, so the amplitude trajectory, the lattice and the accumulated observables
+    agree to rounding."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    Z, T = 32, 24
+    P = dict(wavenumber=1.0, radius=1.0, gamma=1.0, kappa=0.2, intrinsic_curvature=0.1, alpha=-1.0, u=1.0, C=1.0, n=2, temperature=.3)
+    par = ops.make_params(cuda, **P)
+    Zt = torch.tensor([Z], dtype=torch.int32, device=cuda)
+    psi = torch.zeros(1, Z, T, dtype=torch.complex128, device=cuda)
+    ops.lattice_init(psi, Zt, .3, seed=21)
+    ws = ops.HbmWorkspace(Z, T, torch.complex128, cuda)
+    ws.pack(psi[0])
+    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
+    c1, c2 = ops.new_chain(1, cuda, amplitude=.1, sigma_site=.2, sigma_amp=.05), ops.new_chain(1, cuda, amplitude=.1, sigma_site=.2, sigma_amp=.05)
+    o1, p1 = ops.new_obs(1, Z, cuda)
+    o2, p2 = ops.new_obs(1, Z, cuda)
+    nsw = 25
+    ops.sweep_smem(psi, Zt, par, c1, 5, 0, nsw, 0, flags, obs=o1, prof=p1)
+    ws.sweep(par, c2[0], 5, 0, nsw, 0, flags, obs=o2[0], prof=p2[0])
+    assert c1[0, _abi.CH_AMP_ACCEPTED].item() >= 2
+    np.testing.assert_allclose(c2.cpu().numpy()[:, :3], c1.cpu().numpy()[:, :3], rtol=1e-10)
+    assert c2[0, _abi.CH_AMP_ACCEPTED].item() == c1[0, _abi.CH_AMP_ACCEPTED].item()
+    assert c2[0, _abi.CH_SITE_ACCEPTED].item() == c1[0, _abi.CH_SITE_ACCEPTED].item()
+    np.testing.assert_allclose(ws.unpack().cpu().numpy(), psi[0].cpu().numpy(), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(o2.cpu().numpy()[0, :9], o1.cpu().numpy()[0, :9], rtol=1e-9)
+    np.testing.assert_allclose(p2.cpu().numpy(), p1.cpu().numpy(), rtol=1e-9, atol=1e-11)
+
+
+def test_step_host_equals_device_resident_run(cuda):
+    """The pipelined host round trip (ReplicaBatch.step_host) gives the same chains as the device-resident run."""
+    import torch
+    from cylinder_b200.replicas import ReplicaBatch
+    P = dict(wavenumber=np.linspace(.5, 1.25, 12), radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=.01)
+    a = ReplicaBatch(P, dims=(50, 50), dtype=torch.complex64, device=cuda, seed=3)
+    b = ReplicaBatch(P, dims=(50, 50), dtype=torch.complex64, device=cuda, seed=3)
+    psi_h, chain_h = b.psi.cpu().pin_memory(), b.chain.cpu().pin_memory()
+    psi_out = torch.empty_like(psi_h).pin_memory()
+    rec = b.record()
+    rec_out = torch.empty(rec.shape, dtype=rec.dtype).pin_memory()
+    a.run(7)
+    b.step_host(psi_h, chain_h, psi_out, rec_out, 7, nchunks=5)
+    assert torch.equal(psi_out, a.psi.cpu())
+    assert torch.equal(rec_out, a.record().cpu())
