@@ -57,6 +57,8 @@ _SIGNATURES = {
     "cyl_hbm_row_moments_f64": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "cyl_fourier_energy_f64": [_vp, _i, _i, _vp, _vp, _i, _vp, _vp],
     "cyl_fourier_surface_energy_f64": [_vp, _vp, _i, _vp, _vp],
+    "cyl_fourier_am_state_doubles": [_i, _i],
+    "cyl_fourier_am_steps_f64": [_vp, _i, _i, _vp, _vp, _vp, _i, _u64, _i64, _u64, _i, _i, _i, _d, _d, _d, _vp],
 }
 _RESTYPES = {"cyl_last_error": C.c_char_p}
 

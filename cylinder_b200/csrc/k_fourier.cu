@@ -1,5 +1,6 @@
 // Fourier-mode field model (config 2): Cylinder2D.calc_field_energy / calc_field_energy_amplitude_change,
-// system_cylinder2D.py:151-198, and Cylinder1D.calc_surface_energy, system_cylinder1D.py:189-194.
+// system_cylinder2D.py:151-198, Cylinder1D.calc_surface_energy, system_cylinder1D.py:189-194, and the adaptive
+// Metropolis engine that run.py:286-294 (method "sequential") drives over them, batched: one warp per chain.
 //
 // The reference builds Toeplitz tensors A (from 8 nz + 1 Fourier integrals of sqrt(g)), B and D with
 // scipy.integrate.quad -- 184 adaptive quadratures per amplitude proposal at (nz, nth) = (2, 1) -- and contracts
@@ -8,16 +9,39 @@
 //   psi_b(z) = sum_j c[b][j] e^{i j k z},   Psi(z, th) = sum_b psi_b(z) e^{i b th}
 //   E(a, c) = int_0^{2pi/k} dz { Gth Gz [ alpha sum_b |psi_b|^2 + u/2 <|Psi|^4>_th ]
 //                               + C [ Gth Gz sum_b |d_z psi_b|^2 + (Gz/Gth) sum_b (b - n A_th)^2 |psi_b|^2 ] }
-// evaluated with a 256-node periodic trapezoid in z and an exact (>= 4 nth + 1 node) trapezoid in theta.  No A/B/D
-// tensors, no save_temporary_matrices bookkeeping: the same function serves amplitude changes and fixed-amplitude
-// coefficient moves.  One warp per chain, lanes over z nodes.
+// evaluated with a 256-node periodic trapezoid in z and an exact (4 nth + 2 node) trapezoid in theta.  The phases
+// e^{i j k z_n} are 256th roots of unity and e^{i b th_m} are (4 nth + 2)th roots: both come from small tables, so the
+// integrand needs no trigonometry.  No A/B/D tensors, no save_temporary_matrices bookkeeping: the same function
+// serves amplitude changes and fixed-amplitude coefficient moves.
 #include "cyl_common.cuh"
+#include "cyl_site.cuh"
 #include "cyl_surface.cuh"
 
 #define FOURIER_MAX_NZ 8
 #define FOURIER_MAX_NTH 4
+#define FOURIER_MAX_COEF 32            // adaptive-engine kernel: 1 + ncoef <= 33 state dimensions, one per lane
+#define FOURIER_NTHQ_MAX (4 * FOURIER_MAX_NTH + 2)
 
-__device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, double a, const double2* __restrict__ c) {
+// roots of unity: wz[n] = e^{2 pi i n / 256}, wt[m] = e^{2 pi i m / nthq}
+struct FourierTables { double2 wz[CYL_QUAD_NODES]; double2 wt[FOURIER_NTHQ_MAX]; };
+
+__device__ __forceinline__ void fourier_tables_init(FourierTables* t, int nth) {
+  const int nthq = 4 * nth + 2;
+  for (int n = threadIdx.x; n < CYL_QUAD_NODES; n += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * n / CYL_QUAD_NODES, &s, &c);
+    t->wz[n] = make_double2(c, s);
+  }
+  for (int m = threadIdx.x; m < nthq; m += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * m / nthq, &s, &c);
+    t->wt[m] = make_double2(c, s);
+  }
+}
+
+// Warp-cooperative energy; c = coefficients [2 nth + 1][2 nz + 1] (any address space), all lanes return the value.
+__device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, double a, const double2* __restrict__ c,
+                                      const FourierTables* __restrict__ tab) {
   const int lane = threadIdx.x & 31;
   const int lz = 2 * nz + 1, lth = 2 * nth + 1;
   const int nthq = 4 * nth + 2;                       // theta nodes: exact for |Psi|^4 (degree 4 nth in e^{i th})
@@ -26,21 +50,17 @@ __device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, doubl
   const double Lz = 2.0 * 3.14159265358979323846 / k;
   double acc = 0.0;
   for (int node = lane; node < CYL_QUAD_NODES; node += 32) {
-    const double z = Lz * node / CYL_QUAD_NODES;
-    double s1, c1;
-    sincospi(2.0 * node / CYL_QUAD_NODES, &s1, &c1);            // kz = 2 pi node / N exactly
-    const Geo g = geo_from_sc(k, ra, a, s1, c1);
-    (void)z;
+    const double2 w1 = tab->wz[node];                               // (cos kz, sin kz), kz = 2 pi node / N exactly
+    const Geo g = geo_from_sc(k, ra, a, w1.y, w1.x);
     double2 psi[2 * FOURIER_MAX_NTH + 1];
     double sum_p2 = 0.0, sum_dz2 = 0.0, sum_th = 0.0;
     for (int b = 0; b < lth; ++b) {
       double pr = 0.0, pi_ = 0.0, dr = 0.0, di = 0.0;
       for (int j = 0; j < lz; ++j) {
         const int jj = j - nz;
-        double sj, cj;
-        sincospi(2.0 * ((jj * node) % CYL_QUAD_NODES) / CYL_QUAD_NODES, &sj, &cj);    // e^{i jj k z}
+        const double2 e = tab->wz[(jj * node) & (CYL_QUAD_NODES - 1)];             // e^{i jj k z}
         const double2 cc = c[b * lz + j];
-        const double tr = cc.x * cj - cc.y * sj, ti = cc.x * sj + cc.y * cj;
+        const double tr = cc.x * e.x - cc.y * e.y, ti = cc.x * e.y + cc.y * e.x;
         pr += tr; pi_ += ti;
         dr += -(jj * k) * ti; di += (jj * k) * tr;              // d/dz = i jj k
       }
@@ -55,10 +75,11 @@ __device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, doubl
     for (int m = 0; m < nthq; ++m) {
       double Pr = 0.0, Pi = 0.0;
       for (int b = 0; b < lth; ++b) {
-        double sb, cb;
-        sincospi(2.0 * (((b - nth) * m) % nthq) / nthq, &sb, &cb);
-        Pr += psi[b].x * cb - psi[b].y * sb;
-        Pi += psi[b].x * sb + psi[b].y * cb;
+        int idx = ((b - nth) * m) % nthq;
+        if (idx < 0) idx += nthq;
+        const double2 e = tab->wt[idx];
+        Pr += psi[b].x * e.x - psi[b].y * e.y;
+        Pi += psi[b].x * e.y + psi[b].y * e.x;
       }
       const double P2 = Pr * Pr + Pi * Pi;
       quart += P2 * P2;
@@ -70,13 +91,25 @@ __device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, doubl
   return warp_sum(acc) * (Lz / CYL_QUAD_NODES);
 }
 
+// Cylinder1D.calc_surface_energy: effective_gamma * int Gth Gz dz + kappa * calc_bending_energy   (system_cylinder1D.py:189-194;
+// no 2 pi prefactor, kappa not halved -- a different normalisation from Cylinder.calc_surface_energy)
+__device__ __forceinline__ double fourier_surface_energy_warp(const CylParams& p, double a) {
+  const double gamma_eff = p.gamma + p.kappa / 2.0 * p.intrinsic_curvature * p.intrinsic_curvature;
+  const double area = surface_area_integral(p.wavenumber, p.radius, a);            // = int_0^{2pi/k} Gth Gz dz
+  const double bend = (p.kappa != 0.0) ? bending_energy_warp(p.wavenumber, p.radius, p.intrinsic_curvature, a) : 0.0;
+  return gamma_eff * area + p.kappa * bend;
+}
+
 __global__ void fourier_energy_kernel(const CylParams* __restrict__ params, int nz, int nth, const double* __restrict__ amp,
                                       const double2* __restrict__ coeffs, int B, double* __restrict__ E_out) {
+  __shared__ FourierTables tab;
+  fourier_tables_init(&tab, nth);
+  __syncthreads();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const CylParams p = params[b];
   const int ncoef = (2 * nz + 1) * (2 * nth + 1);
-  const double e = fourier_energy_warp(p, nz, nth, amp[b], coeffs + (size_t)b * ncoef);
+  const double e = fourier_energy_warp(p, nz, nth, amp[b], coeffs + (size_t)b * ncoef, &tab);
   if ((threadIdx.x & 31) == 0) E_out[b] = e;
 }
 
@@ -92,8 +125,6 @@ extern "C" int cyl_fourier_energy_f64(const CylParams* params, int nz, int nth, 
   return CYL_OK;
 }
 
-// Cylinder1D.calc_surface_energy: effective_gamma * int Gth Gz dz + kappa * calc_bending_energy   (system_cylinder1D.py:189-194;
-// no 2 pi prefactor, kappa not halved -- a different normalisation from Cylinder.calc_surface_energy)
 __global__ void fourier_surface_energy_kernel(const CylParams* __restrict__ params, const double* __restrict__ amp, int B,
                                               double* __restrict__ E_out) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -101,7 +132,7 @@ __global__ void fourier_surface_energy_kernel(const CylParams* __restrict__ para
   const CylParams p = params[b];
   const double a = amp[b];
   const double gamma_eff = p.gamma + p.kappa / 2.0 * p.intrinsic_curvature * p.intrinsic_curvature;
-  const double area = surface_area_integral(p.wavenumber, p.radius, a);            // = int_0^{2pi/k} Gth Gz dz
+  const double area = surface_area_integral(p.wavenumber, p.radius, a);
   const double bend = bending_energy_warp(p.wavenumber, p.radius, p.intrinsic_curvature, a);
   if ((threadIdx.x & 31) == 0) E_out[b] = gamma_eff * area + p.kappa * bend;
 }
@@ -110,6 +141,189 @@ extern "C" int cyl_fourier_surface_energy_f64(const CylParams* params, const dou
   CYL_CHECK_ARG(params && amp && E_out && B > 0, "cyl_fourier_surface_energy_f64: bad arguments");
   const int warps = 4;
   fourier_surface_energy_kernel<<<(B + warps - 1) / warps, warps * 32, 0, as_stream(stream)>>>(params, amp, B, E_out);
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Batched adaptive Metropolis for the Fourier model: run.py:286-294 (method "sequential") with the engine
+// arithmetic of SURVEY.md Appendix B, one warp per chain, state dimension d = 1 + ncoef <= 33 (one per lane).
+//   per step:  measure_every x [ real-group move ; fieldsteps x complex-group move ] ; measure()
+//   real group    a' = a + sigma_r sqrt(Sigma[0][0]) N(0,1); rejected outright when |a'| >= amp_bound; energy
+//                 E_field(a', c) + E_surf(a'); Robbins-Monro on sigma_r (m = 1)
+//   complex group |c_i|' = |c_i| + sigma_c (L z)_i with L L^T = Sigma_c (Cholesky; the reference draws the same law with
+//                 numpy's SVD-based multivariate_normal), arg c_i' = arg c_i + 0.1 N(0,1) ("magnitude-phase");
+//                 energy E_field(a, c'); Robbins-Monro on sigma_c (m = ncoef)
+//   measure       running mean of x = (|a|, |c_i|), and once k > 50 the recursive covariance
+//                 Sigma <- Sigma (k-2)/(k-1) + mu_old mu_old^T - k/(k-1) mu mu^T + x x^T/(k-1) + sigma_r^2/k I
+// Draws: Philox4x32-10 at counter (lane, chain, move index, tag).  Engine state per chain (doubles):
+//   [0] sigma_r [1] sigma_c [2] real moves [3] complex moves [4] measurements [5] real accepted [6] complex accepted
+//   [7] E_field [8] E_surf [9] sum a^2 [10] sum E [11..15] reserved | mean[d] | Sigma[d][d]
+// ----------------------------------------------------------------------------------------------------
+#define FAM_HDR 16
+#define CYL_TAG_FREAL 3u
+#define CYL_TAG_FCPLX 4u
+
+__global__ void __launch_bounds__(128)
+fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double* __restrict__ amp, double2* __restrict__ coeffs,
+                  double* __restrict__ est, int B, uint64_t seed, int64_t chain0, uint64_t step0, int n_steps, int measure_every,
+                  int fieldsteps, double target, double ratio_real, double ratio_cplx) {
+  extern __shared__ __align__(16) unsigned char fam_smem[];
+  FourierTables* tab = reinterpret_cast<FourierTables*>(fam_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int ncoef = (2 * nz + 1) * (2 * nth + 1), d = ncoef + 1;
+  // per-warp scratch: c[ncoef], cp[ncoef] (double2), L[ncoef][ncoef]
+  double2* c_all = reinterpret_cast<double2*>(fam_smem + sizeof(FourierTables));
+  double2* c = c_all + (size_t)warp * 2 * ncoef;
+  double2* cp = c + ncoef;
+  double* L = reinterpret_cast<double*>(c_all + (size_t)nwarp * 2 * ncoef) + (size_t)warp * ncoef * ncoef;
+  fourier_tables_init(tab, nth);
+  __syncthreads();
+  const int b = blockIdx.x * nwarp + warp;
+  if (b >= B) return;
+  const CylParams p = params[b];
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t chain = (uint32_t)(chain0 + b);
+  double* st = est + (size_t)b * (FAM_HDR + d + (size_t)d * d);
+  double* mean = st + FAM_HDR;
+  double* cov = mean + d;
+  double a = amp[b];
+  for (int i = lane; i < ncoef; i += 32) c[i] = coeffs[(size_t)b * ncoef + i];
+  __syncwarp();
+  double sig_r = st[0], sig_c = st[1], n_real = st[2], n_cplx = st[3], n_meas = st[4], acc_r = st[5], acc_c = st[6];
+  double sum_a2 = st[9], sum_e = st[10];
+  double e_field = fourier_energy_warp(p, nz, nth, a, c, tab);
+  double e_surf = fourier_surface_energy_warp(p, a);
+
+  auto cholesky = [&]() {              // L L^T = Sigma_c = cov[1:,1:]; lane i owns row i
+    for (int i = lane; i < ncoef; i += 32)
+      for (int j = 0; j < ncoef; ++j) L[i * ncoef + j] = (j <= i) ? cov[(i + 1) * d + (j + 1)] : 0.0;
+    __syncwarp();
+    for (int kx = 0; kx < ncoef; ++kx) {
+      const double dk = sqrt(fmax(L[kx * ncoef + kx], 1e-300));
+      __syncwarp();
+      if (lane == kx) L[kx * ncoef + kx] = dk;
+      if (lane > kx && lane < ncoef) L[lane * ncoef + kx] /= dk;
+      __syncwarp();
+      if (lane > kx && lane < ncoef) {
+        const double lik = L[lane * ncoef + kx];
+        for (int j = kx + 1; j <= lane; ++j) L[lane * ncoef + j] -= lik * L[j * ncoef + kx];
+      }
+      __syncwarp();
+    }
+  };
+  cholesky();
+
+  uint64_t move = step0 * (uint64_t)measure_every * (uint64_t)(1 + fieldsteps);      // global move index: counter word 2
+  for (int s = 0; s < n_steps; ++s) {
+    for (int me = 0; me < measure_every; ++me) {
+      // ---- real group ----
+      {
+        const uint4 x = philox4x32<10>(0u, chain, (uint32_t)move, philox_c3(CYL_TAG_FREAL, move), k0, k1);
+        double z, u;
+        amp_draw(x, z, u);
+        const double a_new = a + sig_r * sqrt(cov[0]) * z;
+        bool accept = false;
+        if (fabs(a_new) < p.amp_bound) {
+          const double ef = fourier_energy_warp(p, nz, nth, a_new, c, tab);
+          const double es = fourier_surface_energy_warp(p, a_new);
+          const double diff = (ef + es) - (e_field + e_surf);
+          accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
+          if (accept) { a = a_new; e_field = ef; e_surf = es; }
+        }
+        n_real += 1;
+        acc_r += accept;
+        const double f = fmax(n_real, 200.0), cc = sig_r * ratio_real;
+        sig_r = accept ? sig_r + cc * (1 - target) / f : sig_r - cc * target / f;
+        ++move;
+      }
+      // ---- complex group ----
+      for (int fs = 0; fs < fieldsteps; ++fs) {
+        const uint4 x = philox4x32<10>((uint32_t)lane, chain, (uint32_t)move, philox_c3(CYL_TAG_FCPLX, move), k0, k1);
+        double z, u, zph, dummy;
+        amp_draw(x, z, u);                                   // z: magnitude component of this lane; u used from lane 0
+        amp_draw(philox4x32<10>((uint32_t)lane + 64u, chain, (uint32_t)move, philox_c3(CYL_TAG_FCPLX, move), k0, k1), zph, dummy);  // phase jitter
+        u = __shfl_sync(0xffffffffu, u, 0);
+        double dm = 0.0;
+        for (int j = 0; j < ncoef; ++j) {
+          const double zj = __shfl_sync(0xffffffffu, z, j);
+          if (lane < ncoef && j <= lane) dm += L[lane * ncoef + j] * zj;
+        }
+        if (lane < ncoef) {
+          const double2 ci = c[lane];
+          const double mag = hypot(ci.x, ci.y) + sig_c * dm, ph = atan2(ci.y, ci.x) + 0.1 * zph;
+          double sn, cs;
+          sincos(ph, &sn, &cs);
+          cp[lane] = make_double2(mag * cs, mag * sn);
+        }
+        __syncwarp();
+        const double ef = fourier_energy_warp(p, nz, nth, a, cp, tab);
+        const double diff = ef - e_field;
+        const bool accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
+        if (accept) {
+          if (lane < ncoef) c[lane] = cp[lane];
+          e_field = ef;
+        }
+        __syncwarp();
+        n_cplx += 1;
+        acc_c += accept;
+        const double f = fmax(n_cplx / ncoef, 200.0), cc = sig_c * ratio_cplx;
+        sig_c = accept ? sig_c + cc * (1 - target) / f : sig_c - cc * target / f;
+        ++move;
+      }
+    }
+    // ---- measure ----
+    n_meas += 1;
+    const double kk = n_meas;
+    const double xi = (lane == 0) ? fabs(a) : (lane < d ? hypot(c[lane - 1].x, c[lane - 1].y) : 0.0);
+    const double mu_old = (lane < d) ? mean[lane] : 0.0;
+    const double mu = mu_old * (kk - 1) / kk + xi / kk;
+    if (lane < d) mean[lane] = mu;
+    if (kk > 50) {
+      for (int j = 0; j < d; ++j) {
+        const double xj = __shfl_sync(0xffffffffu, xi, j), mo = __shfl_sync(0xffffffffu, mu_old, j), mn = __shfl_sync(0xffffffffu, mu, j);
+        if (lane < d)
+          cov[lane * d + j] = cov[lane * d + j] * (kk - 2) / (kk - 1) +
+                              (mu_old * mo - kk / (kk - 1) * mu * mn + xi * xj / (kk - 1) + (lane == j ? sig_r * sig_r / kk : 0.0));
+      }
+      __syncwarp();
+      cholesky();
+    }
+    sum_a2 += a * a;
+    sum_e += e_field + e_surf;
+  }
+  // ---- write back ----
+  __syncwarp();
+  for (int i = lane; i < ncoef; i += 32) coeffs[(size_t)b * ncoef + i] = c[i];
+  if (lane == 0) {
+    amp[b] = a;
+    st[0] = sig_r; st[1] = sig_c; st[2] = n_real; st[3] = n_cplx; st[4] = n_meas; st[5] = acc_r; st[6] = acc_c;
+    st[7] = e_field; st[8] = e_surf; st[9] = sum_a2; st[10] = sum_e;
+  }
+}
+
+extern "C" int cyl_fourier_am_state_doubles(int nz, int nth) {
+  const int d = (2 * nz + 1) * (2 * nth + 1) + 1;
+  return FAM_HDR + d + d * d;
+}
+
+extern "C" int cyl_fourier_am_steps_f64(const CylParams* params, int nz, int nth, double* amp, double* coeffs, double* engine_state,
+                                        int B, uint64_t seed, int64_t chain0, uint64_t step0, int n_steps, int measure_every,
+                                        int fieldsteps, double target_acceptance, double ratio_real, double ratio_complex,
+                                        void* stream) {
+  CYL_CHECK_ARG(params && amp && coeffs && engine_state && B > 0 && n_steps >= 0 && measure_every > 0 && fieldsteps >= 0,
+                "cyl_fourier_am_steps_f64: bad arguments");
+  CYL_CHECK_ARG(nz >= 0 && nz <= FOURIER_MAX_NZ && nth >= 0 && nth <= FOURIER_MAX_NTH, "cyl_fourier_am_steps_f64: bad num_field_coeffs");
+  const int ncoef = (2 * nz + 1) * (2 * nth + 1);
+  CYL_CHECK_ARG(ncoef <= FOURIER_MAX_COEF - 1, "cyl_fourier_am_steps_f64: %d coefficients > %d (one state component per lane)", ncoef,
+                FOURIER_MAX_COEF - 1);
+  if (n_steps == 0) return CYL_OK;
+  const int warps = 4;
+  const size_t smem = sizeof(FourierTables) + (size_t)warps * (2 * ncoef * sizeof(double2) + (size_t)ncoef * ncoef * sizeof(double));
+  CYL_CUDA(cudaFuncSetAttribute(fourier_am_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fourier_am_kernel<<<(B + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(
+      params, nz, nth, amp, (double2*)coeffs, engine_state, B, seed, chain0, step0, n_steps, measure_every, fieldsteps,
+      target_acceptance, ratio_real, ratio_complex);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

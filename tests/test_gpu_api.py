@@ -147,3 +147,34 @@ def test_single_run_lattice_and_fourier(cuda, tmp_path, monkeypatch):
                                             wavenumber=.5, amplitude=0, outdir=str(out), title="four")
     assert len(names) == 1 + 9 and names[1] == "coeff_-1_-1" and cov.shape == (9, 9)
     assert (out / "four.csv").exists() and (tmp_path / "last_cov.pickle").exists()
+
+
+def test_batched_fourier_chains_match_oracle(cuda):
+    """cyl_fourier_am_steps_f64 (one warp per chain: amplitude + coefficient moves, Robbins-Monro widths, recursive mean and
+    covariance with re-factorisation after measurement 50) vs the numpy restatement on the same Philox draws."""
+    import torch
+    from cylinder_b200.fourier_chains import FourierChains
+    from oracle import fourier_am_oracle as fa
+    B, nfc = 3, (1, 1)
+    P = dict(wavenumber=[.5, .8, 1.0], radius=1.0, gamma=1.0, kappa=[0.0, .3, 0.0], intrinsic_curvature=0.0, alpha=-1.0, u=1.0, C=1.0,
+             n=[6.0, 2.0, 1.0], temperature=.1, amp_bound=.99)
+    rng = np.random.RandomState(3)
+    c0 = rng.normal(0, .15, (B, 9)) + 1j * rng.normal(0, .15, (B, 9))
+    fc = FourierChains(P, num_field_coeffs=nfc, amplitude=.05, field_coeffs=c0, seed=99, chain0=10)
+    fc.run(40, measure_every=2, fieldsteps_per_ampstep=2)
+    fc.run(25, measure_every=2, fieldsteps_per_ampstep=2)          # resumes; crosses measurement 50 (covariance adaptation on)
+    for b in range(B):
+        Pb = {k: (v[b] if isinstance(v, list) else v) for k, v in P.items()}
+        ch = fa.Chain(Pb, 1, 1, .05, c0[b], bound=.99)
+        ch.run(40, 2, 2, seed=99, chain=10 + b)
+        ch.run(25, 2, 2, seed=99, chain=10 + b, step0=40)
+        s = fc.state[b].cpu().numpy()
+        assert (s[5], s[6]) == (ch.acc_r, ch.acc_c) and ch.acc_c > 5
+        assert fc.amp[b].item() == pytest.approx(ch.a, rel=1e-9, abs=1e-12)
+        np.testing.assert_allclose(fc.coeffs[b].cpu().numpy(), ch.c, rtol=1e-8, atol=1e-11)
+        assert s[0] == pytest.approx(ch.sig_r, rel=1e-10) and s[1] == pytest.approx(ch.sig_c, rel=1e-10)
+        assert s[7] == pytest.approx(ch.e_field, rel=1e-9) and s[8] == pytest.approx(ch.e_surf, rel=1e-9)
+        np.testing.assert_allclose(fc.mean[b].cpu().numpy(), ch.mean, rtol=1e-9)
+        np.testing.assert_allclose(fc.covariance[b].cpu().numpy(), ch.cov, rtol=1e-7, atol=1e-12)
+    summ = fc.summary()
+    assert torch.all(summ["complex_acceptance"] > 0) and torch.all(fc.amp.abs() < .99)
