@@ -1,0 +1,131 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot run 4096 x 4096 or
+4096 replicas in seconds): round trips, determinism / exact resume, periodic-halo consistency, monotone energy at
+T = 0, sharding independence, energy bookkeeping."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 4096
+
+
+@pytest.fixture(scope="module")
+def big(cuda):
+    import torch
+    from cylinder_b200 import ops
+    par = ops.make_params(cuda, wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=.01)
+    Zt = torch.tensor([N], dtype=torch.int32, device=cuda)
+    psi = torch.zeros(1, N, N, dtype=torch.complex64, device=cuda)
+    ops.lattice_init(psi, Zt, .1, 77, 0)
+    return par, Zt, psi
+
+
+def _energy(ops, ws, par, a, variant=0):
+    import torch
+    S = ws.row_moments(par)[None].contiguous()
+    Zt = torch.tensor([ws.Z], dtype=torch.int32, device=S.device)
+    return ops.field_energy(S, Zt, ws.T, par, [a], None, variant).item()
+
+
+def test_c4_pack_unpack_round_trip_and_halo(cuda, big):
+    """4096 x 4096: pack -> unpack is the identity; after sweeps every periodic halo copy equals its interior source."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    par, Zt, psi = big
+    ws = ops.HbmWorkspace(N, N, torch.complex64, cuda)
+    ws.pack(psi[0])
+    assert torch.equal(ws.unpack(), psi[0])
+    chain = ops.new_chain(1, cuda, amplitude=.3)[0]
+    ws.sweep(par, chain, 5, 0, 3, 0, _abi.SWEEP_ADAPT_SIGMA)
+    lay = ws.layout
+    hr, hc, pitch = lay["halo_rows"], lay["halo_cols"], lay["pitch"]
+    rows = N + 2 * hr
+    buf = ws.work[ws.cur.value * lay["buffer_elems"]:(ws.cur.value + 1) * lay["buffer_elems"]].reshape(2, rows, pitch // 2)
+    padded = torch.empty(rows, pitch, dtype=torch.complex64, device=cuda)
+    padded[:, 0::2], padded[:, 1::2] = buf[0], buf[1]                     # column-parity planes -> padded lattice
+    inner = padded[hr:hr + N, hc:hc + N]
+    assert torch.equal(inner, ws.unpack())
+    assert torch.equal(padded[:hr, hc:hc + N], inner[-hr:]) and torch.equal(padded[hr + N:, hc:hc + N], inner[:hr])
+    assert torch.equal(padded[hr:hr + N, :hc], inner[:, -hc:]) and torch.equal(padded[hr:hr + N, hc + N:hc + N + hc], inner[:, :hc])
+    assert torch.equal(padded[:hr, :hc], inner[-hr:, -hc:]) and torch.equal(padded[hr + N:, hc + N:hc + N + hc], inner[:hr, :hc])
+
+
+def test_c4_deterministic_and_exactly_resumable(cuda, big):
+    """Counter-based RNG: the same (seed, sweep range) gives bit-identical lattices; 2 + 3 sweeps == 5 sweeps."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    par, Zt, psi = big
+    outs = []
+    for split in ((5,), (2, 3), (5,)):
+        ws = ops.HbmWorkspace(N, N, torch.complex64, cuda)
+        ws.pack(psi[0])
+        chain = ops.new_chain(1, cuda, amplitude=.3)[0]
+        s0 = 0
+        for n in split:
+            ws.sweep(par, chain, 9, s0, n, 0, _abi.SWEEP_ADAPT_SIGMA)
+            s0 += n
+        outs.append((ws.unpack().clone(), chain.clone()))
+        del ws
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert 0.3 < (outs[0][1][_abi.CH_SITE_ACCEPTED] / outs[0][1][_abi.CH_SITE_PROPOSED]).item() < 0.9
+    assert not torch.equal(outs[0][0], psi[0])
+
+
+def test_c4_energy_never_increases_at_zero_temperature(cuda, big):
+    """T = 0 accepts only dE <= 0 (accept rule B.2).  With a = 0 the local dE equals the change of the global energy
+    (SURVEY F5), and same-colour moves touch disjoint bonds, so the total field energy is non-increasing sweep by sweep."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    _, Zt, psi = big
+    par0 = ops.make_params(cuda, wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=0.0)
+    ws = ops.HbmWorkspace(N, N, torch.complex64, cuda)
+    ws.pack(psi[0])
+    chain = ops.new_chain(1, cuda, amplitude=0.0, sigma_site=.02)[0]
+    e = [_energy(ops, ws, par0, 0.0)]
+    for s in range(4):
+        ws.sweep(par0, chain, 3, s, 1, 0, 0)
+        e.append(_energy(ops, ws, par0, 0.0))
+    assert all(e[i + 1] <= e[i] + 1e-7 * abs(e[i]) for i in range(4)), e
+    assert e[-1] < e[0]
+
+
+def test_c3_batch_is_independent_of_batching(cuda):
+    """4096 replicas (C3's grid): replica r gives the same chain whether it runs inside the full batch or inside a
+    shard that starts at r0 (replica0 = r0) -- the property multi-GPU sharding relies on; identical parameters with
+    different replica indices give different chains."""
+    import sys, os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from cylinder_b200.replicas import ReplicaBatch
+    full = ReplicaBatch(bench.grid_params(4096, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=0x5EED)
+    full.run(6)
+    lo, hi = 1000, 1512
+    shard = ReplicaBatch(bench.grid_params(hi - lo, lo), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=0x5EED, replica0=lo)
+    shard.run(6)
+    zs = shard.Zmax
+    assert torch.equal(shard.psi, full.psi[lo:hi, :zs]) and torch.equal(shard.chain, full.chain[lo:hi])
+    assert torch.equal(shard.obs, full.obs[lo:hi])
+    twin = ReplicaBatch(bench.grid_params(8192, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=0x5EED)
+    twin.run(2)
+    assert not torch.equal(twin.psi[:4096], twin.psi[4096:])            # same grid point, different replica index
+    o = full.observables()
+    assert torch.isfinite(o["field_energy"]).all() and (full.chain[:, 0].abs() < .8).all()
+    assert int(full.Z_host.min()) == 40 and int(full.Z_host.max()) == 100 and (full.Z_host % 2 == 1).any()
+
+
+def test_c3_energy_bookkeeping(cuda):
+    """The field energy recorded by the fused in-kernel accumulation equals an independent evaluation (row moments +
+    weights) of the lattice the kernel leaves behind, for every replica of a C3-like batch (fp32 storage, <= 2e-5)."""
+    import sys, os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from cylinder_b200 import ops, _abi
+    from cylinder_b200.replicas import ReplicaBatch
+    b = ReplicaBatch(bench.grid_params(512, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=4, amplitude=.2)
+    b.run(20, amp_moves=False, measure=True)            # amplitude fixed: the last measurement refers to the final lattice
+    S = ops.row_moments(b.psi, b.Z, b.params)
+    E = ops.field_energy(S, b.Z, b.T, b.params, b.chain[:, _abi.CH_AMPLITUDE].contiguous(), None, 0)
+    np.testing.assert_allclose(b.chain[:, _abi.CH_E_FIELD].cpu().numpy(), E.cpu().numpy(), rtol=2e-5, atol=1e-4)
