@@ -55,15 +55,32 @@ static HbmGeom hbm_geom(int Z, int T) {
   return g;
 }
 
-// scratch: [0,64) counters | RowCoef[Z] | moments [Z][8]
-struct HbmCounters { unsigned long long accepted; unsigned long long pad[7]; };
+// scratch: header (HbmAmp) | RowCoef[2][Z] | RowW[Z] | per-tile partial sums [max tiles][8] | per-block constants of the
+// weights [ceil(Z/128)][2] | per-tile-column row sums of the profiles [ceil(T/128)][3][Z]
+struct HbmAmp {                      // header: the amplitude proposal of the current sweep + kernel bookkeeping (device)
+  double a, a_new, u_acc, e_surf_new;
+  int try_move;
+  int coef_sel;                      // which of the two RowCoef tables belongs to the current amplitude
+  unsigned int done;                 // tiles of the running sweep that have delivered their partial sums
+  int pad;
+};
+#define HBM_NPART 8                  // doubles per tile: accepts, E(a,a), E(a',a)-E(a,a), sum |psi|^2, sum |psi|, 3 spare
+#define HBM_MIN_TH 24
+#define HBM_PREP_NT 128
 template <typename R>
 struct HbmScratch {
-  size_t off_coef, off_mom, total;
-  __host__ __device__ explicit HbmScratch(int Z) {
-    off_coef = 64;
-    off_mom = (off_coef + (size_t)Z * sizeof(RowCoef<R>) + 63) & ~(size_t)63;
-    total = off_mom + (size_t)Z * CYL_NMOM * sizeof(double);
+  size_t off_coef, off_roww, off_part, off_cst, off_rowp, total;
+  int ncst, ntx;
+  __host__ __device__ HbmScratch(int Z, int T) {
+    ncst = (Z + HBM_PREP_NT - 1) / HBM_PREP_NT;
+    ntx = (T + HBM_TW - 1) / HBM_TW;
+    off_coef = 128;
+    off_roww = (off_coef + 2 * (size_t)Z * sizeof(RowCoef<R>) + 63) & ~(size_t)63;
+    off_part = (off_roww + (size_t)Z * sizeof(RowW<R>) + 63) & ~(size_t)63;
+    const size_t tiles = (size_t)ntx * ((Z + HBM_MIN_TH - 1) / HBM_MIN_TH);
+    off_cst = off_part + tiles * HBM_NPART * sizeof(double);
+    off_rowp = off_cst + (size_t)ncst * 2 * sizeof(double);
+    total = off_rowp + (size_t)ntx * 3 * Z * sizeof(R);
   }
 };
 
@@ -75,7 +92,7 @@ extern "C" int cyl_hbm_layout(int Z, int T, int is_f64, int* halo_rows, int* hal
   if (halo_cols) *halo_cols = g.hc;
   if (pitch_elems) *pitch_elems = g.pitch;
   if (buffer_elems) *buffer_elems = g.buffer_elems;
-  if (scratch_bytes) *scratch_bytes = (int64_t)(is_f64 ? HbmScratch<double>(Z).total : HbmScratch<float>(Z).total);
+  if (scratch_bytes) *scratch_bytes = (int64_t)(is_f64 ? HbmScratch<double>(Z, T).total : HbmScratch<float>(Z, T).total);
   return CYL_OK;
 }
 
@@ -147,8 +164,9 @@ extern "C" int cyl_hbm_unpack_f64(const void* work, int cur, int Z, int T, void*
 // ----------------------------------------------------------------------------------------------------
 template <typename R>
 __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const double* __restrict__ chain, int Z, int T, int variant,
-                                RowCoef<R>* __restrict__ coef) {
+                                RowCoef<R>* __restrict__ coef, HbmAmp* __restrict__ hdr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { hdr->coef_sel = 0; hdr->done = 0u; hdr->try_move = 0; }       // scratch arrives uninitialised
   if (i >= Z) return;
   const CylParams p = *params;
   const double a = chain[CYL_CH_AMPLITUDE];
@@ -173,6 +191,11 @@ __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const doub
 __device__ __forceinline__ double ld_early_f64(const double* p) {
   double v;
   asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_early_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -213,18 +236,43 @@ struct HbmSmem {
   static constexpr int SH = TH + 2 * NCOL, SW = TW + 2 * HS, SWH = SW / 2;
   static constexpr size_t plane_bytes = ((size_t)SH * SWH * sizeof(C) + 127) & ~(size_t)127;
   static constexpr size_t off_coef = 2 * plane_bytes;
-  static constexpr size_t off_bar = off_coef + (size_t)SH * sizeof(RowCoef<R>);
+  static constexpr size_t off_roww = off_coef + (size_t)SH * sizeof(RowCoef<R>);
+  static constexpr size_t off_red = off_roww + (size_t)SH * sizeof(RowW<R>);
+  static constexpr size_t off_bar = off_red + ((HBM_NT / 32) * 8 + 8) * sizeof(double);
   static constexpr size_t total = off_bar + 64;
 };
 
 struct HbmMaps { CUtensorMap m[2][2]; int esz; };   // [buffer][plane]; esz = TMA elements per complex value
 
-template <typename R, int NCOL, int TH_>
-__global__ void __launch_bounds__(HBM_NT)
+// everything a sweep launch needs besides the tile maps (device pointers into the caller's chain / scratch / outputs)
+template <typename R>
+struct HbmArgs {
+  const RowCoef<R>* coef2;           // [2][Z], selected by hdr->coef_sel
+  const RowW<R>* roww;
+  const CylParams* params;
+  double* chain;
+  HbmAmp* hdr;
+  double* partials;                  // [tiles][HBM_NPART]
+  const double* cstpart;             // [ncst][2]
+  R* rowpart;                        // [ntx][3][Z] or null
+  double* obs;
+  uint32_t flags;
+  int ncst;
+};
+
+template <typename R>
+__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* tot);
+
+// EXTRAS: the field energy for the current amplitude and for the proposed one (weights staged per tile row) is
+// accumulated while the sites are updated -- own terms when a site is finalised, a bond by its later-finalised endpoint --
+// and the theta-sums of the profiles are taken from the finished tile, so a sweep with measurement / amplitude move needs
+// no second pass over the lattice.  The tile that finishes last adds up all tiles' partial sums (in tile order, so the
+// result does not depend on scheduling) and takes the per-sweep decisions: Robbins-Monro, observables, amplitude move.
+template <typename R, int NCOL, int TH_, bool EXTRAS>
+__global__ void __launch_bounds__(HBM_NT, sizeof(R) == 4 ? 5 : 2)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
-                 int cur, HbmGeom g, const RowCoef<R>* __restrict__ coef_g,
-                 const double* __restrict__ chain, HbmCounters* __restrict__ counters, const __grid_constant__ SiteKeys keys,
-                 uint64_t sweep) {
+                 int cur, const __grid_constant__ HbmGeom g, const __grid_constant__ HbmArgs<R> A,
+                 const __grid_constant__ SiteKeys keys, uint64_t sweep) {
   using C = typename Real<R>::complex_t;
   using L = HbmSmem<R, NCOL, TH_>;
   constexpr int TH = L::TH, TW = L::TW, SH = L::SH, SW = L::SW, SWH = L::SWH, HS = L::HS;
@@ -232,15 +280,13 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   C* pl0 = reinterpret_cast<C*>(smem_raw);
   C* pl1 = reinterpret_cast<C*>(smem_raw + L::plane_bytes);
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + L::off_coef);
+  RowW<R>* roww = reinterpret_cast<RowW<R>*>(smem_raw + L::off_roww);
+  double* red = reinterpret_cast<double*>(smem_raw + L::off_red);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);
+  const double* chain = A.chain;
+  const int measure = (A.flags & CYL_SWEEP_MEASURE) ? 1 : 0;
 
   const int tid = threadIdx.x;
-#ifdef HBM_PHASE_TIMING
-  long long t_ph = clock64();
-#define HBM_MARK(k) do { if (tid == 0) { const long long t__ = clock64(); atomicAdd(&counters->pad[k], (unsigned long long)(t__ - t_ph)); t_ph = t__; } } while (0)
-#else
-#define HBM_MARK(k) do { } while (0)
-#endif
   const int ti0 = blockIdx.y * TH, tj0 = blockIdx.x * TW;          // interior origin (lattice coords)
   // smem (r, q) <-> padded (ti0 + r, Q0 + q);  padded row of r = 0 is ti0 - hr + hr
   const int Q0 = tj0 + g.hc - HS;
@@ -248,7 +294,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
 
   // Prologue.  Global-memory latency under the bulk traffic of this kernel is several microseconds, so everything that
   // comes from global memory is requested up front and in parallel: the tile (TMA, issued by thread 0 as soon as it has
-  // initialised the mbarrier), the row coefficients and the proposal width.
+  // initialised the mbarrier), the row coefficients / weights and the proposal width.
   const R sigma = (R)ld_early_f64(chain + CYL_CH_SIGMA_SITE);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -259,14 +305,21 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     tma_load_2d(pl0, &maps.m[cur][0], x0 * maps.esz, ti0, bar);    // esz: TMA elements per complex value
     tma_load_2d(pl1, &maps.m[cur][1], x1 * maps.esz, ti0, bar);
   }
-  for (int r = tid; r < SH; r += HBM_NT) coef[r] = coef_g[modi(ti0 - NCOL + r, g.Z)];
+  {
+    const RowCoef<R>* coef_g = A.coef2 + (EXTRAS ? (size_t)ld_early_i32(&A.hdr->coef_sel) * g.Z : (size_t)0);
+    for (int r = tid; r < SH; r += HBM_NT) {
+      const int gr = modi(ti0 - NCOL + r, g.Z);
+      coef[r] = coef_g[gr];
+      if (EXTRAS) roww[r] = A.roww[gr];
+    }
+  }
   const uint32_t c1 = (uint32_t)sweep + keys.off;
-  __syncthreads();                                                  // mbarrier initialised, coefficient rows staged
-  HBM_MARK(0);
+  __syncthreads();                                                  // mbarrier initialised, row tables staged
   mbar_wait(bar, 0);
-  HBM_MARK(1);
 
   int nacc = 0;
+  EAcc<R> e = {R(0), R(0), R(0), R(0)};
+  const bool meas = measure != 0;
   // tiles on the lattice boundary wrap their global coordinates, may be partial, and own periodic halo copies
   const bool border = (blockIdx.x == 0) | (blockIdx.y == 0) | (blockIdx.x == gridDim.x - 1) | (blockIdx.y == gridDim.y - 1);
   constexpr int PS = (int)(L::plane_bytes / sizeof(C));             // plane stride in shared memory (elements)
@@ -279,7 +332,9 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     // is fixed per thread, and every address (tile, coefficient row, Philox counter) advances by a constant.
     static_assert(TW == 128 && HBM_NT % 64 == 0 && ((HBM_NT / 64) & 1) == 0, "thread mapping assumes 64 columns per plane row");
     constexpr int RSTEP = HBM_NT / 64;
-    auto move = [&](C* own, const C* oth, const RowCoef<R>& rc, uint32_t site, bool counted) {
+    // one site move; `counted` = the site belongs to this tile's interior (not a redundantly recomputed halo site)
+    auto move = [&](C* own, const C* oth, int r, uint32_t site, bool counted, int c) {
+      const RowCoef<R> rc = coef[r];
       const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
       const uint2 x = philox2x32_10(site, c1, keys);
       R zre, zim;
@@ -288,8 +343,19 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const R dre = w * zre, dim = w * zim;
       const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
       const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-      if (acc) own[0] = Real<R>::make(pv.x + dre, pv.y + dim);
+      const C q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+      if (acc) own[0] = q;
       nacc += (acc && counted);
+      if (EXTRAS && counted) {
+        const RowW<R> rw = roww[r];
+        energy_own<R, C>(e, rw, q, meas);
+        if (c == 1) {                                             // colour 1 closes every bond: its neighbours are final
+          energy_zbond<R, C>(e, rw.cur[2], rw.dif[2], q, Ln, meas);
+          energy_zbond<R, C>(e, roww[r + 1].cur[2], roww[r + 1].dif[2], Rz, q, meas);
+          energy_tbond<R, C>(e, rw, q, W, meas);
+          energy_tbond<R, C>(e, rw, E, q, meas);
+        }
+      }
     };
     auto site_id = [&](int r, int q) -> uint32_t {             // Philox counter word 0 = global site index
       int gi = ti0 - 2 + r, gj = tj0 - HS + q;
@@ -304,51 +370,25 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const int par = (r + c) & 1, q = 2 * col + par;
       C* own = pl0 + par * PS + r * SWH + col;
       const C* oth = pl0 + (par ^ 1) * PS + r * SWH + col - 1 + par;
-      const RowCoef<R>* rcp = coef + r;
       if (!border) {
-        // two rows per trip (same column and plane, RSTEP rows apart: never neighbours): two independent dependency chains
-        // -- Philox of one site overlaps the arithmetic of the other, and the warps of a CTA stop marching through the
-        // same pipe at the same time
         uint32_t site = site_id(r, q);
-        const uint32_t dsite = RSTEP * g.T;
-        for (; r + RSTEP < SH - m; r += 2 * RSTEP, own += 2 * RSTEP * SWH, oth += 2 * RSTEP * SWH, rcp += 2 * RSTEP, site += 2 * dsite) {
-          // all loads first (the compiler must assume the first store aliases the second site's loads), then the two chains
-          C* ownB = own + RSTEP * SWH;
-          const C* othB = oth + RSTEP * SWH;
-          const C pA = own[0], LA = own[-SWH], RA = own[SWH], WA = oth[0], EA = oth[1];
-          const C pB = ownB[0], LB = ownB[-SWH], RB = ownB[SWH], WB = othB[0], EB = othB[1];
-          const RowCoef<R> rcA = rcp[0], rcB = rcp[RSTEP];
-          const uint2 xA = philox2x32_10(site, c1, keys), xB = philox2x32_10(site + dsite, c1, keys);
-          R zA, yA, zB, yB;
-          Draw<R>::normals(xA.x, xA.y, zA, yA);
-          Draw<R>::normals(xB.x, xB.y, zB, yB);
-          const R wA = sigma * rcA.sgmul, wB = sigma * rcB.sgmul;
-          const R dAr = wA * zA, dAi = wA * yA, dBr = wB * zB, dBi = wB * yB;
-          const R denA = site_delta_over_k<R, C>(rcA, pA, LA, RA, WA, EA, dAr, dAi);
-          const R denB = site_delta_over_k<R, C>(rcB, pB, LB, RB, WB, EB, dBr, dBi);
-          const bool accA = Draw<R>::accept(xA.y, denA, rcA.kacc), accB = Draw<R>::accept(xB.y, denB, rcB.kacc);
-          if (accA) own[0] = Real<R>::make(pA.x + dAr, pA.y + dAi);
-          if (accB) ownB[0] = Real<R>::make(pB.x + dBr, pB.y + dBi);
-          nacc += (accA && (c == 1 || r != 1)) + (accB && (c == 1 || r + RSTEP != SH - 2));
-        }
-        if (r < SH - m) move(own, oth, *rcp, site, c == 1 || (r != 1 && r != SH - 2));
+        for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, site += RSTEP * g.T)
+          move(own, oth, r, site, c == 1 || (r != 1 && r != SH - 2), c);
       } else {
-        for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, rcp += RSTEP)
-          move(own, oth, *rcp, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T);
+        for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH)
+          move(own, oth, r, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T, c);
       }
-      if (c == 0) HBM_MARK(2);
       if (c == 0 && tid >= HBM_NT - (SH - 2)) {
         // the 65th colour-0 site of each row of the grown region: halo column q = HS - 1 (odd rows) or HS + TW (even rows)
         const int r1 = 1 + (tid - (HBM_NT - (SH - 2))), q1 = (r1 & 1) ? HS - 1 : HS + TW;
         const int p1 = q1 & 1;
-        move(pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), coef[r1], site_id(r1, q1), false);
+        move(pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), r1, site_id(r1, q1), false, 0);
       }
-      if (c == 0) HBM_MARK(3);
       __syncthreads();
-      HBM_MARK(4 + c);
     }
   } else {
     // odd periodic ring(s): 3 colours, general colour function; every region site is visited and filtered
+    auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
     for (int c = 0; c < NCOL; ++c) {
       const int m = c + 1, mq = m + (HS - NCOL);
       const int nrows = SH - 2 * m, ncl = SW - 2 * mq;
@@ -358,7 +398,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const int ui = ti0 - NCOL + r, uj = tj0 - HS + q;
         if (ui >= g.Z + NCOL || uj >= g.T + NCOL) continue;
         const int gi = wrapi(ui, g.Z), gj = wrapi(uj, g.T);
-        if ((axis_colour(gi, g.Z) + axis_colour(gj, g.T)) % 3 != c) continue;
+        const int ai = axis_colour(gi, g.Z), bj = axis_colour(gj, g.T);
+        if (col3(ai + bj) != c) continue;
         const int par = (Q0 + q) & 1;
         C* own = par ? pl1 : pl0;
         C* oth = par ? pl0 : pl1;
@@ -373,10 +414,20 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const R w = sigma * rc.sgmul;
         const R dre = w * zre, dim = w * zim;
         const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-        if (Draw<R>::accept(x.y, den, rc.kacc)) {
-          own[r * SWH + col] = Real<R>::make(pv.x + dre, pv.y + dim);
-          const int li = r - NCOL, lj = q - HS;
-          nacc += (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
+        const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
+        const C qv = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+        if (acc) own[r * SWH + col] = qv;
+        const int li = r - NCOL, lj = q - HS;
+        const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
+        nacc += (acc && counted);
+        if (EXTRAS && counted) {
+          const RowW<R> rw = roww[r];
+          energy_own<R, C>(e, rw, qv, meas);
+          // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
+          if (col3(axis_colour(wrapi(gi - 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, rw.cur[2], rw.dif[2], qv, Ln, meas);
+          if (col3(axis_colour(wrapi(gi + 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, roww[r + 1].cur[2], roww[r + 1].dif[2], Rz, qv, meas);
+          if (col3(ai + axis_colour(wrapi(gj - 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, qv, W, meas);
+          if (col3(ai + axis_colour(wrapi(gj + 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, E, qv, meas);
         }
       }
       __syncthreads();
@@ -420,24 +471,222 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     }
   }
 
-  HBM_MARK(6);
-  // ---- accept count ----
-  nacc = warp_sum(nacc);
-  if ((tid & 31) == 0 && nacc) atomicAdd(&counters->accepted, (unsigned long long)nacc);
+  const int warp = tid >> 5, lane = tid & 31;
+  // ---- theta-sums of the profiles (Lattice.measure :121-131) of this tile's rows ----
+  if (EXTRAS && meas && A.rowpart) {
+    for (int li = warp; li < TH && ti0 + li < g.Z; li += HBM_NT / 32) {
+      R sre = R(0), sim = R(0), sab = R(0);
+      for (int lj = lane; lj < TW && tj0 + lj < g.T; lj += 32) {
+        const int q = lj + HS, par = (Q0 + q) & 1;
+        const C v = (par ? pl1 : pl0)[(li + NCOL) * SWH + (((Q0 + q) >> 1) - (par ? x1 : x0))];
+        sre += v.x; sim += v.y; sab += sqrt_fast(v.x * v.x + v.y * v.y);
+      }
+      sre = warp_sum(sre); sim = warp_sum(sim); sab = warp_sum(sab);
+      if (lane < 3) A.rowpart[((size_t)blockIdx.x * 3 + lane) * g.Z + ti0 + li] = lane == 0 ? sre : lane == 1 ? sim : sab;
+    }
+  }
+
+  // ---- per-tile partial sums ----
+  constexpr int NV = EXTRAS ? 5 : 1;
+  {
+    double v[5] = {(double)nacc, (double)e.ec, (double)e.ed, (double)e.s2, (double)e.sa};
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) red[warp * 8 + k] = v[k];
+    }
+  }
+  __syncthreads();
+  const unsigned ntiles = gridDim.x * gridDim.y;
+  int* last_flag = reinterpret_cast<int*>(red + (HBM_NT / 32) * 8 + 7);
+  if (tid < NV) {
+    double t = 0.0;
+    for (int w = 0; w < HBM_NT / 32; ++w) t += red[w * 8 + tid];
+    __stcg(&A.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * HBM_NPART + tid], t);
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) *last_flag = (atomicAdd(&A.hdr->done, 1u) == ntiles - 1);
+  __syncthreads();
+  if (!*last_flag) return;
+
+  // ---- the tile that finished last: add up all tiles in tile order, then decide ----
+  __threadfence();
+  {
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (unsigned t = tid; t < ntiles; t += HBM_NT) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[k] += __ldcg(&A.partials[(size_t)t * HBM_NPART + k]);
+    }
+    if (EXTRAS)
+      for (int t = tid; t < A.ncst; t += HBM_NT) { v[5] += A.cstpart[2 * t]; v[6] += A.cstpart[2 * t + 1]; }
+    constexpr int NT7 = EXTRAS ? 7 : 1;
+#pragma unroll
+    for (int k = 0; k < NT7; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NT7; ++k) red[warp * 8 + k] = v[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int w = 0; w < HBM_NT / 32; ++w)
+#pragma unroll
+        for (int k = 0; k < NT7; ++k) tot[k] += red[w * 8 + k];
+      A.hdr->done = 0u;
+      hbm_decide<R>(A, g, tot);
+    }
+  }
 }
 
-// after every sweep: Robbins-Monro on sigma_site, counters, flip the buffer index
+// Per-sweep decisions, one thread.  tot = {accepted site moves, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|, constants of
+// E(a,a), of the difference}, the energies without the pixel-area factor.
 template <typename R>
-__global__ void hbm_post_sweep_kernel(double* __restrict__ chain, HbmCounters* __restrict__ counters,
-                                      double nsite, uint32_t flags) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double acc = (double)counters->accepted;
-  counters->accepted = 0ull;
+__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* v) {
+  double* chain = A.chain;
+  const uint32_t flags = A.flags;
+  const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
+  const CylParams p = *A.params;
+  const double nsite = (double)g.Z * g.T;
+  const double sigma_used = chain[CYL_CH_SIGMA_SITE];
   if (flags & CYL_SWEEP_ADAPT_SIGMA)
-    chain[CYL_CH_SIGMA_SITE] = rm_batch_update<R>(chain[CYL_CH_SIGMA_SITE], chain[CYL_CH_STEP_COUNTER], nsite, acc);
+    chain[CYL_CH_SIGMA_SITE] = rm_batch_update<R>(sigma_used, chain[CYL_CH_STEP_COUNTER], nsite, v[0]);
   chain[CYL_CH_STEP_COUNTER] += nsite;
   chain[CYL_CH_SITE_PROPOSED] += nsite;
-  chain[CYL_CH_SITE_ACCEPTED] += acc;
+  chain[CYL_CH_SITE_ACCEPTED] += v[0];
+  if (!extras) return;
+  const HbmAmp amp = *A.hdr;
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / g.Z, lth = (2 * pi * p.radius) / g.T;
+  const double a = amp.a;
+  const double e_dif = (v[2] + v[6]) * lz * lth;
+  if (flags & CYL_SWEEP_MEASURE) {
+    const double e_cur = (v[1] + v[5]) * lz * lth;                  // :213
+    chain[CYL_CH_E_FIELD] = e_cur;
+    double* obs = A.obs;
+    if (obs) {
+      obs[CYL_OB_COUNT] += 1.0;
+      obs[CYL_OB_ABS_A] += fabs(a);
+      obs[CYL_OB_A] += a;
+      obs[CYL_OB_A2] += a * a;
+      obs[CYL_OB_PSI2] += v[3] / nsite;
+      obs[CYL_OB_ABSPSI] += v[4] / nsite;
+      obs[CYL_OB_E_FIELD] += e_cur;
+      obs[CYL_OB_E_SURF] += chain[CYL_CH_E_SURF];
+      obs[CYL_OB_E_FIELD2] += e_cur * e_cur;
+      obs[CYL_OB_SIGMA] += sigma_used;
+    }
+  }
+  if (!(flags & CYL_SWEEP_AMP_MOVES)) return;
+  int accept = 0;
+  if (amp.try_move) {
+    const double dE = (amp.e_surf_new - chain[CYL_CH_E_SURF]) + e_dif;
+    if (!isfinite(dE)) chain[CYL_CH_FLAGS] = (double)((unsigned)chain[CYL_CH_FLAGS] | 1u);
+    if (dE <= 0) accept = 1;
+    else if (p.temperature == 0) accept = 0;
+    else accept = (amp.u_acc <= exp(-dE / p.temperature));
+  }
+  const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
+  const double ratio = 1.0 / (pt * (1.0 - pt));
+  chain[CYL_CH_AMP_COUNTER] += 1;
+  chain[CYL_CH_AMP_PROPOSED] += 1;
+  const double sigma_amp = chain[CYL_CH_SIGMA_AMP];
+  if (flags & CYL_SWEEP_ADAPT_SIGMA) {
+    const double cf = sigma_amp * ratio * fast_rcp(fmax(chain[CYL_CH_AMP_COUNTER], 200.0));
+    chain[CYL_CH_SIGMA_AMP] = accept ? sigma_amp + cf * (1 - pt) : sigma_amp - cf * pt;
+  }
+  if (accept) {
+    chain[CYL_CH_AMPLITUDE] = amp.a_new;
+    chain[CYL_CH_E_SURF] = amp.e_surf_new;
+    chain[CYL_CH_AMP_ACCEPTED] += 1;
+    A.hdr->coef_sel = amp.coef_sel ^ 1;                             // the table built for a' becomes the current one
+  }
+}
+
+// Add the per-tile-column theta-sums of one sweep into the profile accumulators: thread i = row i.
+template <typename R>
+__device__ __forceinline__ void hbm_prof_flush_row(const R* __restrict__ rowpart, int ntx, int Z, int i, double* __restrict__ prof) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double s = 0.0;
+    for (int tx = 0; tx < ntx; ++tx) s += (double)rowpart[((size_t)tx * 3 + k) * Z + i];
+    prof[3 * i + k] += s;
+  }
+}
+template <typename R>
+__global__ void hbm_prof_flush_kernel(const R* __restrict__ rowpart, int ntx, int Z, double* __restrict__ prof) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Z) hbm_prof_flush_row<R>(rowpart, ntx, Z, i, prof);
+}
+
+// ---- before a sweep with CYL_SWEEP_AMP_MOVES / CYL_SWEEP_MEASURE ----
+// Every thread repeats the (counter-based) amplitude draw.  Blocks [0, ncst): thread i = row i builds the row's energy
+// weights for (a, a') and the site-move coefficients for a' into the spare table; the extra last block evaluates the
+// surface energies and fills the header.
+template <typename R>
+__global__ void __launch_bounds__(HBM_PREP_NT)
+hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain, HbmAmp* __restrict__ hdr, int Z, int T, int variant,
+                uint64_t seed, uint32_t rep, uint64_t sweep, uint32_t flags, int init, RowCoef<R>* __restrict__ coef2,
+                RowW<R>* __restrict__ roww, double* __restrict__ cstpart, const R* __restrict__ rowpart, int ntx,
+                double* __restrict__ prof_flush) {
+  __shared__ double scr[32];
+  const CylParams p = *params;
+  const double a = chain[CYL_CH_AMPLITUDE];
+  const uint4 x = philox4x32<10>(0u, rep, (uint32_t)sweep, philox_c3(CYL_TAG_AMP, sweep), (uint32_t)seed, (uint32_t)(seed >> 32));
+  double zn, u;
+  amp_draw(x, zn, u);
+  double a_new = a + chain[CYL_CH_SIGMA_AMP] * zn;
+  const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
+  if (!try_move) a_new = a;
+  if (blockIdx.x == gridDim.x - 1) {
+    if (threadIdx.x >= 32) return;
+    double es0 = 0.0, es1 = 0.0;
+    if (init) es0 = surface_energy_warp(p, a, nullptr, nullptr, true);
+    if (try_move) es1 = surface_energy_warp(p, a_new, nullptr, nullptr, true);
+    if (threadIdx.x == 0) {
+      if (init) chain[CYL_CH_E_SURF] = es0;
+      hdr->a = a; hdr->a_new = a_new; hdr->u_acc = u; hdr->e_surf_new = es1; hdr->try_move = try_move ? 1 : 0;
+    }
+    return;
+  }
+  const int sel = hdr->coef_sel;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
+  double c_cur = 0.0, c_dif = 0.0;
+  if (i < Z) {
+    if (prof_flush) hbm_prof_flush_row<R>(rowpart, ntx, Z, i, prof_flush);     // theta-sums of the previous sweep
+    // same arithmetic as the shared-memory kernel's weights phase
+    const double ra = fast_radius_rescaled(p.radius, a), rn = try_move ? fast_radius_rescaled(p.radius, a_new) : ra;
+    const int ip = (i + 1 == Z) ? 0 : i + 1;
+    double s0, c0, sm, cm;
+    sincos(p.wavenumber * (lz * i), &s0, &c0);
+    sincos(p.wavenumber * (lz * (i - .5)), &sm, &cm);
+    const Geo g0 = geo_from_sc(p.wavenumber, ra, a, s0, c0), gm = geo_from_sc(p.wavenumber, ra, a, sm, cm);
+    const Geo h0 = geo_from_sc(p.wavenumber, rn, a_new, s0, c0), hm = geo_from_sc(p.wavenumber, rn, a_new, sm, cm);
+    double Wc[6], Wn[6];
+    field_energy_weights(variant, p, lz, lth, T, g0, gm, g0, Wc);
+    field_energy_weights(variant, p, lz, lth, T, h0, hm, g0, Wn);              // a_ref = current amplitude (:75)
+    const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
+    RowW<R> w;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { w.cur[q] = (R)(Wc[q] * fold[q]); w.dif[q] = (R)((Wn[q] - Wc[q]) * fold[q]); }
+    w.pad[0] = w.pad[1] = R(0);
+    roww[i] = w;
+    c_cur = Wc[5];
+    c_dif = Wn[5] - Wc[5];
+    if (try_move) {
+      double sp, cp;
+      sincos(p.wavenumber * (lz * (ip - .5)), &sp, &cp);
+      const Geo hp = geo_from_sc(p.wavenumber, rn, a_new, sp, cp);
+      coef2[(size_t)(sel ^ 1) * Z + i] = row_coef<R>(p, variant, lz, lth, h0, hm, hp);
+    }
+  }
+  c_cur = block_sum<double>(c_cur, scr);
+  c_dif = block_sum<double>(c_dif, scr);
+  if (threadIdx.x == 0) { cstpart[2 * blockIdx.x] = c_cur; cstpart[2 * blockIdx.x + 1] = c_dif; }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -490,86 +739,6 @@ extern "C" int cyl_hbm_row_moments_f32(const void* work, int cur, int Z, int T, 
 }
 extern "C" int cyl_hbm_row_moments_f64(const void* work, int cur, int Z, int T, const CylParams* params, double* S, void* s) {
   return hbm_row_moments<double>(work, cur, Z, T, params, S, s);
-}
-
-// ----------------------------------------------------------------------------------------------------
-// measurement + amplitude move from the row moments (one CTA)
-// ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-hbm_amp_kernel(const double* __restrict__ S, int Z, int T, const CylParams* __restrict__ params, double* __restrict__ chain,
-               uint64_t seed, uint32_t rep, uint64_t sweep, int variant, uint32_t flags, double* __restrict__ obs,
-               double* __restrict__ prof) {
-  __shared__ double scr[64];
-  __shared__ double sh_es[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const CylParams p = *params;
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
-  const double a = chain[CYL_CH_AMPLITUDE], sigma_amp = chain[CYL_CH_SIGMA_AMP];
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  const uint4 x = philox4x32<10>(0u, rep, (uint32_t)sweep, philox_c3(CYL_TAG_AMP, sweep), k0, k1);
-  double zre, u_acc;
-  amp_draw(x, zre, u_acc);
-  const double a_new = a + sigma_amp * zre;
-  const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
-  double e_cur = 0.0, e_new = 0.0, s_p2 = 0.0, s_abs = 0.0;
-  for (int i = tid; i < Z; i += blockDim.x) {
-    const double* Sr = S + (size_t)i * CYL_NMOM;
-    const Geo g0 = geo_eval(p.wavenumber, p.radius, a, lz * i), gm = geo_eval(p.wavenumber, p.radius, a, lz * (i - .5));
-    e_cur += field_energy_row(variant, p, lz, lth, T, g0, gm, g0, Sr);
-    if (try_move) {
-      const Geo h0 = geo_eval(p.wavenumber, p.radius, a_new, lz * i), hm = geo_eval(p.wavenumber, p.radius, a_new, lz * (i - .5));
-      e_new += field_energy_row(variant, p, lz, lth, T, h0, hm, g0, Sr);
-    }
-    s_p2 += Sr[0];
-    s_abs += Sr[5];
-    if ((flags & CYL_SWEEP_MEASURE) && prof) {
-      prof[3 * i] += Sr[6]; prof[3 * i + 1] += Sr[7]; prof[3 * i + 2] += Sr[5];
-    }
-  }
-  e_cur = block_sum<double>(e_cur, scr) * lz * lth;
-  e_new = block_sum<double>(e_new, scr) * lz * lth;
-  s_p2 = block_sum<double>(s_p2, scr);
-  s_abs = block_sum<double>(s_abs, scr);
-  if (warp == 0) { const double es = surface_energy_warp(p, a, nullptr, nullptr, true); if (lane == 0) sh_es[0] = es; }
-  if (warp == 1 && try_move) { const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true); if (lane == 0) sh_es[1] = es; }
-  __syncthreads();
-  if (tid != 0) return;
-  const double nsite = (double)Z * T;
-  chain[CYL_CH_E_FIELD] = e_cur;
-  chain[CYL_CH_E_SURF] = sh_es[0];
-  if ((flags & CYL_SWEEP_MEASURE) && obs) {
-    obs[CYL_OB_COUNT] += 1.0;
-    obs[CYL_OB_ABS_A] += fabs(a);
-    obs[CYL_OB_A] += a;
-    obs[CYL_OB_A2] += a * a;
-    obs[CYL_OB_PSI2] += s_p2 / nsite;
-    obs[CYL_OB_ABSPSI] += s_abs / nsite;
-    obs[CYL_OB_E_FIELD] += e_cur;
-    obs[CYL_OB_E_SURF] += sh_es[0];
-    obs[CYL_OB_E_FIELD2] += e_cur * e_cur;
-    obs[CYL_OB_SIGMA] += chain[CYL_CH_SIGMA_SITE];
-  }
-  if (!(flags & CYL_SWEEP_AMP_MOVES)) return;
-  int accept = 0;
-  if (try_move) {
-    const double dE = (sh_es[1] + e_new) - (sh_es[0] + e_cur);
-    if (!isfinite(dE)) chain[CYL_CH_FLAGS] = (double)((unsigned)chain[CYL_CH_FLAGS] | 1u);
-    if (dE <= 0) accept = 1;
-    else if (p.temperature == 0) accept = 0;
-    else accept = (u_acc <= exp(-dE / p.temperature));
-  }
-  const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
-  const double ratio = 1.0 / (pt * (1.0 - pt));
-  chain[CYL_CH_AMP_COUNTER] += 1;
-  chain[CYL_CH_AMP_PROPOSED] += 1;
-  const double f = fmax(chain[CYL_CH_AMP_COUNTER], 200.0), c = sigma_amp * ratio;
-  if (flags & CYL_SWEEP_ADAPT_SIGMA) chain[CYL_CH_SIGMA_AMP] = accept ? sigma_amp + c * (1 - pt) / f : sigma_amp - c * pt / f;
-  if (accept) {
-    chain[CYL_CH_AMPLITUDE] = a_new;
-    chain[CYL_CH_E_SURF] = sh_es[1];
-    chain[CYL_CH_AMP_ACCEPTED] += 1;
-  }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -631,31 +800,39 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   using C = typename Real<R>::complex_t;
   using L = HbmSmem<R, NCOL, TH_>;
   static_assert((L::SWH * sizeof(C)) % 16 == 0, "TMA box rows must be a multiple of 16 bytes");
+  static_assert(TH_ >= HBM_MIN_TH, "scratch is sized for tiles of at least HBM_MIN_TH rows");
   HbmMaps maps;
   int rc = make_maps<R>(g, work, L::SWH, L::SH, &maps);
   if (rc) return rc;
-  const HbmScratch<R> sl(g.Z);
-  HbmCounters* counters = reinterpret_cast<HbmCounters*>(scratch);
-  RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>((char*)scratch + sl.off_coef);
-  double* S = reinterpret_cast<double*>((char*)scratch + sl.off_mom);
-  auto kern = sweep_hbm_kernel<R, NCOL, TH_>;
+  const HbmScratch<R> sl(g.Z, g.T);
+  const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
+  const bool profiles = (flags & CYL_SWEEP_MEASURE) && prof;
+  char* sb = (char*)scratch;
+  HbmArgs<R> A;
+  A.hdr = reinterpret_cast<HbmAmp*>(sb);
+  RowCoef<R>* coef2 = reinterpret_cast<RowCoef<R>*>(sb + sl.off_coef);
+  RowW<R>* roww = reinterpret_cast<RowW<R>*>(sb + sl.off_roww);
+  double* cstpart = reinterpret_cast<double*>(sb + sl.off_cst);
+  R* rowpart = reinterpret_cast<R*>(sb + sl.off_rowp);
+  A.coef2 = coef2; A.roww = roww; A.params = params; A.chain = chain;
+  A.partials = reinterpret_cast<double*>(sb + sl.off_part);
+  A.cstpart = cstpart; A.rowpart = profiles ? rowpart : nullptr; A.obs = obs; A.flags = flags; A.ncst = sl.ncst;
+  auto kern = extras ? sweep_hbm_kernel<R, NCOL, TH_, true> : sweep_hbm_kernel<R, NCOL, TH_, false>;
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
-  CYL_CUDA(cudaMemsetAsync(counters, 0, sizeof(HbmCounters), st));
   const dim3 grid((g.T + L::TW - 1) / L::TW, (g.Z + L::TH - 1) / L::TH);
-  const bool amp = flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE);
   const SiteKeys keys = site_keys_expand(seed, (uint64_t)replica);
-  hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
+  const int nrb = (g.Z + HBM_PREP_NT - 1) / HBM_PREP_NT;
+  hbm_coef_kernel<R><<<nrb, HBM_PREP_NT, 0, st>>>(params, chain, g.Z, g.T, variant, coef2, A.hdr);
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
-    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, *cur, g, coef, chain, counters, keys, sweep);
+    if (extras)
+      hbm_prep_kernel<R><<<nrb + 1, HBM_PREP_NT, 0, st>>>(params, chain, A.hdr, g.Z, g.T, variant, seed, (uint32_t)replica, sweep, flags,
+                                                         s == 0, coef2, roww, cstpart, rowpart, sl.ntx,
+                                                         (profiles && s > 0) ? prof : nullptr);
+    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, *cur, g, A, keys, sweep);
     *cur ^= 1;                                                      // host-side ping-pong index
-    hbm_post_sweep_kernel<R><<<1, 32, 0, st>>>(chain, counters, (double)g.Z * g.T, flags);
-    if (amp) {
-      hbm_row_moments_kernel<R><<<(g.Z + 7) / 8, 256, 0, st>>>((const C*)work, *cur, g, params, S);
-      hbm_amp_kernel<<<1, 256, 0, st>>>(S, g.Z, g.T, params, chain, seed, (uint32_t)replica, sweep, variant, flags, obs, prof);
-      if (flags & CYL_SWEEP_AMP_MOVES) hbm_coef_kernel<R><<<(g.Z + 127) / 128, 128, 0, st>>>(params, chain, g.Z, g.T, variant, coef);
-    }
   }
+  if (profiles && nsweeps > 0) hbm_prof_flush_kernel<R><<<nrb, HBM_PREP_NT, 0, st>>>(rowpart, sl.ntx, g.Z, prof);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }
@@ -665,7 +842,7 @@ template <typename R, int NCOL, int TH_>
 static double tile_cost(const HbmGeom& g, int sms) {
   using L = HbmSmem<R, NCOL, TH_>;
   int occ = 0;
-  auto kern = sweep_hbm_kernel<R, NCOL, TH_>;
+  auto kern = sweep_hbm_kernel<R, NCOL, TH_, true>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HBM_NT, L::total) != cudaSuccess || occ <= 0) {
     cudaGetLastError();

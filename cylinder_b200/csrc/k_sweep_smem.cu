@@ -48,10 +48,6 @@ struct SmemScalars {
 // sin/cos(k z) at z_i and z_{i-1/2}
 struct RowTrig { double s0, c0, sm, cm; };
 
-// energy weights of a row: current amplitude, and (proposed - current); pixel-length factors folded in
-template <typename R>
-struct __align__(16) RowW { R cur[5]; R dif[5]; R pad[2]; };
-
 template <typename R>
 struct SweepSmemLayout {
   using C = typename Real<R>::complex_t;
@@ -120,33 +116,6 @@ __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz
   q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
   if (acc) psi[idx] = q;
   return acc;
-}
-
-// energy accumulators of one thread: E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|
-template <typename R> struct EAcc { R ec, ed, s2, sa; };
-__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
-
-template <typename R, typename C>
-__device__ __forceinline__ void energy_own(EAcc<R>& e, const RowW<R>& w, C q, bool measure) {
-  const R p2 = q.x * q.x + q.y * q.y, p4 = p2 * p2;
-  e.ed += w.dif[0] * p2 + w.dif[1] * p4;
-  if (measure) { e.ec += w.cur[0] * p2 + w.cur[1] * p4; e.s2 += p2; e.sa += sqrt_fast(p2); }
-}
-// z-bond between the site `hi` of a row and the site `lo` of the row above it; (wc, wd) = that row's |dz|^2 weights
-template <typename R, typename C>
-__device__ __forceinline__ void energy_zbond(EAcc<R>& e, R wc, R wd, C hi, C lo, bool measure) {
-  const R dr = hi.x - lo.x, di = hi.y - lo.y, m = dr * dr + di * di;
-  e.ed += wd * m;
-  if (measure) e.ec += wc * m;
-}
-// theta-bond between the site `hi` (column j) and `lo` (column j-1) of one row
-template <typename R, typename C>
-__device__ __forceinline__ void energy_tbond(EAcc<R>& e, const RowW<R>& w, C hi, C lo, bool measure) {
-  const R tr = hi.x - lo.x, ti = hi.y - lo.y;
-  const R m4 = tr * tr + ti * ti, m5 = hi.x * ti - hi.y * tr;        // |dth|^2, Im(conj(psi) dth)
-  e.ed += w.dif[3] * m4 + w.dif[4] * m5;
-  if (measure) e.ec += w.cur[3] * m4 + w.cur[4] * m5;
 }
 
 // EXTRAS = amplitude moves and/or measurement requested: a compile-time switch so that the plain-sweep instantiation
