@@ -61,9 +61,16 @@ struct HbmAmp {                      // header: the amplitude proposal of the cu
   double a, a_new, u_acc, e_surf_new;
   int try_move;
   int coef_sel;                      // which of the two RowCoef tables belongs to the current amplitude
-  unsigned int done;                 // tiles of the running sweep that have delivered their partial sums
-  int pad;
+  int pad[2];
 };
+#ifndef HBM_MINB_F32
+#define HBM_MINB_F32 5             // co-resident CTAs per SM the fp32 sweep kernel is compiled for
+#endif
+#ifdef HBM_ABL_NO_ENERGY
+#define HBM_ENERGY_ON false
+#else
+#define HBM_ENERGY_ON true
+#endif
 #define HBM_NPART 8                  // doubles per tile: accepts, E(a,a), E(a',a)-E(a,a), sum |psi|^2, sum |psi|, 3 spare
 #define HBM_MIN_TH 24
 #define HBM_PREP_NT 128
@@ -166,7 +173,7 @@ template <typename R>
 __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const double* __restrict__ chain, int Z, int T, int variant,
                                 RowCoef<R>* __restrict__ coef, HbmAmp* __restrict__ hdr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { hdr->coef_sel = 0; hdr->done = 0u; hdr->try_move = 0; }       // scratch arrives uninitialised
+  if (i == 0) { hdr->coef_sel = 0; hdr->try_move = 0; }       // scratch arrives uninitialised
   if (i >= Z) return;
   const CylParams p = *params;
   const double a = chain[CYL_CH_AMPLITUDE];
@@ -193,6 +200,32 @@ __device__ __forceinline__ double ld_early_f64(const double* p) {
   asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+// Programmatic dependent launch (sm_90+): every kernel of the sweep loop is launched with the stream-serialisation attribute,
+// so its CTAs may become resident while its predecessor in the stream is still running.  A kernel must execute pdl_wait()
+// (returns once the predecessor has completed and its writes are visible) before touching anything the predecessor writes,
+// and lets its own successor start early with pdl_trigger().  Rule used below: a kernel triggers only AFTER its own wait, so
+// a successor never overtakes the kernel two places up the stream; before its wait a kernel reads only data that is at least
+// two kernels old (the sweep kernel: its input tiles, issued by TMA while the decision kernel is still finishing).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// two adjacent complex values of a plane row (16-byte aligned pair)
+__device__ __forceinline__ void load_pair(const float2* p, float2& a, float2& b) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
+}
+__device__ __forceinline__ void load_pair(const double2* p, double2& a, double2& b) { a = p[0]; b = p[1]; }
 __device__ __forceinline__ int ld_early_i32(const int* p) {
   int v;
   asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -252,7 +285,7 @@ struct HbmArgs {
   const CylParams* params;
   double* chain;
   HbmAmp* hdr;
-  double* partials;                  // [tiles][HBM_NPART]
+  double* partials;                  // [HBM_NPART][tiles of this launch]
   const double* cstpart;             // [ncst][2]
   R* rowpart;                        // [ntx][3][Z] or null
   double* obs;
@@ -260,16 +293,12 @@ struct HbmArgs {
   int ncst;
 };
 
-template <typename R>
-__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* tot);
-
 // EXTRAS: the field energy for the current amplitude and for the proposed one (weights staged per tile row) is
 // accumulated while the sites are updated -- own terms when a site is finalised, a bond by its later-finalised endpoint --
 // and the theta-sums of the profiles are taken from the finished tile, so a sweep with measurement / amplitude move needs
-// no second pass over the lattice.  The tile that finishes last adds up all tiles' partial sums (in tile order, so the
-// result does not depend on scheduling) and takes the per-sweep decisions: Robbins-Monro, observables, amplitude move.
+// no second pass over the lattice.  Each tile leaves its partial sums in scratch for hbm_decide_kernel.
 template <typename R, int NCOL, int TH_, bool EXTRAS>
-__global__ void __launch_bounds__(HBM_NT, sizeof(R) == 4 ? 5 : 2)
+__global__ void __launch_bounds__(HBM_NT, sizeof(R) == 4 ? HBM_MINB_F32 : 2)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
                  int cur, const __grid_constant__ HbmGeom g, const __grid_constant__ HbmArgs<R> A,
                  const __grid_constant__ SiteKeys keys, uint64_t sweep) {
@@ -295,7 +324,6 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // Prologue.  Global-memory latency under the bulk traffic of this kernel is several microseconds, so everything that
   // comes from global memory is requested up front and in parallel: the tile (TMA, issued by thread 0 as soon as it has
   // initialised the mbarrier), the row coefficients / weights and the proposal width.
-  const R sigma = (R)ld_early_f64(chain + CYL_CH_SIGMA_SITE);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -305,13 +333,21 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     tma_load_2d(pl0, &maps.m[cur][0], x0 * maps.esz, ti0, bar);    // esz: TMA elements per complex value
     tma_load_2d(pl1, &maps.m[cur][1], x1 * maps.esz, ti0, bar);
   }
-  {
-    const RowCoef<R>* coef_g = A.coef2 + (EXTRAS ? (size_t)ld_early_i32(&A.hdr->coef_sel) * g.Z : (size_t)0);
+  pdl_wait();                       // the tiles are two kernels old; everything below comes from the preceding kernel
+  pdl_trigger();
+  const R sigma = (R)ld_early_f64(chain + CYL_CH_SIGMA_SITE);
+  if (EXTRAS) {
+    // which coefficient table is current is only known on the device: fetch the row from both tables together with the
+    // selector instead of chaining two global-memory latencies
+    const int sel = ld_early_i32(&A.hdr->coef_sel);
     for (int r = tid; r < SH; r += HBM_NT) {
       const int gr = modi(ti0 - NCOL + r, g.Z);
-      coef[r] = coef_g[gr];
-      if (EXTRAS) roww[r] = A.roww[gr];
+      const RowCoef<R> c0 = A.coef2[gr], c1 = A.coef2[(size_t)g.Z + gr];
+      roww[r] = A.roww[gr];
+      coef[r] = sel ? c1 : c0;
     }
+  } else {
+    for (int r = tid; r < SH; r += HBM_NT) coef[r] = A.coef2[modi(ti0 - NCOL + r, g.Z)];
   }
   const uint32_t c1 = (uint32_t)sweep + keys.off;
   __syncthreads();                                                  // mbarrier initialised, row tables staged
@@ -346,7 +382,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const C q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
       if (acc) own[0] = q;
       nacc += (acc && counted);
-      if (EXTRAS && counted) {
+      if (EXTRAS && HBM_ENERGY_ON && counted) {
         const RowW<R> rw = roww[r];
         energy_own<R, C>(e, rw, q, meas);
         if (c == 1) {                                             // colour 1 closes every bond: its neighbours are final
@@ -420,7 +456,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const int li = r - NCOL, lj = q - HS;
         const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
         nacc += (acc && counted);
-        if (EXTRAS && counted) {
+        if (EXTRAS && HBM_ENERGY_ON && counted) {
           const RowW<R> rw = roww[r];
           energy_own<R, C>(e, rw, qv, meas);
           // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
@@ -473,72 +509,108 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
 
   const int warp = tid >> 5, lane = tid & 31;
   // ---- theta-sums of the profiles (Lattice.measure :121-131) of this tile's rows ----
+#ifndef HBM_ABL_NO_PROF
   if (EXTRAS && meas && A.rowpart) {
-    for (int li = warp; li < TH && ti0 + li < g.Z; li += HBM_NT / 32) {
+    if (NCOL == 2 && !border) {
+      // thread = (row, 16-column segment): 8 consecutive values from each plane, then a 3-step exchange over the 8 segments.
+      // The chunk order is rotated by segment so that the 16-byte loads of a quarter-warp hit distinct banks.
+      static_assert(TH <= HBM_NT / 8 && TW == 128, "one thread per (row, 16 columns)");
+      const int li = tid >> 3, seg = tid & 7;
       R sre = R(0), sim = R(0), sab = R(0);
-      for (int lj = lane; lj < TW && tj0 + lj < g.T; lj += 32) {
-        const int q = lj + HS, par = (Q0 + q) & 1;
-        const C v = (par ? pl1 : pl0)[(li + NCOL) * SWH + (((Q0 + q) >> 1) - (par ? x1 : x0))];
-        sre += v.x; sim += v.y; sab += sqrt_fast(v.x * v.x + v.y * v.y);
+      if (li < TH) {
+        const C* rowp = pl0 + (li + NCOL) * SWH + HS / 2 + 8 * seg;
+#pragma unroll
+        for (int pk = 0; pk < 8; ++pk) {
+          const int kk = ((pk & 3) + (seg >> 1)) & 3;
+          C va, vb;
+          load_pair(rowp + (pk >> 2) * PS + 2 * kk, va, vb);
+          sre += va.x + vb.x; sim += va.y + vb.y;
+          sab += sqrt_fast(va.x * va.x + va.y * va.y) + sqrt_fast(vb.x * vb.x + vb.y * vb.y);
+        }
       }
-      sre = warp_sum(sre); sim = warp_sum(sim); sab = warp_sum(sab);
-      if (lane < 3) A.rowpart[((size_t)blockIdx.x * 3 + lane) * g.Z + ti0 + li] = lane == 0 ? sre : lane == 1 ? sim : sab;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sre += __shfl_xor_sync(0xffffffffu, sre, o); sim += __shfl_xor_sync(0xffffffffu, sim, o); sab += __shfl_xor_sync(0xffffffffu, sab, o);
+      }
+      if (li < TH && seg < 3) A.rowpart[((size_t)blockIdx.x * 3 + seg) * g.Z + ti0 + li] = seg == 0 ? sre : seg == 1 ? sim : sab;
+    } else {
+      for (int li = warp; li < TH && ti0 + li < g.Z; li += HBM_NT / 32) {
+        R sre = R(0), sim = R(0), sab = R(0);
+        for (int lj = lane; lj < TW && tj0 + lj < g.T; lj += 32) {
+          const int q = lj + HS, par = (Q0 + q) & 1;
+          const C v = (par ? pl1 : pl0)[(li + NCOL) * SWH + (((Q0 + q) >> 1) - (par ? x1 : x0))];
+          sre += v.x; sim += v.y; sab += sqrt_fast(v.x * v.x + v.y * v.y);
+        }
+        sre = warp_sum(sre); sim = warp_sum(sim); sab = warp_sum(sab);
+        if (lane < 3) A.rowpart[((size_t)blockIdx.x * 3 + lane) * g.Z + ti0 + li] = lane == 0 ? sre : lane == 1 ? sim : sab;
+      }
     }
   }
+#endif
 
-  // ---- per-tile partial sums ----
+  // ---- per-tile partial sums: within a warp in working precision, across warps and tiles in double ----
   constexpr int NV = EXTRAS ? 5 : 1;
   {
-    double v[5] = {(double)nacc, (double)e.ec, (double)e.ed, (double)e.s2, (double)e.sa};
+    const int wacc = __reduce_add_sync(0xffffffffu, nacc);
+    R v[4] = {e.ec, e.ed, e.s2, e.sa};
+    if (EXTRAS) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+      for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+    }
     if (lane == 0) {
+      red[warp * 8] = (double)wacc;
+      if (EXTRAS) {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) red[warp * 8 + k] = v[k];
+        for (int k = 0; k < 4; ++k) red[warp * 8 + 1 + k] = (double)v[k];
+      }
     }
   }
   __syncthreads();
-  const unsigned ntiles = gridDim.x * gridDim.y;
-  int* last_flag = reinterpret_cast<int*>(red + (HBM_NT / 32) * 8 + 7);
   if (tid < NV) {
     double t = 0.0;
     for (int w = 0; w < HBM_NT / 32; ++w) t += red[w * 8 + tid];
-    __stcg(&A.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * HBM_NPART + tid], t);
-    __threadfence();
+    A.partials[(size_t)tid * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
-  __syncthreads();
-  if (tid == 0) *last_flag = (atomicAdd(&A.hdr->done, 1u) == ntiles - 1);
-  __syncthreads();
-  if (!*last_flag) return;
+}
 
-  // ---- the tile that finished last: add up all tiles in tile order, then decide ----
-  __threadfence();
-  {
-    double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (unsigned t = tid; t < ntiles; t += HBM_NT) {
+template <typename R>
+__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* tot);
+
+// ---- after a sweep: add up the tiles' partial sums (in a fixed order: the result does not depend on scheduling), then the
+// per-sweep decisions.  One CTA; the loads of a thread are independent, so the kernel costs a few memory latencies. ----
+#define HBM_DECIDE_NT 1024
+template <typename R>
+__global__ void __launch_bounds__(HBM_DECIDE_NT)
+hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ HbmGeom g, int ntiles) {
+  __shared__ double red[(HBM_DECIDE_NT / 32) * 8];
+  pdl_wait();
+  pdl_trigger();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool extras = (A.flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
+  const int nv = extras ? 5 : 1;
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int k = 0; k < NV; ++k) v[k] += __ldcg(&A.partials[(size_t)t * HBM_NPART + k]);
-    }
-    if (EXTRAS)
-      for (int t = tid; t < A.ncst; t += HBM_NT) { v[5] += A.cstpart[2 * t]; v[6] += A.cstpart[2 * t + 1]; }
-    constexpr int NT7 = EXTRAS ? 7 : 1;
-#pragma unroll
-    for (int k = 0; k < NT7; ++k) v[k] = warp_sum(v[k]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < NT7; ++k) red[warp * 8 + k] = v[k];
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double tot[7] = {0, 0, 0, 0, 0, 0, 0};
-      for (int w = 0; w < HBM_NT / 32; ++w)
-#pragma unroll
-        for (int k = 0; k < NT7; ++k) tot[k] += red[w * 8 + k];
-      A.hdr->done = 0u;
-      hbm_decide<R>(A, g, tot);
+  for (int k = 0; k < 5; ++k) {
+    if (k < nv) {
+      const double* pk = A.partials + (size_t)k * ntiles;
+#pragma unroll 8
+      for (int t = tid; t < ntiles; t += HBM_DECIDE_NT) v[k] += pk[t];
     }
   }
+  if (extras)
+    for (int t = tid; t < A.ncst; t += HBM_DECIDE_NT) { v[5] += A.cstpart[2 * t]; v[6] += A.cstpart[2 * t + 1]; }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) red[warp * 8 + k] = v[k];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  double tot[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) tot[k] = warp_sum(red[lane * 8 + k]);
+  if (lane == 0) hbm_decide<R>(A, g, tot);
 }
 
 // Per-sweep decisions, one thread.  tot = {accepted site moves, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|, constants of
@@ -608,30 +680,41 @@ __device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* 
 // Add the per-tile-column theta-sums of one sweep into the profile accumulators: thread i = row i.
 template <typename R>
 __device__ __forceinline__ void hbm_prof_flush_row(const R* __restrict__ rowpart, int ntx, int Z, int i, double* __restrict__ prof) {
+  double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll 8
+  for (int tx = 0; tx < ntx; ++tx) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    double s = 0.0;
-    for (int tx = 0; tx < ntx; ++tx) s += (double)rowpart[((size_t)tx * 3 + k) * Z + i];
-    prof[3 * i + k] += s;
+    for (int k = 0; k < 3; ++k) s[k] += (double)rowpart[((size_t)tx * 3 + k) * Z + i];
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) prof[3 * i + k] += s[k];
 }
 template <typename R>
 __global__ void hbm_prof_flush_kernel(const R* __restrict__ rowpart, int ntx, int Z, double* __restrict__ prof) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Z) hbm_prof_flush_row<R>(rowpart, ntx, Z, i, prof);
 }
 
 // ---- before a sweep with CYL_SWEEP_AMP_MOVES / CYL_SWEEP_MEASURE ----
-// Every thread repeats the (counter-based) amplitude draw.  Blocks [0, ncst): thread i = row i builds the row's energy
-// weights for (a, a') and the site-move coefficients for a' into the spare table; the extra last block evaluates the
-// surface energies and fills the header.
+// Every thread repeats the (counter-based) amplitude draw.  Blocks [0, nrb): thread i = row i builds the row's energy
+// weights for (a, a') and the site-move coefficients for a' into the spare table; block nrb evaluates the surface
+// energies and fills the header; blocks past it (present when profiles are recorded) add the previous sweep's theta-sums
+// into the profile accumulators.
 template <typename R>
 __global__ void __launch_bounds__(HBM_PREP_NT)
 hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain, HbmAmp* __restrict__ hdr, int Z, int T, int variant,
                 uint64_t seed, uint32_t rep, uint64_t sweep, uint32_t flags, int init, RowCoef<R>* __restrict__ coef2,
                 RowW<R>* __restrict__ roww, double* __restrict__ cstpart, const R* __restrict__ rowpart, int ntx,
-                double* __restrict__ prof_flush) {
+                double* __restrict__ prof_flush, int nrb) {
   __shared__ double scr[32];
+  pdl_wait();
+  pdl_trigger();
+  if ((int)blockIdx.x > nrb) {
+    const int i = ((int)blockIdx.x - nrb - 1) * blockDim.x + threadIdx.x;
+    if (i < Z) hbm_prof_flush_row<R>(rowpart, ntx, Z, i, prof_flush);
+    return;
+  }
   const CylParams p = *params;
   const double a = chain[CYL_CH_AMPLITUDE];
   const uint4 x = philox4x32<10>(0u, rep, (uint32_t)sweep, philox_c3(CYL_TAG_AMP, sweep), (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -640,7 +723,7 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
   double a_new = a + chain[CYL_CH_SIGMA_AMP] * zn;
   const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
   if (!try_move) a_new = a;
-  if (blockIdx.x == gridDim.x - 1) {
+  if ((int)blockIdx.x == nrb) {
     if (threadIdx.x >= 32) return;
     double es0 = 0.0, es1 = 0.0;
     if (init) es0 = surface_energy_warp(p, a, nullptr, nullptr, true);
@@ -657,7 +740,6 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
   double c_cur = 0.0, c_dif = 0.0;
   if (i < Z) {
-    if (prof_flush) hbm_prof_flush_row<R>(rowpart, ntx, Z, i, prof_flush);     // theta-sums of the previous sweep
     // same arithmetic as the shared-memory kernel's weights phase
     const double ra = fast_radius_rescaled(p.radius, a), rn = try_move ? fast_radius_rescaled(p.radius, a_new) : ra;
     const int ip = (i + 1 == Z) ? 0 : i + 1;
@@ -825,14 +907,18 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   hbm_coef_kernel<R><<<nrb, HBM_PREP_NT, 0, st>>>(params, chain, g.Z, g.T, variant, coef2, A.hdr);
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
-    if (extras)
-      hbm_prep_kernel<R><<<nrb + 1, HBM_PREP_NT, 0, st>>>(params, chain, A.hdr, g.Z, g.T, variant, seed, (uint32_t)replica, sweep, flags,
-                                                         s == 0, coef2, roww, cstpart, rowpart, sl.ntx,
-                                                         (profiles && s > 0) ? prof : nullptr);
-    kern<<<grid, HBM_NT, L::total, st>>>(maps, (C*)work, *cur, g, A, keys, sweep);
+    if (extras) {
+      const bool flush = profiles && s > 0;
+      CYL_CUDA(launch_pdl(hbm_prep_kernel<R>, dim3(nrb + 1 + (flush ? nrb : 0)), dim3(HBM_PREP_NT), 0, st, params, chain, A.hdr, g.Z,
+                          g.T, variant, seed, (uint32_t)replica, sweep, flags, (int)(s == 0), coef2, roww, cstpart,
+                          (const R*)rowpart, sl.ntx, flush ? prof : (double*)nullptr, nrb));
+    }
+    CYL_CUDA(launch_pdl(kern, grid, dim3(HBM_NT), L::total, st, maps, (C*)work, (int)*cur, g, A, keys, sweep));
     *cur ^= 1;                                                      // host-side ping-pong index
+    CYL_CUDA(launch_pdl(hbm_decide_kernel<R>, dim3(1), dim3(HBM_DECIDE_NT), 0, st, A, g, (int)(grid.x * grid.y)));
   }
-  if (profiles && nsweeps > 0) hbm_prof_flush_kernel<R><<<nrb, HBM_PREP_NT, 0, st>>>(rowpart, sl.ntx, g.Z, prof);
+  if (profiles && nsweeps > 0)
+    CYL_CUDA(launch_pdl(hbm_prof_flush_kernel<R>, dim3(nrb), dim3(HBM_PREP_NT), 0, st, (const R*)rowpart, sl.ntx, g.Z, prof));
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

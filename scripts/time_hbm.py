@@ -3,6 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cylinder_b200 import _abi, ops
+if os.environ.get("CYL_LIB"):
+    _abi.LIB_PATH = os.path.abspath(os.environ["CYL_LIB"])      # a variant built by scripts/build_variant.sh
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nsw = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 dev = torch.device("cuda", 0)
