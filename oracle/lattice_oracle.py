@@ -16,7 +16,12 @@ import numpy as np
 
 SIMPLE = 0             # On_lattice_simple.py
 RESCALED_0TH = 1       # On_lattice_rescaled_0thorder.py
-VARIANTS = {"simple": SIMPLE, "rescaled_0thorder": RESCALED_0TH}
+RESCALED_1ST = 2       # On_lattice_rescaled_1storder.py   ("1st:" in the citations below)
+DECOUPLED = 3          # On_lattice_decoupled.py           ("dec:")
+VARIANTS = {"simple": SIMPLE, "rescaled_0thorder": RESCALED_0TH, "rescaled_1storder": RESCALED_1ST, "decoupled": DECOUPLED}
+# defaults that differ by variant: initial |psi| bound (:164 / dec:157) and initial sampling width (:101 / dec:99)
+INIT_MAGNITUDE = {SIMPLE: .1, RESCALED_0TH: .1, RESCALED_1ST: .1, DECOUPLED: .001}
+INIT_SIGMA = {SIMPLE: .005, RESCALED_0TH: .005, RESCALED_1ST: .005, DECOUPLED: .0001}
 
 
 # --------------------------------------------------------------------------------------
@@ -194,7 +199,7 @@ def metropolis_decision(T, old, new, draw_uniform):
 # single-site proposal: local energy difference
 # --------------------------------------------------------------------------------------
 def proposal_sigma(st, a, iz):
-    """Std-dev of the Gaussian increment: sigma (simple :613) or sigma*sqrt_g(z_i) (0th order :135-136)."""
+    """Std-dev of the Gaussian increment: sigma (simple :613) or sigma*sqrt_g(z_i) (0th:135-136, 1st:153-154, dec:274-275)."""
     if st.variant == SIMPLE:
         return st.sigma
     z = st.lz * iz
@@ -212,6 +217,8 @@ def delta_energy(st, a, iz, ith, new_value):
     z_loc = lz * iz
     z_m = lz * (iz - .5)
     z_p = lz * (iz + .5)
+    if st.variant in (RESCALED_1ST, DECOUPLED):
+        return _delta_energy_interstitial(st, a, iz, ith, new_value)
     if st.variant == SIMPLE:
         A = A_theta(k, r, a, z_m)                                            # :603
         R = 1 / g_theta(k, r, a, z_m)                                        # :604
@@ -266,6 +273,65 @@ def delta_energy(st, a, iz, ith, new_value):
     return dE, (new_p2, ndz, nnz, ndth, nnth)
 
 
+def _delta_energy_interstitial(st, a, iz, ith, new_value):
+    """rescaled_1storder: On_lattice_rescaled_1storder.py:138-210; decoupled: On_lattice_decoupled.py:259-330.
+    Both take A_theta and the index raise at the interstitial rows z -+ lz/2 (like `simple`); they differ from it in
+    the metric factors of the gradient and cross terms."""
+    k, r = st.k, st.r
+    lz, lth = st.lz, st.lth
+    psi, dz, dth = st.psi, st.dz, st.dth
+    first = st.variant == RESCALED_1ST
+    z_loc = lz * iz                                                          # 1st:139 / dec:260
+    z_m = lz * (iz - .5)                                                     # 1st:140 / dec:261
+    z_p = lz * (iz + .5)                                                     # 1st:141 / dec:262
+    A = A_theta(k, r, a, z_m)                                                # 1st:143 / dec:264
+    R = 1 / g_theta(k, r, a, z_m)                                            # 1st:144 / dec:265
+    A_nb = A_theta(k, r, a, z_p)                                             # 1st:145 / dec:266
+    R_nb = 1 / g_theta(k, r, a, z_p)                                         # 1st:146 / dec:267
+    sg = sqrt_g_theta(k, r, a, z_loc) * sqrt_g_z(k, r, a, z_loc)             # 1st:148 / dec:269
+    value = psi[iz, ith]
+    new_p2 = squared(new_value)                                              # 1st:158 / dec:279
+    old_p2 = st.psi2[iz, ith]                                                # 1st:160 / dec:281
+    dE = (st.alpha * new_p2 + st.u / 2 * new_p2 ** 2) - (st.alpha * old_p2 + st.u / 2 * old_p2 ** 2)   # 1st:161-163 / dec:282-284
+    left_z, left_th = psi[iz - 1, ith], psi[iz, ith - 1]                     # 1st:166-167 / dec:289-290
+    ndz = (new_value - left_z) / lz                                          # 1st:168 / dec:291
+    ndth = (new_value - left_th) / lth                                       # 1st:169 / dec:292
+    if first:
+        d_z = (squared(ndz) - squared(dz[iz, ith])) / (sqrt_g_z(k, r, a, z_m)) ** 2               # 1st:171
+    else:
+        d_z = (squared(ndz) - squared(dz[iz, ith]))                                               # dec:294
+    d_th = (squared(ndth) - squared(dth[iz, ith])) * R                       # 1st:172 / dec:295
+    dE += st.C * (d_z + d_th)                                                # 1st:174 / dec:297
+    right_z, right_th = psi[iz + 1, ith], psi[iz, ith + 1]                   # 1st:177-178 / dec:300-301
+    nnz = (right_z - new_value) / lz                                         # 1st:179 / dec:302
+    nnth = (right_th - new_value) / lth                                      # 1st:180 / dec:303
+    if first:
+        dn_z = (squared(nnz) - squared(dz[iz + 1, ith])) / sqrt_g_z(k, r, a, z_p) ** 2            # 1st:181
+    else:
+        dn_z = (squared(nnz) - squared(dz[iz + 1, ith]))                                          # dec:304
+    dn_th = (squared(nnth) - squared(dth[iz, ith + 1])) * R_nb               # 1st:182 / dec:305
+    dE += st.C * (dn_z + dn_th)                                              # 1st:184 / dec:307
+    if first:
+        gth_m, gth_p = sqrt_g_theta(k, r, a, z_m), sqrt_g_theta(k, r, a, z_p)
+        old_cross = (A * value.conjugate() * dth[iz, ith] / gth_m).imag      # 1st:190-191
+        new_cross = (A * new_value.conjugate() * ndth / gth_m).imag          # 1st:194-195
+    else:
+        old_cross = (A * value.conjugate() * dth[iz, ith]).imag              # dec:312-313
+        new_cross = (A * new_value.conjugate() * ndth).imag                  # dec:315-316
+    dE += st.C * 2 * st.n * R * (new_cross - old_cross)                      # 1st:196 / dec:317
+    if first:
+        old_nb = (A_nb * right_th.conjugate() * dth[iz, ith + 1] / gth_p).imag   # 1st:199-200
+        new_nb = (A_nb * right_th.conjugate() * nnth / gth_p).imag               # 1st:201-202
+    else:
+        old_nb = (A_nb * right_th.conjugate() * dth[iz, ith + 1]).imag       # dec:320-321
+        new_nb = (A_nb * right_th.conjugate() * nnth).imag                   # dec:322-323
+    dE += st.C * 2 * st.n * R_nb * (new_nb - old_nb)                         # 1st:203 / dec:324
+    dE += st.Cn2 * R * squared(complex(A)) * (squared(new_value) - squared(value))   # 1st:205-206 / dec:326-327
+    dE *= sg                                                                 # 1st:209 / dec:329
+    dE *= lz * lth                                                           # 1st:210 / dec:330
+    return dE, (new_p2, ndz, nnz, ndth, nnth)
+
+
 def commit(st, iz, ith, new_value, derived):
     """On accept: On_lattice_simple.py:671-685."""
     new_p2, ndz, nnz, ndth, nnth = derived
@@ -317,9 +383,53 @@ def background_energy(st, cell_dims):
     return ans / area + ordered
 
 
+def background_energy_1st(st, cell_dims):
+    """On_lattice_rescaled_1storder.py:66-114 (ordered_reference=True): the 0th-order background plus an O(u)
+    fluctuation correction; the ValueError branches of the reference (log of a non-positive number) are
+    restated as explicit sign tests -- math.log raises exactly for arguments <= 0."""
+    area = cell_dims[0] * cell_dims[1]                                        # 1st:69
+    ans = -st.temperature                                                     # 1st:86
+    area_factor = 2 / math.sqrt(math.pi)                                      # 1st:34
+    upper = 1 * area_factor                                                   # 1st:89
+    lower = (1 / max((st.Z, st.T_len))) * area_factor                         # 1st:90
+    alpha_cell = st.alpha * area                                              # 1st:92
+    hi = st.C * upper ** 2 + alpha_cell
+    lo = st.C * lower ** 2 + alpha_cell
+    if hi > 0 and lo > 0:
+        integral = math.pi / st.C * (math.log(hi) - math.log(lo))             # 1st:96
+    elif hi > 0:                                                              # 1st:98-102
+        lower = math.sqrt(abs(alpha_cell) / st.C) + .0000001
+        integral = math.pi / st.C * (math.log(st.C * upper ** 2 + alpha_cell) - math.log(st.C * lower ** 2 + alpha_cell))
+    else:
+        integral = 0                                                          # 1st:103-105
+    correction = st.u * st.temperature ** 3 * 4 * integral ** 2               # 1st:106
+    correction /= st.Z * st.T_len                                             # 1st:107
+    ans += correction                                                         # 1st:108
+    ordered = .5 * st.alpha ** 2 / st.u if st.alpha < 0 else 0                # 1st:110-113
+    return ans / area + ordered                                               # 1st:114
+
+
+def _decoupled_field_energy(st, a, psi):
+    """On_lattice_decoupled.py:179-202: only the C n^2 |A_theta psi|^2 coupling enters an amplitude move."""
+    k, r = st.k, st.r
+    energy = 0
+    for i in range(st.Z):
+        z_loc = i * st.lz                                                     # dec:188
+        z_m = (i - .5) * st.lz                                                # dec:189
+        col_raise = sqrt_g_z(k, r, a, z_loc) / sqrt_g_theta(k, r, a, z_m)     # dec:190
+        col_A = A_theta(k, r, a, z_m)                                         # dec:191
+        e = st.Cn2 * sum(np.abs(psi[i] * psi[i].conj())) * squared(complex(col_A)) * col_raise   # dec:198
+        energy += e
+    return energy * st.lz * st.lth                                            # dec:202
+
+
 def surface_field_energy(st, a, a_ref=None, psi=None, psi2=None, dz=None, dth=None):
     """simple: On_lattice_simple.py:185-213 (ignores a_ref);
-    rescaled_0thorder: On_lattice_rescaled_0thorder.py:247-278 (mixes a_ref and a in the metric)."""
+    rescaled_0thorder: On_lattice_rescaled_0thorder.py:247-278 (mixes a_ref and a in the metric);
+    rescaled_1storder: On_lattice_rescaled_1storder.py:265-296 (as 0th order, A_theta at z - lz/2, 1st-order background);
+    decoupled: On_lattice_decoupled.py:179-202 (takes the amplitude only)."""
+    if st.variant == DECOUPLED:
+        return _decoupled_field_energy(st, a, st.psi if psi is None else psi)
     psi = st.psi if psi is None else psi
     psi2 = st.psi2 if psi2 is None else psi2
     dz = st.dz if dz is None else dz
@@ -342,7 +452,7 @@ def surface_field_energy(st, a, a_ref=None, psi=None, psi2=None, dz=None, dth=No
             th_spacing = sqrt_g_theta(k, r, a_ref, z_loc)                     # 0th:254
             col_sqrtg = sqrt_g_z(k, r, a_ref, z_loc) * sqrt_g_theta(k, r, a, z_loc)   # 0th:255
             col_raise = col_sqrtg / th_spacing ** 2                           # 0th:256
-            col_A = A_theta(k, r, a, z_loc)                                   # 0th:257
+            col_A = A_theta(k, r, a, z_loc if st.variant == RESCALED_0TH else z_m)   # 0th:257 / 1st:275
         p2 = psi2[i]
         e = (st.alpha * sum(p2) + st.u / 2 * sum(p2 ** 2)) * col_sqrtg        # :199
         dz_col = dz[i] / z_spacing                                            # :200
@@ -351,9 +461,10 @@ def surface_field_energy(st, a, a_ref=None, psi=None, psi2=None, dz=None, dth=No
         e += st.C * sum(np.abs(dth_col * dth_col.conj())) * col_raise         # :206
         e += st.C * st.n * 2 * sum((col_A * psi[i].conj() * dth_col).imag) * col_raise    # :208
         e += st.Cn2 * sum(np.abs(psi[i] * psi[i].conj())) * squared(complex(col_A)) * col_raise   # :210
-        if st.variant == RESCALED_0TH:
-            cell = (st.lz * sqrt_g_z(k, r, a, z_loc), st.lth * sqrt_g_theta(k, r, a, z_loc))       # 0th:261
-            e += st.T_len * background_energy(st, cell) * col_sqrtg                                # 0th:275
+        if st.variant != SIMPLE:
+            cell = (st.lz * sqrt_g_z(k, r, a, z_loc), st.lth * sqrt_g_theta(k, r, a, z_loc))       # 0th:261 / 1st:279
+            bg = background_energy(st, cell) if st.variant == RESCALED_0TH else background_energy_1st(st, cell)
+            e += st.T_len * bg * col_sqrtg                                                         # 0th:275 / 1st:293
         energy += e
     return energy * st.lz * st.lth                                            # :213
 

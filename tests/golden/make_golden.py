@@ -7,7 +7,7 @@ What is recorded:
   geometry.npz          metric factors of system_cylinder.py:25-41 on a grid of (k, r, a, z)
   surface_energy.npz    a sub-sample of the reference's own tables surfenergy_H0.csv / curvenergy_H0.csv
                         plus Cylinder.calc_surface_energy at assorted (k, r, gamma, kappa, H0, a)
-  lattice_<variant>_<case>.npz
+  lattice_<variant>_<case>.npz   (variants: simple, rescaled0, rescaled1, decoupled)
                         seeded Lattice construction (random.seed), then a recorded random tape of
                         proposals driven through the reference's own step_lattice(); per proposal
                         (iz, ith, z_re, z_im, u|NaN, dE, accept, sigma_after), final psi and caches,
@@ -79,8 +79,14 @@ def record_lattice_case(modname, tag, seed, kwargs, amp, nprop, amps_eval):
     random.seed(seed)
     lat = rh.quiet(mod.Lattice, **kwargs)
     psi0 = lat.lattice.copy()
-    e0 = [(a2, ar, rh.quiet(lat.surface_field_energy, a2, ar, lat.lattice, lat.psi_squared, lat.dz, lat.dth))
-          for (a2, ar) in amps_eval]
+    sigma0 = lat.sampling_width
+
+    def field_energy(a2, ar):
+        if modname == "On_lattice_decoupled":          # surface_field_energy(amplitude) only, On_lattice_decoupled.py:179
+            return rh.quiet(lat.surface_field_energy, a2)
+        return rh.quiet(lat.surface_field_energy, a2, ar, lat.lattice, lat.psi_squared, lat.dz, lat.dth)
+
+    e0 = [(a2, ar, field_energy(a2, ar)) for (a2, ar) in amps_eval]
     dec = lat.me.decisions
     iz = np.zeros(nprop, np.int32)
     ith = np.zeros(nprop, np.int32)
@@ -103,13 +109,12 @@ def record_lattice_case(modname, tag, seed, kwargs, amp, nprop, amps_eval):
             u[i] = uu
         dE[i], acc[i], sig[i] = new, accept, lat.sampling_width
     assert len(dec) == nprop
-    e1 = [(a2, ar, rh.quiet(lat.surface_field_energy, a2, ar, lat.lattice, lat.psi_squared, lat.dz, lat.dth))
-          for (a2, ar) in amps_eval]
+    e1 = [(a2, ar, field_energy(a2, ar)) for (a2, ar) in amps_eval]
     surf = [(a2, lat.surface.calc_surface_energy(a2)) for (a2, _) in amps_eval]
     prof = np.array([sum(col) for col in lat.lattice]), np.array([sum(abs(col)) for col in lat.lattice])
     np.savez_compressed(
         os.path.join(HERE, "lattice_%s.npz" % tag),
-        variant=np.array(modname), seed=seed, amp=amp,
+        variant=np.array(modname), seed=seed, amp=amp, sigma0=sigma0,
         params=np.array([kwargs[x] for x in ("wavenumber", "radius", "gamma", "kappa", "intrinsic_curvature",
                                                "alpha", "u", "C", "n", "temperature")], dtype=float),
         params_names=np.array(["wavenumber", "radius", "gamma", "kappa", "intrinsic_curvature", "alpha", "u",
@@ -139,6 +144,30 @@ def gen_lattice():
         # T = 0 branch of the accept rule
         cold = dict(base, temperature=0, dims=(20, 10), wavenumber=1)
         record_lattice_case(modname, short + "_T0", 5, cold, 0.79, 600, amps_eval)
+
+
+def gen_lattice_more_variants():
+    """rescaled_1storder and decoupled: the same four situations as the two live variants, plus for the
+    1st-order background a case whose log argument goes non-positive (alpha*area < -C q_min^2: On_lattice_rescaled_1storder.py:97-102)
+    and one where the whole O(u) correction is skipped (:103-105)."""
+    base = dict(amplitude=0, wavenumber=1, radius=1, gamma=1, kappa=0, intrinsic_curvature=0, alpha=-1, u=1,
+                C=1, n=6, temperature=.01, temperature_final=.01, dims=(50, 50))
+    amps_eval = [(0.0, 0.0), (0.3, 0.3), (-0.6, -0.6), (0.35, 0.3), (0.25, 0.3), (-0.79, -0.6)]
+    for modname, short in (("On_lattice_rescaled_1storder", "rescaled1"), ("On_lattice_decoupled", "decoupled")):
+        record_lattice_case(modname, short + "_c1_a03", 12345, base, 0.3, 3000, amps_eval)
+        record_lattice_case(modname, short + "_c1_a0", 1234, base, 0.0, 1500, amps_eval)
+        odd = dict(base, wavenumber=.7, dims=(50, 25), temperature=.1, alpha=-.5, C=.75, n=2, u=1.5, radius=1.25)
+        record_lattice_case(modname, short + "_odd_am06", 777, odd, -0.6, 2000, amps_eval)
+        cold = dict(base, temperature=0, dims=(20, 10), wavenumber=1)
+        record_lattice_case(modname, short + "_T0", 5, cold, 0.79, 600, amps_eval)
+    # coarse lattice, strongly negative alpha: large cells make alpha*area + C q^2 <= 0 for the lower (and the upper) cut-off
+    coarse = dict(base, dims=(8, 6), alpha=-3, C=.5, temperature=.2)
+    record_lattice_case("On_lattice_rescaled_1storder", "rescaled1_lowcut", 21, coarse, 0.2, 300, amps_eval)
+    coarser = dict(base, dims=(6, 4), alpha=-8, C=.25, temperature=.2)
+    record_lattice_case("On_lattice_rescaled_1storder", "rescaled1_nocorr", 22, coarser, -0.3, 300, amps_eval)
+    # alpha > 0: both logarithms regular (:96), no ordered-reference term (:110-113)
+    warm = dict(base, dims=(12, 10), alpha=.5, temperature=.3)
+    record_lattice_case("On_lattice_rescaled_1storder", "rescaled1_posalpha", 23, warm, 0.4, 300, amps_eval)
 
 
 def gen_known_answers():
@@ -207,13 +236,15 @@ def gen_fourier():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["geometry", "surface", "lattice", "known", "fourier"]
+    what = sys.argv[1:] or ["geometry", "surface", "lattice", "lattice2", "known", "fourier"]
     if "geometry" in what:
         gen_geometry()
     if "surface" in what:
         gen_surface_energy()
     if "lattice" in what:
         gen_lattice()
+    if "lattice2" in what:
+        gen_lattice_more_variants()
     if "known" in what:
         gen_known_answers()
     if "fourier" in what:

@@ -20,7 +20,7 @@ LATTICE_CASES = sorted(os.path.basename(p)[len("lattice_"):-4] for p in glob.glo
 def _load_case(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, "lattice_%s.npz" % tag))
     P = dict(zip(g["params_names"].tolist(), g["params"].tolist()))
-    variant = lo.SIMPLE if str(g["variant"]) == "On_lattice_simple" else lo.RESCALED_0TH
+    variant = lo.VARIANTS[str(g["variant"])[len("On_lattice_"):]]
     return g, P, variant
 
 

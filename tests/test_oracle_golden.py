@@ -16,9 +16,11 @@ LATTICE_CASES = sorted(os.path.basename(p)[len("lattice_"):-4]
 def load_case(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, "lattice_%s.npz" % tag))
     P = dict(zip(g["params_names"].tolist(), g["params"].tolist()))
-    variant = lo.SIMPLE if str(g["variant"]) == "On_lattice_simple" else lo.RESCALED_0TH
+    variant = lo.VARIANTS[str(g["variant"])[len("On_lattice_"):]]
     st = lo.LatticeState(g["psi0"], P["wavenumber"], P["radius"], P["alpha"], P["u"], P["C"], P["n"],
-                         P["temperature"], variant=variant)
+                         P["temperature"], variant=variant, sigma=lo.INIT_SIGMA[variant])
+    if "sigma0" in g.files:
+        assert float(g["sigma0"]) == lo.INIT_SIGMA[variant]
     return g, P, st
 
 
