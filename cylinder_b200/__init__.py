@@ -2,12 +2,14 @@
 
 Reference-facing classes (same names / arguments as the reference):
     Cylinder, Cylinder2D, Lattice (On_lattice_simple), LatticeRescaled0thOrder (On_lattice_rescaled_0thorder),
+    LatticeRescaled1stOrder (On_lattice_rescaled_1storder), LatticeDecoupled (On_lattice_decoupled),
     MetropolisEngine, run.single_run
 Batched / multi-GPU form of the reference's job farm: replicas.ReplicaBatch, run.grid_run.
 Everything numerical runs in libcylinder_b200.so (CUDA, sm_100a) through the C-ABI of include/cylinder_b200.h;
 importing this package does not need a GPU, using it does.
 """
-__all__ = ["Cylinder", "Cylinder2D", "Lattice", "LatticeRescaled0thOrder", "MetropolisEngine", "ReplicaBatch"]
+__all__ = ["Cylinder", "Cylinder2D", "Lattice", "LatticeRescaled0thOrder", "LatticeRescaled1stOrder", "LatticeDecoupled",
+           "MetropolisEngine", "ReplicaBatch"]
 
 
 def __getattr__(name):
@@ -17,7 +19,7 @@ def __getattr__(name):
     if name == "Cylinder2D":
         from .system_cylinder2D import Cylinder2D
         return Cylinder2D
-    if name in ("Lattice", "LatticeRescaled0thOrder"):
+    if name in ("Lattice", "LatticeRescaled0thOrder", "LatticeRescaled1stOrder", "LatticeDecoupled"):
         from . import lattice
         return getattr(lattice, name)
     if name == "MetropolisEngine":

@@ -14,8 +14,9 @@ HEADER = os.path.join(HERE, "..", "include", "cylinder_b200.h")
 ABI_VERSION = 3
 
 # constants mirrored from the header (checked against it in tests/test_abi_cpu.py)
-VARIANT_SIMPLE, VARIANT_RESCALED_0TH = 0, 1
-VARIANTS = {"simple": VARIANT_SIMPLE, "rescaled_0thorder": VARIANT_RESCALED_0TH}
+VARIANT_SIMPLE, VARIANT_RESCALED_0TH, VARIANT_RESCALED_1ST, VARIANT_DECOUPLED = 0, 1, 2, 3
+VARIANTS = {"simple": VARIANT_SIMPLE, "rescaled_0thorder": VARIANT_RESCALED_0TH, "rescaled_1storder": VARIANT_RESCALED_1ST,
+            "decoupled": VARIANT_DECOUPLED}
 SWEEP_ADAPT_SIGMA, SWEEP_AMP_MOVES, SWEEP_MEASURE = 1, 2, 4
 CHAIN_DOUBLES, OBS_DOUBLES, NMOM = 16, 16, 8
 CH_AMPLITUDE, CH_SIGMA_SITE, CH_SIGMA_AMP, CH_E_FIELD, CH_E_SURF, CH_STEP_COUNTER = 0, 1, 2, 3, 4, 5

@@ -31,11 +31,39 @@ __device__ __forceinline__ void moments_accumulate(double (&m)[CYL_NMOM], C p, C
 // Row weights of the energy: E_i = W[0] S1 + W[1] S2 + W[2] S3 + W[3] S4 + W[4] S5 + W[5], at trial amplitude a_eval
 // given the metric reference amplitude a_ref (only the 0th-order variant distinguishes them).  g0e / gme = metric at
 // z_i / z_{i-1/2} for a_eval, g0r = metric at z_i for a_ref.  WITHOUT the global lz*lth factor.
-__device__ __forceinline__ void field_energy_weights(int variant, const CylParams& p, double lz, double lth, int T,
+// O(u) fluctuation correction to the thermal background of the 1st-order variant, per cell
+// (On_lattice_rescaled_1storder.py:87-108; the reference's ValueError branches are its log arguments going <= 0)
+__device__ __forceinline__ double background_correction_1st(const CylParams& p, double area, int Z, int T) {
+  const double pi = 3.14159265358979323846;
+  const double area_factor = 2.0 / sqrt(pi);                    // 1st:34
+  const double upper = 1 * area_factor;                         // 1st:89
+  const double lower = (1.0 / (double)max(Z, T)) * area_factor; // 1st:90
+  const double alpha_cell = p.alpha * area;                     // 1st:92
+  const double hi = p.C * (upper * upper) + alpha_cell;
+  double lo = p.C * (lower * lower) + alpha_cell;
+  double integral = 0.0;                                        // 1st:103-105
+  if (hi > 0) {
+    if (!(lo > 0)) {                                            // 1st:98-102
+      const double l2 = sqrt(fabs(alpha_cell) / p.C) + .0000001;
+      lo = p.C * (l2 * l2) + alpha_cell;
+    }
+    integral = pi / p.C * (log(hi) - log(lo));                  // 1st:96
+  }
+  double correction = p.u * (p.temperature * p.temperature * p.temperature) * 4 * (integral * integral);   // 1st:106
+  correction /= (double)Z * (double)T;                          // 1st:107
+  return correction;
+}
+
+__device__ __forceinline__ void field_energy_weights(int variant, const CylParams& p, double lz, double lth, int Z, int T,
                                                      const Geo& g0e, const Geo& gme, const Geo& g0r, double (&W)[6]) {
   const double Cn2 = p.C * p.n * p.n;
   double w0, wir, zs, A;
   W[5] = 0.0;
+  if (variant == CYL_VARIANT_DECOUPLED) {                      // dec:179-202: only the C n^2 |A psi|^2 coupling
+    W[0] = Cn2 * (gme.ath * gme.ath) * (g0e.gz * fast_rcp(gme.gth));            // dec:190-198
+    W[1] = W[2] = W[3] = W[4] = 0.0;
+    return;
+  }
   if (variant == CYL_VARIANT_SIMPLE) {
     zs = gme.gz;                                               // :191
     w0 = zs * g0e.gth;                                         // :193
@@ -45,10 +73,12 @@ __device__ __forceinline__ void field_energy_weights(int variant, const CylParam
     zs = g0r.gz;                                               // 0th:253
     w0 = g0r.gz * g0e.gth;                                     // 0th:255
     wir = w0 * fast_rcp(g0r.gth * g0r.gth);                    // 0th:254,256
-    A = g0e.ath;                                               // 0th:257
+    A = (variant == CYL_VARIANT_RESCALED_0TH) ? g0e.ath : gme.ath;      // 0th:257 / 1st:275
     const double area = (lz * g0e.gz) * (lth * g0e.gth);       // 0th:261, :68
-    const double bg = -p.temperature * fast_rcp(area) + ((p.alpha < 0) ? .5 * p.alpha * p.alpha * fast_rcp(p.u) : 0.0);   // 0th:66-92
-    W[5] = T * bg * w0;                                        // 0th:275
+    double thermal = -p.temperature;                           // 0th:66-92 / 1st:86
+    if (variant == CYL_VARIANT_RESCALED_1ST) thermal += background_correction_1st(p, area, Z, T);   // 1st:87-108
+    const double bg = thermal * fast_rcp(area) + ((p.alpha < 0) ? .5 * p.alpha * p.alpha * fast_rcp(p.u) : 0.0);
+    W[5] = T * bg * w0;                                        // 0th:275 / 1st:293
   }
   W[0] = p.alpha * w0 + Cn2 * (A * A) * wir;                   // :199 (alpha part) + :210
   W[1] = p.u / 2 * w0;                                         // :199
@@ -57,20 +87,20 @@ __device__ __forceinline__ void field_energy_weights(int variant, const CylParam
   W[4] = p.C * p.n * 2 * A * wir;                              // :208
 }
 
-__device__ __forceinline__ double field_energy_row(int variant, const CylParams& p, double lz, double lth, int T,
+__device__ __forceinline__ double field_energy_row(int variant, const CylParams& p, double lz, double lth, int Z, int T,
                                                    const Geo& g0e, const Geo& gme, const Geo& g0r, const double* S) {
   double W[6];
-  field_energy_weights(variant, p, lz, lth, T, g0e, gme, g0r, W);
+  field_energy_weights(variant, p, lz, lth, Z, T, g0e, gme, g0r, W);
   return W[0] * S[0] + W[1] * S[1] + W[2] * S[2] + W[3] * S[3] + W[4] * S[4] + W[5];
 }
 
 // convenience: evaluate the metric with sincos (standalone kernels; the sweep kernels use cached sin/cos tables)
-__device__ __forceinline__ double field_energy_row_eval(int variant, const CylParams& p, double lz, double lth, int T, int i,
+__device__ __forceinline__ double field_energy_row_eval(int variant, const CylParams& p, double lz, double lth, int Z, int T, int i,
                                                         double a_eval, double a_ref, const double* S) {
   const double k = p.wavenumber, r = p.radius;
   const Geo g0e = geo_eval(k, r, a_eval, i * lz), gme = geo_eval(k, r, a_eval, (i - .5) * lz);
   const Geo g0r = geo_eval(k, r, a_ref, i * lz);
-  return field_energy_row(variant, p, lz, lth, T, g0e, gme, g0r, S);
+  return field_energy_row(variant, p, lz, lth, Z, T, g0e, gme, g0r, S);
 }
 
 // ------------------------------------------------------------------------------------------------------

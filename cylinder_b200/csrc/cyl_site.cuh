@@ -16,6 +16,11 @@
 //             clt = crt = C/(lth^2 Gth(z)^2)                                     (0th:154,:164)
 //             xl = xr = 2Cn A(z)/(lth Gth(z)^2); mass = alpha + C n^2 A(z)^2/Gth(z)^2 (0th:168-188)
 //             proposal width sigma*sg(z)                                         (0th:135-136)
+//   1storder: clz = C/(lz^2 Gz(z-)^2)        crz = C/(lz^2 Gz(z+)^2)             (1st:171,:181)
+//             clt = C/(lth^2 Gth(z-)^2)      crt = C/(lth^2 Gth(z+)^2)           (1st:172,:182)
+//             xl  = 2Cn A(z-)/(lth Gth(z-)^3) xr = 2Cn A(z+)/(lth Gth(z+)^3)     (1st:190-203)
+//             mass as simple (1st:205); proposal width sigma*sg(z) (1st:153-154)
+//   decoupled: as 1storder with clz = crz = C/lz^2 (dec:294,:304) and xl,xr = 2Cn A(z-+)/(lth Gth(z-+)^2) (dec:312-324)
 //   K = sg(z) lz lth (:668-669), z = lz*i, z-+ = lz*(i -+ 1/2).
 //
 // This is algebraically identical to the reference expression (verified against the oracle's verbatim
@@ -68,6 +73,18 @@ __device__ __forceinline__ RowCoef<R> row_coef(const CylParams& p, int variant, 
     xr = 2 * C * n * Rp * gpa * ilth;
     mass = alpha + Cn2 * Rm * gma * gma;
     sgmul = A(1);
+  } else if (variant == CYL_VARIANT_RESCALED_1ST || variant == CYL_VARIANT_DECOUPLED) {
+    const bool first = variant == CYL_VARIANT_RESCALED_1ST;
+    const A igtm = coef_rcp<A>(gmt), igtp = coef_rcp<A>(gpt);
+    const A Rm = igtm * igtm, Rp = igtp * igtp;
+    clz = first ? C * ilz2 * igzm * igzm : C * ilz2;
+    crz = first ? C * ilz2 * igzp * igzp : C * ilz2;
+    clt = C * Rm * ilth * ilth;
+    crt = C * Rp * ilth * ilth;
+    xl = 2 * C * n * Rm * gma * ilth * (first ? igtm : A(1));
+    xr = 2 * C * n * Rp * gpa * ilth * (first ? igtp : A(1));
+    mass = alpha + Cn2 * Rm * gma * gma;
+    sgmul = sg;
   } else {
     const A igt0 = coef_rcp<A>(g0t);
     const A R0 = igt0 * igt0, isg = igt0 * coef_rcp<A>(g0z);

@@ -76,7 +76,7 @@ __global__ void field_energy_kernel(const double* __restrict__ S, int B, const i
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
   const double ae = amp_eval[b], ar = amp_ref ? amp_ref[b] : ae;
   double e = 0.0;
-  for (int i = lane; i < Z; i += 32) e += field_energy_row_eval(variant, p, lz, lth, T, i, ae, ar, S + ((size_t)b * Zmax + i) * CYL_NMOM);
+  for (int i = lane; i < Z; i += 32) e += field_energy_row_eval(variant, p, lz, lth, Z, T, i, ae, ar, S + ((size_t)b * Zmax + i) * CYL_NMOM);
   e = warp_sum(e);
   if (lane == 0) E_out[b] = e * lz * lth;                       // :213
 }
@@ -85,7 +85,7 @@ extern "C" int cyl_field_energy_f64(const double* S, int B, const int32_t* Z, in
                                     const double* amp_eval, const double* amp_ref, int variant, double* E_out,
                                     void* stream) {
   CYL_CHECK_ARG(S && Z && params && amp_eval && E_out && B > 0 && Zmax > 0 && T > 0, "cyl_field_energy_f64: bad arguments");
-  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_field_energy_f64: unknown variant %d", variant);
+  CYL_CHECK_ARG(variant >= 0 && variant < CYL_NUM_VARIANTS, "cyl_field_energy_f64: unknown variant %d", variant);
   const int warps = 4;
   field_energy_kernel<<<(B + warps - 1) / warps, warps * 32, 0, as_stream(stream)>>>(S, B, Z, Zmax, T, params, amp_eval,
                                                                                     amp_ref, variant, E_out);

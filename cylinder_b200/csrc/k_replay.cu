@@ -6,6 +6,8 @@
 // of the reference are pure functions of psi and are recomputed on the fly.
 //   simple            On_lattice_simple.py:598-686
 //   rescaled_0thorder On_lattice_rescaled_0thorder.py:116-209
+//   rescaled_1storder On_lattice_rescaled_1storder.py:138-227   ("1st:")
+//   decoupled         On_lattice_decoupled.py:259-347           ("dec:")
 //   update_sigma      On_lattice_simple.py:688-696
 //   accept rule       metropolisengine.metropolis_decision (predecessor metropolis_engine.py:226-246)
 // The chain is strictly sequential (sigma adapts after every proposal), so one thread walks the tape.
@@ -32,9 +34,9 @@ __device__ __forceinline__ SiteGeo site_geo(const CylParams& p, double a, double
   const double z_p = lz * (iz + .5);                  // :601
   const Geo g0 = geo_eval(k, r, a, z_loc), gm = geo_eval(k, r, a, z_m), gp = geo_eval(k, r, a, z_p);
   SiteGeo s;
-  if (variant == CYL_VARIANT_SIMPLE) {
-    s.A = gm.ath;  s.R = 1.0 / (gm.gth * gm.gth);       // :603-604
-    s.A_nb = gp.ath; s.R_nb = 1.0 / (gp.gth * gp.gth);  // :605-606
+  if (variant != CYL_VARIANT_RESCALED_0TH) {
+    s.A = gm.ath;  s.R = 1.0 / (gm.gth * gm.gth);       // :603-604 / 1st:143-144 / dec:264-265
+    s.A_nb = gp.ath; s.R_nb = 1.0 / (gp.gth * gp.gth);  // :605-606 / 1st:145-146 / dec:266-267
   } else {
     s.A = g0.ath;  s.R = 1.0 / (g0.gth * g0.gth);       // 0th:122-123
     s.A_nb = s.A;  s.R_nb = s.R;                        // 0th:164,184-188
@@ -71,6 +73,16 @@ __device__ double delta_energy(const double2* __restrict__ psi, int Z, int T, co
     d_th = (csq(ndth) - csq(dth_c)) * g.R / (g.gth_m * g.gth_m);                // :634
     dn_z = (csq(nnz) - csq(dz_n)) / (g.gz_p * g.gz_p);                          // :643
     dn_th = (csq(nnth) - csq(dth_n)) * g.R_nb / (g.gth_p * g.gth_p);            // :644
+  } else if (variant == CYL_VARIANT_RESCALED_1ST) {
+    d_z = (csq(ndz) - csq(dz_c)) / (g.gz_m * g.gz_m);                           // 1st:171
+    d_th = (csq(ndth) - csq(dth_c)) * g.R;                                      // 1st:172
+    dn_z = (csq(nnz) - csq(dz_n)) / (g.gz_p * g.gz_p);                          // 1st:181
+    dn_th = (csq(nnth) - csq(dth_n)) * g.R_nb;                                  // 1st:182
+  } else if (variant == CYL_VARIANT_DECOUPLED) {
+    d_z = (csq(ndz) - csq(dz_c));                                               // dec:294
+    d_th = (csq(ndth) - csq(dth_c)) * g.R;                                      // dec:295
+    dn_z = (csq(nnz) - csq(dz_n));                                              // dec:304
+    dn_th = (csq(nnth) - csq(dth_n)) * g.R_nb;                                  // dec:305
   } else {
     d_z = (csq(ndz) - csq(dz_c)) / (g.gz_m * g.gz_m) * g.sg_m / g.sg;           // 0th:153
     d_th = (csq(ndth) - csq(dth_c)) * g.R;                                      // 0th:154
@@ -79,11 +91,24 @@ __device__ double delta_energy(const double2* __restrict__ psi, int Z, int T, co
   }
   dE += p.C * (d_z + d_th);                                                     // :636
   dE += p.C * (dn_z + dn_th);                                                   // :646
-  const double old_cross = cross_im(g.A, v, dth_c);                             // :651-652
-  const double new_cross = cross_im(g.A, nv, ndth);                             // :654-655
-  dE += p.C * 2 * p.n * g.R * (new_cross - old_cross);                          // :656
   const double A2 = g.A * g.A;
-  if (variant == CYL_VARIANT_SIMPLE) {
+  if (variant == CYL_VARIANT_RESCALED_1ST) {
+    // the cross terms carry an extra 1/sqrt_g_theta at the interstitial row: Im(((A conj(x)) y) / G) = Im(...) / G
+    const double old_cross = cross_im(g.A, v, dth_c) / g.gth_m;                 // 1st:190-191
+    const double new_cross = cross_im(g.A, nv, ndth) / g.gth_m;                 // 1st:194-195
+    dE += p.C * 2 * p.n * g.R * (new_cross - old_cross);                        // 1st:196
+    const double old_nb = cross_im(g.A_nb, right_th, dth_n) / g.gth_p;          // 1st:199-200
+    const double new_nb = cross_im(g.A_nb, right_th, nnth) / g.gth_p;           // 1st:201-202
+    dE += p.C * 2 * p.n * g.R_nb * (new_nb - old_nb);                           // 1st:203
+    dE += Cn2 * g.R * A2 * (new_p2 - old_p2);                                   // 1st:205-206
+    dE *= g.sg;                                                                 // 1st:209
+    dE *= lz * lth;                                                             // 1st:210
+    return dE;
+  }
+  const double old_cross = cross_im(g.A, v, dth_c);                             // :651-652 / dec:312-313
+  const double new_cross = cross_im(g.A, nv, ndth);                             // :654-655 / dec:315-316
+  dE += p.C * 2 * p.n * g.R * (new_cross - old_cross);                          // :656 / dec:317
+  if (variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_DECOUPLED) {      // dec:320-327 has the same shape
     const double old_nb = cross_im(g.A_nb, right_th, dth_n);                    // :659-660
     const double new_nb = cross_im(g.A_nb, right_th, nnth);                     // :661-662
     dE += p.C * 2 * p.n * g.R_nb * (new_nb - old_nb);                           // :663
@@ -116,7 +141,7 @@ __global__ void replay_kernel(double2* __restrict__ psi, int Z, int T, const Cyl
   for (int64_t s = 0; s < n; ++s) {
     const int i = iz[s], j = ith[s];
     const SiteGeo g = site_geo(p, amp, lz, i, variant);
-    const double sw = (variant == CYL_VARIANT_SIMPLE) ? sigma : sigma * g.sg;     // :613 / 0th:135-136
+    const double sw = (variant == CYL_VARIANT_SIMPLE) ? sigma : sigma * g.sg;     // :613 / 0th:135-136 / 1st:153-154 / dec:274-275
     const int i0 = wrap(i, Z), j0 = wrap(j, T);
     const double2 v = psi[(size_t)i0 * T + j0];
     const Cplx nv = {v.x + (0.0 + zre[s] * sw), v.y + (0.0 + zim[s] * sw)};        // :617  gauss = mu + z*sigma
@@ -146,7 +171,7 @@ extern "C" int cyl_replay_f64(double* psi, int Z, int T, const CylParams* params
                               double* sigma_out, void* stream) {
   CYL_CHECK_ARG(psi && params && rm_state && Z > 0 && T > 0 && n >= 0, "cyl_replay_f64: bad arguments");
   CYL_CHECK_ARG(n == 0 || (iz && ith && zre && zim && u), "cyl_replay_f64: tape buffers are null");
-  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_replay_f64: unknown variant %d", variant);
+  CYL_CHECK_ARG(variant >= 0 && variant < CYL_NUM_VARIANTS, "cyl_replay_f64: unknown variant %d", variant);
   if (n == 0) return CYL_OK;
   replay_kernel<<<1, 32, 0, as_stream(stream)>>>((double2*)psi, Z, T, params, amp, variant, iz, ith, zre, zim, u, n,
                                                  rm_state, accept_out, dE_out, sigma_out);
@@ -174,7 +199,7 @@ __global__ void site_delta_kernel(const double2* __restrict__ psi, int Z, int T,
 extern "C" int cyl_site_delta_f64(const double* psi, int Z, int T, const CylParams* params, double amp, int variant,
                                   int iz, int ith, double zre, double zim, double sigma, double* out, void* stream) {
   CYL_CHECK_ARG(psi && params && out && Z > 0 && T > 0, "cyl_site_delta_f64: bad arguments");
-  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_site_delta_f64: unknown variant %d", variant);
+  CYL_CHECK_ARG(variant >= 0 && variant < CYL_NUM_VARIANTS, "cyl_site_delta_f64: unknown variant %d", variant);
   site_delta_kernel<<<1, 32, 0, as_stream(stream)>>>((const double2*)psi, Z, T, params, amp, variant, iz, ith, zre, zim, sigma, out);
   CYL_LAUNCH_CHECK();
   return CYL_OK;

@@ -749,8 +749,8 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
     const Geo g0 = geo_from_sc(p.wavenumber, ra, a, s0, c0), gm = geo_from_sc(p.wavenumber, ra, a, sm, cm);
     const Geo h0 = geo_from_sc(p.wavenumber, rn, a_new, s0, c0), hm = geo_from_sc(p.wavenumber, rn, a_new, sm, cm);
     double Wc[6], Wn[6];
-    field_energy_weights(variant, p, lz, lth, T, g0, gm, g0, Wc);
-    field_energy_weights(variant, p, lz, lth, T, h0, hm, g0, Wn);              // a_ref = current amplitude (:75)
+    field_energy_weights(variant, p, lz, lth, Z, T, g0, gm, g0, Wc);
+    field_energy_weights(variant, p, lz, lth, Z, T, h0, hm, g0, Wn);              // a_ref = current amplitude (:75)
     const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
     RowW<R> w;
 #pragma unroll
@@ -979,7 +979,7 @@ static int sweep_hbm(void* work, int32_t* cur, int Z, int T, const CylParams* pa
                      double* prof, void* stream) {
   CYL_CHECK_ARG(work && cur && (*cur == 0 || *cur == 1) && params && chain && scratch && nsweeps >= 0, "cyl_sweep_hbm: bad arguments");
   CYL_CHECK_ARG(Z >= 8 && T >= 8, "cyl_sweep_hbm: the HBM path needs Z, T >= 8 (got %d x %d)", Z, T);
-  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_sweep_hbm: unknown variant %d", variant);
+  CYL_CHECK_ARG(variant >= 0 && variant < CYL_NUM_VARIANTS, "cyl_sweep_hbm: unknown variant %d", variant);
   CYL_CHECK_ARG(!(flags & CYL_SWEEP_MEASURE) || obs, "cyl_sweep_hbm: CYL_SWEEP_MEASURE needs obs");
   CYL_CHECK_ARG(((uintptr_t)work & 127) == 0, "cyl_sweep_hbm: work must be 128-byte aligned");
   const HbmGeom g = hbm_geom(Z, T);

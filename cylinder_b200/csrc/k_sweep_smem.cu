@@ -234,7 +234,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           Geo g0r = g0e;                                                 // a_ref = current amplitude (:75); 0th order only
           if (variant != CYL_VARIANT_SIMPLE && (tid & 1)) g0r = geo_from_sc(p.wavenumber, ra, a, tr.s0, tr.c0);
           double W[6];
-          field_energy_weights(variant, p, lz, lth, T, g0e, gme, g0r, W);
+          field_energy_weights(variant, p, lz, lth, Z, T, g0e, gme, g0r, W);
           RowW<R> w;
           double dif5 = 0.0;
 #pragma unroll
@@ -447,7 +447,7 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
                       uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags,
                       double* obs, double* prof, void* stream) {
   CYL_CHECK_ARG(psi && Z && params && chain && B > 0 && Zmax > 0 && T > 1 && nsweeps >= 0, "cyl_sweep_smem: bad arguments");
-  CYL_CHECK_ARG(variant == CYL_VARIANT_SIMPLE || variant == CYL_VARIANT_RESCALED_0TH, "cyl_sweep_smem: unknown variant %d", variant);
+  CYL_CHECK_ARG(variant >= 0 && variant < CYL_NUM_VARIANTS, "cyl_sweep_smem: unknown variant %d", variant);
   CYL_CHECK_ARG(!(flags & CYL_SWEEP_MEASURE) || obs, "cyl_sweep_smem: CYL_SWEEP_MEASURE needs obs");
   if (nsweeps == 0) return CYL_OK;
   const SweepSmemLayout<R> lay(Zmax, T);

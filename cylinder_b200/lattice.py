@@ -1,6 +1,8 @@
 """Drop-in mirror of the reference's lattice field model:
   Lattice                  = surfaces_and_fields/On_lattice_simple.py:17-696
   LatticeRescaled0thOrder  = surfaces_and_fields/On_lattice_rescaled_0thorder.py (the class run.py:18 imports)
+  LatticeRescaled1stOrder  = surfaces_and_fields/On_lattice_rescaled_1storder.py
+  LatticeDecoupled         = surfaces_and_fields/On_lattice_decoupled.py
 Same constructor arguments, public attributes and methods; psi lives on the GPU and every energy / move is a kernel
 of libcylinder_b200 (no CPU fallback).
 
@@ -32,6 +34,7 @@ from .system_cylinder import Cylinder
 class Lattice:
     VARIANT = "simple"
     INIT_MAGNITUDE = .1                       # On_lattice_simple.py:164
+    INIT_SAMPLING_WIDTH = .005                # On_lattice_simple.py:101
 
     def __init__(self, amplitude, wavenumber, radius, gamma, kappa, intrinsic_curvature, alpha, u, C, n, temperature,
                  temperature_final, dims=(100, 50), n_substeps=None, fieldsteps_per_ampstep=1, dtype=torch.complex128,
@@ -93,7 +96,7 @@ class Lattice:
         self.target_acceptance = .5
         self.m = 1
         self.ratio = robbins_monro_ratio(self.target_acceptance, self.m)
-        self.sampling_width = .005
+        self.sampling_width = self.INIT_SAMPLING_WIDTH
         self.bump_sampling_width = .005
         # production path state: the Philox seed is a function of the state of Python's generator (random.seed(...) makes
         # runs repeatable) but does not CONSUME it -- the compatibility path stays on the reference's stream
@@ -369,3 +372,44 @@ class LatticeRescaled0thOrder(Lattice):
         for z_index in range(self.z_len):
             cell_dims = (self.z_pixel_len * g[z_index, 3], self.th_pixel_len * g[z_index, 1])
             self.background_energy[z_index] = self.get_background_energy(cell_dims)
+
+
+class LatticeRescaled1stOrder(LatticeRescaled0thOrder):
+    """On_lattice_rescaled_1storder.Lattice: A_theta and the index raise at the interstitial rows, cross terms with an extra
+    1/sqrt(g_theta), and an O(u) fluctuation correction in the background energy (1st:66-114).  The reference's constructor
+    has no `fieldsteps_per_ampstep` (1st:20-21); it is accepted here and defaults to the base class's 1."""
+    VARIANT = "rescaled_1storder"
+
+    def get_background_energy(self, cell_dims, ordered_reference=True):                        # 1st:66-114
+        area = cell_dims[0] * cell_dims[1]
+        ans = -self._temperature_for_background
+        upper_limit = 1 * self.area_factor
+        lower_limit = (1 / max((self.z_len, self.th_len))) * self.area_factor
+        alpha_cell = self.alpha * area
+        hi, lo = self.C * upper_limit ** 2 + alpha_cell, self.C * lower_limit ** 2 + alpha_cell
+        if hi > 0 and lo > 0:
+            integral = math.pi / self.C * (math.log(hi) - math.log(lo))
+        elif hi > 0:                                                                           # 1st:98-102
+            lower_limit = math.sqrt(abs(alpha_cell) / self.C) + .0000001
+            integral = math.pi / self.C * (math.log(hi) - math.log(self.C * lower_limit ** 2 + alpha_cell))
+        else:
+            integral = 0                                                                       # 1st:103-105
+        correction = self.u * self._temperature_for_background ** 3 * 4 * integral ** 2
+        correction /= self.z_len * self.th_len
+        ans += correction
+        ordered = .5 * self.alpha ** 2 / self.u if (self.alpha < 0 and ordered_reference) else 0
+        return ans / area + ordered
+
+
+class LatticeDecoupled(Lattice):
+    """On_lattice_decoupled.Lattice: the field feels the metric, the shape only feels the C n^2 |A_theta psi|^2 coupling
+    (dec:179-202).  Differences from `simple`: psi_0 = rect(U(0,.001), U(0,2pi)) (dec:157), initial sampling width 1e-4
+    (dec:99), proposal width sigma*sqrt(g) (dec:274-275), bare z-gradient and cross terms (dec:294-324), and
+    `surface_field_energy(amplitude)` takes the amplitude only (the other arguments of the base signature are accepted and
+    ignored so that the engine wiring of the base class keeps working)."""
+    VARIANT = "decoupled"
+    INIT_MAGNITUDE = .001
+    INIT_SAMPLING_WIDTH = .0001
+
+    def surface_field_energy(self, amplitude, reference_amplitude=None, lattice=None, psi_squared=None, dz=None, dth=None):
+        return super().surface_field_energy(amplitude, amplitude, lattice)

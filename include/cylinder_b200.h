@@ -36,6 +36,9 @@ extern "C" {
 /* dE variants: which reference class the single-site move restates */
 #define CYL_VARIANT_SIMPLE        0   /* On_lattice_simple.py:598-686            */
 #define CYL_VARIANT_RESCALED_0TH  1   /* On_lattice_rescaled_0thorder.py:116-209 */
+#define CYL_VARIANT_RESCALED_1ST  2   /* On_lattice_rescaled_1storder.py:138-227 */
+#define CYL_VARIANT_DECOUPLED     3   /* On_lattice_decoupled.py:259-347         */
+#define CYL_NUM_VARIANTS          4
 
 /* flags of the sweep entry points */
 #define CYL_SWEEP_ADAPT_SIGMA   1u    /* Robbins-Monro width adaptation (On_lattice_simple.py:688-696) */

@@ -154,7 +154,7 @@ def delta_energy_vec(st, a, I, J, new_values):
     gth0, gz0, ath0 = _geo(st, a, lz * I)
     gthm, gzm, athm = _geo(st, a, lz * (I - .5))
     gthp, gzp, athp = _geo(st, a, lz * (I + .5))
-    if st.variant == lo.SIMPLE:
+    if st.variant != lo.RESCALED_0TH:
         A, R, A_nb, R_nb = athm, 1 / gthm ** 2, athp, 1 / gthp ** 2
     else:
         A, R = ath0, 1 / gth0 ** 2
@@ -174,6 +174,16 @@ def delta_energy_vec(st, a, I, J, new_values):
         d_th = (_sq(ndth) - _sq(dth_c)) * R / gthm ** 2
         dn_z = (_sq(nnz) - _sq(dz_n)) / gzp ** 2
         dn_th = (_sq(nnth) - _sq(dth_n)) * R_nb / gthp ** 2
+    elif st.variant == lo.RESCALED_1ST:
+        d_z = (_sq(ndz) - _sq(dz_c)) / gzm ** 2
+        d_th = (_sq(ndth) - _sq(dth_c)) * R
+        dn_z = (_sq(nnz) - _sq(dz_n)) / gzp ** 2
+        dn_th = (_sq(nnth) - _sq(dth_n)) * R_nb
+    elif st.variant == lo.DECOUPLED:
+        d_z = (_sq(ndz) - _sq(dz_c))
+        d_th = (_sq(ndth) - _sq(dth_c)) * R
+        dn_z = (_sq(nnz) - _sq(dz_n))
+        dn_th = (_sq(nnth) - _sq(dth_n)) * R_nb
     else:
         d_z = (_sq(ndz) - _sq(dz_c)) / gzm ** 2 * (gthm * gzm) / sg
         d_th = (_sq(ndth) - _sq(dth_c)) * R
@@ -181,6 +191,8 @@ def delta_energy_vec(st, a, I, J, new_values):
         dn_th = (_sq(nnth) - _sq(dth_n)) * R
     dE = dE + st.C * (d_z + d_th)
     dE = dE + st.C * (dn_z + dn_th)
+    if st.variant == lo.RESCALED_1ST:            # cross terms carry 1/sqrt_g_theta of the interstitial row (1st:190-203)
+        dth_c, ndth, dth_n, nnth = dth_c / gthm, ndth / gthm, dth_n / gthp, nnth / gthp
     old_cross = (A * v.conj() * dth_c).imag
     new_cross = (A * new_values.conj() * ndth).imag
     dE = dE + st.C * 2 * st.n * R * (new_cross - old_cross)

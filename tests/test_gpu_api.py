@@ -23,7 +23,8 @@ def _case(golden_dir, tag):
 
 
 @pytest.mark.parametrize("tag,cls", [("simple_c1_a03", "Lattice"), ("rescaled0_odd_am06", "LatticeRescaled0thOrder"),
-                                     ("simple_T0", "Lattice")])
+                                     ("simple_T0", "Lattice"), ("rescaled1_odd_am06", "LatticeRescaled1stOrder"),
+                                     ("decoupled_c1_a03", "LatticeDecoupled")])
 def test_lattice_sequential_path_reproduces_reference_stream(cuda, golden_dir, tag, cls):
     """random.seed(s); Lattice(...); step_lattice(a) x N consumes Python's generator exactly like the reference: same
     initial field, same accept/reject sequence, same adaptive width, same final field."""

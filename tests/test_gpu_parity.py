@@ -82,7 +82,7 @@ def test_replay_reproduces_reference_chain(cuda, golden_dir, tag):
     g, P, variant = _load_case(golden_dir, tag)
     par = _params(ops, cuda, P)
     psi = torch.tensor(g["psi0"], dtype=torch.complex128, device=cuda).contiguous()
-    rm = torch.tensor([.005, 0.0], dtype=torch.float64, device=cuda)
+    rm = torch.tensor([lo.INIT_SIGMA[variant], 0.0], dtype=torch.float64, device=cuda)       # :101 / dec:99
     u = np.where(np.isfinite(g["u"]), g["u"], 2.0)          # never consulted where the reference drew none
     acc, dE, sig = ops.replay(psi, par, float(g["amp"]), variant, torch.tensor(g["iz"], device=cuda), torch.tensor(g["ith"], device=cuda),
                               torch.tensor(g["zre"], device=cuda), torch.tensor(g["zim"], device=cuda), torch.tensor(u, device=cuda), rm)
@@ -143,6 +143,8 @@ def _oracle_state(psi, P, variant, sigma):
 CHECKER_CASES = [  # (Z, T, variant, a, temperature)
     (12, 10, lo.SIMPLE, 0.3, .05), (12, 10, lo.RESCALED_0TH, -0.45, .05), (11, 10, lo.SIMPLE, 0.3, .05),
     (12, 9, lo.RESCALED_0TH, 0.2, .05), (7, 5, lo.SIMPLE, -0.6, .2), (10, 8, lo.SIMPLE, 0.5, 0.0),
+    (12, 10, lo.RESCALED_1ST, 0.3, .05), (11, 9, lo.RESCALED_1ST, -0.5, .1), (12, 10, lo.DECOUPLED, 0.3, .05),
+    (9, 10, lo.DECOUPLED, -0.45, 0.0),
 ]
 
 
@@ -170,7 +172,7 @@ def test_smem_sweep_f64_matches_oracle(cuda, Z, T, variant, a, temp):
     assert ch[_abi.CH_SIGMA_SITE] == pytest.approx(st.sigma, rel=1e-12)
 
 
-@pytest.mark.parametrize("variant", [lo.SIMPLE, lo.RESCALED_0TH])
+@pytest.mark.parametrize("variant", [lo.SIMPLE, lo.RESCALED_0TH, lo.RESCALED_1ST, lo.DECOUPLED])
 def test_smem_sweep_with_amplitude_moves_matches_oracle(cuda, variant):
     """Sweeps + global amplitude moves + measurement, fp64, vs the oracle: same amplitude trajectory end point,
     same accept counts, energies within 1e-10."""
@@ -213,7 +215,7 @@ def test_smem_sweep_with_amplitude_moves_matches_oracle(cuda, variant):
 
 
 @pytest.mark.parametrize("Z,T,variant", [(64, 128, lo.SIMPLE), (40, 24, lo.RESCALED_0TH), (71, 25, lo.SIMPLE), (70, 131, lo.SIMPLE),
-                                         (130, 260, lo.SIMPLE)])
+                                         (130, 260, lo.SIMPLE), (40, 24, lo.RESCALED_1ST), (33, 130, lo.DECOUPLED)])
 def test_hbm_sweep_f64_matches_oracle(cuda, Z, T, variant):
     """TMA-tiled HBM kernel (fp64) vs the oracle: tiles with halos, partial tiles, multi-tile lattices and odd rings
     reproduce the oracle's checkerboard sweep on the whole lattice."""
@@ -366,8 +368,8 @@ def test_fourier_energy_matches_reference(cuda, golden_dir, tag):
 
 
 def test_hbm_path_with_amplitude_moves_tracks_smem_path(cuda):
-    """fp64: the HBM path (row-moment kernel + one-CTA amplitude kernel) and the shared-memory path (energy fused into the
-    colour passes) see the same Philox streams, so the amplitude trajectory, the lattice and the accumulated observables
+    """fp64: the HBM path (energy and profile sums accumulated per tile, decision kernel) and the shared-memory path (one CTA
+    per replica) see the same Philox streams, so the amplitude trajectory, the lattice and the accumulated observables
     agree to rounding."""
     import torch
     from cylinder_b200 import ops, _abi
@@ -393,6 +395,54 @@ def test_hbm_path_with_amplitude_moves_tracks_smem_path(cuda):
     np.testing.assert_allclose(ws.unpack().cpu().numpy(), psi[0].cpu().numpy(), rtol=0, atol=1e-10)
     np.testing.assert_allclose(o2.cpu().numpy()[0, :9], o1.cpu().numpy()[0, :9], rtol=1e-9)
     np.testing.assert_allclose(p2.cpu().numpy(), p1.cpu().numpy(), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("Z,T,variant,temp", [(70, 260, lo.SIMPLE, .3), (71, 131, lo.RESCALED_1ST, .3), (40, 136, lo.RESCALED_0TH, .5),
+                                              (33, 130, lo.DECOUPLED, .3), (64, 256, lo.SIMPLE, 0.0)])
+def test_hbm_sweep_with_amplitude_moves_matches_oracle(cuda, Z, T, variant, temp):
+    """Multi-tile lattices (interior, border and partial tiles, 2 and 3 colours): the energies accumulated tile by tile while
+    the sites are updated, the profile sums and the amplitude decisions of the HBM path equal the oracle's whole-lattice
+    evaluation (fp64, same Philox streams)."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.3, intrinsic_curvature=0.2, alpha=-.8, u=1.2, C=.9, n=3, temperature=temp)
+    rng = np.random.RandomState(Z + 7 * T)
+    psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
+    st = _oracle_state(psi0.copy(), P, variant, .05)
+    am = cb.AmpState(amplitude=.1, sigma_amp=.004, target=.3, bound=.8)
+    par = _params(ops, cuda, P, amp_bound=.8, amp_target_acceptance=.3)
+    ws = ops.HbmWorkspace(Z, T, torch.complex128, cuda)
+    ws.pack(torch.tensor(psi0, dtype=torch.complex128, device=cuda))
+    chain = ops.new_chain(1, cuda, amplitude=.1, sigma_site=.05, sigma_amp=.004)
+    obs, prof = ops.new_obs(1, Z, cuda)
+    seed, rep, nsw = 4711, 6, 8
+    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
+    ws.sweep(par, chain[0], seed, 3, nsw, variant, flags, replica=rep, obs=obs[0], prof=prof[0])
+    sum_abs_a = sum_ef = sum_p2 = 0.0
+    prof_o = np.zeros((Z, 3))
+    for s in range(3, 3 + nsw):
+        cb.sweep(st, am.a, seed, rep, s)
+        sum_abs_a += abs(am.a)
+        sum_ef += lo.surface_field_energy(st, am.a, am.a)
+        sum_p2 += float(np.mean(st.psi2))
+        ps, pa = lo.measure_profiles(st.psi)
+        prof_o += np.stack([ps.real, ps.imag, pa], 1)
+        cb.amplitude_move(st, am, P, seed, rep, s)
+    ch = chain[0].cpu().numpy()
+    assert ch[_abi.CH_AMP_ACCEPTED] == am.accepted and ch[_abi.CH_AMP_PROPOSED] == am.proposed == nsw
+    assert ch[_abi.CH_SITE_ACCEPTED] == st.accepted
+    assert ch[_abi.CH_AMPLITUDE] == pytest.approx(am.a, rel=1e-12)
+    assert ch[_abi.CH_SIGMA_AMP] == pytest.approx(am.sigma, rel=1e-12)
+    assert ch[_abi.CH_SIGMA_SITE] == pytest.approx(st.sigma, rel=1e-12)
+    np.testing.assert_allclose(ws.unpack().cpu().numpy(), st.psi, rtol=0, atol=1e-11)
+    o = obs[0].cpu().numpy()
+    assert o[_abi.OB_COUNT] == nsw
+    assert o[_abi.OB_ABS_A] == pytest.approx(sum_abs_a, rel=1e-12)
+    assert o[_abi.OB_E_FIELD] == pytest.approx(sum_ef, rel=1e-10)
+    assert o[_abi.OB_PSI2] == pytest.approx(sum_p2, rel=1e-11)
+    np.testing.assert_allclose(prof[0].cpu().numpy(), prof_o, rtol=1e-10, atol=1e-11)
+    if temp > 0:
+        assert 1 <= am.accepted, "case should exercise an accepted amplitude move"
 
 
 def test_step_host_equals_device_resident_run(cuda):

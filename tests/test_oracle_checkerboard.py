@@ -49,7 +49,10 @@ def _state(Z, T, variant, seed=3, **kw):
     return lo.LatticeState(psi, P["k"], P["r"], P["alpha"], P["u"], P["C"], P["n"], P["temp"], variant=variant)
 
 
-@pytest.mark.parametrize("variant", [lo.SIMPLE, lo.RESCALED_0TH])
+ALL_VARIANTS = [lo.SIMPLE, lo.RESCALED_0TH, lo.RESCALED_1ST, lo.DECOUPLED]
+
+
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
 @pytest.mark.parametrize("a", [0.0, 0.35, -0.7])
 def test_vectorised_dE_equals_scalar(variant, a):
     st = _state(9, 6, variant)
@@ -93,7 +96,7 @@ def _batch_err(x, nb=10):
     return b.std(ddof=1) / math.sqrt(nb)
 
 
-@pytest.mark.parametrize("variant", [lo.SIMPLE, lo.RESCALED_0TH])
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
 def test_checkerboard_matches_sequential_statistics(variant):
     """<|psi|^2> of the checkerboard ordering agrees with the sequential ordering within statistical error
     (6x5 lattice incl. an odd ring, a = 0.3)."""
