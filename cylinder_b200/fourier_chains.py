@@ -24,7 +24,7 @@ class FourierChains:
         self.d = self.ncoef + 1
         self.seed, self.chain0, self.steps_done = int(seed), int(chain0), 0
         self.target = float(target_acceptance)
-        self.amp = torch.full((self.B,), float(amplitude), dtype=torch.float64, device=self.device)
+        self.amp = torch.as_tensor(amplitude, dtype=torch.float64).expand(self.B).contiguous().to(self.device)
         if field_coeffs is None:
             # gaussian_complex(sigma=.1) = rect(N(0, sigma), U(0, 2 pi))  (run.py:219), from a seeded torch generator
             g = torch.Generator(device="cpu").manual_seed(self.seed)

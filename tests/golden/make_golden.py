@@ -14,6 +14,7 @@ What is recorded:
                         and surface_field_energy(a', a_ref) at several amplitudes.
   known_answers.npz     psi==1 field energy -2*pi^2 (tests/test_On_lattice.py:75-88) on both lattices
   fourier.npz           Cylinder2D / Cylinder1D tensors and energies (system_cylinder2D.py:103-198)
+  farm/                 varfile.txt written by parallel_preprocessing.py; tables written by parallel_postprocessing.py
 """
 import math
 import os
@@ -235,8 +236,38 @@ def gen_fourier():
     np.savez_compressed(os.path.join(HERE, "fourier.npz"), **out)
 
 
+def gen_farm():
+    """File formats of the job farm, produced by the reference's own scripts (run as subprocesses in a scratch directory):
+    varfile.txt of parallel_preprocessing.py and the per-column tables of parallel_postprocessing.py for a small set of
+    synthetic *_mean.csv files (committed as inputs)."""
+    import shutil
+    import subprocess
+    import tempfile
+    import pandas as pd
+    dst = os.path.join(HERE, "farm")
+    os.makedirs(dst, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([sys.executable, os.path.join(rh.REFERENCE_ROOT, "parallel_preprocessing.py"), "-n", "golden scan",
+                        "--var1name", "alpha", "--var1range", "-2", "1.1", ".75", "--var2name", "C", "--var2range", ".3", "1.0", ".3"],
+                       cwd=tmp, check=True)
+        shutil.copy(os.path.join(tmp, "varfile.txt"), os.path.join(dst, "varfile_ref.txt"))
+        shutil.copy(os.path.join(tmp, "notes.txt"), os.path.join(dst, "notes_ref.txt"))
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.RandomState(3)
+        for v1 in ("-2.0", "-1.25", "0.25"):
+            for v2 in ("0.3", "0.6"):
+                d = {"abs_amplitude": [rng.rand()], "amplitude_squared": [rng.rand()], "field_energy": [rng.randn()]}
+                name = "alpha_%s_C_%s_mean.csv" % (v1, v2)
+                pd.DataFrame.from_dict(d).to_csv(os.path.join(tmp, name))
+                shutil.copy(os.path.join(tmp, name), os.path.join(dst, name))
+        subprocess.run([sys.executable, os.path.join(rh.REFERENCE_ROOT, "parallel_postprocessing.py")], cwd=tmp, check=True)
+        for col in ("abs_amplitude", "amplitude_squared", "field_energy"):
+            shutil.copy(os.path.join(tmp, col + ".csv"), os.path.join(dst, col + "_ref.csv"))
+    print("farm fixtures:", sorted(os.listdir(dst)))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["geometry", "surface", "lattice", "lattice2", "known", "fourier"]
+    what = sys.argv[1:] or ["geometry", "surface", "lattice", "lattice2", "known", "fourier", "farm"]
     if "geometry" in what:
         gen_geometry()
     if "surface" in what:
@@ -249,3 +280,5 @@ if __name__ == "__main__":
         gen_known_answers()
     if "fourier" in what:
         gen_fourier()
+    if "farm" in what:
+        gen_farm()

@@ -179,3 +179,31 @@ def test_batched_fourier_chains_match_oracle(cuda):
         np.testing.assert_allclose(fc.covariance[b].cpu().numpy(), ch.cov, rtol=1e-7, atol=1e-12)
     summ = fc.summary()
     assert torch.all(summ["complex_acceptance"] > 0) and torch.all(fc.amp.abs() < .99)
+
+
+def test_farm_run_writes_the_reference_files(cuda, tmp_path):
+    """infile.txt + varfile.txt -> one batched launch: one <var1>_<x1>_<var2>_<x2>_mean.csv (+ profile CSVs) per line, named
+    with the strings of the varfile, joinable by postprocess(); results do not depend on how the lines are batched."""
+    import pandas as pd
+    from cylinder_b200 import farm
+    (tmp_path / "infile.txt").write_text("--n_steps 12\n--field_type lattice\n--method sequential\n--alpha -1\n--C 1\n--u 1\n--n 2\n"
+                                         "--kappa 0\n--gamma 1\n--temp .2\n--intrinsic_curvature 0\n--amplitude 0\n--radius 1\n"
+                                         "--wavenumber 1\n--measure_every 1\n--fieldsteps_per_ampstep 10\n--dims 12 10\n")
+    farm.preprocess("t", "alpha", [-1.5, 0, .5], "wavenumber", [.8, 1.3, .25], outdir=str(tmp_path))
+    names, lines = farm.read_varfile(str(tmp_path / "varfile.txt"))
+    assert len(lines) == 6
+    out = farm.run(str(tmp_path / "infile.txt"), str(tmp_path / "varfile.txt"), outdir=str(tmp_path / "out"), seed=3)
+    assert out["abs_amplitude"].shape == (6,) and np.all(out["n_measurements"] == 6) if "n_measurements" in out else True
+    for strings in lines:
+        t = farm.title_of(names, strings)
+        df = pd.read_csv(tmp_path / "out" / (t + "_mean.csv"), index_col=0)
+        assert {"abs_amplitude", "amplitude_squared", "field_energy", "surface_energy", "energy"} <= set(df.columns)
+        Z = int(round(12 / float(strings[1])))
+        assert len(pd.read_csv(tmp_path / "out" / (t + "_profile_abs.csv"), index_col=0)) == Z
+    cols = farm.postprocess(str(tmp_path / "out"))
+    tab = pd.read_csv(tmp_path / "out" / "abs_amplitude.csv", index_col=0)
+    assert "abs_amplitude" in cols and tab.shape == (2, 3)
+    # a sub-range of the lines run alone gives the same numbers (replica streams depend on the global line index only)
+    (tmp_path / "var2.txt").write_text("alpha wavenumber\n" + "\n".join(" ".join(s) for s in lines[:1]) + "\n")
+    out1 = farm.run(str(tmp_path / "infile.txt"), str(tmp_path / "var2.txt"), outdir=str(tmp_path / "out1"), seed=3, write_profiles=False)
+    assert out1["abs_amplitude"][0] == out["abs_amplitude"][0] and out1["field_energy"][0] == out["field_energy"][0]
