@@ -62,7 +62,16 @@ struct HbmAmp {                      // header: the amplitude proposal of the cu
   int try_move;
   int coef_sel;                      // which of the two RowCoef tables belongs to the current amplitude
   int pad[2];
+  // Robbins-Monro record of the site moves when no decision kernel runs (sweeps without measurement / amplitude move):
+  // slot s % 3 of sweep s holds the width it used, the step counter it started from and its accept count, the latter in
+  // HBM_NBUCKET buckets so that the no-return atomics of the tiles finishing together do not queue on one address.
+  double rm_sigma[3], rm_counter[3];
+  double acc_total;                  // accepts of all sweeps of this call but the last
+  unsigned int nacc[3][32];
 };
+#define HBM_NBUCKET 32
+#define HBM_HDR_BYTES 1024
+static_assert(sizeof(HbmAmp) <= HBM_HDR_BYTES, "scratch header");
 #ifndef HBM_MINB_F32
 #define HBM_MINB_F32 5             // co-resident CTAs per SM the fp32 sweep kernel is compiled for
 #endif
@@ -81,7 +90,7 @@ struct HbmScratch {
   __host__ __device__ HbmScratch(int Z, int T) {
     ncst = (Z + HBM_PREP_NT - 1) / HBM_PREP_NT;
     ntx = (T + HBM_TW - 1) / HBM_TW;
-    off_coef = 128;
+    off_coef = HBM_HDR_BYTES;
     off_roww = (off_coef + 2 * (size_t)Z * sizeof(RowCoef<R>) + 63) & ~(size_t)63;
     off_part = (off_roww + (size_t)Z * sizeof(RowW<R>) + 63) & ~(size_t)63;
     const size_t tiles = (size_t)ntx * ((Z + HBM_MIN_TH - 1) / HBM_MIN_TH);
@@ -173,7 +182,8 @@ template <typename R>
 __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const double* __restrict__ chain, int Z, int T, int variant,
                                 RowCoef<R>* __restrict__ coef, HbmAmp* __restrict__ hdr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { hdr->coef_sel = 0; hdr->try_move = 0; }       // scratch arrives uninitialised
+  if (i == 0) { hdr->coef_sel = 0; hdr->try_move = 0; hdr->acc_total = 0.0; }       // scratch arrives uninitialised
+  if (i < 3 * HBM_NBUCKET) (&hdr->nacc[0][0])[i] = 0u;
   if (i >= Z) return;
   const CylParams p = *params;
   const double a = chain[CYL_CH_AMPLITUDE];
@@ -226,6 +236,7 @@ __device__ __forceinline__ void load_pair(const float2* p, float2& a, float2& b)
   a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
 }
 __device__ __forceinline__ void load_pair(const double2* p, double2& a, double2& b) { a = p[0]; b = p[1]; }
+__device__ __forceinline__ int warp_id_of(int tid) { return tid >> 5; }
 __device__ __forceinline__ int ld_early_i32(const int* p) {
   int v;
   asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -301,7 +312,7 @@ template <typename R, int NCOL, int TH_, bool EXTRAS>
 __global__ void __launch_bounds__(HBM_NT, sizeof(R) == 4 ? HBM_MINB_F32 : 2)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
                  int cur, const __grid_constant__ HbmGeom g, const __grid_constant__ HbmArgs<R> A,
-                 const __grid_constant__ SiteKeys keys, uint64_t sweep) {
+                 const __grid_constant__ SiteKeys keys, uint64_t sweep, int rm_slot) {
   using C = typename Real<R>::complex_t;
   using L = HbmSmem<R, NCOL, TH_>;
   constexpr int TH = L::TH, TW = L::TW, SH = L::SH, SW = L::SW, SWH = L::SWH, HS = L::HS;
@@ -324,6 +335,9 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // Prologue.  Global-memory latency under the bulk traffic of this kernel is several microseconds, so everything that
   // comes from global memory is requested up front and in parallel: the tile (TMA, issued by thread 0 as soon as it has
   // initialised the mbarrier), the row coefficients / weights and the proposal width.
+  // Plain sweeps follow each other directly, so their tiles come from the preceding kernel: wait first.  With EXTRAS the
+  // decision and preparation kernels sit between two sweeps and the tiles are at least two kernels old: load, then wait.
+  if (!EXTRAS) pdl_wait();
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -333,10 +347,36 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     tma_load_2d(pl0, &maps.m[cur][0], x0 * maps.esz, ti0, bar);    // esz: TMA elements per complex value
     tma_load_2d(pl1, &maps.m[cur][1], x1 * maps.esz, ti0, bar);
   }
-  pdl_wait();                       // the tiles are two kernels old; everything below comes from the preceding kernel
+  if (EXTRAS) pdl_wait();           // everything below comes from the preceding kernel
   pdl_trigger();
-  const R sigma = (R)ld_early_f64(chain + CYL_CH_SIGMA_SITE);
+  R sigma;
+  if (!EXTRAS && warp_id_of(tid) == 1) {
+    // No decision kernel between plain sweeps: every tile derives this sweep's proposal width from the previous sweep's
+    // record (rm_slot < 0: first sweep of the call, the width comes from the chain state); tile 0 files this sweep's record.
+    const int lane = tid & 31;
+    HbmAmp* hdr = A.hdr;
+    const int r = rm_slot < 0 ? 0 : rm_slot, pslot = r == 0 ? 2 : r - 1;
+    double sg, cnt, prev_acc = 0.0;
+    if (rm_slot < 0) {
+      sg = chain[CYL_CH_SIGMA_SITE];
+      cnt = chain[CYL_CH_STEP_COUNTER];
+    } else {
+      const unsigned tot = __reduce_add_sync(0xffffffffu, hdr->nacc[pslot][lane]);
+      const double nsite = (double)g.Z * g.T;
+      sg = hdr->rm_sigma[pslot];
+      cnt = hdr->rm_counter[pslot];
+      if (A.flags & CYL_SWEEP_ADAPT_SIGMA) sg = rm_batch_update<R>(sg, cnt, nsite, (double)tot);
+      cnt += nsite;
+      prev_acc = (double)tot;
+    }
+    if (lane == 0) red[(HBM_NT / 32) * 8 + 7] = sg;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (lane == 0) { hdr->rm_sigma[r] = sg; hdr->rm_counter[r] = cnt; hdr->acc_total += prev_acc; }
+      hdr->nacc[r == 2 ? 0 : r + 1][lane] = 0u;                    // the slot of the next sweep; nobody reads it now
+    }
+  }
   if (EXTRAS) {
+    sigma = (R)ld_early_f64(chain + CYL_CH_SIGMA_SITE);
     // which coefficient table is current is only known on the device: fetch the row from both tables together with the
     // selector instead of chaining two global-memory latencies
     const int sel = ld_early_i32(&A.hdr->coef_sel);
@@ -351,6 +391,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
   const uint32_t c1 = (uint32_t)sweep + keys.off;
   __syncthreads();                                                  // mbarrier initialised, row tables staged
+  if (!EXTRAS) sigma = (R)red[(HBM_NT / 32) * 8 + 7];
   mbar_wait(bar, 0);
 
   int nacc = 0;
@@ -566,11 +607,38 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     }
   }
   __syncthreads();
+  if (!EXTRAS) {
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < HBM_NT / 32; ++w) t += red[w * 8];
+      const int r = rm_slot < 0 ? 0 : rm_slot;
+      atomicAdd(&A.hdr->nacc[r][(blockIdx.y * gridDim.x + blockIdx.x) & (HBM_NBUCKET - 1)], (unsigned int)t);   // no return value: RED
+    }
+    return;
+  }
   if (tid < NV) {
     double t = 0.0;
     for (int w = 0; w < HBM_NT / 32; ++w) t += red[w * 8 + tid];
     A.partials[(size_t)tid * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
+}
+
+// After the last plain sweep of a call: apply its Robbins-Monro update and hand the totals back to the chain state (one warp).
+template <typename R>
+__global__ void hbm_rm_finalize_kernel(HbmAmp* __restrict__ hdr, double* __restrict__ chain, int Z, int T, uint32_t flags,
+                                       int last_slot, int nsweeps) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const unsigned tot = __reduce_add_sync(0xffffffffu, hdr->nacc[last_slot][lane]);
+  if (lane != 0) return;
+  const double nsite = (double)Z * T;
+  double sg = hdr->rm_sigma[last_slot];
+  const double cnt = hdr->rm_counter[last_slot];
+  if (flags & CYL_SWEEP_ADAPT_SIGMA) sg = rm_batch_update<R>(sg, cnt, nsite, (double)tot);
+  chain[CYL_CH_SIGMA_SITE] = sg;
+  chain[CYL_CH_STEP_COUNTER] = cnt + nsite;
+  chain[CYL_CH_SITE_PROPOSED] += nsite * nsweeps;
+  chain[CYL_CH_SITE_ACCEPTED] += hdr->acc_total + (double)tot;
 }
 
 template <typename R>
@@ -913,10 +981,12 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
                           g.T, variant, seed, (uint32_t)replica, sweep, flags, (int)(s == 0), coef2, roww, cstpart,
                           (const R*)rowpart, sl.ntx, flush ? prof : (double*)nullptr, nrb));
     }
-    CYL_CUDA(launch_pdl(kern, grid, dim3(HBM_NT), L::total, st, maps, (C*)work, (int)*cur, g, A, keys, sweep));
+    CYL_CUDA(launch_pdl(kern, grid, dim3(HBM_NT), L::total, st, maps, (C*)work, (int)*cur, g, A, keys, sweep, s == 0 ? -1 : s % 3));
     *cur ^= 1;                                                      // host-side ping-pong index
-    CYL_CUDA(launch_pdl(hbm_decide_kernel<R>, dim3(1), dim3(HBM_DECIDE_NT), 0, st, A, g, (int)(grid.x * grid.y)));
+    if (extras) CYL_CUDA(launch_pdl(hbm_decide_kernel<R>, dim3(1), dim3(HBM_DECIDE_NT), 0, st, A, g, (int)(grid.x * grid.y)));
   }
+  if (!extras && nsweeps > 0)
+    CYL_CUDA(launch_pdl(hbm_rm_finalize_kernel<R>, dim3(1), dim3(32), 0, st, A.hdr, chain, g.Z, g.T, flags, (nsweeps - 1) % 3, nsweeps));
   if (profiles && nsweeps > 0)
     CYL_CUDA(launch_pdl(hbm_prof_flush_kernel<R>, dim3(nrb), dim3(HBM_PREP_NT), 0, st, (const R*)rowpart, sl.ntx, g.Z, prof));
   CYL_LAUNCH_CHECK();
