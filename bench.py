@@ -36,7 +36,7 @@ SWEEPS_PER_STEP = 200
 DIMS = (50, 50)
 SEED = 0x5EED
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
-NCU_HBM_TRAFFIC_BYTES = 135.776e6 + 82.401e6   # sweep_hbm_kernel<float,2,30>, 4096x4096, one launch (profiles/r01_ncu_full.md)
+NCU_HBM_TRAFFIC_BYTES = 135.754e6 + 82.246e6   # sweep_hbm_kernel<float,2,30,0>, 4096x4096, one launch (profiles/r01_ncu_full_c.md)
 
 
 def grid_params(n_replicas, replica0=0):
@@ -304,15 +304,15 @@ def main():
         achieved = upd * ALG_BYTES_PER_UPDATE_F32 / (ms_hbm * 1e-3) / 1e9
         traffic = NCU_HBM_TRAFFIC_BYTES if (n == 4096) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_ncu_full.md "
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_ncu_full_c.md "
                                       "(below the 24 B/update algorithmic figure: the kernel updates all colours per pass, 8.1 B read + "
                                       "8 B written per site; part of the writes is still dirty in the 126 MB L2 when the kernel ends)",
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE_F32 * n * n,
-                    "peak_source": peak_src, "kernel": "sweep_hbm_kernel<float,2> (TMA-tiled, ping-pong)",
+                    "peak_source": peak_src, "kernel": "sweep_hbm_kernel<float,2,TH,false> (TMA-tiled, ping-pong)",
                     "workload": "C4: %dx%d fp32 lattice (%.0f MB > L2), a=0.3 fixed, %d sweeps" % (n, n, n * n * 8 / 1e6, args.hbm_sweeps),
                     "algorithmic_bytes_per_update": ALG_BYTES_PER_UPDATE_F32, "site_updates_per_s": upd / (ms_hbm * 1e-3),
                     "us_per_sweep": 1e3 * ms_hbm / args.hbm_sweeps,
-                    "note": "time = whole call / sweeps: includes the 1-thread post-sweep kernel (sigma update, buffer flip)"}
+                    "note": "time = whole call / sweeps: one sweep kernel per sweep (it carries the Robbins-Monro record itself) + one coefficient and one finalize kernel per call"}
         del ws
 
     # ---- CPU baseline (rank 0, N = 1 only) ----

@@ -19,6 +19,8 @@ out = []
 seen = {}
 for r in rows[2:]:
     name = r[idx["Kernel Name"]].split("(")[0]
+    if "Function Name" in idx and "<" not in name:
+        name = r[idx["Function Name"]]
     seen[name] = seen.get(name, 0) + 1
     if seen[name] > 1:
         continue
@@ -28,12 +30,13 @@ for r in rows[2:]:
             out.append("- %s = %s %s" % (k, r[idx[k]], units[idx[k]]))
     st = []
     for h, i in idx.items():
-        if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
             try:
-                st.append((float(r[i].replace(",", "")), h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")))
+                st.append((float(r[i].replace(",", "")), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
             except ValueError:
                 pass
-    out.append("- top stalls (% of warp-active cycles): " + ", ".join("%s %.1f" % (h, v) for v, h in sorted(st, reverse=True)[:7]))
+    out.append("- warps stalled per issued instruction, by reason (smsp__average_warps_issue_stalled_*_per_issue_active): "
+               + ", ".join("%s %.2f" % (h, v) for v, h in sorted(st, reverse=True)[:8]))
 text = "\n".join(out)
 print(text)
 if len(sys.argv) > 2:

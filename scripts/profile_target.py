@@ -25,5 +25,8 @@ if which in ("hbm", "both"):
     ws.pack(psi[0])
     chain = ops.new_chain(1, dev, amplitude=0.3)[0]
     ws.sweep(par, chain, 1, 0, 4, 0, _abi.SWEEP_ADAPT_SIGMA)
+    obs = torch.zeros(16, dtype=torch.float64, device=dev)
+    prof = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+    ws.sweep(par, chain, 1, 4, 3, 0, 7, obs=obs, prof=prof)            # measurement + profiles + amplitude move every sweep
     torch.cuda.synchronize()
     print("hbm ok", chain[:8].tolist())
