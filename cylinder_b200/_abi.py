@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcylinder_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "cylinder_b200.h")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # constants mirrored from the header (checked against it in tests/test_abi_cpu.py)
 VARIANT_SIMPLE, VARIANT_RESCALED_0TH, VARIANT_RESCALED_1ST, VARIANT_DECOUPLED = 0, 1, 2, 3
@@ -44,6 +44,10 @@ _SIGNATURES = {
     "cyl_site_delta_f64": [_vp, _i, _i, _vp, _d, _i, _i, _i, _d, _d, _d, _vp, _vp],
     "cyl_row_moments_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp],
     "cyl_row_moments_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp],
+    "cyl_move_row_moments_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "cyl_move_row_moments_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "cyl_move_apply_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp],
+    "cyl_move_apply_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp],
     "cyl_field_energy_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "cyl_sweep_smem_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
     "cyl_sweep_smem_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],

@@ -204,6 +204,72 @@ class Lattice:
     def update_rescale_params(self, amplitude):
         pass
 
+    # ---- whole-lattice proposals (:247-382) ------------------------------------------------------------
+    # The proposed field is never materialised: cyl_move_row_moments_* evaluates its row moments with the transform applied
+    # on load, cyl_field_energy_f64 gives its energy, cyl_move_apply_* commits it on accept.  Random draws come from
+    # Python's generator in the reference's order; the accept goes through the engine like the reference's.
+    def _collective(self, amplitude, moves, old_energy):
+        S = ops.move_row_moments(self._psi, self._Z, self._params, moves)
+        new_energy = ops.field_energy(S, self._Z, self.th_len, self._params, [float(amplitude)], [float(amplitude)], self.variant).item()
+        accept = self.me.metropolis_decision(old_energy, new_energy)
+        if accept:
+            ops.move_apply(self._psi, self._Z, moves)
+            self._invalidate()
+        return accept, new_energy
+
+    def step_lattice_all(self, amplitude):
+        """One complex number added to every site (:247-261); `self.energy` must hold the current field energy, as in the
+        reference's run loop (:524)."""
+        addition = random.gauss(0, self.sampling_width) + random.gauss(0, self.sampling_width) * 1j              # :248
+        accept, new_energy = self._collective(amplitude, ops.make_moves(self.device, ops.MOVE_SHIFT, c=addition), self.energy)
+        if accept:
+            self.energy = new_energy
+            self.me.energy["field"] = new_energy
+        self.update_sigma(accept)
+        return accept
+
+    def step_lattice_random_wavevector(self, amplitude, qzmax=4, qthmax=8):                                     # :263-265
+        wavevector = (random.randint(-qzmax, qzmax + 1) * 2 * math.pi, random.randint(-qthmax, qthmax + 1) * 2 * math.pi)
+        return self.step_lattice_wavevector(amplitude, wavevector)
+
+    def wave_array(self, base, wavevector, z_len, th_len):                                                       # :267-271
+        qz, qth = wavevector
+        return np.fromfunction(lambda i, j: base * np.exp(1j * (i * qz / z_len + j * qth / th_len)), (z_len, th_len))
+
+    def step_lattice_wavevector(self, amplitude, wavevector):
+        """A plane wave c exp(i(i qz/Z + j qth/T)) added to the field (:273-300), width `bump_sampling_width`."""
+        addition = random.gauss(0, self.bump_sampling_width) + random.gauss(0, self.bump_sampling_width) * 1j    # :274
+        moves = ops.make_moves(self.device, ops.MOVE_WAVE, c=addition, qz=wavevector[0], qth=wavevector[1])
+        accept, new_energy = self._collective(amplitude, moves, self.energy)
+        if accept:
+            self.energy = new_energy
+        self.update_bump_sigma(accept)
+        return accept
+
+    def step_row_rotate(self, amplitude, maxrows=1):
+        """A block of rows gets one more (or one less) turn of phase around the cylinder plus a random global phase
+        (:303-382): the move that changes the winding number of a row.  Same draws as the reference, in its order."""
+        n_rot = random.choice([-1, 1])                                                                           # :304
+        phase = random.uniform(0, 2 * math.pi)                                                                   # :305
+        num_rows = random.randint(1, maxrows)                                                                    # :306
+        row_index = random.randint(0, self.z_len - 1)                                                            # :310
+        old_energy = self.surface_field_energy(amplitude, amplitude)
+        moves = ops.make_moves(self.device, ops.MOVE_TWIST, r0=row_index, nr=num_rows, n_rot=n_rot, phase=phase)
+        accept, new_energy = self._collective(amplitude, moves, old_energy)
+        if accept:
+            self.energy = new_energy
+        return accept
+
+    def update_bump_sigma(self, accept):                               # :700-708 (step factor from step_counter, as committed)
+        self.bump_step_counter += 1
+        step_number_factor = max((self.step_counter / self.m, 200))
+        steplength_c = self.bump_sampling_width * self.ratio
+        if accept:
+            self.bump_sampling_width += steplength_c * (1 - self.target_acceptance) / step_number_factor
+        else:
+            self.bump_sampling_width -= steplength_c * self.target_acceptance / step_number_factor
+        assert (self.bump_sampling_width) > 0
+
     # ---- production path: checkerboard sweeps on the device --------------------------------------------
     def _fits_shared_memory(self):
         return self.z_len * self.th_len * self._psi.element_size() <= 160 * 1024

@@ -221,3 +221,36 @@ def fourier_surface_energy(params, amp):
     E = torch.empty(B, dtype=F64, device=params.device)
     call("cyl_fourier_surface_energy_f64", _dev(params), ptr(params), ptr(amp), B, ptr(E), stream())
     return E
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole-lattice proposals (cyl_move_*): shift / plane wave / row twist
+# ------------------------------------------------------------------------------------------------------
+MOVE_SHIFT, MOVE_WAVE, MOVE_TWIST = 0, 1, 2
+_MOVE_DTYPE = np.dtype([("kind", "<i4"), ("r0", "<i4"), ("nr", "<i4"), ("n_rot", "<i4"), ("c_re", "<f8"), ("c_im", "<f8"),
+                        ("qz", "<f8"), ("qth", "<f8"), ("phase", "<f8"), ("reserved", "<f8")])          # struct CylMove, 64 bytes
+
+
+def make_moves(device, kind, B=1, c=0j, qz=0.0, qth=0.0, r0=0, nr=0, n_rot=0, phase=0.0):
+    """[B] CylMove records (uint8 tensor [B, 64] on `device`) from scalars / arrays (broadcast)."""
+    m = np.zeros(B, dtype=_MOVE_DTYPE)
+    c = np.broadcast_to(np.asarray(c, dtype=complex), (B,))
+    m["kind"], m["r0"], m["nr"], m["n_rot"] = kind, r0, nr, n_rot
+    m["c_re"], m["c_im"], m["qz"], m["qth"], m["phase"] = c.real, c.imag, qz, qth, phase
+    return torch.from_numpy(m.view(np.uint8).reshape(B, _MOVE_DTYPE.itemsize).copy()).to(device)
+
+
+def move_row_moments(psi, Z, params, moves):
+    """Row moments [B, Zmax, 8] of the field the moves would produce (psi itself is not touched)."""
+    B, Zmax, T = psi.shape
+    S = torch.empty(B, Zmax, NMOM, dtype=F64, device=psi.device)
+    call("cyl_move_row_moments_" + _suffix(psi), _dev(psi), ptr(psi), B, ptr(Z), Zmax, T, ptr(params), ptr(moves), ptr(S), stream())
+    return S
+
+
+def move_apply(psi, Z, moves, accept=None):
+    """Commit the moves in place where accept[b] != 0 (uint8 tensor; None = everywhere)."""
+    B, Zmax, T = psi.shape
+    call("cyl_move_apply_" + _suffix(psi), _dev(psi), ptr(psi), B, ptr(Z), Zmax, T, ptr(moves), ptr(accept) if accept is not None else None,
+         stream())
+    return psi

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CYL_ABI_VERSION 3
+#define CYL_ABI_VERSION 4
 
 /* error codes */
 #define CYL_OK             0
@@ -147,6 +147,26 @@ int cyl_row_moments_f32(const void* psi, int B, const int32_t* Z, int Zmax, int 
                         double* S, void* stream);
 int cyl_row_moments_f64(const void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
                         double* S, void* stream);
+
+/* Whole-lattice proposals (On_lattice_simple.py: step_lattice_all :247-259, step_lattice_wavevector :267-300,
+ * step_row_rotate :303-382).  A move is described by 8 doubles per replica; cyl_move_row_moments_* returns the row moments
+ * of the PROPOSED field (feed them to cyl_field_energy_f64), cyl_move_apply_* commits it where accept[b] != 0 (accept may
+ * be NULL: all replicas). */
+#define CYL_MOVE_SHIFT 0   /* psi + c                                                                  */
+#define CYL_MOVE_WAVE  1   /* psi + c exp(i (i qz/Z + j qth/T))                                        */
+#define CYL_MOVE_TWIST 2   /* rows [r0, r0+nr) mod Z: psi exp(i (2 pi j n_rot / T + phase))            */
+typedef struct CylMove {
+  int32_t kind, r0, nr, n_rot;
+  double c_re, c_im, qz, qth, phase, reserved;
+} CylMove;
+int cyl_move_row_moments_f32(const void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                             const CylMove* moves, double* S, void* stream);
+int cyl_move_row_moments_f64(const void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                             const CylMove* moves, double* S, void* stream);
+int cyl_move_apply_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylMove* moves, const uint8_t* accept,
+                       void* stream);
+int cyl_move_apply_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylMove* moves, const uint8_t* accept,
+                       void* stream);
 
 /* Lattice.surface_field_energy(a_eval, a_ref, ...) (On_lattice_simple.py:185-213; 0th-order :247-278)
  * from row moments: E_out[b]. */

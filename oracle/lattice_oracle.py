@@ -147,6 +147,8 @@ class LatticeState:
         self.sigma = sigma
         self.step_counter = step_counter
         self.accepted = 0
+        self.bump_sigma = .005                                 # :102 bump_sampling_width
+        self.bump_step_counter = 0
 
     def rebuild_caches(self):
         """psi_squared, dz, dth as in random_initialize :159-182 (left differences, periodic)."""
@@ -488,3 +490,89 @@ def row_moments(st):
 def measure_profiles(psi):
     """(sum_theta psi, sum_theta |psi|) per z-row  -- Lattice.measure :123,:128."""
     return psi.sum(axis=1), np.abs(psi).sum(axis=1)
+
+
+# --------------------------------------------------------------------------------------
+# whole-lattice proposals (On_lattice_simple.py:247-382)
+# --------------------------------------------------------------------------------------
+def update_bump_sigma(st, accept):
+    """On_lattice_simple.py:700-708 -- note the step factor uses step_counter, not bump_step_counter (as committed)."""
+    st.bump_step_counter += 1
+    f = max(st.step_counter / st.m, 200)
+    c = st.bump_sigma * st.ratio
+    if accept:
+        st.bump_sigma += c * (1 - st.target) / f
+    else:
+        st.bump_sigma -= c * st.target / f
+    assert st.bump_sigma > 0
+
+
+def _decide_and_commit(st, old_energy, new_energy, new_psi, uniform):
+    draw = uniform if callable(uniform) else (lambda: uniform)
+    accept, u_used = metropolis_decision(st.temperature, old_energy, new_energy, draw)
+    if accept:
+        st.psi = new_psi
+        st.rebuild_caches()
+    return accept, u_used
+
+
+def step_lattice_all(st, a, old_energy, z_re, z_im, uniform):
+    """Lattice.step_lattice_all :247-259: the same complex number added to every site.  dz / dth do not change (:251); the
+    reference's psi_squared of the proposal is the complex product psi*conj(psi), whose real part is what is restated
+    here (its imaginary part is rounding noise of order 1e-19).  Returns (accept, new_energy, u_used)."""
+    addition = (0.0 + z_re * st.sigma) + (0.0 + z_im * st.sigma) * 1j                      # :248 (gauss = mu + z*sigma)
+    new = st.psi + np.full((st.Z, st.T_len), addition)                                      # :249-250
+    new_p2 = new.real * new.real + new.imag * new.imag                                      # :251 (real part)
+    new_energy = surface_field_energy(st, a, a, new, new_p2, st.dz, st.dth)                 # :252
+    accept, u_used = _decide_and_commit(st, old_energy, new_energy, new, uniform)           # :254-260
+    update_sigma(st, accept)                                                                # :261
+    return accept, new_energy, u_used
+
+
+def wave_array(base, wavevector, Z, T):
+    """Lattice.wave_array :267-271."""
+    qz, qth = wavevector
+    i, j = np.meshgrid(np.arange(Z, dtype=float), np.arange(T, dtype=float), indexing="ij")
+    return base * np.exp(1j * (i * qz / Z + j * qth / T))
+
+
+def _energy_of(st, a, psi):
+    """surface_field_energy of a whole proposed field with its own derived arrays."""
+    p2 = psi.real * psi.real + psi.imag * psi.imag
+    dz = (psi - np.roll(psi, 1, axis=0)) / st.lz
+    dth = (psi - np.roll(psi, 1, axis=1)) / st.lth
+    return surface_field_energy(st, a, a, psi, p2, dz, dth)
+
+
+def step_lattice_wavevector(st, a, old_energy, wavevector, z_re, z_im, uniform):
+    """Lattice.step_lattice_wavevector :273-300 with COMPLEX derivatives of the proposal (adopted semantics: the reference
+    allocates new_dz / new_dth as real arrays, :279-280, which silently drops their imaginary parts)."""
+    addition = (0.0 + z_re * st.bump_sigma) + (0.0 + z_im * st.bump_sigma) * 1j            # :274
+    new = st.psi + wave_array(addition, wavevector, st.Z, st.T_len)                         # :276-277
+    new_energy = _energy_of(st, a, new)                                                     # :279-290
+    accept, u_used = _decide_and_commit(st, old_energy, new_energy, new, uniform)           # :291-299
+    update_bump_sigma(st, accept)                                                           # :300
+    return accept, new_energy, u_used
+
+
+def step_row_rotate(st, a, n_rot, phase, num_rows, row_index, uniform):
+    """Lattice.step_row_rotate :303-382, adopted semantics: rows row_index .. row_index+num_rows-1 (mod Z) are multiplied by
+    exp(i (2 pi n n_rot / T + phase)), n = theta index (:307,:319); the decision compares the energies of the affected rows
+    (:372-374), which is the difference of the whole-lattice energies because nothing else changes.  (As committed the
+    reference copies dth / dz of the FIRST row of the block into every row, :323-324, and its sublattice energy omits the
+    metric's row offset for wrapped blocks.)  Returns (accept, old_energy, new_energy, u_used)."""
+    angle_per_cell = math.pi * 2 / st.T_len                                                 # :307
+    new = st.psi.copy()
+    n = np.arange(st.T_len)
+    for row in range(row_index, row_index + num_rows):
+        new[row % st.Z] = st.psi[row % st.Z] * np.exp(1j * (angle_per_cell * n * n_rot + phase))   # :319
+    old_energy = _energy_of(st, a, st.psi)
+    new_energy = _energy_of(st, a, new)
+    accept, u_used = _decide_and_commit(st, old_energy, new_energy, new, uniform)           # :374-381
+    return accept, old_energy, new_energy, u_used
+
+
+def winding_numbers(psi):
+    """Winding number of the phase around each z-row: sum of the wrapped phase differences / 2 pi."""
+    d = np.angle(psi * np.conj(np.roll(psi, 1, axis=1)))
+    return np.rint(d.sum(axis=1) / (2 * math.pi)).astype(int)

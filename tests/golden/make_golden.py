@@ -14,6 +14,7 @@ What is recorded:
                         and surface_field_energy(a', a_ref) at several amplitudes.
   known_answers.npz     psi==1 field energy -2*pi^2 (tests/test_On_lattice.py:75-88) on both lattices
   fourier.npz           Cylinder2D / Cylinder1D tensors and energies (system_cylinder2D.py:103-198)
+  collective.npz        sequences of Lattice.step_lattice_all moves (On_lattice_simple.py:247-261)
   farm/                 varfile.txt written by parallel_preprocessing.py; tables written by parallel_postprocessing.py
 """
 import math
@@ -236,6 +237,45 @@ def gen_fourier():
     np.savez_compressed(os.path.join(HERE, "fourier.npz"), **out)
 
 
+def gen_collective():
+    """Lattice.step_lattice_all (On_lattice_simple.py:247-261) driven on the unmodified reference: per move the two unit
+    normals, the uniform (NaN if none was drawn), the real parts of old / new energy, the decision and the adapted width.
+    (The reference's energies pick up an imaginary rounding residue of order 1e-19 from psi*conj(psi); only real parts are kept.)"""
+    import warnings
+    mod = rh.load("On_lattice_simple")
+    out = {}
+    for tag, seed, kw, amp, n in (("warm", 31, dict(temperature=.5, dims=(20, 10), alpha=-1, n=2), 0.25, 60),
+                                  ("cold", 32, dict(temperature=.01, dims=(16, 12), alpha=-.5, n=6), -0.4, 60)):
+        base = dict(amplitude=0, wavenumber=1, radius=1, gamma=1, kappa=0, intrinsic_curvature=0, alpha=-1, u=1, C=1, n=6,
+                    temperature=.01, temperature_final=.01, dims=(50, 50))
+        base.update(kw)
+        random.seed(seed)
+        lat = rh.quiet(mod.Lattice, **base)
+        lat.sampling_width = .02
+        lat.energy = lat.surface_field_energy(amp, amp, lat.lattice, lat.psi_squared, lat.dz, lat.dth)
+        rec = dict(psi0=lat.lattice.copy(), e0=float(np.real(lat.energy)), zre=[], zim=[], u=[], e_old=[], e_new=[], accept=[], sigma=[])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(n):
+                with rh.Tape() as tape:
+                    rh.quiet(lat.step_lattice_all, amp)
+                old, new, accept, uu = lat.me.decisions[-1]
+                rec["zre"].append(tape.normals[0]); rec["zim"].append(tape.normals[1])
+                rec["u"].append(np.nan if uu is None else uu)
+                rec["e_old"].append(float(np.real(old))); rec["e_new"].append(float(np.real(new)))
+                rec["accept"].append(bool(accept)); rec["sigma"].append(lat.sampling_width)
+        rec["psi_final"] = lat.lattice.copy()
+        P = [base[x] for x in ("wavenumber", "radius", "gamma", "kappa", "intrinsic_curvature", "alpha", "u", "C", "n", "temperature")]
+        for k, v in rec.items():
+            out[tag + "_" + k] = np.array(v)
+        out[tag + "_params"] = np.array(P, dtype=float)
+        out[tag + "_amp"] = amp
+        out[tag + "_seed"] = seed
+        out[tag + "_dims"] = np.array(base["dims"])
+        print("collective", tag, "accepted", int(np.sum(rec["accept"])), "of", n, "uniforms", int(np.isfinite(rec["u"]).sum()))
+    np.savez_compressed(os.path.join(HERE, "collective.npz"), **out)
+
+
 def gen_farm():
     """File formats of the job farm, produced by the reference's own scripts (run as subprocesses in a scratch directory):
     varfile.txt of parallel_preprocessing.py and the per-column tables of parallel_postprocessing.py for a small set of
@@ -267,7 +307,7 @@ def gen_farm():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["geometry", "surface", "lattice", "lattice2", "known", "fourier", "farm"]
+    what = sys.argv[1:] or ["geometry", "surface", "lattice", "lattice2", "known", "fourier", "farm", "collective"]
     if "geometry" in what:
         gen_geometry()
     if "surface" in what:
@@ -282,3 +322,5 @@ if __name__ == "__main__":
         gen_fourier()
     if "farm" in what:
         gen_farm()
+    if "collective" in what:
+        gen_collective()

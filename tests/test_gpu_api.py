@@ -207,3 +207,89 @@ def test_farm_run_writes_the_reference_files(cuda, tmp_path):
     (tmp_path / "var2.txt").write_text("alpha wavenumber\n" + "\n".join(" ".join(s) for s in lines[:1]) + "\n")
     out1 = farm.run(str(tmp_path / "infile.txt"), str(tmp_path / "var2.txt"), outdir=str(tmp_path / "out1"), seed=3, write_profiles=False)
     assert out1["abs_amplitude"][0] == out["abs_amplitude"][0] and out1["field_energy"][0] == out["field_energy"][0]
+
+
+@pytest.mark.parametrize("tag", ["warm", "cold"])
+def test_step_lattice_all_reproduces_the_reference_stream(cuda, golden_dir, tag):
+    """random.seed(s); Lattice(...); step_lattice_all(a) x N: same draws, same energies, same decisions, same adapted width and
+    same final field as the sequence recorded from the reference (On_lattice_simple.py:247-261)."""
+    import cylinder_b200
+    g = np.load(os.path.join(golden_dir, "collective.npz"))
+    P = g[tag + "_params"].tolist()
+    random.seed(int(g[tag + "_seed"]))
+    lat = cylinder_b200.Lattice(amplitude=0, wavenumber=P[0], radius=P[1], gamma=P[2], kappa=P[3], intrinsic_curvature=P[4], alpha=P[5],
+                                u=P[6], C=P[7], n=P[8], temperature=P[9], temperature_final=P[9], dims=tuple(int(x) for x in g[tag + "_dims"]))
+    np.testing.assert_allclose(lat.lattice, g[tag + "_psi0"], rtol=0, atol=1e-17)
+    a = float(g[tag + "_amp"])
+    lat.sampling_width = .02
+    lat.energy = lat.surface_field_energy(a, a, lat.lattice, lat.psi_squared, lat.dz, lat.dth)
+    assert lat.energy == pytest.approx(float(g[tag + "_e0"]), rel=1e-10)
+    for i in range(len(g[tag + "_accept"])):
+        assert lat.energy == pytest.approx(float(g[tag + "_e_old"][i]), rel=1e-10)
+        acc = lat.step_lattice_all(a)
+        assert acc == bool(g[tag + "_accept"][i])
+        assert lat.sampling_width == pytest.approx(float(g[tag + "_sigma"][i]), rel=1e-12)
+    np.testing.assert_allclose(lat.lattice, g[tag + "_psi_final"], rtol=0, atol=1e-14)
+
+
+def test_collective_moves_match_oracle_and_batch(cuda):
+    """cyl_move_row_moments / cyl_move_apply for the three proposal kinds, a ragged batch, fp64: energy of the proposal equals the
+    oracle's energy of the explicitly transformed field (1e-10), the committed field equals the numpy transform, the accept mask
+    leaves the other replicas untouched; the Lattice methods draw from Python's generator in the reference's order."""
+    import torch
+    import cylinder_b200
+    from cylinder_b200 import ops
+    from oracle import lattice_oracle as lo
+    Zs, T = [9, 12, 7], 10
+    ks = [12 / z for z in Zs]                                                  # dims[0] = 12 -> z_len = round(12 / k)
+    P = dict(radius=1.1, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-.8, u=1.2, C=.9, n=3, temperature=.2)
+    par = ops.make_params(cuda, wavenumber=ks, **P)
+    rng = np.random.RandomState(0)
+    psi_h = np.zeros((3, 12, T), complex)
+    for b, z in enumerate(Zs):
+        psi_h[b, :z] = rng.normal(0, .4, (z, T)) + 1j * rng.normal(0, .4, (z, T))
+    Zt = torch.tensor(Zs, dtype=torch.int32, device=cuda)
+    a = torch.tensor([.3, -.2, .5], device=cuda)
+    kinds = [ops.MOVE_SHIFT, ops.MOVE_WAVE, ops.MOVE_TWIST]
+    moves = ops.make_moves(cuda, kinds, B=3, c=[.05 - .02j, .1 + .03j, 0], qz=[0, 2 * math.pi, 0], qth=[0, -4 * math.pi, 0],
+                           r0=[0, 0, 5], nr=[0, 0, 3], n_rot=[0, 0, -1], phase=[0, 0, 1.1])
+    for variant in (lo.SIMPLE, lo.RESCALED_1ST):
+        psi = torch.tensor(psi_h, dtype=torch.complex128, device=cuda)
+        S = ops.move_row_moments(psi, Zt, par, moves)
+        E = ops.field_energy(S, Zt, T, par, a, a, variant).cpu().numpy()
+        np.testing.assert_array_equal(psi.cpu().numpy(), psi_h)                # evaluation does not touch the field
+        expect = []
+        for b, z in enumerate(Zs):
+            st = lo.LatticeState(psi_h[b, :z], ks[b], P["radius"], P["alpha"], P["u"], P["C"], P["n"], P["temperature"], variant=variant)
+            if b == 0:
+                new = st.psi + (.05 - .02j)
+            elif b == 1:
+                new = st.psi + lo.wave_array(.1 + .03j, (2 * math.pi, -4 * math.pi), z, T)
+            else:
+                new = st.psi.copy()
+                for row in (5, 6, 0):
+                    new[row] = st.psi[row] * np.exp(1j * (2 * math.pi / T * np.arange(T) * -1 + 1.1))
+            expect.append(new)
+            assert E[b] == pytest.approx(lo._energy_of(st, float(a[b]), new), rel=1e-10)
+        ops.move_apply(psi, Zt, moves, accept=torch.tensor([1, 0, 1], dtype=torch.uint8, device=cuda))
+        out = psi.cpu().numpy()
+        np.testing.assert_allclose(out[0, :9], expect[0], atol=1e-15)
+        np.testing.assert_array_equal(out[1], psi_h[1])
+        np.testing.assert_allclose(out[2, :7], expect[2], atol=1e-15)
+        assert np.all(out[2, 7:] == 0)
+    # Lattice methods: row twist at T = 1e9 is always accepted and winds exactly the drawn block
+    random.seed(4)
+    lat = cylinder_b200.Lattice(amplitude=0, wavenumber=1, radius=1, gamma=1, kappa=0, intrinsic_curvature=0, alpha=-1, u=1, C=1, n=2,
+                                temperature=1e9, temperature_final=1e9, dims=(10, 8))
+    lat.lattice = np.abs(lat.lattice) + .5
+    st_r = random.getstate()
+    n_rot, phase, num_rows, row_index = random.choice([-1, 1]), random.uniform(0, 2 * math.pi), random.randint(1, 3), random.randint(0, 9)
+    random.setstate(st_r)
+    assert lat.step_row_rotate(.2, maxrows=3)
+    w = lo.winding_numbers(lat.lattice)
+    assert w.tolist() == [n_rot if (i - row_index) % 10 < num_rows else 0 for i in range(10)]
+    lat.energy = lat.surface_field_energy(.2, .2)
+    lat.step_lattice_wavevector(.2, (2 * math.pi, 0.0))
+    lat.step_lattice_random_wavevector(.2)
+    assert lat.bump_step_counter == 2
+    assert lat.surface_field_energy(.2, .2) == pytest.approx(lat.energy, rel=1e-10)      # bookkeeping follows the accepted moves
