@@ -126,7 +126,8 @@ def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescale
 
     field_type "lattice": the adopted schedule of Lattice.run (On_lattice_simple.py:532-563): burn-in of
     500 x 50 proposals, then n_steps x (measurement, amplitude move, fieldsteps_per_ampstep x 50 proposals), proposals executed as
-    whole checkerboard sweeps (>= 1 per step); the means are taken over the second half of the steps (equilibrium cut-off).
+    whole checkerboard sweeps (>= 1 per step); means and their standard errors over the equilibrated part of every line's own
+    series (stats.py: MSER cut-off on block means).
     field_type "fourier", method "sequential": run.py:286-294 batched (FourierChains)."""
     import pandas as pd
     import torch
@@ -155,19 +156,22 @@ def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescale
         sweeps = lambda nprop: max(1, int(round(nprop / float(args.dims[0] * args.dims[1]))))          # noqa: E731
         per_step = sweeps((args.fieldsteps_per_ampstep or 1) * 50)                      # :533 n_sub_steps = 50
         batch.run(sweeps(500 * 50), amp_moves=False, measure=False)                     # :534-536
-        for i in range(steps):
-            if i == steps // 2:
-                batch.reset_observables()                                               # equilibrium cut-off
-            if per_step > 1:
-                batch.run(per_step - 1, amp_moves=False, measure=False)
-            batch.run(1)
+        # the steps are recorded as block means; every line's series is then cut at the end of its transient (MSER on <|a|>,
+        # at most half of the run) -- me.save_equilibrium_stats / equilibrated_means of run.py:341-346
+        nblocks = max(2, min(20, steps))
+        per_block = -(-steps // nblocks)
+        series = batch.run_blocks(nblocks, per_block, stride=per_step)
+        means, errs, cut = batch.equilibrated_means(series)
+        for k in OBS_NAMES:
+            out[k] = means[k].cpu().numpy()
+            out[k + "_err"] = errs[k].cpu().numpy()
         obs = batch.observables()
-        for k in OBS_NAMES + ("site_acceptance", "amplitude_acceptance"):
+        for k in ("site_acceptance", "amplitude_acceptance"):
             out[k] = obs[k].cpu().numpy()
         out["energy"] = out["field_energy"] + out["surface_energy"]
+        out["equilibration_cut_steps"] = cut.cpu().numpy() * per_block
         if write_profiles:
-            pz, pa = batch.profiles()
-            profiles = (pz.cpu().numpy(), pa.cpu().numpy(), batch.Z_host)
+            profiles = (means["profile"].cpu().numpy(), means["profile_abs"].cpu().numpy(), batch.Z_host)
     elif args.field_type == "fourier":
         if args.method != "sequential":
             raise ValueError("farm: field_type fourier supports method 'sequential' (got %r)" % args.method)

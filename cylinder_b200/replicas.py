@@ -78,6 +78,45 @@ class ReplicaBatch:
         self.obs.zero_()
         self.prof.zero_()
 
+    def run_blocks(self, nblocks, sweeps_per_block, amp_moves=True, adapt=True, stride=1):
+        """nblocks blocks of sweeps_per_block measured sweeps (each preceded by stride-1 plain sweeps: the reference's
+        fieldsteps_per_ampstep); returns the block means as a dict name -> tensor [nblocks, B] (device) -- the time series
+        the equilibrium cut-off works on (stats.equilibrated) -- and keeps the per-block profile means in
+        `self.block_profiles` [nblocks, B, Zmax, 3]."""
+        series = {name: [] for name in OBS_NAMES}
+        profs = []
+        for _ in range(int(nblocks)):
+            o0, p0 = self.obs.clone(), self.prof.clone()
+            if stride <= 1:
+                self.run(sweeps_per_block, amp_moves=amp_moves, measure=True, adapt=adapt)
+            else:
+                for _ in range(int(sweeps_per_block)):
+                    self.run(stride - 1, amp_moves=False, measure=False, adapt=adapt)
+                    self.run(1, amp_moves=amp_moves, measure=True, adapt=adapt)
+            d = self.obs - o0
+            n = d[:, _abi.OB_COUNT].clamp(min=1.0)
+            for i, name in enumerate(OBS_NAMES):
+                series[name].append(d[:, 1 + i] / n)
+            profs.append((self.prof - p0) / (n[:, None, None] * self.T))
+        self.block_profiles = torch.stack(profs)
+        return {name: torch.stack(v) for name, v in series.items()}
+
+    def equilibrated_means(self, series, by="abs_amplitude", max_fraction=.5):
+        """Means over the equilibrated part of a run_blocks series: every replica's series is cut where the MSER rule puts
+        the end of the transient of `by`.  Returns (means, standard errors, cut index per replica); profiles are averaged
+        over the same blocks."""
+        from . import stats
+        cut = stats.mser_cut(series[by], max_fraction)
+        means, errs = {}, {}
+        for name, x in series.items():
+            means[name], errs[name] = stats.truncated_mean(x, cut)
+        if getattr(self, "block_profiles", None) is not None and self.block_profiles.shape[0] == series[by].shape[0]:
+            c = cut.reshape(-1, 1, 1)
+            p, _ = stats.truncated_mean(self.block_profiles, c.expand(-1, self.Zmax, 3))
+            means["profile"] = torch.complex(p[..., 0], p[..., 1])
+            means["profile_abs"] = p[..., 2]
+        return means, errs, cut
+
     # ---- observables -----------------------------------------------------------------------------------
     def observables(self):
         """Per-replica means over the measurements so far: dict name -> tensor[B] (device)."""
