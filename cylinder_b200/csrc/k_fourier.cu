@@ -163,20 +163,26 @@ extern "C" int cyl_fourier_surface_energy_f64(const CylParams* params, const dou
 #define FAM_HDR 16
 #define CYL_TAG_FREAL 3u
 #define CYL_TAG_FCPLX 4u
+#define CYL_TAG_FALL 5u
 
 __global__ void __launch_bounds__(128)
 fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double* __restrict__ amp, double2* __restrict__ coeffs,
                   double* __restrict__ est, int B, uint64_t seed, int64_t chain0, uint64_t step0, int n_steps, int measure_every,
-                  int fieldsteps, double target, double ratio_real, double ratio_cplx) {
+                  int fieldsteps, double target, double ratio_real, double ratio_cplx, int method) {
   extern __shared__ __align__(16) unsigned char fam_smem[];
   FourierTables* tab = reinterpret_cast<FourierTables*>(fam_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int ncoef = (2 * nz + 1) * (2 * nth + 1), d = ncoef + 1;
-  // per-warp scratch: c[ncoef], cp[ncoef] (double2), L[ncoef][ncoef]
+  // The four drivers of run.py:286-317: sequential (amplitude move, then `fieldsteps` coefficient moves), simultaneous (one
+  // joint move of [|a|, |c_i|]), fixed-amplitude (coefficient moves only), no-field (amplitude moves on the bare surface).
+  const bool do_real = method == CYL_FOURIER_SEQUENTIAL || method == CYL_FOURIER_NO_FIELD;
+  const bool do_cplx = method == CYL_FOURIER_SEQUENTIAL || method == CYL_FOURIER_FIXED_AMPLITUDE;
+  const bool has_field = method != CYL_FOURIER_NO_FIELD;
+  // per-warp scratch: c[ncoef], cp[ncoef] (double2), L[d][d]
   double2* c_all = reinterpret_cast<double2*>(fam_smem + sizeof(FourierTables));
   double2* c = c_all + (size_t)warp * 2 * ncoef;
   double2* cp = c + ncoef;
-  double* L = reinterpret_cast<double*>(c_all + (size_t)nwarp * 2 * ncoef) + (size_t)warp * ncoef * ncoef;
+  double* L = reinterpret_cast<double*>(c_all + (size_t)nwarp * 2 * ncoef) + (size_t)warp * d * d;
   fourier_tables_init(tab, nth);
   __syncthreads();
   const int b = blockIdx.x * nwarp + warp;
@@ -192,40 +198,45 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
   __syncwarp();
   double sig_r = st[0], sig_c = st[1], n_real = st[2], n_cplx = st[3], n_meas = st[4], acc_r = st[5], acc_c = st[6];
   double sum_a2 = st[9], sum_e = st[10];
-  double e_field = fourier_energy_warp(p, nz, nth, a, c, tab);
+  double e_field = has_field ? fourier_energy_warp(p, nz, nth, a, c, tab) : 0.0;
   double e_surf = fourier_surface_energy_warp(p, a);
 
-  auto cholesky = [&]() {              // L L^T = Sigma_c = cov[1:,1:]; lane i owns row i
-    for (int i = lane; i < ncoef; i += 32)
-      for (int j = 0; j < ncoef; ++j) L[i * ncoef + j] = (j <= i) ? cov[(i + 1) * d + (j + 1)] : 0.0;
+  // L L^T = the block of the covariance the proposal needs: cov[1:,1:] (coefficient moves) or all of it (joint move);
+  // lane i owns row i
+  const int coff = (method == CYL_FOURIER_SIMULTANEOUS) ? 0 : 1, cn = d - coff;
+  auto cholesky = [&]() {
+    if (!has_field) return;
+    for (int i = lane; i < cn; i += 32)
+      for (int j = 0; j < cn; ++j) L[i * cn + j] = (j <= i) ? cov[(i + coff) * d + (j + coff)] : 0.0;
     __syncwarp();
-    for (int kx = 0; kx < ncoef; ++kx) {
-      const double dk = sqrt(fmax(L[kx * ncoef + kx], 1e-300));
+    for (int kx = 0; kx < cn; ++kx) {
+      const double dk = sqrt(fmax(L[kx * cn + kx], 1e-300));
       __syncwarp();
-      if (lane == kx) L[kx * ncoef + kx] = dk;
-      if (lane > kx && lane < ncoef) L[lane * ncoef + kx] /= dk;
+      if (lane == kx) L[kx * cn + kx] = dk;
+      if (lane > kx && lane < cn) L[lane * cn + kx] /= dk;
       __syncwarp();
-      if (lane > kx && lane < ncoef) {
-        const double lik = L[lane * ncoef + kx];
-        for (int j = kx + 1; j <= lane; ++j) L[lane * ncoef + j] -= lik * L[j * ncoef + kx];
+      if (lane > kx && lane < cn) {
+        const double lik = L[lane * cn + kx];
+        for (int j = kx + 1; j <= lane; ++j) L[lane * cn + j] -= lik * L[j * cn + kx];
       }
       __syncwarp();
     }
   };
   cholesky();
+  const int moves_per_iter = (do_real ? 1 : 0) + (do_cplx ? fieldsteps : 0) + (method == CYL_FOURIER_SIMULTANEOUS ? 1 : 0);
 
-  uint64_t move = step0 * (uint64_t)measure_every * (uint64_t)(1 + fieldsteps);      // global move index: counter word 2
+  uint64_t move = step0 * (uint64_t)measure_every * (uint64_t)moves_per_iter;         // global move index: counter word 2
   for (int s = 0; s < n_steps; ++s) {
     for (int me = 0; me < measure_every; ++me) {
       // ---- real group ----
-      {
+      if (do_real) {
         const uint4 x = philox4x32<10>(0u, chain, (uint32_t)move, philox_c3(CYL_TAG_FREAL, move), k0, k1);
         double z, u;
         amp_draw(x, z, u);
         const double a_new = a + sig_r * sqrt(cov[0]) * z;
         bool accept = false;
         if (fabs(a_new) < p.amp_bound) {
-          const double ef = fourier_energy_warp(p, nz, nth, a_new, c, tab);
+          const double ef = has_field ? fourier_energy_warp(p, nz, nth, a_new, c, tab) : 0.0;
           const double es = fourier_surface_energy_warp(p, a_new);
           const double diff = (ef + es) - (e_field + e_surf);
           accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
@@ -237,8 +248,50 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
         sig_r = accept ? sig_r + cc * (1 - target) / f : sig_r - cc * target / f;
         ++move;
       }
+      // ---- joint move of [|a|, |c_i|] ~ N(0, sigma^2 Sigma) + phase jitter (engine step_all, predecessor :213-218) ----
+      if (method == CYL_FOURIER_SIMULTANEOUS) {
+        double z, u, zph, dummy;
+        amp_draw(philox4x32<10>((uint32_t)lane, chain, (uint32_t)move, philox_c3(CYL_TAG_FALL, move), k0, k1), z, u);
+        amp_draw(philox4x32<10>((uint32_t)lane + 64u, chain, (uint32_t)move, philox_c3(CYL_TAG_FALL, move), k0, k1), zph, dummy);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        double dv = 0.0;
+        for (int j = 0; j < d; ++j) {
+          const double zj = __shfl_sync(0xffffffffu, z, j);
+          if (lane < d && j <= lane) dv += L[lane * d + j] * zj;
+        }
+        double a_new = 0.0;
+        if (lane == 0) {
+          const double mag = fabs(a) + sig_r * dv;
+          a_new = (a != 0.0) ? copysign(mag, a) : mag;                   // the sign of a is restored (:218)
+        } else if (lane < d) {
+          const double2 ci = c[lane - 1];
+          const double mag = hypot(ci.x, ci.y) + sig_r * dv, ph = atan2(ci.y, ci.x) + 0.1 * zph;
+          double sn, cs;
+          sincos(ph, &sn, &cs);
+          cp[lane - 1] = make_double2(mag * cs, mag * sn);
+        }
+        a_new = __shfl_sync(0xffffffffu, a_new, 0);
+        __syncwarp();
+        bool accept = false;
+        if (fabs(a_new) < p.amp_bound) {
+          const double ef = fourier_energy_warp(p, nz, nth, a_new, cp, tab);
+          const double es = fourier_surface_energy_warp(p, a_new);
+          const double diff = (ef + es) - (e_field + e_surf);
+          accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
+          if (accept) {
+            if (lane < ncoef) c[lane] = cp[lane];
+            a = a_new; e_field = ef; e_surf = es;
+          }
+        }
+        __syncwarp();
+        n_real += 1;
+        acc_r += accept;
+        const double f = fmax(n_real / d, 200.0), cc = sig_r * ratio_real;       // host passes the ratio for m = d
+        sig_r = accept ? sig_r + cc * (1 - target) / f : sig_r - cc * target / f;
+        ++move;
+      }
       // ---- complex group ----
-      for (int fs = 0; fs < fieldsteps; ++fs) {
+      for (int fs = 0; do_cplx && fs < fieldsteps; ++fs) {
         const uint4 x = philox4x32<10>((uint32_t)lane, chain, (uint32_t)move, philox_c3(CYL_TAG_FCPLX, move), k0, k1);
         double z, u, zph, dummy;
         amp_draw(x, z, u);                                   // z: magnitude component of this lane; u used from lane 0
@@ -275,14 +328,15 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
     // ---- measure ----
     n_meas += 1;
     const double kk = n_meas;
-    const double xi = (lane == 0) ? fabs(a) : (lane < d ? hypot(c[lane - 1].x, c[lane - 1].y) : 0.0);
-    const double mu_old = (lane < d) ? mean[lane] : 0.0;
+    const int dm_ = has_field ? d : 1;                                   // no-field: the state is the amplitude alone
+    const double xi = (lane == 0) ? fabs(a) : (lane < dm_ ? hypot(c[lane - 1].x, c[lane - 1].y) : 0.0);
+    const double mu_old = (lane < dm_) ? mean[lane] : 0.0;
     const double mu = mu_old * (kk - 1) / kk + xi / kk;
-    if (lane < d) mean[lane] = mu;
+    if (lane < dm_) mean[lane] = mu;
     if (kk > 50) {
-      for (int j = 0; j < d; ++j) {
+      for (int j = 0; j < dm_; ++j) {
         const double xj = __shfl_sync(0xffffffffu, xi, j), mo = __shfl_sync(0xffffffffu, mu_old, j), mn = __shfl_sync(0xffffffffu, mu, j);
-        if (lane < d)
+        if (lane < dm_)
           cov[lane * d + j] = cov[lane * d + j] * (kk - 2) / (kk - 1) +
                               (mu_old * mo - kk / (kk - 1) * mu * mn + xi * xj / (kk - 1) + (lane == j ? sig_r * sig_r / kk : 0.0));
       }
@@ -310,20 +364,21 @@ extern "C" int cyl_fourier_am_state_doubles(int nz, int nth) {
 extern "C" int cyl_fourier_am_steps_f64(const CylParams* params, int nz, int nth, double* amp, double* coeffs, double* engine_state,
                                         int B, uint64_t seed, int64_t chain0, uint64_t step0, int n_steps, int measure_every,
                                         int fieldsteps, double target_acceptance, double ratio_real, double ratio_complex,
-                                        void* stream) {
+                                        int method, void* stream) {
   CYL_CHECK_ARG(params && amp && coeffs && engine_state && B > 0 && n_steps >= 0 && measure_every > 0 && fieldsteps >= 0,
                 "cyl_fourier_am_steps_f64: bad arguments");
   CYL_CHECK_ARG(nz >= 0 && nz <= FOURIER_MAX_NZ && nth >= 0 && nth <= FOURIER_MAX_NTH, "cyl_fourier_am_steps_f64: bad num_field_coeffs");
   const int ncoef = (2 * nz + 1) * (2 * nth + 1);
   CYL_CHECK_ARG(ncoef <= FOURIER_MAX_COEF - 1, "cyl_fourier_am_steps_f64: %d coefficients > %d (one state component per lane)", ncoef,
                 FOURIER_MAX_COEF - 1);
+  CYL_CHECK_ARG(method >= CYL_FOURIER_SEQUENTIAL && method <= CYL_FOURIER_NO_FIELD, "cyl_fourier_am_steps_f64: unknown method %d", method);
   if (n_steps == 0) return CYL_OK;
-  const int warps = 4;
-  const size_t smem = sizeof(FourierTables) + (size_t)warps * (2 * ncoef * sizeof(double2) + (size_t)ncoef * ncoef * sizeof(double));
+  const int warps = 4, dd = ncoef + 1;
+  const size_t smem = sizeof(FourierTables) + (size_t)warps * (2 * ncoef * sizeof(double2) + (size_t)dd * dd * sizeof(double));
   CYL_CUDA(cudaFuncSetAttribute(fourier_am_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fourier_am_kernel<<<(B + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(
       params, nz, nth, amp, (double2*)coeffs, engine_state, B, seed, chain0, step0, n_steps, measure_every, fieldsteps,
-      target_acceptance, ratio_real, ratio_complex);
+      target_acceptance, ratio_real, ratio_complex, method);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

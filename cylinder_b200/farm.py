@@ -128,7 +128,8 @@ def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescale
     500 x 50 proposals, then n_steps x (measurement, amplitude move, fieldsteps_per_ampstep x 50 proposals), proposals executed as
     whole checkerboard sweeps (>= 1 per step); means and their standard errors over the equilibrated part of every line's own
     series (stats.py: MSER cut-off on block means).
-    field_type "fourier", method "sequential": run.py:286-294 batched (FourierChains)."""
+    field_type "fourier": the drivers of run.py:286-317 (sequential, simultaneous, fixed-amplitude, no-field) batched
+    (FourierChains)."""
     import pandas as pd
     import torch
     import torch.distributed as dist
@@ -173,11 +174,12 @@ def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescale
         if write_profiles:
             profiles = (means["profile"].cpu().numpy(), means["profile_abs"].cpu().numpy(), batch.Z_host)
     elif args.field_type == "fourier":
-        if args.method != "sequential":
-            raise ValueError("farm: field_type fourier supports method 'sequential' (got %r)" % args.method)
-        from .fourier_chains import FourierChains
+        from .fourier_chains import METHODS, FourierChains
+        if args.method not in METHODS:
+            raise ValueError("farm: method must be one of %s (got %r)" % (sorted(METHODS), args.method))
         ch = FourierChains(cols, num_field_coeffs=args.num_field_coeffs, amplitude=amp, device=device, seed=seed, chain0=lo)
-        ch.run(steps, measure_every=args.measure_every or 1, fieldsteps_per_ampstep=args.fieldsteps_per_ampstep or 1)
+        ch.run(steps, measure_every=args.measure_every or 1, fieldsteps_per_ampstep=args.fieldsteps_per_ampstep or 1,
+               method=args.method)
         for k, v in ch.summary().items():
             out[k] = v.cpu().numpy()
         mean = ch.mean.cpu().numpy()

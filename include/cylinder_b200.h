@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CYL_ABI_VERSION 4
+#define CYL_ABI_VERSION 5
 
 /* error codes */
 #define CYL_OK             0
@@ -236,18 +236,25 @@ int cyl_fourier_energy_f64(const CylParams* params /*[B]*/, int nz, int nth, con
 int cyl_fourier_surface_energy_f64(const CylParams* params, const double* amp, int B, double* E_out,
                                    void* stream);
 
-/* Batched adaptive Metropolis over the Fourier model: run.py:286-294 (method "sequential") with the engine arithmetic
+/* The drivers of run.py:286-317 ("method") */
+#define CYL_FOURIER_SEQUENTIAL      0   /* run.py:286-294: amplitude move, then fieldsteps coefficient moves          */
+#define CYL_FOURIER_SIMULTANEOUS    1   /* run.py:295-304: one joint move of [|a|, |c_i|] (engine step_all)           */
+#define CYL_FOURIER_FIXED_AMPLITUDE 2   /* run.py:305-312: coefficient moves only                                     */
+#define CYL_FOURIER_NO_FIELD        3   /* run.py:313-318: amplitude moves on the bare surface energy                 */
+
+/* Batched adaptive Metropolis over the Fourier model: run.py:286-317 with the engine arithmetic
  * of SURVEY.md Appendix B (real-group / complex-group moves, Robbins-Monro widths, recursive mean and covariance, proposals
  * sigma_c L z with L L^T = Sigma_c), one warp per chain.  amp [B], coeffs [B][ncoef] complex128 and engine_state
  * [B][cyl_fourier_am_state_doubles(nz, nth)] are read and written:
  *   engine_state = { sigma_real, sigma_complex, real moves, complex moves, measurements, real accepted, complex accepted,
  *                    E_field, E_surf, sum a^2, sum E, 5 reserved | mean[d] | Sigma[d][d] },  d = 1 + ncoef <= 32.
- * ratio_real / ratio_complex are the Robbins-Monro constants for m = 1 / m = ncoef (On_lattice_simple.py:96-100). */
+ * ratio_real / ratio_complex are the Robbins-Monro constants for m = 1 / m = ncoef (On_lattice_simple.py:96-100); for
+ * the simultaneous method sigma_real is the joint width and ratio_real the constant for m = d. */
 int cyl_fourier_am_state_doubles(int nz, int nth);
 int cyl_fourier_am_steps_f64(const CylParams* params /*[B]*/, int nz, int nth, double* amp, double* coeffs,
                              double* engine_state, int B, uint64_t seed, int64_t chain0, uint64_t step0, int n_steps,
                              int measure_every, int fieldsteps_per_ampstep, double target_acceptance, double ratio_real,
-                             double ratio_complex, void* stream);
+                             double ratio_complex, int method, void* stream);
 
 #ifdef __cplusplus
 }

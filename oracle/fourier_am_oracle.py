@@ -14,7 +14,7 @@ from . import checkerboard_oracle as cb
 from . import fourier_oracle as fo
 from . import lattice_oracle as lo
 
-TAG_FREAL, TAG_FCPLX = 3, 4
+TAG_FREAL, TAG_FCPLX, TAG_FALL = 3, 4, 5
 
 
 def _draw(word0, chain, move, tag, seed):
@@ -57,26 +57,60 @@ class Chain:
         T = self.P["temperature"]
         return diff <= 0 or (T > 0 and u <= math.exp(-diff / T))
 
-    def run(self, n_steps, measure_every, fieldsteps, seed, chain, step0=0):
-        move = step0 * measure_every * (1 + fieldsteps)
-        rr, rc = rm_ratio(self.target, 1), rm_ratio(self.target, max(1, self.ncoef))
-        L = np.linalg.cholesky(self.cov[1:, 1:])
+    def run(self, n_steps, measure_every, fieldsteps, seed, chain, step0=0, method="sequential"):
+        """method: the driver of run.py:286-317 -- "sequential", "simultaneous" (engine step_all), "fixed-amplitude",
+        "no-field"."""
+        do_real = method in ("sequential", "no-field")
+        do_cplx = method in ("sequential", "fixed-amplitude")
+        joint = method == "simultaneous"
+        has_field = method != "no-field"
+        per_iter = (1 if do_real else 0) + (fieldsteps if do_cplx else 0) + (1 if joint else 0)
+        move = step0 * measure_every * per_iter
+        rr = rm_ratio(self.target, self.d if joint else 1)
+        rc = rm_ratio(self.target, max(1, self.ncoef))
+        if not has_field:
+            self.e_field = 0.0
+        block = (lambda: self.cov) if joint else (lambda: self.cov[1:, 1:])
+        L = np.linalg.cholesky(block()) if has_field else None
         for _ in range(n_steps):
             for _ in range(measure_every):
-                z, u = _draw(0, chain, move, TAG_FREAL, seed)
-                a_new = self.a + self.sig_r * math.sqrt(self.cov[0, 0]) * float(z)
-                accept = False
-                if abs(a_new) < self.bound:
-                    ef, es = self.energy(a_new, self.c), surface_energy_1d(self.P, a_new)
-                    accept = self.accept_rule((ef + es) - (self.e_field + self.e_surf), float(u))
-                    if accept:
-                        self.a, self.e_field, self.e_surf = a_new, ef, es
-                self.n_real += 1
-                self.acc_r += accept
-                f, cc = max(self.n_real, 200.0), self.sig_r * rr
-                self.sig_r = self.sig_r + cc * (1 - self.target) / f if accept else self.sig_r - cc * self.target / f
-                move += 1
-                for _ in range(fieldsteps):
+                if do_real:
+                    z, u = _draw(0, chain, move, TAG_FREAL, seed)
+                    a_new = self.a + self.sig_r * math.sqrt(self.cov[0, 0]) * float(z)
+                    accept = False
+                    if abs(a_new) < self.bound:
+                        ef = self.energy(a_new, self.c) if has_field else 0.0
+                        es = surface_energy_1d(self.P, a_new)
+                        accept = self.accept_rule((ef + es) - (self.e_field + self.e_surf), float(u))
+                        if accept:
+                            self.a, self.e_field, self.e_surf = a_new, ef, es
+                    self.n_real += 1
+                    self.acc_r += accept
+                    f, cc = max(self.n_real, 200.0), self.sig_r * rr
+                    self.sig_r = self.sig_r + cc * (1 - self.target) / f if accept else self.sig_r - cc * self.target / f
+                    move += 1
+                if joint:
+                    lanes = np.arange(self.d)
+                    z, u = _draw(lanes, chain, move, TAG_FALL, seed)
+                    zph, _ = _draw(lanes + 64, chain, move, TAG_FALL, seed)
+                    dv = L @ z
+                    mag0 = abs(self.a) + self.sig_r * dv[0]
+                    a_new = math.copysign(mag0, self.a) if self.a != 0 else mag0
+                    mag = np.abs(self.c) + self.sig_r * dv[1:]
+                    ph = np.angle(self.c) + 0.1 * zph[1:]
+                    cp = mag * np.cos(ph) + 1j * mag * np.sin(ph)
+                    accept = False
+                    if abs(a_new) < self.bound:
+                        ef, es = self.energy(a_new, cp), surface_energy_1d(self.P, a_new)
+                        accept = self.accept_rule((ef + es) - (self.e_field + self.e_surf), float(u[0]))
+                        if accept:
+                            self.a, self.c, self.e_field, self.e_surf = a_new, cp, ef, es
+                    self.n_real += 1
+                    self.acc_r += accept
+                    f, cc = max(self.n_real / self.d, 200.0), self.sig_r * rr
+                    self.sig_r = self.sig_r + cc * (1 - self.target) / f if accept else self.sig_r - cc * self.target / f
+                    move += 1
+                for _ in range(fieldsteps if do_cplx else 0):
                     lanes = np.arange(self.ncoef)
                     z, u = _draw(lanes, chain, move, TAG_FCPLX, seed)
                     zph, _ = _draw(lanes + 64, chain, move, TAG_FCPLX, seed)
@@ -95,10 +129,14 @@ class Chain:
                     move += 1
             self.n_meas += 1
             k = self.n_meas
-            x = np.concatenate([[abs(self.a)], np.abs(self.c)])
-            mu_old = self.mean.copy()
-            self.mean = mu_old * (k - 1) / k + x / k
+            dm_ = self.d if has_field else 1
+            x = np.concatenate([[abs(self.a)], np.abs(self.c)])[:dm_]
+            mu_old = self.mean[:dm_].copy()
+            self.mean[:dm_] = mu_old * (k - 1) / k + x / k
             if k > 50:
-                self.cov = self.cov * (k - 2) / (k - 1) + (np.outer(mu_old, mu_old) - k / (k - 1) * np.outer(self.mean, self.mean)
-                                                           + np.outer(x, x) / (k - 1) + (self.sig_r ** 2 / k) * np.identity(self.d))
-                L = np.linalg.cholesky(self.cov[1:, 1:])
+                mu = self.mean[:dm_]
+                self.cov[:dm_, :dm_] = self.cov[:dm_, :dm_] * (k - 2) / (k - 1) + (
+                    np.outer(mu_old, mu_old) - k / (k - 1) * np.outer(mu, mu) + np.outer(x, x) / (k - 1)
+                    + (self.sig_r ** 2 / k) * np.identity(dm_))
+                if has_field:
+                    L = np.linalg.cholesky(block())

@@ -181,6 +181,40 @@ def test_batched_fourier_chains_match_oracle(cuda):
     assert torch.all(summ["complex_acceptance"] > 0) and torch.all(fc.amp.abs() < .99)
 
 
+@pytest.mark.parametrize("method", ["simultaneous", "fixed-amplitude", "no-field"])
+def test_batched_fourier_chains_other_drivers_match_oracle(cuda, method):
+    """The other drivers of run.py:295-317 in the batched kernel vs the numpy restatement, same Philox draws; the run crosses
+    measurement 50, so the joint proposal is re-factorised from the adapted covariance."""
+    import torch
+    from cylinder_b200.fourier_chains import FourierChains
+    from oracle import fourier_am_oracle as fa
+    B, nfc = 2, (1, 1)
+    P = dict(wavenumber=[.6, 1.0], radius=1.0, gamma=1.0, kappa=[0.2, 0.0], intrinsic_curvature=0.0, alpha=-1.0, u=1.0, C=1.0,
+             n=[2.0, 1.0], temperature=.1, amp_bound=.99)
+    rng = np.random.RandomState(8)
+    c0 = rng.normal(0, .15, (B, 9)) + 1j * rng.normal(0, .15, (B, 9))
+    fc = FourierChains(P, num_field_coeffs=nfc, amplitude=.1, field_coeffs=c0, seed=5, chain0=3)
+    fc.run(35, measure_every=3, fieldsteps_per_ampstep=2, method=method)
+    fc.run(30, measure_every=3, fieldsteps_per_ampstep=2, method=method)
+    for b in range(B):
+        Pb = {k: (v[b] if isinstance(v, list) else v) for k, v in P.items()}
+        ch = fa.Chain(Pb, 1, 1, .1, c0[b], bound=.99)
+        ch.run(35, 3, 2, seed=5, chain=3 + b, method=method)
+        ch.run(30, 3, 2, seed=5, chain=3 + b, step0=35, method=method)
+        s = fc.state[b].cpu().numpy()
+        assert (s[5], s[6]) == (ch.acc_r, ch.acc_c) and ch.acc_r + ch.acc_c > 5
+        assert fc.amp[b].item() == pytest.approx(ch.a, rel=1e-9, abs=1e-12)
+        np.testing.assert_allclose(fc.coeffs[b].cpu().numpy(), ch.c, rtol=1e-8, atol=1e-11)
+        assert s[0] == pytest.approx(ch.sig_r, rel=1e-10) and s[1] == pytest.approx(ch.sig_c, rel=1e-10)
+        assert s[7] == pytest.approx(ch.e_field, rel=1e-9, abs=1e-14) and s[8] == pytest.approx(ch.e_surf, rel=1e-9)
+        np.testing.assert_allclose(fc.mean[b].cpu().numpy(), ch.mean, rtol=1e-9)
+        np.testing.assert_allclose(fc.covariance[b].cpu().numpy(), ch.cov, rtol=1e-7, atol=1e-12)
+    if method == "fixed-amplitude":
+        assert torch.all(fc.amp == .1)
+    if method == "no-field":
+        np.testing.assert_array_equal(fc.coeffs.cpu().numpy(), c0)
+
+
 def test_farm_run_writes_the_reference_files(cuda, tmp_path):
     """infile.txt + varfile.txt -> one batched launch: one <var1>_<x1>_<var2>_<x2>_mean.csv (+ profile CSVs) per line, named
     with the strings of the varfile, joinable by postprocess(); results do not depend on how the lines are batched."""
