@@ -30,6 +30,7 @@
 
 struct SmemScalars {
   double amp, amp_new, sigma_site, sigma_amp, e_field, e_surf, e_surf_new;
+  double cst;                       // sum over rows of the constant term W[5] of the energy at the current amplitude
   double step_counter, site_proposed, site_accepted, amp_proposed, amp_accepted, amp_counter, flags;
   double obs[CYL_OBS_DOUBLES];      // observable sums of this launch, flushed once at the end
   int amp_accept;
@@ -78,6 +79,41 @@ __device__ __forceinline__ void build_row_coefs(RowCoef<R>* coef, const RowTrig*
     const Geo gp = geo_from_sc(p.wavenumber, ra, a, tp.sm, tp.cm);      // z_{i+1/2} = z_{(i+1)-1/2}, periodic
     coef[i] = row_coef<R>(p, variant, lz, lth, g0, gm, gp);
   }
+}
+
+// Energy weights of row `tr` at amplitude a_eval (metric reference a_ref), pixel lengths folded in, rounded to the working
+// precision; returns the row's constant term W[5] (kept in double: it only enters through a per-replica sum).
+// The weights a sweep uses are ALWAYS this function of the amplitude -- `cur` is refreshed from it when a move is accepted,
+// `dif` is the difference of two such roundings -- so the chain samples exactly the model with the rounded weights.
+template <typename R>
+__device__ __forceinline__ double row_weights(const CylParams& p, int variant, double lz, double lth, int Z, int T, const RowTrig& tr,
+                                              double ra_eval, double a_eval, double ra_ref, double a_ref, R (&wf)[5]) {
+  const Geo g0e = geo_from_sc(p.wavenumber, ra_eval, a_eval, tr.s0, tr.c0), gme = geo_from_sc(p.wavenumber, ra_eval, a_eval, tr.sm, tr.cm);
+  Geo g0r = g0e;                                                         // a_ref = current amplitude (:75); rescaled variants only
+  if (variant != CYL_VARIANT_SIMPLE && a_ref != a_eval) g0r = geo_from_sc(p.wavenumber, ra_ref, a_ref, tr.s0, tr.c0);
+  double W[6];
+  field_energy_weights(variant, p, lz, lth, Z, T, g0e, gme, g0r, W);
+  const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
+#pragma unroll
+  for (int q = 0; q < 5; ++q) wf[q] = (R)(W[q] * fold[q]);
+  return W[5];
+}
+
+// cur <- weights at the current amplitude, dif <- 0, for every row; returns this thread's share of the constant term
+template <typename R>
+__device__ __forceinline__ double build_row_weights(RowW<R>* roww, const RowTrig* trig, const CylParams& p, int variant, double a,
+                                                    double lz, double lth, int Z, int T) {
+  const double ra = fast_radius_rescaled(p.radius, a);
+  double cst = 0.0;
+  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
+    RowW<R> w;
+    cst += row_weights<R>(p, variant, lz, lth, Z, T, trig[i], ra, a, ra, a, w.cur);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) w.dif[q] = R(0);
+    w.pad[0] = w.pad[1] = R(0);
+    roww[i] = w;
+  }
+  return cst;
 }
 
 // Sum N doubles over the CTA (result in every thread).  scratch: N * SWEEP_NWARP doubles.
@@ -179,9 +215,14 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   }
   __syncthreads();
   build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
-  if (extras && warp == 0) {
-    const double es = surface_energy_warp(p, sc->amp, nullptr, nullptr, true);
-    if (lane == 0) sc->e_surf = es;
+  if (extras) {
+    double c0[1] = {build_row_weights<R>(roww, trig, p, variant, sc->amp, lz, lth, Z, T)};
+    block_sum_n<1>(c0, scr);
+    if (tid == 0) sc->cst = c0[0];
+    if (warp == 0) {
+      const double es = surface_energy_warp(p, sc->amp, nullptr, nullptr, true);
+      if (lane == 0) sc->e_surf = es;
+    }
   }
   __syncthreads();
 
@@ -212,41 +253,23 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     const double a = sc->amp;
     const double a_new = extras ? a + sc->sigma_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
     const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
-    double cst_cur = 0.0, cst_dif = 0.0;
+    double cst_new = 0.0;
 
-    // ---- 0. row weights on warps 0..6: lane pair (2i, 2i+1) = (current, proposed amplitude) of row i;
-    //         warp 7 meanwhile evaluates the surface energy of the proposal ----
+    // ---- 0. weights of the proposed amplitude on warps 0..6, one row per thread (the current amplitude's are in place since
+    //         the last accepted move); warp 7 meanwhile evaluates the surface energy of the proposal ----
     if (extras) {
-      if (warp == SWEEP_NWARP - 1) {
-        if (try_move) {
+      if (try_move) {
+        if (warp == SWEEP_NWARP - 1) {
           const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
           if (lane == 0) sc->e_surf_new = es;
-        }
-      } else {
-        const double ae = (try_move && (tid & 1)) ? a_new : a;
-        const double ra = fast_radius_rescaled(p.radius, a), rae = (tid & 1) ? fast_radius_rescaled(p.radius, ae) : ra;
-        const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
-        for (int base = 0; base < 2 * Z; base += SWEEP_NT - 32) {
-          const int t = base + tid;
-          const int i = min(t >> 1, Z - 1);
-          const RowTrig tr = trig[i];
-          const Geo g0e = geo_from_sc(p.wavenumber, rae, ae, tr.s0, tr.c0), gme = geo_from_sc(p.wavenumber, rae, ae, tr.sm, tr.cm);
-          Geo g0r = g0e;                                                 // a_ref = current amplitude (:75); 0th order only
-          if (variant != CYL_VARIANT_SIMPLE && (tid & 1)) g0r = geo_from_sc(p.wavenumber, ra, a, tr.s0, tr.c0);
-          double W[6];
-          field_energy_weights(variant, p, lz, lth, Z, T, g0e, gme, g0r, W);
-          RowW<R> w;
-          double dif5 = 0.0;
+        } else if (warp * 32 < Z) {
+          const double ra = fast_radius_rescaled(p.radius, a), rn = fast_radius_rescaled(p.radius, a_new);
+          for (int i = tid; i < Z; i += SWEEP_NT - 32) {
+            R wn[5];
+            cst_new += row_weights<R>(p, variant, lz, lth, Z, T, trig[i], rn, a_new, ra, a, wn);
+            RowW<R>& w = roww[i];
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const double other = __shfl_xor_sync(0xffffffffu, W[q], 1);  // even lane receives W(a')
-            if (q < 5) { w.cur[q] = (R)(W[q] * fold[q]); w.dif[q] = (R)((other - W[q]) * fold[q]); }
-            else dif5 = other - W[q];
-          }
-          if (t < 2 * Z && !(tid & 1)) {
-            roww[i] = w;
-            cst_cur += W[5];
-            cst_dif += dif5;
+            for (int q = 0; q < 5; ++q) w.dif[q] = wn[q] - w.cur[q];
           }
         }
       }
@@ -329,8 +352,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     PHASE_MARK(1);
 
     // ---- 2. one reduction: accepts, energies, moments ----
-    double red[7] = {(double)nacc, (double)e.ec, (double)e.ed, cst_cur, cst_dif, (double)e.s2, (double)e.sa};
-    block_sum_n<7>(red, scr);
+    double red[6] = {(double)nacc, (double)e.ec, (double)e.ed, cst_new, (double)e.s2, (double)e.sa};
+    block_sum_n<6>(red, scr);
     PHASE_MARK(2);
 
     // ---- 3. Robbins-Monro on sigma_site (last thread) and the amplitude decision (thread 0), concurrently ----
@@ -342,17 +365,17 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       sc->site_accepted += red[0];
     }
     if (extras && tid == 0) {
-      const double e_dif = (red[2] + red[4]) * lz * lth;
+      const double e_dif = (red[2] + (red[3] - sc->cst)) * lz * lth;
       if (measure) {                                                     // measure_avgs :135-156 + engine record
-        const double e_cur = (red[1] + red[3]) * lz * lth;               // :213
+        const double e_cur = (red[1] + sc->cst) * lz * lth;              // :213
         sc->e_field = e_cur;
         double* o = sc->obs;
         o[CYL_OB_COUNT] += 1.0;
         o[CYL_OB_ABS_A] += fabs(a);
         o[CYL_OB_A] += a;
         o[CYL_OB_A2] += a * a;
-        o[CYL_OB_PSI2] += red[5] * inv_nsite;
-        o[CYL_OB_ABSPSI] += red[6] * inv_nsite;
+        o[CYL_OB_PSI2] += red[4] * inv_nsite;
+        o[CYL_OB_ABSPSI] += red[5] * inv_nsite;
         o[CYL_OB_E_FIELD] += e_cur;
         o[CYL_OB_E_SURF] += sc->e_surf;
         o[CYL_OB_E_FIELD2] += e_cur * e_cur;
@@ -387,7 +410,12 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     PHASE_MARK(3);
     // ---- 4. metric tables follow the amplitude ----
     if (extras && sc->amp_accept) {
+      // the accepted amplitude becomes the metric reference too (rescaled variants), so the weights are rebuilt rather
+      // than taken from the proposal's
       build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
+      double c0[1] = {build_row_weights<R>(roww, trig, p, variant, sc->amp, lz, lth, Z, T)};
+      block_sum_n<1>(c0, scr);
+      if (tid == 0) sc->cst = c0[0];
       __syncthreads();
     }
     PHASE_MARK(4);
