@@ -44,6 +44,17 @@ struct SmemScalars {
 #define PHASE_MARK(k) do { } while (0)
 #endif
 
+// one-off ablation switches (scripts/build_variant.sh ... -DSMEM_ABL_NO_ENERGY etc.); the product build has them all on
+#ifdef SMEM_ABL_NO_ENERGY
+#define SMEM_ENERGY_ON false
+#else
+#define SMEM_ENERGY_ON true
+#endif
+#ifdef SMEM_ABL_NO_WEIGHTS
+#define SMEM_WEIGHTS_ON false
+#else
+#define SMEM_WEIGHTS_ON true
+#endif
 #define AMP_CHUNK 64                // amplitude-move draws are precomputed for this many sweeps at a time
 
 // sin/cos(k z) at z_i and z_{i-1/2}
@@ -250,8 +261,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 #endif
     // The proposal a' = a + sigma_amp N(0,1) is known to every thread: the unit normal was drawn ahead of time, a and
     // sigma_amp were fixed by the previous sweep's decision.
-    const double a = sc->amp;
-    const double a_new = extras ? a + sc->sigma_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
+    // Chain scalars are read once here (the previous sweep ended with a barrier): during the decision phase several
+    // threads work from these copies while thread 0 updates the shared ones.
+    const double a = sc->amp, sig_amp = sc->sigma_amp, amp_cnt = sc->amp_counter, e_surf_cur = sc->e_surf;
+    const double a_new = extras ? a + sig_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
     const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
     double cst_new = 0.0;
 
@@ -260,9 +273,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     if (extras) {
       if (try_move) {
         if (warp == SWEEP_NWARP - 1) {
+#ifndef SMEM_ABL_NO_ESURF
           const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
           if (lane == 0) sc->e_surf_new = es;
-        } else if (warp * 32 < Z) {
+#endif
+        } else if (warp * 32 < Z && SMEM_WEIGHTS_ON) {
           const double ra = fast_radius_rescaled(p.radius, a), rn = fast_radius_rescaled(p.radius, a_new);
           for (int i = tid; i < Z; i += SWEEP_NT - 32) {
             R wn[5];
@@ -292,7 +307,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const C L = psi[im + j], Rz = psi[ip + j], W = psi[row + jm], E = psi[row + jp];
           C q;
           nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
-          if (extras) {
+          if (extras && SMEM_ENERGY_ON) {
             const RowW<R> w = roww[i];
             energy_own<R, C>(e, w, q, measure);
             if (colour == 1) {                                             // all four neighbours are final
@@ -332,7 +347,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             const C L = psi[iprev * T + j], Rz = psi[inext * T + j], W = psi[row + jm], E = psi[row + jp];
             C q;
             nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
-            if (extras) {
+            if (extras && SMEM_ENERGY_ON) {
               const RowW<R> w = roww[i];
               energy_own<R, C>(e, w, q, measure);
               // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
@@ -351,52 +366,73 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     PHASE_MARK(1);
 
-    // ---- 2. one reduction: accepts, energies, moments ----
-    double red[6] = {(double)nacc, (double)e.ec, (double)e.ed, cst_new, (double)e.s2, (double)e.sa};
-    block_sum_n<6>(red, scr);
+    // ---- 2. reduction: sums within a warp (working precision), the eight partials are added by whoever needs them ----
+    {
+      const int wacc = __reduce_add_sync(0xffffffffu, nacc);
+      R v[4] = {e.ec, e.ed, e.s2, e.sa};
+      double wc = 0.0;
+      if (extras) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+        if (try_move) wc = warp_sum(cst_new);
+      }
+      if (lane == 0) {
+        double* s = scr + warp * 8;
+        s[0] = (double)wacc;
+        if (extras) { s[1] = (double)v[0]; s[2] = (double)v[1]; s[3] = (double)v[2]; s[4] = (double)v[3]; s[5] = wc; }
+      }
+    }
+    __syncthreads();
     PHASE_MARK(2);
+    auto total = [&](int k) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < SWEEP_NWARP; ++w) t += scr[w * 8 + k];
+      return t;
+    };
 
-    // ---- 3. Robbins-Monro on sigma_site (last thread) and the amplitude decision (thread 0), concurrently ----
-    if (tid == SWEEP_NT - 1) {
+    // ---- 3. decisions, spread over threads of different warps: Robbins-Monro on sigma_site (warp 2), the measurement record
+    //         (warp 1), the amplitude move (warp 0) ----
+    if (tid == 64) {
+      const double nac = total(0);
       if (flags & CYL_SWEEP_ADAPT_SIGMA)
-        sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, red[0]);
+        sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, nac);
       sc->step_counter += nsite;
       sc->site_proposed += nsite;
-      sc->site_accepted += red[0];
+      sc->site_accepted += nac;
+    }
+    if (extras && measure && tid == 32) {                                // measure_avgs :135-156 + engine record
+      const double e_cur = (total(1) + sc->cst) * lz * lth;              // :213
+      sc->e_field = e_cur;
+      double* o = sc->obs;
+      o[CYL_OB_COUNT] += 1.0;
+      o[CYL_OB_ABS_A] += fabs(a);
+      o[CYL_OB_A] += a;
+      o[CYL_OB_A2] += a * a;
+      o[CYL_OB_PSI2] += total(3) * inv_nsite;
+      o[CYL_OB_ABSPSI] += total(4) * inv_nsite;
+      o[CYL_OB_E_FIELD] += e_cur;
+      o[CYL_OB_E_SURF] += e_surf_cur;
+      o[CYL_OB_E_FIELD2] += e_cur * e_cur;
+      o[CYL_OB_SIGMA] += (double)sigma;
     }
     if (extras && tid == 0) {
-      const double e_dif = (red[2] + (red[3] - sc->cst)) * lz * lth;
-      if (measure) {                                                     // measure_avgs :135-156 + engine record
-        const double e_cur = (red[1] + sc->cst) * lz * lth;              // :213
-        sc->e_field = e_cur;
-        double* o = sc->obs;
-        o[CYL_OB_COUNT] += 1.0;
-        o[CYL_OB_ABS_A] += fabs(a);
-        o[CYL_OB_A] += a;
-        o[CYL_OB_A2] += a * a;
-        o[CYL_OB_PSI2] += red[4] * inv_nsite;
-        o[CYL_OB_ABSPSI] += red[5] * inv_nsite;
-        o[CYL_OB_E_FIELD] += e_cur;
-        o[CYL_OB_E_SURF] += sc->e_surf;
-        o[CYL_OB_E_FIELD2] += e_cur * e_cur;
-        o[CYL_OB_SIGMA] += (double)sigma;
-      }
       int accept = 0;
       if (flags & CYL_SWEEP_AMP_MOVES) {
         if (try_move) {
-          const double dE = (sc->e_surf_new - sc->e_surf) + e_dif;
+          const double e_dif = (total(2) + (total(5) - sc->cst)) * lz * lth;
+          const double dE = (sc->e_surf_new - e_surf_cur) + e_dif;
           if (!isfinite(dE)) sc->flags = (double)((unsigned)sc->flags | 1u);
           if (dE <= 0) accept = 1;                                       // accept rule B.2
           else if (p.temperature == 0) accept = 0;
           else accept = (ampu[sw & (AMP_CHUNK - 1)] <= exp(-dE / p.temperature));
         }
         // Robbins-Monro on sigma_amp (engine, SURVEY.md B.3: m = 1, target p*)
-        sc->amp_counter += 1;
+        sc->amp_counter = amp_cnt + 1;
         sc->amp_proposed += 1;
         if (flags & CYL_SWEEP_ADAPT_SIGMA) {
-          const double cf = sc->sigma_amp * amp_ratio * fast_rcp(fmax(sc->amp_counter, 200.0));
-          if (accept) sc->sigma_amp += cf * (1 - amp_pt);
-          else sc->sigma_amp -= cf * amp_pt;
+          const double cf = sig_amp * amp_ratio * fast_rcp(fmax(amp_cnt + 1, 200.0));
+          sc->sigma_amp = accept ? sig_amp + cf * (1 - amp_pt) : sig_amp - cf * amp_pt;
         }
         if (accept) {
           sc->amp = a_new;
