@@ -243,6 +243,14 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const int ncol = num_colours(Z, T);
   const int Th = (T + 1) >> 1, Teven = T & ~1;
   const int di = SWEEP_NT / Th, dj = SWEEP_NT % Th;
+  // Column-mapped site loops (T even): thread = (row group rg, column pair jj); a thread keeps its two columns and walks
+  // down the rows in steps of the (even) number of row groups, so the parity of its rows, hence the column of its colour and
+  // the periodic wrap in theta, are fixed per pass and all addresses advance by constants.  Fallback for T odd or T > 256:
+  // the generic loops further down.
+  const int RGe = ((T & 1) == 0) ? ((SWEEP_NT / Th) & ~1) : 0;
+  const bool mapped = RGe >= 2;
+  const int rg = mapped ? tid / Th : 0, cj = mapped ? tid - rg * Th : 0;
+  const bool col_active = mapped && rg < RGe;
 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
@@ -295,7 +303,76 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     // ---- 1. site moves, energy accumulated as bonds become final ----
     int nacc = 0;
     EAcc<R> e = {R(0), R(0), R(0), R(0)};
-    if (ncol == 2) {
+    // one site of row i (row = i*T; up / dn = offsets of the rows above / below): the move, then the energy terms this site
+    // closes -- its own, and the bonds to the neighbours flagged in `own` (bit 0: i-1, 1: i+1, 2: j-1, 3: j+1)
+    auto visit = [&](int i, int row, int up, int dn, int j, int jm, int jp, int own) {
+      const C L = psi[up + j], Rz = psi[dn + j], W = psi[row + jm], E = psi[row + jp];
+      C q;
+      nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
+      if (extras && SMEM_ENERGY_ON) {
+        const RowW<R> w = roww[i];
+        energy_own<R, C>(e, w, q, measure);
+        if (own & 1) energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, L, measure);
+        if (own & 2) {
+          const int inext = (i == Z - 1 ? 0 : i + 1);
+          energy_zbond<R, C>(e, roww[inext].cur[2], roww[inext].dif[2], Rz, q, measure);
+        }
+        if (own & 4) energy_tbond<R, C>(e, w, q, W, measure);
+        if (own & 8) energy_tbond<R, C>(e, w, E, q, measure);
+      }
+    };
+    if (mapped && ncol == 2) {
+      // both lengths even: colour = (i + j) & 1; colour 1 closes every bond (all its neighbours are final)
+      const int step = RGe * T;
+      for (int colour = 0; colour < 2; ++colour) {
+        if (col_active) {
+          const int j = 2 * cj + ((colour + rg) & 1);
+          const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
+          const int own = colour ? 15 : 0;
+          for (int i = rg, row = rg * T; i < Z; i += RGe, row += step)
+            visit(i, row, (i == 0 ? nsite : row) - T, (i == Z - 1 ? 0 : row + T), j, jm, jp, own);
+        }
+        __syncthreads();
+      }
+    } else if (mapped) {
+      // T even, Z odd: colour = (a(i) + (j & 1)) % 3 with a(i) = i & 1 except a(Z-1) = 2.  Pass 0: even rows (not the last),
+      // even columns + the last row, odd columns; pass 1: rows 0..Z-2, the column parity opposite to the row's; pass 2: odd
+      // rows, odd columns + the last row, even columns.  A bond is closed by its later-coloured endpoint.
+      auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
+      auto own_of = [&](int i, int b, int colour) {                       // which bonds a site of row i, column parity b closes
+        const int ai = axis_colour(i, Z);
+        const int aprev = axis_colour(i == 0 ? Z - 1 : i - 1, Z), anext = axis_colour(i == Z - 1 ? 0 : i + 1, Z);
+        const int side = col3(ai + 1 - b) < colour ? 12 : 0;               // both theta neighbours have the other parity
+        return (col3(aprev + b) < colour ? 1 : 0) | (col3(anext + b) < colour ? 2 : 0) | side;
+      };
+      const int half = (Z - 1) >> 1;
+      for (int colour = 0; colour < 3; ++colour) {
+        if (col_active) {
+          if (colour == 1) {
+            const int b = (rg & 1) ? 0 : 1;                                // rows keep their parity: the step is even
+            const int j = 2 * cj + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
+            for (int i = rg; i < Z - 1; i += RGe) {
+              const int row = i * T;
+              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp, own_of(i, b, 1));
+            }
+          } else {
+            const int b = colour ? 1 : 0;
+            const int j = 2 * cj + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
+            for (int ii = rg; ii < half; ii += RGe) {
+              const int i = 2 * ii + b, row = i * T;                       // even rows in pass 0, odd rows in pass 2
+              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp, own_of(i, b, colour));
+            }
+          }
+        }
+        if (colour != 1 && tid >= SWEEP_NT - Th) {                         // the last row, from the top of the CTA (those
+          const int b = colour ? 0 : 1;                                    // threads have the fewest rows above)
+          const int j = 2 * (tid - (SWEEP_NT - Th)) + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
+          const int i = Z - 1, row = i * T;
+          visit(i, row, row - T, 0, j, jm, jp, own_of(i, b, colour));
+        }
+        __syncthreads();
+      }
+    } else if (ncol == 2) {
       // both lengths even: colour = (i + j) & 1, T/2 sites of each colour in every row
       for (int colour = 0; colour < 2; ++colour) {
         int i = tid / Th, jj = tid - i * Th;
