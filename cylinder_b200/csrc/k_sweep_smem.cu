@@ -127,6 +127,8 @@ __device__ __forceinline__ double build_row_weights(RowW<R>* roww, const RowTrig
   return cst;
 }
 
+__device__ __forceinline__ double surface_energy_of(const CylParams& p, double a) { return surface_energy_warp(p, a, nullptr, nullptr, true); }
+
 // Sum N doubles over the CTA (result in every thread).  scratch: N * SWEEP_NWARP doubles.
 template <int N>
 __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
@@ -231,7 +233,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     block_sum_n<1>(c0, scr);
     if (tid == 0) sc->cst = c0[0];
     if (warp == 0) {
-      const double es = surface_energy_warp(p, sc->amp, nullptr, nullptr, true);
+      const double es = surface_energy_of(p, sc->amp);
       if (lane == 0) sc->e_surf = es;
     }
   }
@@ -282,7 +284,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       if (try_move) {
         if (warp == SWEEP_NWARP - 1) {
 #ifndef SMEM_ABL_NO_ESURF
-          const double es = surface_energy_warp(p, a_new, nullptr, nullptr, true);
+          const double es = surface_energy_of(p, a_new);
           if (lane == 0) sc->e_surf_new = es;
 #endif
         } else if (warp * 32 < Z && SMEM_WEIGHTS_ON) {
@@ -324,6 +326,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     if (mapped && ncol == 2) {
       // both lengths even: colour = (i + j) & 1; colour 1 closes every bond (all its neighbours are final)
       const int step = RGe * T;
+#pragma unroll 1
       for (int colour = 0; colour < 2; ++colour) {
         if (col_active) {
           const int j = 2 * cj + ((colour + rg) & 1);
@@ -346,6 +349,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         return (col3(aprev + b) < colour ? 1 : 0) | (col3(anext + b) < colour ? 2 : 0) | side;
       };
       const int half = (Z - 1) >> 1;
+#pragma unroll 1
       for (int colour = 0; colour < 3; ++colour) {
         if (col_active) {
           if (colour == 1) {
