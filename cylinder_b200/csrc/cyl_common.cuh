@@ -198,12 +198,22 @@ __host__ __device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1
 
 // round keys expanded on the host for single-replica kernels (constant-bank operands of the XOR)
 struct SiteKeys { uint32_t k[10]; uint32_t off; uint32_t pad; };
+// a ^ b ^ c as ONE three-input logic op.  Left to itself the compiler combines lo ^ key early and pays a second LOP3 per
+// round to shorten the dependency chain; these kernels are bound by instruction issue, not by that latency.
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 __device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, const SiteKeys& ks) {
+  uint32_t hi, lo;
+  philox_mulhilo(PHILOX2_M, c0, hi, lo);
+  c0 = hi ^ (ks.k[0] ^ c1);                          // c1 = sweep counter: uniform, so is k[0] ^ c1
+  c1 = lo;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi, lo;
+  for (int i = 1; i < 10; ++i) {
     philox_mulhilo(PHILOX2_M, c0, hi, lo);
-    c0 = hi ^ ks.k[i] ^ c1;
+    c0 = xor3(hi, ks.k[i], c1);
     c1 = lo;
   }
   return make_uint2(c0, c1);
