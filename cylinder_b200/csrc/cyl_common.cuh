@@ -219,6 +219,21 @@ __device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, const S
   return make_uint2(c0, c1);
 }
 
+// the same with the round keys in registers; kc = k[0] ^ c1 (c1 = the sweep counter word)
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t kc, const uint32_t (&k)[10]) {
+  uint32_t hi, lo;
+  philox_mulhilo(PHILOX2_M, c0, hi, lo);
+  c0 = hi ^ kc;
+  c1 = lo;
+#pragma unroll
+  for (int i = 1; i < 10; ++i) {
+    philox_mulhilo(PHILOX2_M, c0, hi, lo);
+    c0 = xor3(hi, k[i], c1);
+    c1 = lo;
+  }
+  return make_uint2(c0, c1);
+}
+
 // Stream tags in counter word 3 (upper byte), so that site moves, amplitude moves and initialisation of the
 // same (site, replica, sweep) never share a counter.
 #define CYL_TAG_SITE 0u

@@ -73,7 +73,8 @@ struct HbmAmp {                      // header: the amplitude proposal of the cu
 #define HBM_HDR_BYTES 1024
 static_assert(sizeof(HbmAmp) <= HBM_HDR_BYTES, "scratch header");
 #ifndef HBM_MINB_F32
-#define HBM_MINB_F32 5             // co-resident CTAs per SM the fp32 sweep kernel is compiled for
+#define HBM_MINB_F32 4             // co-resident CTAs per SM the fp32 sweep kernel is compiled for: with the Philox round keys
+                                   // in registers it needs ~60; 4 vs 5 resident CTAs measured no difference (issue-bound)
 #endif
 #ifdef HBM_ABL_NO_ENERGY
 #define HBM_ENERGY_ON false
@@ -283,7 +284,8 @@ struct HbmSmem {
   static constexpr size_t off_roww = off_coef + (size_t)SH * sizeof(RowCoef<R>);
   static constexpr size_t off_red = off_roww + (size_t)SH * sizeof(RowW<R>);
   static constexpr size_t off_bar = off_red + ((HBM_NT / 32) * 8 + 8) * sizeof(double);
-  static constexpr size_t total = off_bar + 64;
+  static constexpr size_t off_keys = off_bar + 64;                  // Philox round keys (see the prologue)
+  static constexpr size_t total = off_keys + 64;
 };
 
 struct HbmMaps { CUtensorMap m[2][2]; int esz; };   // [buffer][plane]; esz = TMA elements per complex value
@@ -389,8 +391,16 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   } else {
     for (int r = tid; r < SH; r += HBM_NT) coef[r] = A.coef2[modi(ti0 - NCOL + r, g.Z)];
   }
+  // The round keys arrive in the constant bank; used from there the compiler re-materialises one move per key per site.
+  // Routed through shared memory they are ordinary loaded values and stay in registers for the whole kernel.
+  uint32_t* keys_s = reinterpret_cast<uint32_t*>(smem_raw + L::off_keys);
+  if (tid < 10) keys_s[tid] = keys.k[tid];
   const uint32_t c1 = (uint32_t)sweep + keys.off;
   __syncthreads();                                                  // mbarrier initialised, row tables staged
+  uint32_t kr[10];
+#pragma unroll
+  for (int r = 0; r < 10; ++r) kr[r] = keys_s[r];
+  const uint32_t kc = kr[0] ^ c1;
   if (!EXTRAS) sigma = (R)red[(HBM_NT / 32) * 8 + 7];
   mbar_wait(bar, 0);
 
@@ -413,7 +423,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     auto move = [&](C* own, const C* oth, int r, uint32_t site, bool counted, int c) {
       const RowCoef<R> rc = coef[r];
       const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
-      const uint2 x = philox2x32_10(site, c1, keys);
+      const uint2 x = philox2x32_10(site, c1, kc, kr);
       R zre, zim;
       Draw<R>::normals(x.x, x.y, zre, zim);
       const R w = sigma * rc.sgmul;
@@ -485,7 +495,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
         const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
         const RowCoef<R> rc = coef[r];
-        const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, keys);
+        const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, kc, kr);
         R zre, zim;
         Draw<R>::normals(x.x, x.y, zre, zim);
         const R w = sigma * rc.sgmul;
