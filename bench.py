@@ -36,7 +36,7 @@ SWEEPS_PER_STEP = 200
 DIMS = (50, 50)
 SEED = 0x5EED
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
-NCU_HBM_TRAFFIC_BYTES = 135.754e6 + 82.246e6   # sweep_hbm_kernel<float,2,30,0>, 4096x4096, one launch (profiles/r01_ncu_full_c.md)
+NCU_HBM_TRAFFIC_BYTES = 135.667e6 + 86.053e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_c.md)
 
 
 def grid_params(n_replicas, replica0=0):
