@@ -35,6 +35,11 @@ REPLICAS_PER_GPU = 8192
 SWEEPS_PER_STEP = 200
 DIMS = (50, 50)
 SEED = 0x5EED
+WORKLOAD = ("C5 per-GPU share: %d replicas/GPU over C3's 16x16x16 (alpha, C, k) grid x seeds, dims (50,50) => Z=round(50/k) in "
+            "[40,100] (odd Z: 3 colours), T=50")
+PER_SWEEP = "site moves + Robbins-Monro + row moments/measure + 1 amplitude move"
+CPU_SAMPLE = ("%d replicas of the same grid, one per host core, whole sweeps of the reference algorithm (Z*T random-site proposals "
+              "with per-proposal Robbins-Monro + 1 amplitude move + 1 measurement per sweep)")
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
 NCU_HBM_TRAFFIC_BYTES = 135.667e6 + 86.053e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_c.md)
 
@@ -57,30 +62,41 @@ def grid_params(n_replicas, replica0=0):
 # the oracle -- the only place bench.py executes oracle/ code, and only as the thing timed for the CPU baseline.
 # ------------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    idx, seconds, warm = args
+    """One host core = one replica of the SAME workload as the GPU arm (a point of C3's grid, Z = round(50/k) rows), advanced
+    by whole sweeps of the reference algorithm: Z*T proposals at uniformly random sites with per-proposal Robbins-Monro
+    (Lattice.step_lattice), one global amplitude move and one measurement per sweep (run_lattice.py:72-90)."""
+    idx, seconds, warm_sweeps = args
     import random
+    import numpy as np
     from oracle import checkerboard_oracle as cb
     from oracle import lattice_oracle as lo
-    psi = cb.random_initialize(50, 50, .1, SEED, idx)
-    st = lo.LatticeState(psi, 1.0, 1.0, -1.0, 1.0, 1.0, 6, .01)           # config C1: alpha=-1, C=1, u=1, n=6, k=1, T=.01
+    g = grid_params(1, (idx * 257) % 4096)                                  # spread the sample over the grid
+    P = {k: float(np.atleast_1d(v)[0]) for k, v in g.items()}
+    Z, T = lo.lattice_dims(DIMS, P["wavenumber"])
+    psi = cb.random_initialize(Z, T, .1, SEED, idx)
+    st = lo.LatticeState(psi, P["wavenumber"], P["radius"], P["alpha"], P["u"], P["C"], P["n"], P["temperature"])
+    am = cb.AmpState(amplitude=0.0, sigma_amp=.005, target=P["amp_target_acceptance"], bound=P["amp_bound"])
     rng = random.Random(12345 + idx)
-    a = 0.3
 
-    def go(n):
-        for _ in range(n):
-            lo.step_lattice_loc(st, a, rng.randrange(-1, st.Z - 1), rng.randrange(-1, st.T_len - 1), rng.gauss(0, 1),
-                                rng.gauss(0, 1), rng.random)
-    go(warm)
-    n_done, t0 = 0, time.perf_counter()
+    def sweep(s):
+        for _ in range(Z * T):
+            lo.step_lattice_loc(st, am.a, rng.randrange(-1, Z - 1), rng.randrange(-1, T - 1), rng.gauss(0, 1), rng.gauss(0, 1),
+                                rng.random)
+        lo.measure_profiles(st.psi)
+        cb.amplitude_move(st, am, P, SEED, idx, s)
+    for s in range(warm_sweeps):
+        sweep(s)
+    n_done, s, t0 = 0, warm_sweeps, time.perf_counter()
     while True:
-        go(2000)
-        n_done += 2000
+        sweep(s)
+        s += 1
+        n_done += Z * T
         dt = time.perf_counter() - t0
         if dt >= seconds:
             return n_done, dt
 
 
-def cpu_reference_rate(seconds, cores=None, warm=2000):
+def cpu_reference_rate(seconds, cores=None, warm=1):
     """Aggregate site-updates/s of `cores` independent replicas (what scripts/taskarray.sh does with one process per
     grid point).  Returns (rate, cores, total updates)."""
     import multiprocessing as mp
@@ -108,12 +124,12 @@ def run_reference_arm(args):
         total += n
     wall = time.perf_counter() - t0
     value = sum(rates) / len(rates)
-    sample = ("%d independent 50x50 replicas (config C1: alpha=-1,C=1,u=1,n=6,k=1,T=.01,a=.3), sequential random-site "
-              "Metropolis with per-proposal Robbins-Monro, %.1f s per step" % (cores, per_step))
+    sample = CPU_SAMPLE % cores + ", %.1f s per step" % per_step
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "reference algorithm on host CPU cores: " + sample},
+            "config": {"workload": WORKLOAD % args.replicas_per_gpu, "per_sweep": PER_SWEEP,
+                       "sample": "reference algorithm on the host cores: " + sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -320,16 +336,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, cores, total = cpu_reference_rate(args.cpu_seconds)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d independent 50x50 replicas (config C1, a=.3), %.0f s wall, %d proposals: oracle restatement of the "
-                         "reference's sequential per-site Python loop" % (cores, args.cpu_seconds, total)}
+               "sample": CPU_SAMPLE % cores + ", %.0f s wall, %d proposals: oracle restatement of the reference's sequential "
+                         "per-site Python loop" % (args.cpu_seconds, total)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "C5 per-GPU share: %d replicas/GPU over C3's 16x16x16 (alpha, C, k) grid x seeds, dims (50,50) "
-                                       "=> Z=round(50/k) in [40,100] (odd Z: 3 colours), T=50, fp32 psi resident in shared memory" % Bg,
-                           "sweeps_per_step": nsw, "per_sweep": "site moves + Robbins-Monro + row moments/measure + 1 amplitude move",
+                "config": {"workload": WORKLOAD % Bg + ", fp32 psi resident in shared memory",
+                           "sweeps_per_step": nsw, "per_sweep": PER_SWEEP,
                            "site_updates_per_step": updates_per_step_all, "variant": "simple", "temperature": 0.01,
                            "l2_policy": "state re-read from HBM once per step (%.0f MB/GPU > L2 not required: lattices live in "
                                         "shared memory during a step)" % (Bg * batch.Zmax * batch.T * 8 / 1e6),
