@@ -354,11 +354,14 @@ class Lattice:
             self.me.measure_real_system()
 
     def run_fixed_amplitude(self, n_steps, n_sub_steps, sweeps_per_step=None):
-        """:519-530 -- field moves on a frozen shape."""
+        """:519-530 -- field moves on a frozen shape: per step one whole-lattice shift proposal (step_lattice_all, :524-525),
+        then the single-site proposals, executed as sweeps."""
         per_step = sweeps_per_step or self._sweeps_for(self.fieldsteps_per_ampstep * n_sub_steps)
         for i in range(n_steps):
             self.measure_avgs()
             self.measure()
+            self.energy = self.surface_field_energy(self.amplitude, self.amplitude)            # :524
+            self.step_lattice_all(self.amplitude)                                              # :525
             if per_step > 1:
                 self.sweep(per_step - 1)
             c = self.sweep(1, amp_moves=False, measure=True)

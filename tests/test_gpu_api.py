@@ -126,6 +126,22 @@ def test_lattice_run_and_engine_wiring(cuda, tmp_path):
     assert lat.me.energy["field"] == pytest.approx(lat.surface_field_energy(lat.amplitude, lat.amplitude), rel=1e-9)
 
 
+@pytest.mark.parametrize("cls", ["Lattice", "LatticeRescaled1stOrder", "LatticeDecoupled"])
+def test_lattice_run_fixed_amplitude(cuda, cls):
+    """run_fixed_amplitude (:519-530): a whole-lattice shift proposal and the site sweeps per step on a frozen shape; the
+    engine's field energy follows the lattice, the amplitude never moves, the width adapts."""
+    import cylinder_b200
+    random.seed(11)
+    lat = getattr(cylinder_b200, cls)(**dict(BASE, amplitude=.25, dims=(16, 12), temperature=.05, fieldsteps_per_ampstep=4))
+    w0 = lat.sampling_width
+    lat.run_fixed_amplitude(12, 50)
+    assert lat.amplitude == .25 and len(lat.field_abs_profile_history) == 12
+    assert lat.me.energy["field"] == pytest.approx(lat.surface_field_energy(.25, .25), rel=1e-9)
+    assert lat.sampling_width != w0 and lat.step_counter >= 12 * (16 * 12 + 1)
+    lat.me.save_time_series()
+    assert len(lat.me.df) == 12
+
+
 def test_single_run_lattice_and_fourier(cuda, tmp_path, monkeypatch):
     from cylinder_b200 import run
     monkeypatch.chdir(tmp_path)
