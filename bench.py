@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--no-hbm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -277,7 +278,7 @@ def main():
         def step_e2e():
             # H2D: lattices + chain state; the sweeps; D2H: lattices (what `.lattice` hands to the caller) + records;
             # pipelined over 4 slices of the batch, returns when the host buffers are complete
-            batch.step_host(psi_h, chain_h, psi_out_h, rec_h, nsw, nchunks=4)
+            batch.step_host(psi_h, chain_h, psi_out_h, rec_h, nsw, nchunks=args.e2e_chunks)
             if world > 1:
                 batch.gather_records()
                 torch.cuda.current_stream().synchronize()
@@ -293,7 +294,7 @@ def main():
         d2h = rec_h.numel() * 8 + psi_out_h.numel() * psi_out_h.element_size()
         e2e = {"value": updates_per_step_all * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K,
-               "api": "ReplicaBatch.step_host: pinned host lattices + chain in, sweeps, lattices + records out, 4-slice stream pipeline, host-synchronised per step"}
+               "api": "ReplicaBatch.step_host: pinned host lattices + chain in, sweeps, lattices + records out, %d-slice stream pipeline, host-synchronised per step" % args.e2e_chunks}
 
     # ---- roofline leg: C4, one large lattice streamed from HBM ----
     roofline = None

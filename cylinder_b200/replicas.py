@@ -157,7 +157,7 @@ class ReplicaBatch:
         if chain_host is not None:
             self.chain.copy_(chain_host, non_blocking=non_blocking)
 
-    def step_host(self, psi_host, chain_host, psi_out_host, rec_out_host, nsweeps, nchunks=4, amp_moves=True, measure=True,
+    def step_host(self, psi_host, chain_host, psi_out_host, rec_out_host, nsweeps, nchunks=16, amp_moves=True, measure=True,
                   adapt=True):
         """One step with HOST buffers in and out (pinned tensors): upload lattices + chain state, run nsweeps, download
         lattices + per-replica records.  The batch is cut into `nchunks` slices, each on its own stream, so the H2D copy of
