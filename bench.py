@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--no-hbm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -332,6 +333,29 @@ def main():
                     "note": "time = whole call / sweeps: one sweep kernel per sweep (it carries the Robbins-Monro record itself) + one coefficient and one finalize kernel per call"}
         del ws
 
+    # ---- config C2 (Fourier-mode model + adaptive engine), batched: reported beside the headline, not part of it ----
+    aux = None
+    if rank == 0 and world == 1 and not args.no_aux:
+        import numpy as np
+        from cylinder_b200.fourier_chains import FourierChains
+        nch, nst = 4096, 40
+        fc = FourierChains(dict(wavenumber=np.full(nch, .5), radius=1.0, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-1.0, u=1.0,
+                                C=1.0, n=6.0, temperature=.1, amp_bound=.99), num_field_coeffs=(2, 1), amplitude=0.0, seed=1, device=dev)
+        fc.run(10, measure_every=10, fieldsteps_per_ampstep=10)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        fc.run(nst, measure_every=10, fieldsteps_per_ampstep=10)
+        f1.record()
+        torch.cuda.synchronize()
+        moves = nch * nst * 10 * 11
+        aux = {"fourier_c2": {"engine_moves_per_s": moves / (f0.elapsed_time(f1) * 1e-3), "chains": nch,
+                              "config": "Cylinder2D (nz, nth) = (2, 1): 15 complex coefficients + amplitude, method sequential, "
+                                        "measure_every 10, fieldsteps_per_ampstep 10, T = .1; one warp per chain",
+                              "reference": "0.24 ms per calc_field_energy, 47 ms per calc_field_energy_amplitude_change on one "
+                                           "CPU core (SURVEY.md section 6)"}}
+        del fc
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -350,7 +374,7 @@ def main():
                            "l2_policy": "state re-read from HBM once per step (%.0f MB/GPU > L2 not required: lattices live in "
                                         "shared memory during a step)" % (Bg * batch.Zmax * batch.T * 8 / 1e6),
                            "mean_site_acceptance": acc},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": K,"roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
