@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--replicas-per-gpu", type=int, default=REPLICAS_PER_GPU)
     ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
     ap.add_argument("--hbm-size", type=int, default=4096)
-    ap.add_argument("--hbm-sweeps", type=int, default=50)
+    ap.add_argument("--hbm-sweeps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-hbm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -360,7 +360,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, cores, total = cpu_reference_rate(args.cpu_seconds)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "per_core": rate / max(1, cores), "kind": "port",
                "sample": CPU_SAMPLE % cores + ", %.0f s wall, %d proposals: oracle restatement of the reference's sequential "
                          "per-site Python loop" % (args.cpu_seconds, total)}
 

@@ -169,8 +169,11 @@ __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz
 
 // EXTRAS = amplitude moves and/or measurement requested: a compile-time switch so that the plain-sweep instantiation
 // does not carry the registers of the energy accumulation.
+#ifndef SMEM_MINB_EXTRAS
+#define SMEM_MINB_EXTRAS 4
+#endif
 template <typename R, bool EXTRAS>
-__global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? 4 : 2))
+__global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? (EXTRAS ? SMEM_MINB_EXTRAS : 4) : 2))
 sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
                   const CylParams* __restrict__ params, double* __restrict__ chain, const __grid_constant__ PhiloxKeys keys,
                   uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
