@@ -16,6 +16,13 @@
 //   3. the interior is written to the other buffer (plus its periodic halo copies).
 // A sweep therefore reads each site once (+ halo overhead) and writes it once, whatever the number of colours.
 //
+// Per sweep, plain (site moves + Robbins-Monro): ONE kernel.  The accept count goes to bucketed no-return atomics, and every
+// tile of the next sweep derives the adapted proposal width from the previous sweep's record itself.
+// Per sweep with measurement / amplitude move (EXTRAS): hbm_prep_kernel (proposal, row weights for a and a', coefficient
+// table for a', E_surf(a')) -> sweep kernel (energies for a and a'-a and the profiles' theta-sums accumulated while the sites
+// are finalised; 5 partial sums per tile) -> hbm_decide_kernel (fixed-order sum of the tiles, Robbins-Monro, observables,
+// amplitude decision).  All of them are launched with programmatic stream serialisation (see pdl_wait / pdl_trigger).
+//
 // Reference semantics restated: Lattice.step_lattice_loc (On_lattice_simple.py:598-686) per site,
 // update_sigma (:688-696) batched per sweep, Lattice.measure (:121-131), amplitude move (:544-550).
 #include <cuda.h>
@@ -32,7 +39,7 @@
 
 // Tile height is a template parameter chosen per launch (see pick_tile_height): co-resident CTAs run in waves, and the
 // last, partially filled wave costs as much as a full one, so the height that makes the wave count of THIS lattice on
-// THIS device (almost) integral wins -- 4096 x 4096 on 148 SMs x 5 CTAs: 32 rows -> 5.53 waves, 30 rows -> 5.92.
+// THIS device (almost) integral wins -- 4096 x 4096 on 148 SMs x 4 CTAs: 32 rows -> 6.92 waves, 30 rows -> 7.41.
 
 struct HbmGeom {
   int Z, T, ncol, hr, hc;

@@ -4,20 +4,23 @@
 // memory, written back once; the per-row metric coefficients, the amplitude-independent sin/cos tables and the
 // per-row energy weights live in shared memory too.  Per sweep:
 //   0. the amplitude proposal a' = a + sigma_amp N(0,1) is known up front (its draws are precomputed, counter-based);
-//      row weights of the field energy for the current amplitude and for (a' - a) are built by lane pairs on warps
-//      0..6 (fp64, fast reciprocals) while warp 7 evaluates E_surf(a');
+//      the row weights of the field energy for a' are built one row per thread (fp64, fast reciprocals; those for the
+//      current amplitude are in place since the last accepted move) while warp 7 evaluates E_surf(a');
 //   1. site moves (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once; draws from
 //      Philox2x32-10 at counter (site, sweep) -- stateless, so a sweep can be re-run or resumed bit-identically.  The
 //      ENERGY is accumulated in the same pass: a site adds its own |psi|^2, |psi|^4 terms when it is finalised, and a
 //      bond (|dz|^2, |dth|^2, Im(conj(psi) dth)) is added by whichever endpoint is finalised LATER
 //      (its neighbour has the lower colour), dotted with the row weights for a and for (a' - a): the energy change of
 //      the amplitude move is accumulated directly, not as a difference of two large sums, and no second pass over the
-//      lattice is needed;
-//   2. one CTA tree reduction of {accepts, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|};
-//   3. Robbins-Monro on sigma_site (On_lattice_simple.py:688-696, batched; cyl_site.cuh) and the amplitude decision
-//      (Lattice.run :544-550 through engine.step_real_group; accept rule B.2; Robbins-Monro on sigma_amp);
-//   4. on accept, rebuild the row coefficients from the sin/cos tables (no trigonometry);
-//   5. with CYL_SWEEP_MEASURE and a profile buffer: row sums of Lattice.measure (:121-131), one warp per row.
+//      lattice is needed.  For even T the loops are column-mapped: a thread keeps its column pair and walks the rows with an
+//      even stride, so colour parity, theta wrap and addresses are loop constants (2 and 3 colours);
+//   2. warp-level sums of {accepts, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|}; the 8 partials are added by the
+//      threads that need them;
+//   3. on three threads of different warps: Robbins-Monro on sigma_site (On_lattice_simple.py:688-696, batched; cyl_site.cuh),
+//      the measurement record, and the amplitude decision (Lattice.run :544-550 through engine.step_real_group; accept
+//      rule B.2; Robbins-Monro on sigma_amp);
+//   4. on accept, rebuild the row coefficients and the current weights from the sin/cos tables (no trigonometry);
+//   5. with CYL_SWEEP_MEASURE and a profile buffer: row sums of Lattice.measure (:121-131), one thread per row.
 // The replicas are the (alpha, C, n, kappa, k) parameter grid that scripts/taskarray.sh farms out as separate CPU
 // jobs in the reference.
 #include "cyl_common.cuh"
