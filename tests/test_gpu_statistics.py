@@ -16,12 +16,15 @@ def _batch_err(x, nb=10):
     return b.std(ddof=1) / math.sqrt(nb)
 
 
-@pytest.mark.parametrize("variant,dtype", [("simple", "complex64"), ("rescaled_0thorder", "complex64"), ("simple", "complex128")])
-def test_ensemble_matches_sequential_oracle(cuda, variant, dtype):
+@pytest.mark.parametrize("variant,dtype,Z,T", [("simple", "complex64", 6, 5), ("rescaled_0thorder", "complex64", 6, 5),
+                                               ("simple", "complex128", 6, 5), ("simple", "complex64", 7, 6), ("simple", "complex64", 6, 6),
+                                               ("rescaled_1storder", "complex64", 7, 6), ("decoupled", "complex64", 6, 6)])
+def test_ensemble_matches_sequential_oracle(cuda, variant, dtype, Z, T):
+    """(6, 5): odd theta ring, generic 3-colour loop; (7, 6): column-mapped 3-colour loop; (6, 6): column-mapped 2-colour loop."""
     import torch
     from cylinder_b200.replicas import ReplicaBatch
     P = dict(wavenumber=1.0, radius=1.0, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-1.0, u=1.0, C=1.0, n=2.0, temperature=.3)
-    a, Z, T = 0.3, 6, 5                                     # odd theta ring: 3 colours on the GPU
+    a = 0.3
     # oracle: one long sequential chain (reference ordering, per-proposal Robbins-Monro)
     rng = random.Random(2)
     psi0 = np.array([[complex(rng.gauss(0, .3), rng.gauss(0, .3)) for _ in range(T)] for _ in range(Z)])
