@@ -65,13 +65,14 @@ class Lattice:
                                        intrinsic_curvature=intrinsic_curvature, alpha=alpha, u=u, C=C, n=n,
                                        temperature=temperature, amp_bound=.8, amp_target_acceptance=.3)
         self._Z = torch.tensor([self.z_len], dtype=torch.int32, device=self.device)
-        self._psi = torch.zeros(1, self.z_len, self.th_len, dtype=dtype, device=self.device)
+        self._psi_store = torch.zeros(1, self.z_len, self.th_len, dtype=dtype, device=self.device)
+        self._psi_stale = False                                # True: the HBM workspace holds the newer field
         self._host_view = None                                 # numpy array last handed out by `.lattice`
         self._hbm, self._hbm_dirty = None, True
         self._delta_out = torch.empty(4, dtype=torch.float64, device=self.device)
         self.surface = Cylinder(wavenumber=wavenumber, radius=radius, gamma=gamma, kappa=kappa,
                                 intrinsic_curvature=intrinsic_curvature, device=self.device)
-        self.avg_lattice = np.zeros((self.z_len, self.th_len), dtype=complex)
+        self._avg_dev = torch.zeros(self.z_len, self.th_len, dtype=torch.complex128, device=self.device)   # avg_lattice, on the device
         self.avg_amplitude_profile = np.zeros((self.z_len))
         self.random_initialize()
         # engine coupled to the bare surface + the field energy the surface change would cause (:72-83)
@@ -109,6 +110,24 @@ class Lattice:
         self.energy = None
 
     # ---- lattice and derived arrays --------------------------------------------------------------------
+    @property
+    def _psi(self):
+        """psi[1, Z, T] in the packed ABI layout.  Large lattices are swept in the tiled HBM workspace; the packed copy is
+        refreshed from it only when something asks for it."""
+        if self._psi_stale:
+            self._hbm.unpack(self._psi_store[0])
+            self._psi_stale = False
+        return self._psi_store
+
+    @property
+    def avg_lattice(self):
+        """Running time average of psi(z, theta) (:147-148), kept on the device, downloaded on access."""
+        return self._avg_dev.cpu().numpy()
+
+    @avg_lattice.setter
+    def avg_lattice(self, value):
+        self._avg_dev.copy_(torch.from_numpy(np.ascontiguousarray(value, dtype=complex)))
+
     @property
     def lattice(self):
         """numpy view of psi, shape (z_len, th_len), complex128 (downloaded; cached until the device copy changes)."""
@@ -162,6 +181,10 @@ class Lattice:
         functions of `lattice` and are derived on the device; they are accepted for signature
         compatibility.  Passing the array obtained from `.lattice` (or None) evaluates the device-resident field."""
         if lattice is None or lattice is self._host_view:
+            if self._psi_stale:                                  # the field lives in the tiled HBM workspace: no repacking
+                S = self._hbm.row_moments(self._params)[None]
+                return ops.field_energy(S, self._Z, self.th_len, self._params, [float(amplitude)], [float(reference_amplitude)],
+                                        self.variant).item()
             psi = self._psi
         else:
             psi = torch.from_numpy(np.ascontiguousarray(lattice, dtype=complex)).to(self.device)[None].contiguous()
@@ -272,7 +295,7 @@ class Lattice:
 
     # ---- production path: checkerboard sweeps on the device --------------------------------------------
     def _fits_shared_memory(self):
-        return self.z_len * self.th_len * self._psi.element_size() <= 160 * 1024
+        return self.z_len * self.th_len * self._psi_store.element_size() <= 160 * 1024
 
     def _push_chain(self):
         c = self._chain_host
@@ -306,11 +329,10 @@ class Lattice:
                 self._hbm = ops.HbmWorkspace(self.z_len, self.th_len, self.dtype, self.device)
                 self._hbm_dirty = True
             if self._hbm_dirty:
-                self._hbm.pack(self._psi[0])
+                self._hbm.pack(self._psi_store[0])                 # dirty implies the packed copy is the current one
             self._hbm.sweep(self._params, self._chain[0], self._seed, self._sweeps_done, nsweeps, self.variant, flags, 0,
                             self._obs[0], self._prof[0])
-            self._hbm.unpack(self._psi[0])
-            self._hbm_dirty = False
+            self._hbm_dirty, self._psi_stale = False, True
         self._sweeps_done += nsweeps
         self._host_view = None
         return self._pull_chain()
@@ -372,7 +394,10 @@ class Lattice:
     # ---- observables -----------------------------------------------------------------------------------
     def measure(self):
         """Per z-row sum_theta psi and sum_theta |psi| appended to the histories (:121-131)."""
-        S = ops.row_moments(self._psi, self._Z, self._params)[0].cpu().numpy()
+        if self._psi_stale:
+            S = self._hbm.row_moments(self._params).cpu().numpy()       # straight from the tiled layout
+        else:
+            S = ops.row_moments(self._psi, self._Z, self._params)[0].cpu().numpy()
         self.field_profile_history.append(S[:, 6] + 1j * S[:, 7])
         self.field_abs_profile_history.append(S[:, 5].copy())
 
@@ -382,8 +407,7 @@ class Lattice:
         self.amplitude_average += abs(self.amplitude) / float(self.step_counter + 1)
         assert (self.amplitude_average < 1)
         divisor = float(self.step_counter + 1)
-        self.avg_lattice *= self.step_counter / divisor
-        self.avg_lattice += self.lattice / divisor
+        self._avg_dev.mul_(self.step_counter / divisor).add_(self._psi[0].to(torch.complex128), alpha=1.0 / divisor)
         self.step_counter += 1
 
     def get_profiles_df(self):
