@@ -317,6 +317,18 @@ def main():
         h1.record()
         barrier()
         ms_hbm = h0.elapsed_time(h1)
+        # the same lattice with measurement, profiles and one amplitude move per sweep ("and with amplitude moves")
+        obs_h = torch.zeros(16, dtype=torch.float64, device=dev)
+        prof_h = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+        full = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
+        nfull = max(1, args.hbm_sweeps // 4)
+        ws.sweep(par, chain, SEED, 10 + args.hbm_sweeps, 4, 0, full, obs=obs_h, prof=prof_h)
+        barrier()
+        h0.record()
+        ws.sweep(par, chain, SEED, 14 + args.hbm_sweeps, nfull, 0, full, obs=obs_h, prof=prof_h)
+        h1.record()
+        barrier()
+        ms_full = h0.elapsed_time(h1)
         peak, peak_src = measured_peak_hbm()
         upd = float(n) * n * args.hbm_sweeps
         achieved = upd * ALG_BYTES_PER_UPDATE_F32 / (ms_hbm * 1e-3) / 1e9
@@ -326,6 +338,9 @@ def main():
                                       "(below the 24 B/update algorithmic figure: the kernel updates all colours per pass, 8.1 B read + "
                                       "8 B written per site; part of the writes is still dirty in the 126 MB L2 when the kernel ends)",
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE_F32 * n * n,
+                    "with_measurement_and_amplitude_move": {"us_per_sweep": 1e3 * ms_full / nfull, "sweeps": nfull,
+                                                            "site_updates_per_s": float(n) * n * nfull / (ms_full * 1e-3),
+                                                            "frac": float(n) * n * nfull * ALG_BYTES_PER_UPDATE_F32 / (ms_full * 1e-3) / 1e9 / peak},
                     "peak_source": peak_src, "kernel": "sweep_hbm_kernel<float,2,TH,false> (TMA-tiled, ping-pong)",
                     "workload": "C4: %dx%d fp32 lattice (%.0f MB > L2), a=0.3 fixed, %d sweeps" % (n, n, n * n * 8 / 1e6, args.hbm_sweeps),
                     "algorithmic_bytes_per_update": ALG_BYTES_PER_UPDATE_F32, "site_updates_per_s": upd / (ms_hbm * 1e-3),
