@@ -478,6 +478,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const int p1 = q1 & 1;
         move(pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), r1, site_id(r1, q1), false, 0);
       }
+      if (c == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
       __syncthreads();
     }
   } else {
@@ -530,15 +531,19 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
 
   // ---- write the interior (and its periodic halo copies) to the other buffer ----
   if (NCOL == 2 && !border) {
-    // interior tile: every (row, plane) is 64 contiguous complex values on both sides, 16-byte aligned
-    constexpr int NV = (TW / 2) * (int)sizeof(C) / 16;              // 16-byte vectors per plane row
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int pr = warp; pr < 2 * TH; pr += HBM_NT / 32) {
-      const int li = pr >> 1, p = pr & 1;
-      const int4* src = reinterpret_cast<const int4*>(pl0 + p * PS + (li + NCOL) * SWH + HS / 2);
-      int4* dst = reinterpret_cast<int4*>(out + p * g.plane_elems + (int64_t)(ti0 + li + g.hr) * ph + ((tj0 + g.hc) >> 1));
-#pragma unroll
-      for (int v = lane; v < NV; v += 32) dst[v] = src[v];
+    // interior tile: every (row, plane) is 64 contiguous complex values on both sides, 16-byte aligned: one bulk copy
+    // (cp.async.bulk shared -> global, SASS UBLKCP) per row and plane, issued by 2*TH threads, instead of a load + store
+    // per 16 bytes by everyone.  The shared-memory writes of the colour passes were made visible to the async proxy by the
+    // fence before the last barrier; the issuing threads wait until their sources have been read before the CTA may retire.
+    static_assert(2 * TH <= HBM_NT, "one thread per (row, plane)");
+    if (tid < 2 * TH) {
+      const int li = tid >> 1, p = tid & 1;
+      const C* src = pl0 + p * PS + (li + NCOL) * SWH + HS / 2;
+      C* dst = out + p * g.plane_elems + (int64_t)(ti0 + li + g.hr) * ph + ((tj0 + g.hc) >> 1);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+                   "r"((uint32_t)((TW / 2) * sizeof(C)))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   } else {
     for (int idx = tid; idx < 2 * TH * (TW / 2); idx += HBM_NT) {
@@ -624,6 +629,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     }
   }
   __syncthreads();
+  // the bulk copies of the write-out must have read their shared-memory sources before the CTA retires
+  if (NCOL == 2 && !border && tid < 2 * TH) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   if (!EXTRAS) {
     if (tid == 0) {
       double t = 0.0;
