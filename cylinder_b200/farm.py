@@ -247,8 +247,9 @@ def main(argv=None):
         import torch
         import torch.distributed as dist
         if "RANK" in os.environ and not dist.is_initialized():
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
-            dist.init_process_group("nccl")
+            local = int(os.environ.get("LOCAL_RANK", 0))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         run(a.infile, a.varfile, a.outdir, variant=a.variant, seed=a.seed)
         if dist.is_initialized():
             dist.barrier()
