@@ -193,12 +193,13 @@ def test_smem_sweep_with_amplitude_moves_matches_oracle(cuda, variant, Z, T):
     seed, rep, nsw = 77, 3, 12
     flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
     ops.sweep_smem(psi, Zt, par, chain, seed, 0, nsw, variant, flags, replica0=rep, obs=obs, prof=prof)
-    sum_abs_a = sum_ef = 0.0
+    sum_abs_a = sum_ef = sum_abs_psi = 0.0
     prof_o = np.zeros((Z, 3))
     for s in range(nsw):
         cb.sweep(st, am.a, seed, rep, s)
         sum_abs_a += abs(am.a)
         sum_ef += lo.surface_field_energy(st, am.a, am.a)
+        sum_abs_psi += float(np.mean(np.abs(st.psi)))
         ps, pa = lo.measure_profiles(st.psi)
         prof_o += np.stack([ps.real, ps.imag, pa], 1)
         cb.amplitude_move(st, am, P, seed, rep, s)
@@ -212,7 +213,14 @@ def test_smem_sweep_with_amplitude_moves_matches_oracle(cuda, variant, Z, T):
     assert o[_abi.OB_COUNT] == nsw
     assert o[_abi.OB_ABS_A] == pytest.approx(sum_abs_a, rel=1e-12)
     assert o[_abi.OB_E_FIELD] == pytest.approx(sum_ef, rel=1e-10)
+    assert o[_abi.OB_ABSPSI] == pytest.approx(sum_abs_psi, rel=1e-11)        # assembled from the profile pass's row sums
     np.testing.assert_allclose(prof[0].cpu().numpy(), prof_o, rtol=1e-10, atol=1e-12)
+    # without a profile buffer the site loop accumulates sum |psi| itself
+    chain2 = ops.new_chain(1, cuda, amplitude=.1, sigma_site=.05, sigma_amp=.05)
+    psi2 = torch.tensor(psi0, dtype=torch.complex128, device=cuda)[None].contiguous()
+    obs2, _ = ops.new_obs(1, Z, cuda)
+    ops.sweep_smem(psi2, Zt, par, chain2, seed, 0, nsw, variant, flags, replica0=rep, obs=obs2, prof=None)
+    assert obs2[0, _abi.OB_ABSPSI].item() == pytest.approx(sum_abs_psi, rel=1e-11)
 
 
 @pytest.mark.parametrize("Z,T,variant", [(64, 128, lo.SIMPLE), (40, 24, lo.RESCALED_0TH), (71, 25, lo.SIMPLE), (70, 131, lo.SIMPLE),
