@@ -17,7 +17,29 @@ from .lattice import LatticeRescaled0thOrder
 from .metropolisengine import MetropolisEngine
 
 me_version = "cylinder_b200"
+
+# module-level defaults of the reference driver (run.py:356-380): used when a value is not a loop variable
+alpha = -1
+C = 1
+u = 1
+n = 6
+kappa = 0
+gamma = 1
+temp = .1
+intrinsic_curvature = 0
 initial_amplitude = 0
+radius = 1
+wavenumber = .5
+num_field_coeffs = (2, 1)
+measure_every = 10
+fieldsteps_per_ampstep = 10
+dims = (100, 50)
+n_steps = 1000
+field_type = "lattice"
+method = "sequential"
+notes = ""
+EXPERIMENT_TYPES = (("num_field_coeffs", "fieldsteps_per_ampstep"), ("amplitude", "C"), ("wavenumber", "gamma"), ("wavenumber", "kappa"),
+                    ("wavenumber", "alpha"), ("wavenumber", "intrinsic_curvature"), ("alpha", "C"))            # run.py:60-99
 
 
 def single_run(temp, temp_final, n_steps, field_type, method, num_field_coeffs, fieldsteps_per_ampstep, measure_every,
@@ -178,3 +200,116 @@ def grid_run(var1, values1, var2, values2, n_sweeps, base, dims=(50, 50), varian
             row = {k: [v[r]] for k, v in means.items()}
             pd.DataFrame(row).to_csv(os.path.join(outdir, "%s_%s_%s_%s_mean.csv" % (var1, grid[var1][r], var2, grid[var2][r])))
     return means
+
+
+# ------------------------------------------------------------------------------------------------------
+# the 2-D scan driver of run.py:21-179 (loop / plot_save / run_experiment)
+# ------------------------------------------------------------------------------------------------------
+def loop(single_run_lambda, range1, range2):
+    """run.py:21-58: call single_run_lambda(var1, var2) over the grid and collect, per result name, a 2-D list
+    [len(range1)][len(range2)]: `<name>_mean`, `time_per_experiment`, `<coeff>_variance`, `<c1>_<c2>_covariance`."""
+    import collections
+    import timeit
+    results = collections.defaultdict(list)
+    for var1 in range1:
+        results_line = collections.defaultdict(list)
+        for var2 in range2:
+            start_time = timeit.default_timer()
+            param_names, observables_names, means_dict, cov_matrix = single_run_lambda(var1, var2)
+            elapsed = timeit.default_timer() - start_time
+            coeffs_names = param_names[1:]
+            if cov_matrix is None:
+                coeffs_names = []
+            for name in means_dict:
+                results_line[name + "_mean"].append(means_dict[name])
+            results_line["time_per_experiment"].append(elapsed)
+            for i, name in enumerate(coeffs_names):
+                results_line[name + "_variance"].append(cov_matrix[i][i])
+                for j, name2 in enumerate(coeffs_names):
+                    if j > i:
+                        results_line[name + "_" + name2 + "_covariance"].append(cov_matrix[i][j])
+        for name in results_line:
+            results[name].append(results_line[name])
+    return results
+
+
+def plot_save(range1, range2, results, title, exp_dir='.'):
+    """run.py:103-130 without the heat map: <title>.csv, rows = range1, columns = range2 (ranges cut to the data's shape)."""
+    import pandas as pd
+    range1 = list(range1)[-len(results):]
+    range2 = list(range2)[-len(results[0]):]
+    pd.DataFrame(index=range1, columns=range2, data=results).to_csv(os.path.join(exp_dir, title + ".csv"))
+
+
+def run_experiment(exp_type, range1, range2, batched=True, exp_dir=None, seed=0, variant="rescaled_0thorder", **overrides):
+    """run.py:133-179: a 2-D grid of simulations over the two variables named by `exp_type`, results as one CSV table per
+    observable in out/exp-<timestamp>/ plus notes.csv.  Values that are not scanned come from the module-level defaults
+    (as in the reference) or from `overrides`.  With batched=True (lattice field, or Fourier field with a fixed number of
+    coefficients) the whole grid is ONE ReplicaBatch / FourierChains launch; otherwise the reference's serial loop over
+    single_run."""
+    import datetime
+    import pandas as pd
+    exp_type = tuple(exp_type)
+    if exp_type not in EXPERIMENT_TYPES:
+        raise KeyError("experiment type not found: %r; set exp_type to one of %r" % (exp_type, EXPERIMENT_TYPES))
+    g = dict(globals())
+    g.update(overrides)
+    range1, range2 = list(range1), list(range2)
+    now = datetime.datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
+    if exp_dir is None:
+        exp_dir = os.path.join("out", "exp-" + now)
+    os.makedirs(exp_dir, exist_ok=True)
+    exp_notes = {"experiment type": " ".join(exp_type), "n_steps": g["n_steps"], "me_temp": g["temp"], "C": g["C"], "kappa": g["kappa"],
+                 "gamma": g["gamma"], "alpha": g["alpha"], "n": g["n"], "u": g["u"], "range1": range1,
+                 "intrinsic curvature": g["intrinsic_curvature"], "range2": range2, "radius": g["radius"],
+                 "amplitude": g["initial_amplitude"], "wavenumber": g["wavenumber"], "measure every n ampsteps": g["measure_every"],
+                 "total number ampsteps": g["n_steps"] * g["measure_every"], "notes": g["notes"], "start_time": now,
+                 "me-version": me_version, "field_type": g["field_type"], "method": g["method"], "dims": g["dims"],
+                 "num_field_coeffs": g["num_field_coeffs"], "fieldsteps per ampstep": g["fieldsteps_per_ampstep"]}
+    pd.DataFrame.from_dict({k: str(v) for k, v in exp_notes.items()}, orient="index", columns=["value"]).to_csv(
+        os.path.join(exp_dir, "notes.csv"))
+    names = {"amplitude": "amplitude", "C": "C", "wavenumber": "wavenumber", "gamma": "gamma", "kappa": "kappa", "alpha": "alpha",
+             "intrinsic_curvature": "intrinsic_curvature"}
+    if not batched or exp_type == EXPERIMENT_TYPES[0]:
+        def one(v1, v2):
+            kw = dict(temp=g["temp"], temp_final=g["temp"], n_steps=g["n_steps"], field_type=g["field_type"], method=g["method"],
+                      num_field_coeffs=g["num_field_coeffs"], fieldsteps_per_ampstep=g["fieldsteps_per_ampstep"],
+                      measure_every=g["measure_every"], alpha=g["alpha"], C=g["C"], n=g["n"], u=g["u"], gamma=g["gamma"],
+                      kappa=g["kappa"], radius=g["radius"], intrinsic_curvature=g["intrinsic_curvature"],
+                      n_substeps=g["dims"][0] * g["dims"][1], dims=g["dims"], wavenumber=g["wavenumber"],
+                      amplitude=g["initial_amplitude"], outdir=exp_dir, title="%s%s_%s%s" % (exp_type[0], round(v1, 5), exp_type[1], round(v2, 5)))
+            for name, v in zip(exp_type, (v1, v2)):
+                kw[name] = v
+            return single_run(**kw)
+        results = loop(one, range1, range2)
+    else:
+        from .replicas import OBS_NAMES, ReplicaBatch, parameter_grid
+        grid = parameter_grid(**{exp_type[0]: range1, exp_type[1]: range2})
+        base = dict(wavenumber=g["wavenumber"], radius=g["radius"], gamma=g["gamma"], kappa=g["kappa"],
+                    intrinsic_curvature=g["intrinsic_curvature"], alpha=g["alpha"], u=g["u"], C=g["C"], n=g["n"], temperature=g["temp"],
+                    amp_bound=.99)
+        amp0 = g["initial_amplitude"]
+        for name in exp_type:
+            if name == "amplitude":
+                amp0 = grid[name]
+            else:
+                base[names[name]] = grid[name]
+        if g["field_type"] == "lattice":
+            batch = ReplicaBatch(base, dims=tuple(g["dims"]), variant=variant, seed=seed, amplitude=amp0)
+            per = max(1, int(round(g["fieldsteps_per_ampstep"] * 50 / float(g["dims"][0] * g["dims"][1]))))
+            batch.run(max(1, int(round(500 * 50 / float(g["dims"][0] * g["dims"][1])))), amp_moves=False, measure=False)
+            nb = max(2, min(20, g["n_steps"]))
+            series = batch.run_blocks(nb, -(-g["n_steps"] // nb), stride=per)
+            means, errs, cut = batch.equilibrated_means(series)
+            flat = {k + "_mean": means[k].cpu().numpy() for k in OBS_NAMES}
+            flat.update({k + "_err": errs[k].cpu().numpy() for k in OBS_NAMES})
+        else:
+            from .fourier_chains import FourierChains
+            ch = FourierChains(base, num_field_coeffs=g["num_field_coeffs"], amplitude=amp0, seed=seed)
+            ch.run(g["n_steps"], measure_every=g["measure_every"], fieldsteps_per_ampstep=g["fieldsteps_per_ampstep"], method=g["method"])
+            flat = {k + "_mean": v.cpu().numpy() for k, v in ch.summary().items()}
+        shape = (len(range1), len(range2))
+        results = {k: np.asarray(v).reshape(shape).tolist() for k, v in flat.items()}
+    for name in results:
+        plot_save(range1=range1, range2=range2, results=results[name], title=name, exp_dir=exp_dir)
+    return results, exp_dir

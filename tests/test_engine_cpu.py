@@ -96,3 +96,28 @@ def test_measure_running_mean_and_covariance():
     assert len(e.df) == 300 and "energy" in e.df.columns
     means = e.save_equilibrium_stats()
     assert "s_energy" in means
+
+
+def test_scan_driver_loop_and_plot_save(tmp_path):
+    """run.loop / run.plot_save (reference run.py:21-58, :103-130): result naming and table layout, with a stand-in single_run."""
+    import pandas as pd
+    from cylinder_b200 import run
+    calls = []
+
+    def fake(v1, v2):
+        calls.append((v1, v2))
+        cov = np.array([[1.0 + v1, .5], [.5, 2.0 + v2]])
+        return ["amplitude", "coeff_0_0", "coeff_0_1"], ["abs_amplitude"], {"abs_amplitude": v1 * 10 + v2}, cov
+    res = run.loop(fake, [1, 2, 3], [0, 5])
+    assert calls == [(1, 0), (1, 5), (2, 0), (2, 5), (3, 0), (3, 5)]
+    assert res["abs_amplitude_mean"] == [[10, 15], [20, 25], [30, 35]]
+    assert res["coeff_0_0_variance"][1] == [3.0, 3.0] and res["coeff_0_1_variance"][2] == [2.0, 7.0]
+    assert res["coeff_0_0_coeff_0_1_covariance"] == [[.5, .5]] * 3 and len(res["time_per_experiment"]) == 3
+    run.plot_save([1, 2, 3], [0, 5], res["abs_amplitude_mean"], "abs_amplitude_mean", str(tmp_path))
+    df = pd.read_csv(tmp_path / "abs_amplitude_mean.csv", index_col=0)
+    assert df.shape == (3, 2) and df.loc[2, "5"] == 25
+    # results shorter than the ranges belong to the END of the ranges (run.py:117-118)
+    run.plot_save([1, 2, 3], [0, 5], res["abs_amplitude_mean"][1:], "tail", str(tmp_path))
+    assert list(pd.read_csv(tmp_path / "tail.csv", index_col=0).index) == [2, 3]
+    with pytest.raises(KeyError):
+        run.run_experiment(("alpha", "n"), [0], [1], exp_dir=str(tmp_path / "x"))

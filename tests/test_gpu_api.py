@@ -371,3 +371,24 @@ def test_lattice_run_on_the_tiled_hbm_path(cuda):
     e_hbm = lat.surface_field_energy(.1, .1)                   # from the tiled layout
     e_packed = lat.surface_field_energy(.1, .1, lat.lattice.copy(), None, None, None)
     assert e_hbm == pytest.approx(e_packed, rel=1e-12)
+
+
+def test_run_experiment_scans_a_grid(cuda, tmp_path):
+    """run.run_experiment (reference run.py:133-179): notes.csv + one table per observable; the batched route runs the grid as
+    one launch, the serial route is the reference's loop over single_run; both fill the same `<name>_mean` tables."""
+    import pandas as pd
+    from cylinder_b200 import run
+    kw = dict(n_steps=8, dims=(12, 10), temp=.05, fieldsteps_per_ampstep=10, measure_every=1, field_type="lattice", n=2, notes="t")
+    res, d = run.run_experiment(("wavenumber", "alpha"), [.8, 1.0, 1.2], [-1.0, 0.0], exp_dir=str(tmp_path / "b"), **kw)
+    assert os.path.exists(os.path.join(d, "notes.csv"))
+    tab = pd.read_csv(os.path.join(d, "abs_amplitude_mean.csv"), index_col=0)
+    assert tab.shape == (3, 2) and np.isfinite(tab.to_numpy()).all()
+    assert np.asarray(res["field_energy_mean"]).shape == (3, 2)
+    random.seed(2)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)                                        # single_run drops last_sigma.pickle in the working directory
+    try:
+        res2, d2 = run.run_experiment(("alpha", "C"), [-1.0], [.5, 1.0], batched=False, exp_dir=str(tmp_path / "s"), **dict(kw, n_steps=3))
+    finally:
+        os.chdir(cwd)
+    assert np.asarray(res2["abs_amplitude_mean"]).shape == (1, 2) and os.path.exists(os.path.join(d2, "abs_amplitude_mean.csv"))
