@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcylinder_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "cylinder_b200.h")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # constants mirrored from the header (checked against it in tests/test_abi_cpu.py)
 VARIANT_SIMPLE, VARIANT_RESCALED_0TH, VARIANT_RESCALED_1ST, VARIANT_DECOUPLED = 0, 1, 2, 3
@@ -51,6 +51,8 @@ _SIGNATURES = {
     "cyl_field_energy_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "cyl_sweep_smem_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
     "cyl_sweep_smem_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
+    "cyl_sweep_smem_series_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
+    "cyl_sweep_smem_series_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
     "cyl_hbm_layout": [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)],
     "cyl_hbm_pack_f32": [_vp, _i, _i, _vp, C.POINTER(C.c_int32), _vp],
     "cyl_hbm_pack_f64": [_vp, _i, _i, _vp, C.POINTER(C.c_int32), _vp],

@@ -175,12 +175,12 @@ __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz
 #ifndef SMEM_MINB_EXTRAS
 #define SMEM_MINB_EXTRAS 4
 #endif
-template <typename R, bool EXTRAS>
+template <typename R, bool EXTRAS, bool SERIES>
 __global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? (EXTRAS ? SMEM_MINB_EXTRAS : 4) : 2))
 sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
                   const CylParams* __restrict__ params, double* __restrict__ chain, const __grid_constant__ PhiloxKeys keys,
                   uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
-                  double* __restrict__ prof) {
+                  double* __restrict__ prof, double* __restrict__ series) {
   using C = typename Real<R>::complex_t;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SweepSmemLayout<R> lay(Zmax, T);
@@ -480,8 +480,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 
     // ---- 3. decisions, spread over threads of different warps: Robbins-Monro on sigma_site (warp 2), the measurement record
     //         (warp 1), the amplitude move (warp 0) ----
+    // optional time series: one record of CYL_SERIES_DOUBLES per measured sweep and replica (the engine's me.df)
+    double* rec = (SERIES && extras && measure && series) ? series + ((size_t)b * nsweeps + sw) * CYL_SERIES_DOUBLES : nullptr;
     if (tid == 64) {
       const double nac = total(0);
+      if (rec) rec[CYL_TS_SITE_ACCEPTANCE] = nac * inv_nsite;
       if (flags & CYL_SWEEP_ADAPT_SIGMA)
         sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, nac);
       sc->step_counter += nsite;
@@ -502,6 +505,14 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       o[CYL_OB_E_SURF] += e_surf_cur;
       o[CYL_OB_E_FIELD2] += e_cur * e_cur;
       o[CYL_OB_SIGMA] += (double)sigma;
+      if (rec) {
+        rec[CYL_TS_AMPLITUDE] = a;
+        rec[CYL_TS_E_FIELD] = e_cur;
+        rec[CYL_TS_E_SURF] = e_surf_cur;
+        rec[CYL_TS_PSI2] = total(3) * inv_nsite;
+        rec[CYL_TS_ABSPSI] = total(4) * inv_nsite;
+        rec[CYL_TS_SIGMA_SITE] = (double)sigma;
+      }
     }
     if (extras && tid == 0) {
       int accept = 0;
@@ -528,6 +539,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         }
       }
       sc->amp_accept = accept;
+      if (rec) rec[CYL_TS_AMP_ACCEPTED] = (double)accept;
     }
     __syncthreads();
     PHASE_MARK(3);
@@ -596,7 +608,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 template <typename R>
 static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params, double* chain,
                       uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags,
-                      double* obs, double* prof, void* stream) {
+                      double* obs, double* prof, double* series, void* stream) {
   CYL_CHECK_ARG(psi && Z && params && chain && B > 0 && Zmax > 0 && T > 1 && nsweeps >= 0, "cyl_sweep_smem: bad arguments");
   CYL_CHECK_ARG(variant >= 0 && variant < CYL_NUM_VARIANTS, "cyl_sweep_smem: unknown variant %d", variant);
   CYL_CHECK_ARG(!(flags & CYL_SWEEP_MEASURE) || obs, "cyl_sweep_smem: CYL_SWEEP_MEASURE needs obs");
@@ -611,11 +623,11 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
     return CYL_E_UNSUPPORTED;
   }
   const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
-  auto kern = extras ? sweep_smem_kernel<R, true> : sweep_smem_kernel<R, false>;
+  auto kern = !extras ? sweep_smem_kernel<R, false, false> : (series ? sweep_smem_kernel<R, true, true> : sweep_smem_kernel<R, true, false>);
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const PhiloxKeys keys = philox_expand(seed);
   kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,
-                                                      seed, replica0, sweep0, nsweeps, variant, flags, obs, prof);
+                                                      seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, series);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }
@@ -623,10 +635,24 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
 extern "C" int cyl_sweep_smem_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
                                   double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
                                   int variant, uint32_t flags, double* obs, double* prof, void* stream) {
-  return sweep_smem<float>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, stream);
+  return sweep_smem<float>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, nullptr, stream);
 }
 extern "C" int cyl_sweep_smem_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
                                   double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
                                   int variant, uint32_t flags, double* obs, double* prof, void* stream) {
-  return sweep_smem<double>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, stream);
+  return sweep_smem<double>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, nullptr, stream);
+}
+
+// The same sweeps with a per-sweep record: series[B][nsweeps][CYL_SERIES_DOUBLES] (requires CYL_SWEEP_MEASURE).
+extern "C" int cyl_sweep_smem_series_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                                         double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                                         int variant, uint32_t flags, double* obs, double* prof, double* series, void* stream) {
+  CYL_CHECK_ARG(series && (flags & CYL_SWEEP_MEASURE), "cyl_sweep_smem_series: needs a series buffer and CYL_SWEEP_MEASURE");
+  return sweep_smem<float>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, series, stream);
+}
+extern "C" int cyl_sweep_smem_series_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                                         double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                                         int variant, uint32_t flags, double* obs, double* prof, double* series, void* stream) {
+  CYL_CHECK_ARG(series && (flags & CYL_SWEEP_MEASURE), "cyl_sweep_smem_series: needs a series buffer and CYL_SWEEP_MEASURE");
+  return sweep_smem<double>(psi, B, Z, Zmax, T, params, chain, seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, series, stream);
 }

@@ -143,12 +143,23 @@ def field_energy(S, Z, T, params, amp_eval, amp_ref=None, variant=0):
     return E
 
 
+SERIES_NAMES = ("amplitude", "field_energy", "surface_energy", "psi_squared", "abs_psi", "sampling_width", "amplitude_accepted",
+                "site_acceptance")                                  # CYL_TS_* of include/cylinder_b200.h
+
+
 def sweep_smem(psi, Z, params, chain, seed, sweep0, nsweeps, variant=0, flags=SWEEP_ADAPT_SIGMA, replica0=0, obs=None,
-               prof=None):
-    """nsweeps checkerboard sweeps of B shared-memory-resident replicas (in place on psi, chain, obs, prof)."""
+               prof=None, series=None):
+    """nsweeps checkerboard sweeps of B shared-memory-resident replicas (in place on psi, chain, obs, prof).
+    `series` [B, nsweeps, 8] float64 (optional, needs SWEEP_MEASURE): one record per sweep and replica."""
     B, Zmax, T = psi.shape
-    call("cyl_sweep_smem_" + _suffix(psi), _dev(psi), ptr(psi), B, ptr(Z), Zmax, T, ptr(params), ptr(chain), int(seed),
-         int(replica0), int(sweep0), int(nsweeps), variant_id(variant), int(flags), ptr(obs), ptr(prof), stream())
+    if series is None:
+        call("cyl_sweep_smem_" + _suffix(psi), _dev(psi), ptr(psi), B, ptr(Z), Zmax, T, ptr(params), ptr(chain), int(seed),
+             int(replica0), int(sweep0), int(nsweeps), variant_id(variant), int(flags), ptr(obs), ptr(prof), stream())
+    else:
+        if tuple(series.shape) != (B, int(nsweeps), len(SERIES_NAMES)) or series.dtype != F64:
+            raise ValueError("series must be a float64 tensor of shape [B, nsweeps, %d]" % len(SERIES_NAMES))
+        call("cyl_sweep_smem_series_" + _suffix(psi), _dev(psi), ptr(psi), B, ptr(Z), Zmax, T, ptr(params), ptr(chain), int(seed),
+             int(replica0), int(sweep0), int(nsweeps), variant_id(variant), int(flags), ptr(obs), ptr(prof), ptr(series), stream())
 
 
 def new_obs(B, Zmax, device):

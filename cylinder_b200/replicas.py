@@ -67,12 +67,28 @@ class ReplicaBatch:
         """Site-updates per sweep summed over the batch."""
         return int(self.Z_host.astype(np.int64).sum()) * self.T
 
-    def run(self, nsweeps, amp_moves=True, measure=True, adapt=True):
+    def run(self, nsweeps, amp_moves=True, measure=True, adapt=True, series=False):
+        """nsweeps sweeps of every replica in one launch.  series=True (with measure): also returns the per-sweep records
+        [B, nsweeps, 8] (ops.SERIES_NAMES: amplitude, energies, <|psi|^2>, <|psi|>, width, accept flags) -- the engine's time
+        series (me.df, run.py:324-326) for every replica at once."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
+        ts = torch.zeros(self.B, int(nsweeps), len(ops.SERIES_NAMES), dtype=torch.float64, device=self.device) if (series and measure) else None
         ops.sweep_smem(self.psi, self.Z, self.params, self.chain, self.seed, self.sweeps_done, nsweeps, self.variant, flags,
-                       self.replica0, self.obs, self.prof)
+                       self.replica0, self.obs, self.prof, series=ts)
         self.sweeps_done += int(nsweeps)
-        return self
+        return ts if ts is not None else self
+
+    def time_series_frames(self, series, sweep0=0):
+        """One pandas DataFrame per replica (columns ops.SERIES_NAMES + energy, index = sweep) from a run(..., series=True)
+        result -- what me.save_time_series() leaves in me.df for a single run."""
+        import pandas as pd
+        arr = series.cpu().numpy()
+        frames = []
+        for b in range(arr.shape[0]):
+            df = pd.DataFrame(arr[b], columns=list(ops.SERIES_NAMES), index=pd.RangeIndex(sweep0, sweep0 + arr.shape[1], name="sweep"))
+            df["energy"] = df["field_energy"] + df["surface_energy"]
+            frames.append(df)
+        return frames
 
     def reset_observables(self):
         self.obs.zero_()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CYL_ABI_VERSION 5
+#define CYL_ABI_VERSION 6
 
 /* error codes */
 #define CYL_OK             0
@@ -188,6 +188,24 @@ int cyl_sweep_smem_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, cons
 int cyl_sweep_smem_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
                        double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
                        int variant, uint32_t flags, double* obs, double* prof, void* stream);
+
+/* The same sweeps with a time series (the engine's me.df / save_time_series, run.py:324-326): one record per measured
+ * sweep and replica, series [B][nsweeps][CYL_SERIES_DOUBLES]; requires CYL_SWEEP_MEASURE. */
+#define CYL_SERIES_DOUBLES 8
+#define CYL_TS_AMPLITUDE        0   /* amplitude the sweep ran at (before its amplitude decision) */
+#define CYL_TS_E_FIELD          1
+#define CYL_TS_E_SURF           2
+#define CYL_TS_PSI2             3   /* <|psi|^2> over the lattice */
+#define CYL_TS_ABSPSI           4   /* <|psi|> */
+#define CYL_TS_SIGMA_SITE       5   /* proposal width used by the sweep */
+#define CYL_TS_AMP_ACCEPTED     6   /* 1 if the sweep's amplitude move was accepted */
+#define CYL_TS_SITE_ACCEPTANCE  7   /* accepted site moves / sites */
+int cyl_sweep_smem_series_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                              double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                              int variant, uint32_t flags, double* obs, double* prof, double* series, void* stream);
+int cyl_sweep_smem_series_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,
+                              double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
+                              int variant, uint32_t flags, double* obs, double* prof, double* series, void* stream);
 
 /* ---------------------------------------------------------------- one large lattice ------------------ */
 /* Workspace of the HBM path.  The lattice lives in a ping-pong pair of halo-padded buffers, each split into

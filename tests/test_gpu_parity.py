@@ -469,3 +469,43 @@ def test_step_host_equals_device_resident_run(cuda):
     b.step_host(psi_h, chain_h, psi_out, rec_out, 7, nchunks=5)
     assert torch.equal(psi_out, a.psi.cpu())
     assert torch.equal(rec_out, a.record().cpu())
+
+
+def test_time_series_matches_oracle(cuda):
+    """cyl_sweep_smem_series: one record per sweep (amplitude, energies, <|psi|^2>, <|psi|>, width, accept flags), fp64, against
+    the oracle's sweep-by-sweep values; the records sum to the accumulated observables."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    Z, T, variant = 11, 10, lo.RESCALED_0TH
+    P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.3, intrinsic_curvature=0.2, alpha=-.8, u=1.2, C=.9, n=3, temperature=.3)
+    rng = np.random.RandomState(9)
+    psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
+    st = _oracle_state(psi0.copy(), P, variant, .05)
+    am = cb.AmpState(amplitude=.1, sigma_amp=.05, target=.3, bound=.8)
+    par = _params(ops, cuda, P, amp_bound=.8, amp_target_acceptance=.3)
+    psi = torch.tensor(psi0, dtype=torch.complex128, device=cuda)[None].contiguous()
+    Zt = torch.tensor([Z], dtype=torch.int32, device=cuda)
+    chain = ops.new_chain(1, cuda, amplitude=.1, sigma_site=.05, sigma_amp=.05)
+    obs, prof = ops.new_obs(1, Z, cuda)
+    nsw, seed, rep = 10, 31, 2
+    ts = torch.zeros(1, nsw, 8, dtype=torch.float64, device=cuda)
+    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
+    ops.sweep_smem(psi, Zt, par, chain, seed, 0, nsw, variant, flags, replica0=rep, obs=obs, prof=prof, series=ts)
+    rec = ts[0].cpu().numpy()
+    for s in range(nsw):
+        sigma_used, acc0 = st.sigma, st.accepted
+        cb.sweep(st, am.a, seed, rep, s)
+        assert rec[s, 0] == pytest.approx(am.a, rel=1e-12, abs=1e-15)
+        assert rec[s, 1] == pytest.approx(lo.surface_field_energy(st, am.a, am.a), rel=1e-10)
+        assert rec[s, 2] == pytest.approx(lo.surface_energy(P["wavenumber"], P["radius"], P["gamma"], P["kappa"], P["intrinsic_curvature"], am.a), rel=1e-10)
+        assert rec[s, 3] == pytest.approx(float(np.mean(st.psi2)), rel=1e-11)
+        assert rec[s, 4] == pytest.approx(float(np.mean(np.abs(st.psi))), rel=1e-11)
+        assert rec[s, 5] == pytest.approx(sigma_used, rel=1e-12)
+        assert rec[s, 7] == pytest.approx((st.accepted - acc0) / (Z * T), rel=1e-12)
+        before = am.accepted
+        cb.amplitude_move(st, am, P, seed, rep, s)
+        assert rec[s, 6] == am.accepted - before
+    o = obs[0].cpu().numpy()
+    assert o[_abi.OB_E_FIELD] == pytest.approx(rec[:, 1].sum(), rel=1e-12) and o[_abi.OB_PSI2] == pytest.approx(rec[:, 3].sum(), rel=1e-12)
+    with pytest.raises(Exception):
+        ops.sweep_smem(psi, Zt, par, chain, seed, 0, nsw, variant, _abi.SWEEP_ADAPT_SIGMA, replica0=rep, series=ts)     # needs MEASURE
