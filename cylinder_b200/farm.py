@@ -121,7 +121,7 @@ def _columns(args, names, lines):
 
 # ---- parallel_single_run.py for every line at once --------------------------------------------------------
 def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescaled_0thorder", seed=0, dtype=None, device=None,
-        group=None, n_steps=None, write_profiles=True):
+        group=None, n_steps=None, write_profiles=True, write_series=False):
     """Run every line of `varfile` with the options of `infile`; returns {column: array over this rank's lines}.
 
     field_type "lattice": the adopted schedule of Lattice.run (On_lattice_simple.py:532-563): burn-in of
@@ -161,7 +161,7 @@ def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescale
         # at most half of the run) -- me.save_equilibrium_stats / equilibrated_means of run.py:341-346
         nblocks = max(2, min(20, steps))
         per_block = -(-steps // nblocks)
-        series = batch.run_blocks(nblocks, per_block, stride=per_step)
+        series = batch.run_blocks(nblocks, per_block, stride=per_step, series=write_series)
         means, errs, cut = batch.equilibrated_means(series)
         for k in OBS_NAMES:
             out[k] = means[k].cpu().numpy()
@@ -189,8 +189,13 @@ def run(infile="infile.txt", varfile="varfile.txt", outdir=".", variant="rescale
             out["abs_coeff_%d_%d" % (a, b)] = mean[:, 1 + c]
     else:
         raise ValueError("farm: field_type must be 'lattice' or 'fourier' (got %r)" % args.field_type)
+    frames = None
+    if args.field_type == "lattice" and write_series and batch.block_series is not None:
+        frames = batch.time_series_frames(batch.block_series)                           # <title>.csv of run.py:324-326
     for r, strings in enumerate(mine):
         title = title_of(names, strings)
+        if frames is not None:
+            frames[r].to_csv(os.path.join(outdir, title + ".csv"))
         d = dict([(key, [out[key][r]]) for key in out])                                 # parallel_single_run.py:113
         pd.DataFrame.from_dict(d).to_csv(os.path.join(outdir, title + "_mean.csv"))
         if profiles is not None:
@@ -237,6 +242,7 @@ def main(argv=None):
     pr.add_argument('--outdir', default=".")
     pr.add_argument('--variant', default="rescaled_0thorder")
     pr.add_argument('--seed', type=int, default=0)
+    pr.add_argument('--series', action="store_true", help="also write every line's time series <title>.csv")
     pq = sub.add_parser("postprocess")
     pq.add_argument('--outdir', default=".")
     a = ap.parse_args(argv)
@@ -250,7 +256,7 @@ def main(argv=None):
             local = int(os.environ.get("LOCAL_RANK", 0))
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        run(a.infile, a.varfile, a.outdir, variant=a.variant, seed=a.seed)
+        run(a.infile, a.varfile, a.outdir, variant=a.variant, seed=a.seed, write_series=a.series)
         if dist.is_initialized():
             dist.barrier()
             dist.destroy_process_group()

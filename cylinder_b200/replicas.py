@@ -94,28 +94,33 @@ class ReplicaBatch:
         self.obs.zero_()
         self.prof.zero_()
 
-    def run_blocks(self, nblocks, sweeps_per_block, amp_moves=True, adapt=True, stride=1):
+    def run_blocks(self, nblocks, sweeps_per_block, amp_moves=True, adapt=True, stride=1, series=False):
         """nblocks blocks of sweeps_per_block measured sweeps (each preceded by stride-1 plain sweeps: the reference's
         fieldsteps_per_ampstep); returns the block means as a dict name -> tensor [nblocks, B] (device) -- the time series
         the equilibrium cut-off works on (stats.equilibrated) -- and keeps the per-block profile means in
         `self.block_profiles` [nblocks, B, Zmax, 3]."""
-        series = {name: [] for name in OBS_NAMES}
-        profs = []
+        blocks = {name: [] for name in OBS_NAMES}
+        profs, records = [], []
         for _ in range(int(nblocks)):
             o0, p0 = self.obs.clone(), self.prof.clone()
             if stride <= 1:
-                self.run(sweeps_per_block, amp_moves=amp_moves, measure=True, adapt=adapt)
+                r = self.run(sweeps_per_block, amp_moves=amp_moves, measure=True, adapt=adapt, series=series)
+                if series:
+                    records.append(r)
             else:
                 for _ in range(int(sweeps_per_block)):
                     self.run(stride - 1, amp_moves=False, measure=False, adapt=adapt)
-                    self.run(1, amp_moves=amp_moves, measure=True, adapt=adapt)
+                    r = self.run(1, amp_moves=amp_moves, measure=True, adapt=adapt, series=series)
+                    if series:
+                        records.append(r)
             d = self.obs - o0
             n = d[:, _abi.OB_COUNT].clamp(min=1.0)
             for i, name in enumerate(OBS_NAMES):
-                series[name].append(d[:, 1 + i] / n)
+                blocks[name].append(d[:, 1 + i] / n)
             profs.append((self.prof - p0) / (n[:, None, None] * self.T))
         self.block_profiles = torch.stack(profs)
-        return {name: torch.stack(v) for name, v in series.items()}
+        self.block_series = torch.cat(records, dim=1) if records else None      # [B, measurements, 8] (series=True)
+        return {name: torch.stack(v) for name, v in blocks.items()}
 
     def equilibrated_means(self, series, by="abs_amplitude", max_fraction=.5):
         """Means over the equilibrated part of a run_blocks series: every replica's series is cut where the MSER rule puts

@@ -242,7 +242,9 @@ def test_farm_run_writes_the_reference_files(cuda, tmp_path):
     farm.preprocess("t", "alpha", [-1.5, 0, .5], "wavenumber", [.8, 1.3, .25], outdir=str(tmp_path))
     names, lines = farm.read_varfile(str(tmp_path / "varfile.txt"))
     assert len(lines) == 6
-    out = farm.run(str(tmp_path / "infile.txt"), str(tmp_path / "varfile.txt"), outdir=str(tmp_path / "out"), seed=3)
+    out = farm.run(str(tmp_path / "infile.txt"), str(tmp_path / "varfile.txt"), outdir=str(tmp_path / "out"), seed=3, write_series=True)
+    ts = pd.read_csv(tmp_path / "out" / (farm.title_of(names, lines[2]) + ".csv"), index_col=0)
+    assert len(ts) == 12 and {"amplitude", "field_energy", "surface_energy", "energy", "psi_squared"} <= set(ts.columns)
     assert out["abs_amplitude"].shape == (6,) and np.all(out["n_measurements"] == 6) if "n_measurements" in out else True
     for strings in lines:
         t = farm.title_of(names, strings)
