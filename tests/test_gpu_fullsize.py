@@ -129,3 +129,23 @@ def test_c3_energy_bookkeeping(cuda):
     S = ops.row_moments(b.psi, b.Z, b.params)
     E = ops.field_energy(S, b.Z, b.T, b.params, b.chain[:, _abi.CH_AMPLITUDE].contiguous(), None, 0)
     np.testing.assert_allclose(b.chain[:, _abi.CH_E_FIELD].cpu().numpy(), E.cpu().numpy(), rtol=2e-5, atol=1e-4)
+
+
+def test_replica_batch_checkpoint_resume_is_exact(cuda, tmp_path):
+    """state_dict() / load_state_dict(): a run interrupted, saved with torch.save, and resumed in a NEW batch continues
+    bit-identically (counter-based RNG: nothing but (seed, replica, sweep index) defines the stream)."""
+    import sys, os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from cylinder_b200.replicas import ReplicaBatch
+    P = bench.grid_params(96, 17)
+    a = ReplicaBatch(P, dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11, replica0=17)
+    a.run(30)
+    torch.save(a.state_dict(), tmp_path / "ckpt.pt")
+    a.run(25)
+    b = ReplicaBatch(P, dims=(50, 50), dtype=torch.complex64, device=cuda, seed=999, replica0=0, initialize=False)
+    b.load_state_dict(torch.load(tmp_path / "ckpt.pt", weights_only=False))
+    b.run(25)
+    assert torch.equal(a.psi, b.psi) and torch.equal(a.chain, b.chain) and torch.equal(a.obs, b.obs) and torch.equal(a.prof, b.prof)
+    assert a.sweeps_done == b.sweeps_done == 55
