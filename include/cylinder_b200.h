@@ -212,7 +212,8 @@ int cyl_sweep_smem_series_f64(void* psi, int B, const int32_t* Z, int Zmax, int 
  * two column-parity planes (even / odd padded column) so that one checkerboard colour of a row is contiguous:
  *   work[buf][plane][Z + 2*halo_rows][pitch/2] complex,   padded (row, col) = (i + halo_rows, j + halo_cols),
  * halo rows / columns hold periodic copies.  cyl_hbm_layout reports the geometry; work must hold
- * 2*buffer_elems complex elements, scratch scratch_bytes bytes (row coefficients, row moments, counters). */
+ * 2*buffer_elems complex elements, scratch scratch_bytes bytes (header with the Robbins-Monro record, two row-coefficient
+ * tables, row energy weights, per-tile partial sums, per-tile-column profile sums; need not be initialised). */
 int cyl_hbm_layout(int Z, int T, int is_f64, int* halo_rows, int* halo_cols, int64_t* pitch_elems,
                    int64_t* buffer_elems, int64_t* scratch_bytes);
 /* psi [Z][T] (numpy layout) -> work buffer 0 incl. halos; sets *cur = 0.  `cur` is a HOST integer owned by the
@@ -228,9 +229,13 @@ int cyl_hbm_unpack_f64(const void* work, int cur, int Z, int T, void* psi, void*
  * sites are recomputed redundantly -- the counter-based RNG makes that bit-identical to the neighbour tile's
  * own result) and the interior is written to the other buffer, so a sweep moves 8 B read + 8 B written per
  * site (fp32) instead of one read + one write per colour.  `cur` (HOST int32, in/out) is flipped per sweep.
- * chain [CYL_CHAIN_DOUBLES] device.  Accept counts feed the Robbins-Monro sigma update once per sweep; with
- * CYL_SWEEP_AMP_MOVES / CYL_SWEEP_MEASURE a row-moment pass and an amplitude move / measurement follow every
- * sweep.  obs [CYL_OBS_DOUBLES], prof [Z][3] may be NULL without CYL_SWEEP_MEASURE. */
+ * chain [CYL_CHAIN_DOUBLES] device.  Accept counts feed the Robbins-Monro sigma update once per sweep (carried from
+ * sweep to sweep by the kernel itself: one launch per plain sweep).  With CYL_SWEEP_AMP_MOVES / CYL_SWEEP_MEASURE
+ * the energies for the current and the proposed amplitude and the profile sums are accumulated by the same kernel
+ * while it updates the sites; a small preparation kernel before and a decision kernel after each sweep draw the
+ * proposal, build its row tables and take the amplitude / measurement decisions.  obs [CYL_OBS_DOUBLES], prof [Z][3]
+ * may be NULL without CYL_SWEEP_MEASURE.  The kernels of one call are launched with programmatic stream
+ * serialisation on `stream`; ordering with respect to other work on the stream is the usual stream order. */
 int cyl_sweep_hbm_f32(void* work, int32_t* cur, int Z, int T, const CylParams* params, double* chain,
                       uint64_t seed, int64_t replica, uint64_t sweep0, int nsweeps, int variant,
                       uint32_t flags, void* scratch, double* obs, double* prof, void* stream);
