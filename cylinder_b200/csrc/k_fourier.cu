@@ -13,6 +13,8 @@
 // e^{i j k z_n} are 256th roots of unity and e^{i b th_m} are (4 nth + 2)th roots: both come from small tables, so the
 // integrand needs no trigonometry.  No A/B/D tensors, no save_temporary_matrices bookkeeping: the same function
 // serves amplitude changes and fixed-amplitude coefficient moves.
+#include <stdlib.h>
+
 #include "cyl_common.cuh"
 #include "cyl_site.cuh"
 #include "cyl_surface.cuh"
@@ -39,30 +41,45 @@ __device__ __forceinline__ void fourier_tables_init(FourierTables* t, int nth) {
   }
 }
 
-// Warp-cooperative energy; c = coefficients [2 nth + 1][2 nz + 1] (any address space), all lanes return the value.
-__device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, double a, const double2* __restrict__ c,
-                                      const FourierTables* __restrict__ tab) {
-  const int lane = threadIdx.x & 31;
+// Cooperative energy; c = coefficients [2 nth + 1][2 nz + 1] (any address space), every participating thread returns the
+// value.  By default one warp shares the 256 z-nodes (lane-strided).  With cta_red != nullptr the whole CTA does (thread-
+// strided; every warp must call with the same arguments): warp sums meet in cta_red[warps] and are added in warp order by
+// everyone, so all threads hold the identical total.
+// NZ, NTH >= 0: the mode counts are compile-time constants (loops unrolled, the small arrays in registers); -1: run time.
+template <int NZ, int NTH>
+__device__ __forceinline__ double fourier_energy_t(const CylParams& p, int nz_rt, int nth_rt, double a, const double2* __restrict__ c,
+                                                   const FourierTables* __restrict__ tab, double* cta_red) {
+  const int nz = NZ >= 0 ? NZ : nz_rt, nth = NTH >= 0 ? NTH : nth_rt;
+  const int lane = cta_red ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  const int nstride = cta_red ? (int)blockDim.x : 32;
   const int lz = 2 * nz + 1, lth = 2 * nth + 1;
   const int nthq = 4 * nth + 2;                       // theta nodes: exact for |Psi|^4 (degree 4 nth in e^{i th})
   const double k = p.wavenumber, r = p.radius;
   const double ra = geo_radius_rescaled(r, a);
   const double Lz = 2.0 * 3.14159265358979323846 / k;
   double acc = 0.0;
-  for (int node = lane; node < CYL_QUAD_NODES; node += 32) {
+  for (int node = lane; node < CYL_QUAD_NODES; node += nstride) {
     const double2 w1 = tab->wz[node];                               // (cos kz, sin kz), kz = 2 pi node / N exactly
     const Geo g = geo_from_sc(k, ra, a, w1.y, w1.x);
-    double2 psi[2 * FOURIER_MAX_NTH + 1];
+    // e^{i j k z}, j = 1..nz, by repeated multiplication (the negative powers are the conjugates)
+    double2 pw[(NZ >= 0 ? NZ : FOURIER_MAX_NZ) + 1];
+    pw[1] = w1;
+#pragma unroll
+    for (int j = 2; j <= nz; ++j) pw[j] = make_double2(pw[j - 1].x * w1.x - pw[j - 1].y * w1.y, pw[j - 1].x * w1.y + pw[j - 1].y * w1.x);
+    double2 psi[2 * (NTH >= 0 ? NTH : FOURIER_MAX_NTH) + 1];
     double sum_p2 = 0.0, sum_dz2 = 0.0, sum_th = 0.0;
+#pragma unroll
     for (int b = 0; b < lth; ++b) {
-      double pr = 0.0, pi_ = 0.0, dr = 0.0, di = 0.0;
-      for (int j = 0; j < lz; ++j) {
-        const int jj = j - nz;
-        const double2 e = tab->wz[(jj * node) & (CYL_QUAD_NODES - 1)];             // e^{i jj k z}
-        const double2 cc = c[b * lz + j];
-        const double tr = cc.x * e.x - cc.y * e.y, ti = cc.x * e.y + cc.y * e.x;
-        pr += tr; pi_ += ti;
-        dr += -(jj * k) * ti; di += (jj * k) * tr;              // d/dz = i jj k
+      const double2* cb = c + b * lz + nz;                          // cb[j] = coefficient of e^{i j k z}, j = -nz..nz
+      double pr = cb[0].x, pi_ = cb[0].y, dr = 0.0, di = 0.0;
+#pragma unroll
+      for (int j = 1; j <= nz; ++j) {
+        const double2 e = pw[j], cp_ = cb[j], cm_ = cb[-j];
+        const double tr = cp_.x * e.x - cp_.y * e.y, ti = cp_.x * e.y + cp_.y * e.x;     // c_{+j} e^{+i j k z}
+        const double ur = cm_.x * e.x + cm_.y * e.y, ui = cm_.y * e.x - cm_.x * e.y;     // c_{-j} e^{-i j k z}
+        pr += tr + ur; pi_ += ti + ui;
+        const double jk = j * k;                                    // d/dz = +- i j k
+        dr -= jk * (ti - ui); di += jk * (tr - ur);
       }
       psi[b] = make_double2(pr, pi_);
       const double p2 = pr * pr + pi_ * pi_;
@@ -71,15 +88,19 @@ __device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, doubl
       const double bb = (double)(b - nth) - p.n * g.ath;
       sum_th += bb * bb * p2;
     }
+    // <|Psi|^4>_theta on the nthq-node grid: Psi(th_m) = psi_0 + sum_t (psi_{+t} e^{i t th_m} + psi_{-t} e^{-i t th_m})
     double quart = 0.0;
+#pragma unroll
     for (int m = 0; m < nthq; ++m) {
-      double Pr = 0.0, Pi = 0.0;
-      for (int b = 0; b < lth; ++b) {
-        int idx = ((b - nth) * m) % nthq;
-        if (idx < 0) idx += nthq;
-        const double2 e = tab->wt[idx];
-        Pr += psi[b].x * e.x - psi[b].y * e.y;
-        Pi += psi[b].x * e.y + psi[b].y * e.x;
+      const double2 e1 = tab->wt[m];
+      double2 e = e1;
+      double Pr = psi[nth].x, Pi = psi[nth].y;
+#pragma unroll
+      for (int t = 1; t <= nth; ++t) {
+        const double2 qp = psi[nth + t], qm = psi[nth - t];
+        Pr += (qp.x * e.x - qp.y * e.y) + (qm.x * e.x + qm.y * e.y);
+        Pi += (qp.x * e.y + qp.y * e.x) + (qm.y * e.x - qm.x * e.y);
+        e = make_double2(e.x * e1.x - e.y * e1.y, e.x * e1.y + e.y * e1.x);
       }
       const double P2 = Pr * Pr + Pi * Pi;
       quart += P2 * P2;
@@ -88,7 +109,22 @@ __device__ double fourier_energy_warp(const CylParams& p, int nz, int nth, doubl
     const double sg = g.gth * g.gz;
     acc += sg * (p.alpha * sum_p2 + 0.5 * p.u * quart) + p.C * (sg * sum_dz2 + g.gz / g.gth * sum_th);
   }
-  return warp_sum(acc) * (Lz / CYL_QUAD_NODES);
+  acc = warp_sum(acc);
+  if (cta_red) {
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) cta_red[warp] = acc;
+    __syncthreads();
+    acc = 0.0;
+    for (int w = 0; w < nwarp; ++w) acc += cta_red[w];
+    __syncthreads();                                              // cta_red is free again
+  }
+  return acc * (Lz / CYL_QUAD_NODES);
+}
+
+__device__ __forceinline__ double fourier_energy_warp(const CylParams& p, int nz, int nth, double a, const double2* __restrict__ c,
+                                                      const FourierTables* __restrict__ tab, double* cta_red = nullptr) {
+  if (nz == 2 && nth == 1) return fourier_energy_t<2, 1>(p, nz, nth, a, c, tab, cta_red);      // run.py:369, the reference's default
+  return fourier_energy_t<-1, -1>(p, nz, nth, a, c, tab, cta_red);
 }
 
 // Cylinder1D.calc_surface_energy: effective_gamma * int Gth Gz dz + kappa * calc_bending_energy   (system_cylinder1D.py:189-194;
@@ -165,7 +201,11 @@ extern "C" int cyl_fourier_surface_energy_f64(const CylParams* params, const dou
 #define CYL_TAG_FCPLX 4u
 #define CYL_TAG_FALL 5u
 
-__global__ void __launch_bounds__(128)
+// CTA = false: one warp per chain (many chains).  CTA = true: one CTA per chain (few chains): the eight warps carry identical
+// copies of the chain state and take identical decisions; only the energy quadrature is shared among them, one node per
+// thread, which cuts the latency of a move about five-fold.
+template <bool CTA>
+__global__ void __launch_bounds__(CTA ? 256 : 128)
 fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double* __restrict__ amp, double2* __restrict__ coeffs,
                   double* __restrict__ est, int B, uint64_t seed, int64_t chain0, uint64_t step0, int n_steps, int measure_every,
                   int fieldsteps, double target, double ratio_real, double ratio_cplx, int method) {
@@ -183,9 +223,10 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
   double2* c = c_all + (size_t)warp * 2 * ncoef;
   double2* cp = c + ncoef;
   double* L = reinterpret_cast<double*>(c_all + (size_t)nwarp * 2 * ncoef) + (size_t)warp * d * d;
+  double* cta_red = CTA ? reinterpret_cast<double*>(c_all + (size_t)nwarp * 2 * ncoef) + (size_t)nwarp * d * d : nullptr;
   fourier_tables_init(tab, nth);
   __syncthreads();
-  const int b = blockIdx.x * nwarp + warp;
+  const int b = CTA ? (int)blockIdx.x : (int)(blockIdx.x * nwarp + warp);
   if (b >= B) return;
   const CylParams p = params[b];
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -198,7 +239,7 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
   __syncwarp();
   double sig_r = st[0], sig_c = st[1], n_real = st[2], n_cplx = st[3], n_meas = st[4], acc_r = st[5], acc_c = st[6];
   double sum_a2 = st[9], sum_e = st[10];
-  double e_field = has_field ? fourier_energy_warp(p, nz, nth, a, c, tab) : 0.0;
+  double e_field = has_field ? fourier_energy_warp(p, nz, nth, a, c, tab, cta_red) : 0.0;
   double e_surf = fourier_surface_energy_warp(p, a);
 
   // L L^T = the block of the covariance the proposal needs: cov[1:,1:] (coefficient moves) or all of it (joint move);
@@ -236,7 +277,7 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
         const double a_new = a + sig_r * sqrt(cov[0]) * z;
         bool accept = false;
         if (fabs(a_new) < p.amp_bound) {
-          const double ef = has_field ? fourier_energy_warp(p, nz, nth, a_new, c, tab) : 0.0;
+          const double ef = has_field ? fourier_energy_warp(p, nz, nth, a_new, c, tab, cta_red) : 0.0;
           const double es = fourier_surface_energy_warp(p, a_new);
           const double diff = (ef + es) - (e_field + e_surf);
           accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
@@ -274,7 +315,7 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
         __syncwarp();
         bool accept = false;
         if (fabs(a_new) < p.amp_bound) {
-          const double ef = fourier_energy_warp(p, nz, nth, a_new, cp, tab);
+          const double ef = fourier_energy_warp(p, nz, nth, a_new, cp, tab, cta_red);
           const double es = fourier_surface_energy_warp(p, a_new);
           const double diff = (ef + es) - (e_field + e_surf);
           accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
@@ -310,7 +351,7 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
           cp[lane] = make_double2(mag * cs, mag * sn);
         }
         __syncwarp();
-        const double ef = fourier_energy_warp(p, nz, nth, a, cp, tab);
+        const double ef = fourier_energy_warp(p, nz, nth, a, cp, tab, cta_red);
         const double diff = ef - e_field;
         const bool accept = (diff <= 0) || (p.temperature > 0 && u <= exp(-diff / p.temperature));
         if (accept) {
@@ -325,29 +366,34 @@ fourier_am_kernel(const CylParams* __restrict__ params, int nz, int nth, double*
         ++move;
       }
     }
-    // ---- measure ----
+    // ---- measure ----  (CTA mode: mean and covariance live in global memory once per chain -- warp 0 updates them, the
+    //                     others wait and then re-factorise from the updated covariance like warp 0 does)
     n_meas += 1;
     const double kk = n_meas;
-    const int dm_ = has_field ? d : 1;                                   // no-field: the state is the amplitude alone
-    const double xi = (lane == 0) ? fabs(a) : (lane < dm_ ? hypot(c[lane - 1].x, c[lane - 1].y) : 0.0);
-    const double mu_old = (lane < dm_) ? mean[lane] : 0.0;
-    const double mu = mu_old * (kk - 1) / kk + xi / kk;
-    if (lane < dm_) mean[lane] = mu;
-    if (kk > 50) {
-      for (int j = 0; j < dm_; ++j) {
-        const double xj = __shfl_sync(0xffffffffu, xi, j), mo = __shfl_sync(0xffffffffu, mu_old, j), mn = __shfl_sync(0xffffffffu, mu, j);
-        if (lane < dm_)
-          cov[lane * d + j] = cov[lane * d + j] * (kk - 2) / (kk - 1) +
-                              (mu_old * mo - kk / (kk - 1) * mu * mn + xi * xj / (kk - 1) + (lane == j ? sig_r * sig_r / kk : 0.0));
+    if (!CTA || warp == 0) {
+      const int dm_ = has_field ? d : 1;                                   // no-field: the state is the amplitude alone
+      const double xi = (lane == 0) ? fabs(a) : (lane < dm_ ? hypot(c[lane - 1].x, c[lane - 1].y) : 0.0);
+      const double mu_old = (lane < dm_) ? mean[lane] : 0.0;
+      const double mu = mu_old * (kk - 1) / kk + xi / kk;
+      if (lane < dm_) mean[lane] = mu;
+      if (kk > 50) {
+        for (int j = 0; j < dm_; ++j) {
+          const double xj = __shfl_sync(0xffffffffu, xi, j), mo = __shfl_sync(0xffffffffu, mu_old, j), mn = __shfl_sync(0xffffffffu, mu, j);
+          if (lane < dm_)
+            cov[lane * d + j] = cov[lane * d + j] * (kk - 2) / (kk - 1) +
+                                (mu_old * mo - kk / (kk - 1) * mu * mn + xi * xj / (kk - 1) + (lane == j ? sig_r * sig_r / kk : 0.0));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      cholesky();
     }
+    if (CTA) __syncthreads();
+    if (kk > 50) cholesky();
     sum_a2 += a * a;
     sum_e += e_field + e_surf;
   }
   // ---- write back ----
   __syncwarp();
+  if (CTA && warp != 0) return;                                    // every warp holds the same state
   for (int i = lane; i < ncoef; i += 32) coeffs[(size_t)b * ncoef + i] = c[i];
   if (lane == 0) {
     amp[b] = a;
@@ -373,12 +419,26 @@ extern "C" int cyl_fourier_am_steps_f64(const CylParams* params, int nz, int nth
                 FOURIER_MAX_COEF - 1);
   CYL_CHECK_ARG(method >= CYL_FOURIER_SEQUENTIAL && method <= CYL_FOURIER_NO_FIELD, "cyl_fourier_am_steps_f64: unknown method %d", method);
   if (n_steps == 0) return CYL_OK;
-  const int warps = 4, dd = ncoef + 1;
-  const size_t smem = sizeof(FourierTables) + (size_t)warps * (2 * ncoef * sizeof(double2) + (size_t)dd * dd * sizeof(double));
-  CYL_CUDA(cudaFuncSetAttribute(fourier_am_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fourier_am_kernel<<<(B + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(
-      params, nz, nth, amp, (double2*)coeffs, engine_state, B, seed, chain0, step0, n_steps, measure_every, fieldsteps,
-      target_acceptance, ratio_real, ratio_complex, method);
+  // few chains: a CTA per chain (the energy quadrature shared by eight warps); many: a warp per chain
+  int dev = 0, sms = 0;
+  CYL_CUDA(cudaGetDevice(&dev));
+  CYL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  bool cta = B <= sms;
+  if (const char* mode = getenv("CYL_FOURIER_MODE")) cta = (mode[0] == 'c');      // "cta" / "warp": testing override
+  const int warps = cta ? 8 : 4, dd = ncoef + 1;
+  const size_t smem = sizeof(FourierTables) + (size_t)warps * (2 * ncoef * sizeof(double2) + (size_t)dd * dd * sizeof(double)) +
+                      (size_t)warps * sizeof(double);
+  if (cta) {
+    CYL_CUDA(cudaFuncSetAttribute(fourier_am_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fourier_am_kernel<true><<<B, warps * 32, smem, as_stream(stream)>>>(
+        params, nz, nth, amp, (double2*)coeffs, engine_state, B, seed, chain0, step0, n_steps, measure_every, fieldsteps,
+        target_acceptance, ratio_real, ratio_complex, method);
+  } else {
+    CYL_CUDA(cudaFuncSetAttribute(fourier_am_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fourier_am_kernel<false><<<(B + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(
+        params, nz, nth, amp, (double2*)coeffs, engine_state, B, seed, chain0, step0, n_steps, measure_every, fieldsteps,
+        target_acceptance, ratio_real, ratio_complex, method);
+  }
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

@@ -166,10 +166,13 @@ def test_single_run_lattice_and_fourier(cuda, tmp_path, monkeypatch):
     assert (out / "four.csv").exists() and (tmp_path / "last_cov.pickle").exists()
 
 
-def test_batched_fourier_chains_match_oracle(cuda):
-    """cyl_fourier_am_steps_f64 (one warp per chain: amplitude + coefficient moves, Robbins-Monro widths, recursive mean and
-    covariance with re-factorisation after measurement 50) vs the numpy restatement on the same Philox draws."""
+@pytest.mark.parametrize("mode", ["cta", "warp"])
+def test_batched_fourier_chains_match_oracle(cuda, mode, monkeypatch):
+    """cyl_fourier_am_steps_f64 (amplitude + coefficient moves, Robbins-Monro widths, recursive mean and covariance with
+    re-factorisation after measurement 50) vs the numpy restatement on the same Philox draws, in both layouts: one CTA per chain
+    (few chains: the energy quadrature shared by eight warps) and one warp per chain (many chains)."""
     import torch
+    monkeypatch.setenv("CYL_FOURIER_MODE", mode)
     from cylinder_b200.fourier_chains import FourierChains
     from oracle import fourier_am_oracle as fa
     B, nfc = 3, (1, 1)
