@@ -3,7 +3,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from cylinder_b200 import ops
+from cylinder_b200 import ops, _abi
+if os.environ.get("CYL_LIB"):
+    _abi.LIB_PATH = os.path.abspath(os.environ["CYL_LIB"])      # a variant built by scripts/build_variant.sh
 from cylinder_b200.fourier_chains import FourierChains
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 dev = torch.device("cuda", 0)
