@@ -415,7 +415,9 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   EAcc<R> e = {R(0), R(0), R(0), R(0)};
   const bool meas = measure != 0;
   // tiles on the lattice boundary wrap their global coordinates, may be partial, and own periodic halo copies
-  const bool border = (blockIdx.x == 0) | (blockIdx.y == 0) | (blockIdx.x == gridDim.x - 1) | (blockIdx.y == gridDim.y - 1);
+  // (the last clause: with an odd length the last tile may be thinner than the halo, so its neighbour's halo wraps too)
+  const bool border = (blockIdx.x == 0) | (blockIdx.y == 0) | (blockIdx.x == gridDim.x - 1) | (blockIdx.y == gridDim.y - 1) |
+                      (ti0 + TH + NCOL > g.Z) | (tj0 + TW + HS > g.T);
   constexpr int PS = (int)(L::plane_bytes / sizeof(C));             // plane stride in shared memory (elements)
   C* out = work + (size_t)(cur ^ 1) * g.buffer_elems;
   const int64_t ph = g.pitch / 2;
@@ -482,55 +484,73 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       __syncthreads();
     }
   } else {
-    // odd periodic ring(s): 3 colours, general colour function; every region site is visited and filtered
+    // odd periodic ring(s): 3 colours, colour = (a(i) + a(j)) % 3.  In pass c a row of axis colour a(i) holds the sites whose
+    // column has axis colour (c - a(i)) mod 3: every other column (or, for colour 2, only the odd ring's last column).  A warp
+    // works on ONE row at a time (rows whose sites belong to another pass are skipped by the whole warp) and each lane
+    // examines a pair of adjacent columns, of which at most one has the wanted colour -- so the lanes that get past the filter
+    // are dense.  (Visiting every site of the region in every pass and filtering cost 3.7x the 2-colour sweep.)
     auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
     for (int c = 0; c < NCOL; ++c) {
       const int m = c + 1, mq = m + (HS - NCOL);
-      const int nrows = SH - 2 * m, ncl = SW - 2 * mq;
-      for (int idx = tid; idx < nrows * ncl; idx += HBM_NT) {
-        const int rr = idx / ncl, r = m + rr, q = mq + (idx - rr * ncl);
+      const int ncl = SW - 2 * mq, npairs = (ncl + 1) >> 1;
+      for (int r = m + (tid >> 6); r < SH - m; r += HBM_NT / 64) {
         // lattice coordinates; tiles past the edge hold zero-filled padding that is never stored
-        const int ui = ti0 - NCOL + r, uj = tj0 - HS + q;
-        if (ui >= g.Z + NCOL || uj >= g.T + NCOL) continue;
-        const int gi = wrapi(ui, g.Z), gj = wrapi(uj, g.T);
-        const int ai = axis_colour(gi, g.Z), bj = axis_colour(gj, g.T);
-        if (col3(ai + bj) != c) continue;
-        const int par = (Q0 + q) & 1;
-        C* own = par ? pl1 : pl0;
-        C* oth = par ? pl0 : pl1;
-        const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
-        const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
-        const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
-        const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
-        const RowCoef<R> rc = coef[r];
-        const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, kc, kr);
-        R zre, zim;
-        Draw<R>::normals(x.x, x.y, zre, zim);
-        const R w = sigma * rc.sgmul;
-        const R dre = w * zre, dim = w * zim;
-        const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-        const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-        const C qv = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
-        if (acc) own[r * SWH + col] = qv;
-        const int li = r - NCOL, lj = q - HS;
-        const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
-        nacc += (acc && counted);
-        if (EXTRAS && HBM_ENERGY_ON && counted) {
-          const RowW<R> rw = roww[r];
-          energy_own<R, C>(e, rw, qv, meas);
-          // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
-          if (col3(axis_colour(wrapi(gi - 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, rw.cur[2], rw.dif[2], qv, Ln, meas);
-          if (col3(axis_colour(wrapi(gi + 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, roww[r + 1].cur[2], roww[r + 1].dif[2], Rz, qv, meas);
-          if (col3(ai + axis_colour(wrapi(gj - 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, qv, W, meas);
-          if (col3(ai + axis_colour(wrapi(gj + 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, E, qv, meas);
+        const int ui = ti0 - NCOL + r;
+        if (ui >= g.Z + NCOL) break;
+        const int gi = border ? wrapi(ui, g.Z) : ui;               // interior tiles never leave [0, Z) x [0, T), halo included
+        const int ai = axis_colour(gi, g.Z);
+        int bj = c - ai;
+        if (bj < 0) bj += 3;
+        if (bj == 2 && !(g.T & 1)) continue;                       // an even ring has no column of axis colour 2
+        for (int pp = tid & 63; pp < npairs; pp += 64) {
+          int q = -1, gj = 0;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int qq = mq + 2 * pp + t, uj = tj0 - HS + qq;
+            if (qq < mq + ncl && uj < g.T + NCOL) {
+              const int gjj = border ? wrapi(uj, g.T) : uj;
+              if (axis_colour(gjj, g.T) == bj) { q = qq; gj = gjj; }
+            }
+          }
+          if (q < 0) continue;
+          const int par = (Q0 + q) & 1;
+          C* own = par ? pl1 : pl0;
+          C* oth = par ? pl0 : pl1;
+          const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
+          const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
+          const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
+          const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
+          const RowCoef<R> rc = coef[r];
+          const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, kc, kr);
+          R zre, zim;
+          Draw<R>::normals(x.x, x.y, zre, zim);
+          const R w = sigma * rc.sgmul;
+          const R dre = w * zre, dim = w * zim;
+          const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
+          const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
+          const C qv = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+          if (acc) own[r * SWH + col] = qv;
+          const int li = r - NCOL, lj = q - HS;
+          const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
+          nacc += (acc && counted);
+          if (EXTRAS && HBM_ENERGY_ON && counted) {
+            const RowW<R> rw = roww[r];
+            energy_own<R, C>(e, rw, qv, meas);
+            // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
+            if (col3(axis_colour(wrapi(gi - 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, rw.cur[2], rw.dif[2], qv, Ln, meas);
+            if (col3(axis_colour(wrapi(gi + 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, roww[r + 1].cur[2], roww[r + 1].dif[2], Rz, qv, meas);
+            if (col3(ai + axis_colour(wrapi(gj - 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, qv, W, meas);
+            if (col3(ai + axis_colour(wrapi(gj + 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, E, qv, meas);
+          }
         }
       }
+      if (c == NCOL - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
       __syncthreads();
     }
   }
 
   // ---- write the interior (and its periodic halo copies) to the other buffer ----
-  if (NCOL == 2 && !border) {
+  if (!border) {
     // interior tile: every (row, plane) is 64 contiguous complex values on both sides, 16-byte aligned: one bulk copy
     // (cp.async.bulk shared -> global, SASS UBLKCP) per row and plane, issued by 2*TH threads, instead of a load + store
     // per 16 bytes by everyone.  The shared-memory writes of the colour passes were made visible to the async proxy by the
@@ -630,7 +650,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
   __syncthreads();
   // the bulk copies of the write-out must have read their shared-memory sources before the CTA retires
-  if (NCOL == 2 && !border && tid < 2 * TH) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (!border && tid < 2 * TH) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   if (!EXTRAS) {
     if (tid == 0) {
       double t = 0.0;

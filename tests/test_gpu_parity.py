@@ -509,3 +509,32 @@ def test_time_series_matches_oracle(cuda):
     assert o[_abi.OB_E_FIELD] == pytest.approx(rec[:, 1].sum(), rel=1e-12) and o[_abi.OB_PSI2] == pytest.approx(rec[:, 3].sum(), rel=1e-12)
     with pytest.raises(Exception):
         ops.sweep_smem(psi, Zt, par, chain, seed, 0, nsw, variant, _abi.SWEEP_ADAPT_SIGMA, replica0=rep, series=ts)     # needs MEASURE
+
+
+@pytest.mark.parametrize("Z,T", [(65, 257), (97, 136)])
+def test_hbm_thin_last_tile_matches_oracle(cuda, Z, T):
+    """Odd lengths whose last tile is a single row / column (65 = 2 x 32 + 1, 257 = 2 x 128 + 1; 97 = 3 x 32 + 1): the tile before
+    it reaches across the periodic seam with its halo."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    a = -0.25
+    P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-.8, u=1.2, C=.9, n=3, temperature=.05)
+    rng = np.random.RandomState(Z + T)
+    psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
+    st = _oracle_state(psi0.copy(), P, lo.SIMPLE, .05)
+    par = _params(ops, cuda, P)
+    for th in ("32", "24"):
+        import os
+        os.environ["CYL_HBM_TILE_ROWS"] = th
+        try:
+            st = _oracle_state(psi0.copy(), P, lo.SIMPLE, .05)
+            ws = ops.HbmWorkspace(Z, T, torch.complex128, cuda)
+            ws.pack(torch.tensor(psi0, dtype=torch.complex128, device=cuda))
+            chain = ops.new_chain(1, cuda, amplitude=a, sigma_site=.05)
+            ws.sweep(par, chain[0], 123, 0, 2, lo.SIMPLE, _abi.SWEEP_ADAPT_SIGMA, replica=1)
+        finally:
+            del os.environ["CYL_HBM_TILE_ROWS"]
+        for s in range(2):
+            cb.sweep(st, a, 123, 1, s)
+        np.testing.assert_allclose(ws.unpack().cpu().numpy(), st.psi, rtol=0, atol=1e-11)
+        assert chain[0, _abi.CH_SITE_ACCEPTED].item() == st.accepted
