@@ -490,59 +490,78 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     // examines a pair of adjacent columns, of which at most one has the wanted colour -- so the lanes that get past the filter
     // are dense.  (Visiting every site of the region in every pass and filtering cost 3.7x the 2-colour sweep.)
     auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
+    // one site of pass c at region coordinates (r, q) = lattice (gi, gj), axis colours (ai, bj)
+    auto site3 = [&](int c, int r, int q, int gi, int gj, int ai, int bj) {
+      const int par = (Q0 + q) & 1;
+      C* own = par ? pl1 : pl0;
+      C* oth = par ? pl0 : pl1;
+      const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
+      const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
+      const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
+      const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
+      const RowCoef<R> rc = coef[r];
+      const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, kc, kr);
+      R zre, zim;
+      Draw<R>::normals(x.x, x.y, zre, zim);
+      const R w = sigma * rc.sgmul;
+      const R dre = w * zre, dim = w * zim;
+      const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
+      const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
+      const C qv = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+      if (acc) own[r * SWH + col] = qv;
+      const int li = r - NCOL, lj = q - HS;
+      const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
+      nacc += (acc && counted);
+      if (EXTRAS && HBM_ENERGY_ON && counted) {
+        const RowW<R> rw = roww[r];
+        energy_own<R, C>(e, rw, qv, meas);
+        // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
+        if (col3(axis_colour(wrapi(gi - 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, rw.cur[2], rw.dif[2], qv, Ln, meas);
+        if (col3(axis_colour(wrapi(gi + 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, roww[r + 1].cur[2], roww[r + 1].dif[2], Rz, qv, meas);
+        if (col3(ai + axis_colour(wrapi(gj - 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, qv, W, meas);
+        if (col3(ai + axis_colour(wrapi(gj + 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, E, qv, meas);
+      }
+    };
+    // axis colour and lattice column of region column qq of this pass (-1: outside the region / past the lattice)
+    auto column = [&](int qq, int qend, int& gj) {
+      const int uj = tj0 - HS + qq;
+      if (qq >= qend || uj >= g.T + NCOL) return -1;
+      gj = border ? wrapi(uj, g.T) : uj;                           // interior tiles never leave [0, Z) x [0, T), halo included
+      return axis_colour(gj, g.T);
+    };
+#pragma unroll 1
     for (int c = 0; c < NCOL; ++c) {
       const int m = c + 1, mq = m + (HS - NCOL);
-      const int ncl = SW - 2 * mq, npairs = (ncl + 1) >> 1;
+      const int ncl = SW - 2 * mq, npairs = (ncl + 1) >> 1, qend = mq + ncl;
+      // this thread's column pair is the same in every row of the pass: work out its two candidates once
+      const int q0 = mq + 2 * (tid & 63);
+      int gj0 = 0, gj1 = 0;
+      const int ac0 = column(q0, qend, gj0), ac1 = column(q0 + 1, qend, gj1);
       for (int r = m + (tid >> 6); r < SH - m; r += HBM_NT / 64) {
         // lattice coordinates; tiles past the edge hold zero-filled padding that is never stored
         const int ui = ti0 - NCOL + r;
         if (ui >= g.Z + NCOL) break;
-        const int gi = border ? wrapi(ui, g.Z) : ui;               // interior tiles never leave [0, Z) x [0, T), halo included
+        const int gi = border ? wrapi(ui, g.Z) : ui;
         const int ai = axis_colour(gi, g.Z);
         int bj = c - ai;
         if (bj < 0) bj += 3;
-        if (bj == 2 && !(g.T & 1)) continue;                       // an even ring has no column of axis colour 2
-        for (int pp = tid & 63; pp < npairs; pp += 64) {
-          int q = -1, gj = 0;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int qq = mq + 2 * pp + t, uj = tj0 - HS + qq;
-            if (qq < mq + ncl && uj < g.T + NCOL) {
-              const int gjj = border ? wrapi(uj, g.T) : uj;
-              if (axis_colour(gjj, g.T) == bj) { q = qq; gj = gjj; }
-            }
-          }
-          if (q < 0) continue;
-          const int par = (Q0 + q) & 1;
-          C* own = par ? pl1 : pl0;
-          C* oth = par ? pl0 : pl1;
-          const int col = ((Q0 + q) >> 1) - (par ? x1 : x0);
-          const int colW = ((Q0 + q - 1) >> 1) - (par ? x0 : x1), colE = ((Q0 + q + 1) >> 1) - (par ? x0 : x1);
-          const C pv = own[r * SWH + col], Ln = own[(r - 1) * SWH + col], Rz = own[(r + 1) * SWH + col];
-          const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
-          const RowCoef<R> rc = coef[r];
-          const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, kc, kr);
-          R zre, zim;
-          Draw<R>::normals(x.x, x.y, zre, zim);
-          const R w = sigma * rc.sgmul;
-          const R dre = w * zre, dim = w * zim;
-          const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-          const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-          const C qv = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
-          if (acc) own[r * SWH + col] = qv;
-          const int li = r - NCOL, lj = q - HS;
-          const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
-          nacc += (acc && counted);
-          if (EXTRAS && HBM_ENERGY_ON && counted) {
-            const RowW<R> rw = roww[r];
-            energy_own<R, C>(e, rw, qv, meas);
-            // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
-            if (col3(axis_colour(wrapi(gi - 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, rw.cur[2], rw.dif[2], qv, Ln, meas);
-            if (col3(axis_colour(wrapi(gi + 1, g.Z), g.Z) + bj) < c) energy_zbond<R, C>(e, roww[r + 1].cur[2], roww[r + 1].dif[2], Rz, qv, meas);
-            if (col3(ai + axis_colour(wrapi(gj - 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, qv, W, meas);
-            if (col3(ai + axis_colour(wrapi(gj + 1, g.T), g.T)) < c) energy_tbond<R, C>(e, rw, E, qv, meas);
-          }
-        }
+        if (ac0 == bj) site3(c, r, q0, gi, gj0, ai, bj);
+        else if (ac1 == bj) site3(c, r, q0 + 1, gi, gj1, ai, bj);
+      }
+      // the (at most two) pairs beyond the 64 per row, as one flat list over (row, pair)
+      const int nextra = npairs - 64;
+      for (int idx = tid; idx < nextra * (SH - 2 * m); idx += HBM_NT) {
+        const int rr = nextra == 2 ? idx >> 1 : idx, r = m + rr, qx = mq + 2 * (64 + (nextra == 2 ? idx & 1 : 0));
+        const int ui = ti0 - NCOL + r;
+        if (ui >= g.Z + NCOL) continue;
+        const int gi = border ? wrapi(ui, g.Z) : ui;
+        const int ai = axis_colour(gi, g.Z);
+        int bj = c - ai;
+        if (bj < 0) bj += 3;
+        int gja = 0, gjb = 0;
+        const int aa = column(qx, qend, gja), ab = column(qx + 1, qend, gjb);
+        if (aa == bj) site3(c, r, qx, gi, gja, ai, bj);
+        else if (ab == bj) site3(c, r, qx + 1, gi, gjb, ai, bj);
       }
       if (c == NCOL - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
       __syncthreads();
@@ -594,7 +613,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // ---- theta-sums of the profiles (Lattice.measure :121-131) of this tile's rows ----
 #ifndef HBM_ABL_NO_PROF
   if (EXTRAS && meas && A.rowpart) {
-    if (NCOL == 2 && !border) {
+    if (!border) {
       // thread = (row, 16-column segment): 8 consecutive values from each plane, then a 3-step exchange over the 8 segments.
       // The chunk order is rotated by segment so that the 16-byte loads of a quarter-warp hit distinct banks.
       static_assert(TH <= HBM_NT / 8 && TW == 128, "one thread per (row, 16 columns)");
