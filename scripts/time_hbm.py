@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+DT = torch.complex128 if os.environ.get("CYL_DTYPE") == "f64" else torch.complex64
 from cylinder_b200 import _abi, ops
 if os.environ.get("CYL_LIB"):
     _abi.LIB_PATH = os.path.abspath(os.environ["CYL_LIB"])      # a variant built by scripts/build_variant.sh
@@ -9,9 +10,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nsw = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 dev = torch.device("cuda", 0)
 par = ops.make_params(dev, wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=.01)
-psi = torch.zeros(1, n, n, dtype=torch.complex64, device=dev)
+psi = torch.zeros(1, n, n, dtype=DT, device=dev)
 ops.lattice_init(psi, torch.tensor([n], dtype=torch.int32, device=dev), .1, 1, 0)
-ws = ops.HbmWorkspace(n, n, torch.complex64, dev)
+ws = ops.HbmWorkspace(n, n, DT, dev)
 ws.pack(psi[0])
 chain = ops.new_chain(1, dev, amplitude=0.3)[0]
 ws.sweep(par, chain, 1, 0, 10, 0, _abi.SWEEP_ADAPT_SIGMA)

@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+DT = torch.complex128 if os.environ.get("CYL_DTYPE") == "f64" else torch.complex64
 from cylinder_b200 import _abi
 if os.environ.get("CYL_LIB"):
     _abi.LIB_PATH = os.path.abspath(os.environ["CYL_LIB"])      # a variant built by scripts/build_variant.sh
@@ -10,7 +11,7 @@ import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 nsw = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 dev = torch.device("cuda", 0)
-batch = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=dev, seed=1)
+batch = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=DT, device=dev, seed=1)
 batch.run(nsw)
 torch.cuda.synchronize()
 for kw, name in ((dict(amp_moves=False, measure=False), "sweeps only"), (dict(amp_moves=True, measure=False), "sweeps+amp"), (dict(), "sweeps+amp+measure")):
