@@ -28,6 +28,51 @@ __device__ __forceinline__ void moments_accumulate(double (&m)[CYL_NMOM], C p, C
   m[7] += pi;
 }
 
+// fp32 storage: the per-site terms are formed in fp32 (the inputs carry no more; the differences of neighbouring values are
+// exact or nearly so) and only the accumulation runs in fp64 -- a third of the fp64 instructions of the generic form.
+__device__ __forceinline__ void moments_accumulate(double (&m)[CYL_NMOM], float2 p, float2 L, float2 W, double inv_lz2, double inv_lth2,
+                                                   double inv_lth) {
+  const float p2 = p.x * p.x + p.y * p.y;
+  const float zr = p.x - L.x, zi = p.y - L.y;
+  const float tr = p.x - W.x, ti = p.y - W.y;
+  m[0] += (double)p2;
+  m[1] += (double)(p2 * p2);
+  m[2] += (double)(zr * zr + zi * zi) * inv_lz2;
+  m[3] += (double)(tr * tr + ti * ti) * inv_lth2;
+  m[4] += (double)(p.x * ti - p.y * tr) * inv_lth;     // Im(conj(p) * dth)
+  m[5] += (double)sqrtf(p2);
+  m[6] += (double)p.x;
+  m[7] += (double)p.y;
+}
+
+// Row-moment kernels: a CTA of 8 warps takes 8 / wpr rows with wpr warps per row (wpr = 1, 2, 4 or 8, chosen by the row length:
+// a long row walked by one warp is a chain of dependent memory latencies).  Reduction of the row's warps through shared memory.
+#define CYL_MOM_WARPS 8
+__host__ __device__ __forceinline__ int moments_warps_per_row(int T) { return T >= 2048 ? 8 : T >= 1024 ? 4 : T >= 512 ? 2 : 1; }
+__device__ __forceinline__ void moments_store(double (&m)[CYL_NMOM], int wpr, int row_in_cta, int seg, double* __restrict__ out,
+                                              double (*red)[CYL_NMOM]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
+  if (wpr == 1) {
+    if (lane == 0 && out) {
+#pragma unroll
+      for (int q = 0; q < CYL_NMOM; ++q) out[q] = m[q];
+    }
+    return;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < CYL_NMOM; ++q) red[threadIdx.x >> 5][q] = m[q];
+  }
+  __syncthreads();
+  if (seg == 0 && lane < CYL_NMOM && out) {
+    double t = 0.0;
+    for (int s = 0; s < wpr; ++s) t += red[row_in_cta * wpr + s][lane];
+    out[lane] = t;
+  }
+}
+
 // Row weights of the energy: E_i = W[0] S1 + W[1] S2 + W[2] S3 + W[3] S4 + W[4] S5 + W[5], at trial amplitude a_eval
 // given the metric reference amplitude a_ref (only the 0th-order variant distinguishes them).  g0e / gme = metric at
 // z_i / z_{i-1/2} for a_eval, g0r = metric at z_i for a_ref.  WITHOUT the global lz*lth factor.

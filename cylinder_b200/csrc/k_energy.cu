@@ -11,45 +11,41 @@ __global__ void row_moments_kernel(const typename Real<R>::complex_t* __restrict
                                    int Zmax, int T, int64_t pitch, int64_t batch_stride,
                                    const CylParams* __restrict__ params, double* __restrict__ S) {
   using C = typename Real<R>::complex_t;
+  __shared__ double red[CYL_MOM_WARPS][CYL_NMOM];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int wpr = moments_warps_per_row(T), rows_per_cta = CYL_MOM_WARPS / wpr;
+  const int row_in_cta = warp / wpr, seg = warp - row_in_cta * wpr;
+  const int i = blockIdx.x * rows_per_cta + row_in_cta;
   const int Z = Zs[b];
-  if (i >= Zmax) return;
-  double* out = S + ((size_t)b * Zmax + i) * CYL_NMOM;
-  if (i >= Z) {
-    if (lane < CYL_NMOM) out[lane] = 0.0;
-    return;
-  }
-  const CylParams p = params[b];
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
-  const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
-  const C* row = psi + (size_t)b * batch_stride + (size_t)i * pitch;
-  const C* rowm = psi + (size_t)b * batch_stride + (size_t)(i == 0 ? Z - 1 : i - 1) * pitch;
+  double* out = (i < Zmax) ? S + ((size_t)b * Zmax + i) * CYL_NMOM : nullptr;
   double m[CYL_NMOM];
 #pragma unroll
   for (int q = 0; q < CYL_NMOM; ++q) m[q] = 0.0;
-  for (int j = lane; j < T; j += 32) {
-    const C pv = row[j], L = rowm[j], W = row[j == 0 ? T - 1 : j - 1];
-    moments_accumulate(m, pv, L, W, inv_lz2, inv_lth2, inv_lth);
+  if (i < Z) {
+    const CylParams p = params[b];
+    const double pi = 3.14159265358979323846;
+    const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
+    const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
+    const C* row = psi + (size_t)b * batch_stride + (size_t)i * pitch;
+    const C* rowm = psi + (size_t)b * batch_stride + (size_t)(i == 0 ? Z - 1 : i - 1) * pitch;
+#pragma unroll 4
+    for (int j = seg * 32 + lane; j < T; j += wpr * 32) {
+      const C pv = row[j], L = rowm[j], W = row[j == 0 ? T - 1 : j - 1];
+      moments_accumulate(m, pv, L, W, inv_lz2, inv_lth2, inv_lth);
+    }
   }
-#pragma unroll
-  for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < CYL_NMOM; ++q) out[q] = m[q];
-  }
+  moments_store(m, wpr, row_in_cta, seg, out, red);          // rows in [Z, Zmax) get zeros
 }
 
 template <typename R>
 static int row_moments(const void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params, double* S,
                        void* stream) {
   CYL_CHECK_ARG(psi && Z && params && S && B > 0 && Zmax > 0 && T > 0, "cyl_row_moments: bad arguments");
-  const int warps = 8;
-  dim3 grid((Zmax + warps - 1) / warps, B);
-  row_moments_kernel<R><<<grid, warps * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T,
-                                                                    (int64_t)T, (int64_t)Zmax * T, params, S);
+  const int rows_per_cta = CYL_MOM_WARPS / moments_warps_per_row(T);
+  dim3 grid((Zmax + rows_per_cta - 1) / rows_per_cta, B);
+  row_moments_kernel<R><<<grid, CYL_MOM_WARPS * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T,
+                                                                            (int64_t)T, (int64_t)Zmax * T, params, S);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

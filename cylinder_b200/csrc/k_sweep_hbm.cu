@@ -909,40 +909,40 @@ template <typename R>
 __global__ void hbm_row_moments_kernel(const typename Real<R>::complex_t* __restrict__ work, int cur,
                                        HbmGeom g, const CylParams* __restrict__ params, double* __restrict__ S) {
   using C = typename Real<R>::complex_t;
+  __shared__ double red[CYL_MOM_WARPS][CYL_NMOM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i >= g.Z) return;
-  const CylParams p = *params;
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / g.Z, lth = (2 * pi * p.radius) / g.T;
-  const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
-  const C* buf = work + (size_t)cur * g.buffer_elems;
-  const int64_t ph = g.pitch / 2;
-  const int64_t Rr = i + g.hr;
+  const int wpr = moments_warps_per_row(g.T), rows_per_cta = CYL_MOM_WARPS / wpr;
+  const int row_in_cta = warp / wpr, seg = warp - row_in_cta * wpr;
+  const int i = blockIdx.x * rows_per_cta + row_in_cta;
   double m[CYL_NMOM];
 #pragma unroll
   for (int q = 0; q < CYL_NMOM; ++q) m[q] = 0.0;
-  for (int j = lane; j < g.T; j += 32) {
-    const int64_t Q = j + g.hc;
-    const C pv = buf[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)];
-    const C Ln = buf[(Q & 1) * g.plane_elems + (Rr - 1) * ph + (Q >> 1)];          // halo rows make i-1 valid at i = 0
-    const C W = buf[((Q - 1) & 1) * g.plane_elems + Rr * ph + ((Q - 1) >> 1)];
-    moments_accumulate(m, pv, Ln, W, inv_lz2, inv_lth2, inv_lth);
+  if (i < g.Z) {
+    const CylParams p = *params;
+    const double pi = 3.14159265358979323846;
+    const double lz = (2 * pi / p.wavenumber) / g.Z, lth = (2 * pi * p.radius) / g.T;
+    const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
+    const C* buf = work + (size_t)cur * g.buffer_elems;
+    const int64_t ph = g.pitch / 2;
+    const int64_t Rr = i + g.hr;
+#pragma unroll 4
+    for (int j = seg * 32 + lane; j < g.T; j += wpr * 32) {
+      const int64_t Q = j + g.hc;
+      const C pv = buf[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)];
+      const C Ln = buf[(Q & 1) * g.plane_elems + (Rr - 1) * ph + (Q >> 1)];          // halo rows make i-1 valid at i = 0
+      const C W = buf[((Q - 1) & 1) * g.plane_elems + Rr * ph + ((Q - 1) >> 1)];
+      moments_accumulate(m, pv, Ln, W, inv_lz2, inv_lth2, inv_lth);
+    }
   }
-#pragma unroll
-  for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < CYL_NMOM; ++q) S[(size_t)i * CYL_NMOM + q] = m[q];
-  }
+  moments_store(m, wpr, row_in_cta, seg, i < g.Z ? S + (size_t)i * CYL_NMOM : nullptr, red);
 }
 
 template <typename R>
 static int hbm_row_moments(const void* work, int cur, int Z, int T, const CylParams* params, double* S, void* stream) {
   CYL_CHECK_ARG(work && (cur == 0 || cur == 1) && params && S && Z >= 8 && T >= 8, "cyl_hbm_row_moments: bad arguments");
   const HbmGeom g = hbm_geom(Z, T);
-  const int warps = 8;
-  hbm_row_moments_kernel<R><<<(Z + warps - 1) / warps, warps * 32, 0, as_stream(stream)>>>(
+  const int rows_per_cta = CYL_MOM_WARPS / moments_warps_per_row(T);
+  hbm_row_moments_kernel<R><<<(Z + rows_per_cta - 1) / rows_per_cta, CYL_MOM_WARPS * 32, 0, as_stream(stream)>>>(
       (const typename Real<R>::complex_t*)work, cur, g, params, S);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
