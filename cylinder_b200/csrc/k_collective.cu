@@ -33,44 +33,83 @@ __device__ __forceinline__ C move_value(const CylMove& m, C v, int i, int j, int
   return v;
 }
 
-// one warp per z-row (as row_moments_kernel, k_energy.cu)
+struct Cplx { double re, im; };
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cplx cexpi(double ph) { Cplx r; sincos(ph, &r.im, &r.re); return r; }
+
+// Rows shared between warps as in row_moments_kernel (k_energy.cu).  The phase of a wave or a twist factorises into a row
+// factor and a column factor exp(i j w); a thread walks its columns with a fixed stride, so it takes the column factor from a
+// recurrence (one complex product per site; at most T / 32 <= 128 steps, error ~1e-14) instead of a sincos per loaded value.
 template <typename R>
 __global__ void move_row_moments_kernel(const typename Real<R>::complex_t* __restrict__ psi, int B, const int32_t* __restrict__ Zs,
                                         int Zmax, int T, const CylParams* __restrict__ params, const CylMove* __restrict__ moves,
                                         double* __restrict__ S) {
   using C = typename Real<R>::complex_t;
+  __shared__ double red[CYL_MOM_WARPS][CYL_NMOM];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int wpr = moments_warps_per_row(T), rows_per_cta = CYL_MOM_WARPS / wpr;
+  const int row_in_cta = warp / wpr, seg = warp - row_in_cta * wpr;
+  const int i = blockIdx.x * rows_per_cta + row_in_cta;
   const int Z = Zs[b];
-  if (i >= Zmax) return;
-  double* out = S + ((size_t)b * Zmax + i) * CYL_NMOM;
-  if (i >= Z) {
-    if (lane < CYL_NMOM) out[lane] = 0.0;
-    return;
-  }
-  const CylParams p = params[b];
-  const CylMove mv = moves[b];
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
-  const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
-  const int im = i == 0 ? Z - 1 : i - 1;
-  const C* row = psi + ((size_t)b * Zmax + i) * T;
-  const C* rowm = psi + ((size_t)b * Zmax + im) * T;
+  double* out = (i < Zmax) ? S + ((size_t)b * Zmax + i) * CYL_NMOM : nullptr;
   double m[CYL_NMOM];
 #pragma unroll
   for (int q = 0; q < CYL_NMOM; ++q) m[q] = 0.0;
-  for (int j = lane; j < T; j += 32) {
-    const int jm = j == 0 ? T - 1 : j - 1;
-    const C pv = move_value(mv, row[j], i, j, Z, T), L = move_value(mv, rowm[j], im, j, Z, T), W = move_value(mv, row[jm], i, jm, Z, T);
-    moments_accumulate(m, pv, L, W, inv_lz2, inv_lth2, inv_lth);
+  if (i < Z) {
+    const CylParams p = params[b];
+    const CylMove mv = moves[b];
+    const double pi = 3.14159265358979323846;
+    const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
+    const double inv_lz2 = 1.0 / (lz * lz), inv_lth2 = 1.0 / (lth * lth), inv_lth = 1.0 / lth;
+    const int im = i == 0 ? Z - 1 : i - 1;
+    const C* row = psi + ((size_t)b * Zmax + i) * T;
+    const C* rowm = psi + ((size_t)b * Zmax + im) * T;
+    const int j0 = seg * 32 + lane, stride = wpr * 32;
+    if (mv.kind == CYL_MOVE_SHIFT) {
+#pragma unroll 4
+      for (int j = j0; j < T; j += stride) {
+        C pv = row[j], L = rowm[j], W = row[j == 0 ? T - 1 : j - 1];
+        pv.x += (R)mv.c_re; pv.y += (R)mv.c_im; L.x += (R)mv.c_re; L.y += (R)mv.c_im; W.x += (R)mv.c_re; W.y += (R)mv.c_im;
+        moments_accumulate(m, pv, L, W, inv_lz2, inv_lth2, inv_lth);
+      }
+    } else {
+      const bool wave = mv.kind == CYL_MOVE_WAVE;
+      const double w = wave ? mv.qth / T : 6.283185307179586476925 / T * (double)mv.n_rot;   // column phase per site
+      const double ph0 = wave ? 0.0 : mv.phase;
+      Cplx cf = cexpi((double)j0 * w + ph0);                    // column factor of the thread's current column
+      const Cplx step = cexpi((double)stride * w), back = cexpi(-w);
+      const Cplx wrap = cexpi((double)(T - 1) * w + ph0);       // column T - 1, the left neighbour of column 0
+      // wave: value + c exp(i i qz / Z) cf;   twist: value * cf on the rows of the block
+      const Cplx c = {mv.c_re, mv.c_im};
+      const Cplx ci = cmul(c, cexpi((double)i * mv.qz / Z)), cm = cmul(c, cexpi((double)im * mv.qz / Z));
+      int d = i - mv.r0, dm = im - mv.r0;
+      if (d < 0) d += Z;
+      if (dm < 0) dm += Z;
+      const bool tw_i = !wave && d < mv.nr, tw_m = !wave && dm < mv.nr;
+#pragma unroll 2
+      for (int j = j0; j < T; j += stride) {
+        C pv = row[j], L = rowm[j], W = row[j == 0 ? T - 1 : j - 1];
+        const Cplx cw = j == 0 ? wrap : cmul(cf, back);
+        if (wave) {
+          const Cplx a = cmul(ci, cf), bq = cmul(cm, cf), cq = cmul(ci, cw);
+          pv.x += (R)a.re; pv.y += (R)a.im; L.x += (R)bq.re; L.y += (R)bq.im; W.x += (R)cq.re; W.y += (R)cq.im;
+        } else {
+          if (tw_i) {
+            const Cplx a = cmul({(double)pv.x, (double)pv.y}, cf), cq = cmul({(double)W.x, (double)W.y}, cw);
+            pv.x = (R)a.re; pv.y = (R)a.im; W.x = (R)cq.re; W.y = (R)cq.im;
+          }
+          if (tw_m) {
+            const Cplx bq = cmul({(double)L.x, (double)L.y}, cf);
+            L.x = (R)bq.re; L.y = (R)bq.im;
+          }
+        }
+        moments_accumulate(m, pv, L, W, inv_lz2, inv_lth2, inv_lth);
+        cf = cmul(cf, step);
+      }
+    }
   }
-#pragma unroll
-  for (int q = 0; q < CYL_NMOM; ++q) m[q] = warp_sum(m[q]);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < CYL_NMOM; ++q) out[q] = m[q];
-  }
+  moments_store(m, wpr, row_in_cta, seg, out, red);          // rows in [Z, Zmax) get zeros
 }
 
 template <typename R>
@@ -98,9 +137,9 @@ static int move_row_moments(const void* psi, int B, const int32_t* Z, int Zmax, 
   int rc = check_moves(psi, B, Z, Zmax, T, moves, "cyl_move_row_moments");
   if (rc) return rc;
   CYL_CHECK_ARG(params && S, "cyl_move_row_moments: bad arguments");
-  const int warps = 8;
-  dim3 grid((Zmax + warps - 1) / warps, B);
-  move_row_moments_kernel<R><<<grid, warps * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params,
+  const int rows_per_cta = CYL_MOM_WARPS / moments_warps_per_row(T);
+  dim3 grid((Zmax + rows_per_cta - 1) / rows_per_cta, B);
+  move_row_moments_kernel<R><<<grid, CYL_MOM_WARPS * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params,
                                                                          moves, S);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
