@@ -308,52 +308,32 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     PHASE_MARK(0);
 
-    // ---- 1. site moves, energy accumulated as bonds become final ----
+    // ---- 1. site moves ----
     int nacc = 0;
     EAcc<R> e = {R(0), R(0), R(0), R(0)};
-    // one site of row i (row = i*T; up / dn = offsets of the rows above / below): the move, then the energy terms this site
-    // closes -- its own, and the bonds to the neighbours flagged in `own` (bit 0: i-1, 1: i+1, 2: j-1, 3: j+1)
-    auto visit = [&](int i, int row, int up, int dn, int j, int jm, int jp, int own) {
+    // one site of row i (row = i*T; up / dn = offsets of the rows above / below)
+    auto visit = [&](int i, int row, int up, int dn, int j, int jm, int jp) {
       const C L = psi[up + j], Rz = psi[dn + j], W = psi[row + jm], E = psi[row + jp];
       C q;
       nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
-      if (extras && SMEM_ENERGY_ON) {
-        const RowW<R> w = roww[i];
-        energy_own<R, C>(e, w, q, measure);
-        if (own & 1) energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, L, measure);
-        if (own & 2) {
-          const int inext = (i == Z - 1 ? 0 : i + 1);
-          energy_zbond<R, C>(e, roww[inext].cur[2], roww[inext].dif[2], Rz, q, measure);
-        }
-        if (own & 4) energy_tbond<R, C>(e, w, q, W, measure);
-        if (own & 8) energy_tbond<R, C>(e, w, E, q, measure);
-      }
     };
     if (mapped && ncol == 2) {
-      // both lengths even: colour = (i + j) & 1; colour 1 closes every bond (all its neighbours are final)
+      // both lengths even: colour = (i + j) & 1
       const int step = RGe * T;
 #pragma unroll 1
       for (int colour = 0; colour < 2; ++colour) {
         if (col_active) {
           const int j = 2 * cj + ((colour + rg) & 1);
           const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-          const int own = colour ? 15 : 0;
           for (int i = rg, row = rg * T; i < Z; i += RGe, row += step)
-            visit(i, row, (i == 0 ? nsite : row) - T, (i == Z - 1 ? 0 : row + T), j, jm, jp, own);
+            visit(i, row, (i == 0 ? nsite : row) - T, (i == Z - 1 ? 0 : row + T), j, jm, jp);
         }
         __syncthreads();
       }
     } else if (mapped) {
       // T even, Z odd: colour = (a(i) + (j & 1)) % 3 with a(i) = i & 1 except a(Z-1) = 2.  Pass 0: even rows (not the last),
       // even columns + the last row, odd columns; pass 1: rows 0..Z-2, the column parity opposite to the row's; pass 2: odd
-      // rows, odd columns + the last row, even columns.  A bond is closed by its later-coloured endpoint.
-      auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
-      auto own_of = [&](int i, int b, int colour) {                       // which bonds a site of row i, column parity b closes
-        const int ai = axis_colour(i, Z);
-        const int aprev = axis_colour(i == 0 ? Z - 1 : i - 1, Z), anext = axis_colour(i == Z - 1 ? 0 : i + 1, Z);
-        const int side = col3(ai + 1 - b) < colour ? 12 : 0;               // both theta neighbours have the other parity
-        return (col3(aprev + b) < colour ? 1 : 0) | (col3(anext + b) < colour ? 2 : 0) | side;
-      };
+      // rows, odd columns + the last row, even columns.
       const int half = (Z - 1) >> 1;
 #pragma unroll 1
       for (int colour = 0; colour < 3; ++colour) {
@@ -363,14 +343,14 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             const int j = 2 * cj + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
             for (int i = rg; i < Z - 1; i += RGe) {
               const int row = i * T;
-              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp, own_of(i, b, 1));
+              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp);
             }
           } else {
             const int b = colour ? 1 : 0;
             const int j = 2 * cj + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
             for (int ii = rg; ii < half; ii += RGe) {
               const int i = 2 * ii + b, row = i * T;                       // even rows in pass 0, odd rows in pass 2
-              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp, own_of(i, b, colour));
+              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp);
             }
           }
         }
@@ -378,7 +358,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const int b = colour ? 0 : 1;                                    // threads have the fewest rows above)
           const int j = 2 * (tid - (SWEEP_NT - Th)) + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
           const int i = Z - 1, row = i * T;
-          visit(i, row, row - T, 0, j, jm, jp, own_of(i, b, colour));
+          visit(i, row, row - T, 0, j, jm, jp);
         }
         __syncthreads();
       }
@@ -394,17 +374,6 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const C L = psi[im + j], Rz = psi[ip + j], W = psi[row + jm], E = psi[row + jp];
           C q;
           nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
-          if (extras && SMEM_ENERGY_ON) {
-            const RowW<R> w = roww[i];
-            energy_own<R, C>(e, w, q, measure);
-            if (colour == 1) {                                             // all four neighbours are final
-              const int inext = (i == Z - 1 ? 0 : i + 1);
-              energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, L, measure);
-              energy_zbond<R, C>(e, roww[inext].cur[2], roww[inext].dif[2], Rz, q, measure);
-              energy_tbond<R, C>(e, w, q, W, measure);
-              energy_tbond<R, C>(e, w, E, q, measure);
-            }
-          }
           jj += dj; i += di;
           if (jj >= Th) { jj -= Th; ++i; }
         }
@@ -434,16 +403,6 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             const C L = psi[iprev * T + j], Rz = psi[inext * T + j], W = psi[row + jm], E = psi[row + jp];
             C q;
             nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
-            if (extras && SMEM_ENERGY_ON) {
-              const RowW<R> w = roww[i];
-              energy_own<R, C>(e, w, q, measure);
-              // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
-              auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
-              if (col3(axis_colour(iprev, Z) + beta) < colour) energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, L, measure);
-              if (col3(axis_colour(inext, Z) + beta) < colour) energy_zbond<R, C>(e, roww[inext].cur[2], roww[inext].dif[2], Rz, q, measure);
-              if (col3(ai + axis_colour(jm, T)) < colour) energy_tbond<R, C>(e, w, q, W, measure);
-              if (col3(ai + axis_colour(jp, T)) < colour) energy_tbond<R, C>(e, w, E, q, measure);
-            }
           }
           jj += dj; ii += di;
           if (jj >= Th) { jj -= Th; ++ii; }
@@ -452,6 +411,42 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       }
     }
     PHASE_MARK(1);
+
+    // ---- 1b. field energy of the swept lattice under the current weights and its change under the proposal's: every site's
+    //          own terms and its bonds to the row above and to the column on its left (each bond once).  A separate pass over
+    //          the final field costs fewer instructions than closing bonds inside the colour passes, where the bookkeeping of
+    //          who closes which bond is per site (and divergent with three colours). ----
+    if (extras && SMEM_ENERGY_ON) {
+      if (mapped) {
+        if (col_active) {
+          struct __align__(16) Pair { C a, b; };
+          const int j0 = 2 * cj, jw = (j0 == 0 ? T : j0) - 1, step = RGe * T;
+          for (int i = rg, row = rg * T; i < Z; i += RGe, row += step) {
+            const int up = (i == 0 ? nsite : row) - T;
+            const RowW<R> w = roww[i];
+            const Pair q = *reinterpret_cast<const Pair*>(psi + row + j0), l = *reinterpret_cast<const Pair*>(psi + up + j0);
+            const C wl = psi[row + jw];
+            energy_own<R, C>(e, w, q.a, measure);
+            energy_own<R, C>(e, w, q.b, measure);
+            energy_zbond<R, C>(e, w.cur[2], w.dif[2], q.a, l.a, measure);
+            energy_zbond<R, C>(e, w.cur[2], w.dif[2], q.b, l.b, measure);
+            energy_tbond<R, C>(e, w, q.a, wl, measure);
+            energy_tbond<R, C>(e, w, q.b, q.a, measure);
+          }
+        }
+      } else {
+        for (int i = warp; i < Z; i += SWEEP_NWARP) {                      // T odd or wide: a warp per row
+          const int row = i * T, up = (i == 0 ? nsite : row) - T;
+          const RowW<R> w = roww[i];
+          for (int j = lane; j < T; j += 32) {
+            const C q = psi[row + j], l = psi[up + j], wl = psi[row + (j == 0 ? T : j) - 1];
+            energy_own<R, C>(e, w, q, measure);
+            energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, l, measure);
+            energy_tbond<R, C>(e, w, q, wl, measure);
+          }
+        }
+      }
+    }
 
     // ---- 2. reduction: sums within a warp (working precision), the eight partials are added by whoever needs them ----
     {
