@@ -41,7 +41,7 @@ PER_SWEEP = "site moves + Robbins-Monro + row moments/measure + 1 amplitude move
 CPU_SAMPLE = ("%d replicas of the same grid, one per host core, whole sweeps of the reference algorithm (Z*T random-site proposals "
               "with per-proposal Robbins-Monro + 1 amplitude move + 1 measurement per sweep)")
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
-NCU_HBM_TRAFFIC_BYTES = 135.623e6 + 84.894e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_c.md)
+NCU_HBM_TRAFFIC_BYTES = 135.682e6 + 87.291e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_d.md)
 
 
 def grid_params(n_replicas, replica0=0):
@@ -334,7 +334,7 @@ def main():
         achieved = upd * ALG_BYTES_PER_UPDATE_F32 / (ms_hbm * 1e-3) / 1e9
         traffic = NCU_HBM_TRAFFIC_BYTES if (n == 4096) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_ncu_full_c.md "
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_ncu_full_d.md "
                                       "(below the 24 B/update algorithmic figure: the kernel updates all colours per pass, 8.1 B read + "
                                       "8 B written per site; part of the writes is still dirty in the 126 MB L2 when the kernel ends)",
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE_F32 * n * n,

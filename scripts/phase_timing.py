@@ -2,6 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from cylinder_b200 import _abi
+if os.environ.get("CYL_LIB"):
+    _abi.LIB_PATH = os.path.abspath(os.environ["CYL_LIB"])
 from cylinder_b200.replicas import ReplicaBatch
 import bench
 dev = torch.device("cuda", 0)
