@@ -29,6 +29,29 @@ __host__ __device__ __forceinline__ double surface_area_integral(double k, doubl
   return 4.0 * ra / k * ellipe_agm(-(t * t));
 }
 
+#ifdef __CUDACC__
+// The same for the sweep kernels, where one warp evaluates the proposal's surface energy every sweep and the chain of IEEE
+// square roots and divisions is the critical path of that phase: square roots from the MUFU seed + Newton steps (fast_rsqrt,
+// ~2e-16 relative), the convergence test before the next square root.  The API entry points keep the IEEE version.
+__device__ __forceinline__ double surface_area_integral_fast(double k, double r, double a) {
+  const double ra = fast_radius_rescaled(r, a);
+  const double t = a * ra * k;
+  const double x0 = fma(t, t, 1.0);                             // 1 - m
+  double a0 = 1.0, b0 = x0 * fast_rsqrt(x0);
+  double c2sum = 0.5 * (a0 * a0 - b0 * b0), pw = 0.5;
+  for (int it = 0; it < 40; ++it) {
+    const double an = 0.5 * (a0 + b0), cn = 0.5 * (a0 - b0);
+    pw *= 2.0;
+    c2sum += pw * cn * cn;
+    if (fabs(cn) < 1e-17 * fabs(an)) { a0 = an; break; }
+    const double ab = a0 * b0;
+    b0 = ab * fast_rsqrt(ab);
+    a0 = an;
+  }
+  return 4.0 * ra * fast_rcp(k) * (3.14159265358979323846 * 0.5 * fast_rcp(a0) * (1.0 - c2sum));
+}
+#endif
+
 // calc_bending_energy  system_cylinder.py:108-117, evaluated cooperatively by one warp (all lanes return it).
 __device__ __forceinline__ double bending_energy_warp(double k, double r, double H0, double a) {
   const double ra = geo_radius_rescaled(r, a);
@@ -59,7 +82,8 @@ __device__ __forceinline__ double bending_energy_warp(double k, double r, double
 __device__ __forceinline__ double surface_energy_warp(const CylParams& p, double a, double* area_out = nullptr,
                                                       double* bend_out = nullptr, bool skip_zero_kappa = false) {
   const double gamma_eff = p.gamma + p.kappa / 2.0 * p.intrinsic_curvature * p.intrinsic_curvature;
-  const double area = surface_area_integral(p.wavenumber, p.radius, a);
+  const double area = skip_zero_kappa ? surface_area_integral_fast(p.wavenumber, p.radius, a)      // sweep kernels
+                                      : surface_area_integral(p.wavenumber, p.radius, a);
   double bend = 0.0;
   if (!(skip_zero_kappa && p.kappa == 0.0)) bend = bending_energy_warp(p.wavenumber, p.radius, p.intrinsic_curvature, a);
   if (area_out) *area_out = area;
