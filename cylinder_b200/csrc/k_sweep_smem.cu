@@ -312,10 +312,13 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     int nacc = 0;
     EAcc<R> e = {R(0), R(0), R(0), R(0)};
     // one site of row i (row = i*T; up / dn = offsets of the rows above / below)
-    auto visit = [&](int i, int row, int up, int dn, int j, int jm, int jp) {
-      const C L = psi[up + j], Rz = psi[dn + j], W = psi[row + jm], E = psi[row + jp];
+    // (mapped loops) `o` points at the site, the neighbours sit at element offsets oL / oR (rows above / below, periodic) and
+    // oW / oE (columns left / right, fixed per thread and pass); a thread walks down its rows by advancing o, the coefficient
+    // pointer and the Philox site counter by constants
+    auto visit = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rc, uint32_t site) {
+      const C L = o[oL], Rz = o[oR], W = o[oW], E = o[oE];
       C q;
-      nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
+      nacc += site_move<R, C>(o, 0, L, Rz, W, E, *rc, sigma, site, c1, stream.key, q);
     };
     if (mapped && ncol == 2) {
       // both lengths even: colour = (i + j) & 1
@@ -324,9 +327,12 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       for (int colour = 0; colour < 2; ++colour) {
         if (col_active) {
           const int j = 2 * cj + ((colour + rg) & 1);
-          const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-          for (int i = rg, row = rg * T; i < Z; i += RGe, row += step)
-            visit(i, row, (i == 0 ? nsite : row) - T, (i == Z - 1 ? 0 : row + T), j, jm, jp);
+          const int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+          C* o = psi + rg * T + j;
+          const RowCoef<R>* rc = coef + rg;
+          uint32_t site = (uint32_t)(rg * T + j);
+          for (int i = rg; i < Z; i += RGe, o += step, rc += RGe, site += (uint32_t)step)
+            visit(o, (i == 0 ? nsite : 0) - T, (i == Z - 1 ? -nsite : 0) + T, oW, oE, rc, site);
         }
         __syncthreads();
       }
@@ -340,25 +346,29 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         if (col_active) {
           if (colour == 1) {
             const int b = (rg & 1) ? 0 : 1;                                // rows keep their parity: the step is even
-            const int j = 2 * cj + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-            for (int i = rg; i < Z - 1; i += RGe) {
-              const int row = i * T;
-              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp);
-            }
+            const int j = 2 * cj + b, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            const int step = RGe * T;
+            C* o = psi + rg * T + j;
+            const RowCoef<R>* rc = coef + rg;
+            uint32_t site = (uint32_t)(rg * T + j);
+            for (int i = rg; i < Z - 1; i += RGe, o += step, rc += RGe, site += (uint32_t)step)
+              visit(o, (i == 0 ? nsite : 0) - T, T, oW, oE, rc, site);
           } else {
             const int b = colour ? 1 : 0;
-            const int j = 2 * cj + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-            for (int ii = rg; ii < half; ii += RGe) {
-              const int i = 2 * ii + b, row = i * T;                       // even rows in pass 0, odd rows in pass 2
-              visit(i, row, (i == 0 ? nsite : row) - T, row + T, j, jm, jp);
-            }
+            const int j = 2 * cj + b, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            const int step = 2 * RGe * T;                                  // even rows in pass 0, odd rows in pass 2
+            C* o = psi + (2 * rg + b) * T + j;
+            const RowCoef<R>* rc = coef + (2 * rg + b);
+            uint32_t site = (uint32_t)((2 * rg + b) * T + j);
+            for (int ii = rg; ii < half; ii += RGe, o += step, rc += 2 * RGe, site += (uint32_t)step)
+              visit(o, (ii == 0 && b == 0 ? nsite : 0) - T, T, oW, oE, rc, site);
           }
         }
         if (colour != 1 && tid >= SWEEP_NT - Th) {                         // the last row, from the top of the CTA (those
           const int b = colour ? 0 : 1;                                    // threads have the fewest rows above)
-          const int j = 2 * (tid - (SWEEP_NT - Th)) + b, jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
-          const int i = Z - 1, row = i * T;
-          visit(i, row, row - T, 0, j, jm, jp);
+          const int j = 2 * (tid - (SWEEP_NT - Th)) + b, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+          const int row = (Z - 1) * T;
+          visit(psi + row + j, -T, -row, oW, oE, coef + (Z - 1), (uint32_t)(row + j));
         }
         __syncthreads();
       }
