@@ -156,7 +156,7 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
 // one site move; returns the accept flag, `q` = the site's value after the move
 template <typename R, typename C>
 __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz, const C W, const C E, const RowCoef<R>& rc,
-                                          R sigma, uint32_t site, uint32_t c1, uint32_t key, C& q) {
+                                          R sigma, uint32_t site, uint32_t c1, uint32_t key, C& q, int& nacc) {
   const C pv = psi[idx];
   const uint2 x = philox2x32_10(site, c1, key);
   R zre, zim;
@@ -165,8 +165,8 @@ __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz
   const R dre = w * zre, dim = w * zim;
   const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
   const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-  q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
-  if (acc) psi[idx] = q;
+  q = pv;
+  if (acc) { q = Real<R>::make(pv.x + dre, pv.y + dim); psi[idx] = q; ++nacc; }
   return acc;
 }
 
@@ -318,7 +318,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     auto visit = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rc, uint32_t site) {
       const C L = o[oL], Rz = o[oR], W = o[oW], E = o[oE];
       C q;
-      nacc += site_move<R, C>(o, 0, L, Rz, W, E, *rc, sigma, site, c1, stream.key, q);
+      site_move<R, C>(o, 0, L, Rz, W, E, *rc, sigma, site, c1, stream.key, q, nacc);
     };
     if (mapped && ncol == 2) {
       // both lengths even: colour = (i + j) & 1
@@ -383,7 +383,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
           const C L = psi[im + j], Rz = psi[ip + j], W = psi[row + jm], E = psi[row + jp];
           C q;
-          nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
+          site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q, nacc);
           jj += dj; i += di;
           if (jj >= Th) { jj -= Th; ++i; }
         }
@@ -412,7 +412,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             const int jm = (j == 0 ? T : j) - 1, jp = (j == T - 1 ? 0 : j + 1);
             const C L = psi[iprev * T + j], Rz = psi[inext * T + j], W = psi[row + jm], E = psi[row + jp];
             C q;
-            nacc += site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q);
+            site_move<R, C>(psi, row + j, L, Rz, W, E, coef[i], sigma, (uint32_t)(row + j), c1, stream.key, q, nacc);
           }
           jj += dj; ii += di;
           if (jj >= Th) { jj -= Th; ++ii; }
