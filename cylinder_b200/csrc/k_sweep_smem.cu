@@ -430,18 +430,16 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       if (mapped) {
         if (col_active) {
           struct __align__(16) Pair { C a, b; };
-          const int j0 = 2 * cj, jw = (j0 == 0 ? T : j0) - 1, step = RGe * T;
-          for (int i = rg, row = rg * T; i < Z; i += RGe, row += step) {
-            const int up = (i == 0 ? nsite : row) - T;
-            const RowW<R> w = roww[i];
-            const Pair q = *reinterpret_cast<const Pair*>(psi + row + j0), l = *reinterpret_cast<const Pair*>(psi + up + j0);
-            const C wl = psi[row + jw];
-            energy_own<R, C>(e, w, q.a, measure);
-            energy_own<R, C>(e, w, q.b, measure);
-            energy_zbond<R, C>(e, w.cur[2], w.dif[2], q.a, l.a, measure);
-            energy_zbond<R, C>(e, w.cur[2], w.dif[2], q.b, l.b, measure);
-            energy_tbond<R, C>(e, w, q.a, wl, measure);
-            energy_tbond<R, C>(e, w, q.b, q.a, measure);
+          const int j0 = 2 * cj, oW = (j0 == 0 ? T : 0) - 1, step = RGe * T;
+          const C* o = psi + rg * T + j0;                                  // walks down the thread's rows, as in the site loops
+          const RowW<R>* pw = roww + rg;
+          int oL = (rg == 0 ? nsite : 0) - T;                              // periodic wrap upwards: first row of group 0 only
+          for (int i = rg; i < Z; i += RGe, o += step, pw += RGe) {
+            const RowW<R> w = *pw;
+            const Pair q = *reinterpret_cast<const Pair*>(o), l = *reinterpret_cast<const Pair*>(o + oL);
+            const C wl = o[oW];
+            oL = -T;
+            energy_pair<R, C>(e, w, q.a, q.b, l.a, l.b, wl, measure);
           }
         }
       } else {
