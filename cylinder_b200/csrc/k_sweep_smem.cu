@@ -23,6 +23,7 @@
 //   5. with CYL_SWEEP_MEASURE and a profile buffer: row sums of Lattice.measure (:121-131), one thread per row.
 // The replicas are the (alpha, C, n, kappa, k) parameter grid that scripts/taskarray.sh farms out as separate CPU
 // jobs in the reference.
+#include <type_traits>
 #include "cyl_common.cuh"
 #include "cyl_energy.cuh"
 #include "cyl_site.cuh"
@@ -434,13 +435,17 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const C* o = psi + rg * T + j0;                                  // walks down the thread's rows, as in the site loops
           const RowW<R>* pw = roww + rg;
           int oL = (rg == 0 ? nsite : 0) - T;                              // periodic wrap upwards: first row of group 0 only
-          for (int i = rg; i < Z; i += RGe, o += step, pw += RGe) {
-            const RowW<R> w = *pw;
-            const Pair q = *reinterpret_cast<const Pair*>(o), l = *reinterpret_cast<const Pair*>(o + oL);
-            const C wl = o[oW];
-            oL = -T;
-            energy_pair<R, C>(e, w, q.a, q.b, l.a, l.b, wl, measure);
-          }
+          auto rows = [&](auto meas) {                                     // the measurement terms compiled in or out
+#pragma unroll 1
+            for (int i = rg; i < Z; i += RGe, o += step, pw += RGe) {
+              const RowW<R> w = *pw;
+              const Pair q = *reinterpret_cast<const Pair*>(o), l = *reinterpret_cast<const Pair*>(o + oL);
+              const C wl = o[oW];
+              oL = -T;
+              energy_pair<R, C>(e, w, q.a, q.b, l.a, l.b, wl, decltype(meas)::value);
+            }
+          };
+          if (measure) rows(std::true_type{}); else rows(std::false_type{});
         }
       } else {
         for (int i = warp; i < Z; i += SWEEP_NWARP) {                      // T odd or wide: a warp per row
