@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include "cyl_common.cuh"
 #include "cyl_energy.cuh"
 #include "cyl_site.cuh"
@@ -429,7 +430,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     static_assert(TW == 128 && HBM_NT % 64 == 0 && ((HBM_NT / 64) & 1) == 0, "thread mapping assumes 64 columns per plane row");
     constexpr int RSTEP = HBM_NT / 64;
     // one site move; `counted` = the site belongs to this tile's interior (not a redundantly recomputed halo site)
-    auto move = [&](C* own, const C* oth, int r, uint32_t site, bool counted, int c) {
+    auto move = [&](auto MEAS, C* own, const C* oth, int r, uint32_t site, bool counted, int c) {
+      constexpr bool meas = decltype(MEAS)::value;                // the measurement terms compiled in or out
       const RowCoef<R> rc = coef[r];
       const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
       const uint2 x = philox2x32_10(site, c1, kc, kr);
@@ -458,6 +460,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       if (border) { gi = wrapi(gi, g.Z); gj = wrapi(gj, g.T); }  // past Z + halo only in partial tiles: never stored
       return (uint32_t)(gi * g.T + gj);
     };
+    auto passes = [&](auto MEAS) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int m = c + 1;                                       // rows [m, SH - m)
@@ -469,20 +472,22 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       if (!border) {
         uint32_t site = site_id(r, q);
         for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, site += RSTEP * g.T)
-          move(own, oth, r, site, c == 1 || (r != 1 && r != SH - 2), c);
+          move(MEAS, own, oth, r, site, c == 1 || (r != 1 && r != SH - 2), c);
       } else {
         for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH)
-          move(own, oth, r, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T, c);
+          move(MEAS, own, oth, r, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T, c);
       }
       if (c == 0 && tid >= HBM_NT - (SH - 2)) {
         // the 65th colour-0 site of each row of the grown region: halo column q = HS - 1 (odd rows) or HS + TW (even rows)
         const int r1 = 1 + (tid - (HBM_NT - (SH - 2))), q1 = (r1 & 1) ? HS - 1 : HS + TW;
         const int p1 = q1 & 1;
-        move(pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), r1, site_id(r1, q1), false, 0);
+        move(MEAS, pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), r1, site_id(r1, q1), false, 0);
       }
       if (c == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
       __syncthreads();
     }
+    };
+    if (EXTRAS && meas) passes(std::true_type{}); else passes(std::false_type{});
   } else {
     // odd periodic ring(s): 3 colours, colour = (a(i) + a(j)) % 3.  In pass c a row of axis colour a(i) holds the sites whose
     // column has axis colour (c - a(i)) mod 3: every other column (or, for colour 2, only the odd ring's last column).  A warp
