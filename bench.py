@@ -41,7 +41,7 @@ PER_SWEEP = "site moves + Robbins-Monro + row moments/measure + 1 amplitude move
 CPU_SAMPLE = ("%d replicas of the same grid, one per host core, whole sweeps of the reference algorithm (Z*T random-site proposals "
               "with per-proposal Robbins-Monro + 1 amplitude move + 1 measurement per sweep)")
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
-NCU_HBM_TRAFFIC_BYTES = 135.622e6 + 84.858e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_d.md)
+NCU_HBM_TRAFFIC_BYTES = 135.629e6 + 87.912e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_d.md)
 
 
 def grid_params(n_replicas, replica0=0):
