@@ -23,6 +23,7 @@
 //   5. with CYL_SWEEP_MEASURE and a profile buffer: row sums of Lattice.measure (:121-131), one thread per row.
 // The replicas are the (alpha, C, n, kappa, k) parameter grid that scripts/taskarray.sh farms out as separate CPU
 // jobs in the reference.
+#include <cstdlib>
 #include <type_traits>
 #include "cyl_common.cuh"
 #include "cyl_energy.cuh"
@@ -59,6 +60,7 @@ struct SmemScalars {
 #else
 #define SMEM_WEIGHTS_ON true
 #endif
+#define SWEEP_FLAG_LONGEST_FIRST 0x80000000u   // set by the launcher, not part of the ABI: see the kernel prologue
 #define AMP_CHUNK 64                // amplitude-move draws are precomputed for this many sweeps at a time
 
 // sin/cos(k z) at z_i and z_{i-1/2}
@@ -195,8 +197,55 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   double* scr = reinterpret_cast<double*>(smem_raw + lay.off_scr);
   SmemScalars* sc = reinterpret_cast<SmemScalars*>(smem_raw + lay.off_sc);
 
-  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int b = blockIdx.x;
+  if (flags & SWEEP_FLAG_LONGEST_FIRST) {
+    // Blocks are dispatched in index order and a replica's run time grows with its row count, so block j takes the replica
+    // of rank j in descending row count (ties in index order): the replicas still running when the grid drains are the
+    // short ones.  Every CTA finds its replica by itself -- a histogram of Z, then the k-th replica of its bin -- in scratch
+    // borrowed from the lattice region; no buffer, no extra launch, and the results do not depend on the assignment.
+    int* hist = reinterpret_cast<int*>(smem_raw);                          // (Zmax + 1) ints <= Zmax * T * sizeof(C)
+    int* res = reinterpret_cast<int*>(scr);                                // [0] bin, [1] rank inside the bin, [2] replica, [8..15] warp sums
+    for (int z = tid; z <= Zmax; z += SWEEP_NT) hist[z] = 0;
+    __syncthreads();
+    for (int r = tid; r < B; r += SWEEP_NT) atomicAdd(&hist[min(max(Zs[r], 0), Zmax)], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int cum = 0, z = Zmax;
+      for (; z > 0; --z) {
+        if (cum + hist[z] > (int)blockIdx.x) break;
+        cum += hist[z];
+      }
+      res[0] = z; res[1] = (int)blockIdx.x - cum; res[2] = (int)blockIdx.x;
+    }
+    __syncthreads();
+    const int zbin = res[0], k = res[1];
+    const int chunk = (B + SWEEP_NT - 1) / SWEEP_NT, r0 = min(B, tid * chunk), r1 = min(B, r0 + chunk);
+    int cnt = 0;
+    for (int r = r0; r < r1; ++r) cnt += (min(max(Zs[r], 0), Zmax) == zbin);
+    int incl = cnt;                                                        // inclusive scan over the CTA
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) res[8 + warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += res[8 + w];
+    const int excl = before + incl - cnt;
+    if (k >= excl && k < excl + cnt) {
+      int c = excl;
+      for (int r = r0; r < r1; ++r)
+        if (min(max(Zs[r], 0), Zmax) == zbin) {
+          if (c == k) { res[2] = r; break; }
+          ++c;
+        }
+    }
+    __syncthreads();
+    b = res[2];
+    __syncthreads();                                                       // the scratch is reused below
+  }
   const int Z = Zs[b];
   const int nsite = Z * T;
   const CylParams p = params[b];
@@ -634,6 +683,12 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
   auto kern = !extras ? sweep_smem_kernel<R, false, false> : (series ? sweep_smem_kernel<R, true, true> : sweep_smem_kernel<R, true, false>);
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const PhiloxKeys keys = philox_expand(seed);
+  // longest-first assignment pays when the grid runs in several waves and a CTA lives long enough to amortise the search
+  int sms = 0;
+  CYL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  flags &= ~SWEEP_FLAG_LONGEST_FIRST;
+  const char* lf = getenv("CYL_SMEM_LONGEST_FIRST");                        // "0": keep the index order (tests compare the two)
+  if (B > 8 * sms && nsweeps >= 32 && !(lf && lf[0] == '0')) flags |= SWEEP_FLAG_LONGEST_FIRST;
   kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,
                                                       seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, series);
   CYL_LAUNCH_CHECK();

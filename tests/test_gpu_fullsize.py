@@ -115,6 +115,35 @@ def test_c3_batch_is_independent_of_batching(cuda):
     assert int(full.Z_host.min()) == 40 and int(full.Z_host.max()) == 100 and (full.Z_host % 2 == 1).any()
 
 
+def test_c3_longest_first_assignment_changes_nothing(cuda, monkeypatch):
+    """A launch of many replicas and >= 32 sweeps hands the replicas to the CTAs in descending row count (the kernel's own
+    ranking of Z); CYL_SMEM_LONGEST_FIRST=0, a small shard or a short launch keep the index order.  Same results either
+    way, replica by replica -- lattice, chain, observables and profiles each in the replica's own slot."""
+    import sys, os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from cylinder_b200.replicas import ReplicaBatch
+    B = 2000                                                             # > 8 x SM count: ranked launch
+    ranked = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11)
+    ranked.run(40)
+    monkeypatch.setenv("CYL_SMEM_LONGEST_FIRST", "0")
+    plain = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11)
+    plain.run(40)
+    monkeypatch.delenv("CYL_SMEM_LONGEST_FIRST")
+    assert torch.equal(ranked.psi, plain.psi) and torch.equal(ranked.chain, plain.chain)
+    assert torch.equal(ranked.obs, plain.obs) and torch.equal(ranked.prof, plain.prof)
+    short = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11)
+    short.run(20); short.run(20)                                         # short launches: index order; same chains
+    assert torch.equal(ranked.psi, short.psi) and torch.equal(ranked.chain[:, :3], short.chain[:, :3])
+    lo, hi = 700, 900                                                    # a shard below the threshold, long launch
+    shard = ReplicaBatch(bench.grid_params(hi - lo, lo), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11, replica0=lo)
+    shard.run(40)
+    assert torch.equal(shard.psi, ranked.psi[lo:hi, :shard.Zmax]) and torch.equal(shard.chain, ranked.chain[lo:hi])
+    assert torch.equal(shard.obs, ranked.obs[lo:hi])
+    assert len(set(ranked.Z_host.tolist())) > 8                          # ragged: the ranking is not the identity
+
+
 def test_c3_energy_bookkeeping(cuda):
     """The field energy recorded by the fused in-kernel accumulation equals an independent evaluation (row moments +
     weights) of the lattice the kernel leaves behind, for every replica of a C3-like batch (fp32 storage, <= 2e-5)."""
