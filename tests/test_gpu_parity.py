@@ -538,3 +538,53 @@ def test_hbm_thin_last_tile_matches_oracle(cuda, Z, T):
             cb.sweep(st, a, 123, 1, s)
         np.testing.assert_allclose(ws.unpack().cpu().numpy(), st.psi, rtol=0, atol=1e-11)
         assert chain[0, _abi.CH_SITE_ACCEPTED].item() == st.accepted
+
+
+@pytest.mark.parametrize("T", [50, 600, 1100, 2050])
+def test_row_moments_long_rows_match_torch(cuda, T):
+    """Row moments (cyl_energy.cuh: S1..S5, sum |psi|, sum psi) on rows long enough that 2, 4 or 8 warps share a row, for the
+    packed kernel, the plane-split (HBM workspace) kernel and the whole-lattice-move kernel with a plane wave: all three against
+    the same sums taken in torch fp64.  Odd column counts (2050 / 2 planes, 1100) and a ragged batch included."""
+    import math
+    import torch
+    from cylinder_b200 import ops
+    Zs = [9, 6]
+    P = dict(radius=1.2, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-.7, u=1.1, C=.8, n=2, temperature=.1)
+    ks = [1.0, .8]
+    par = ops.make_params(cuda, wavenumber=ks, **P)
+    g = torch.Generator(device="cpu").manual_seed(T)
+    psi = torch.zeros(2, 9, T, dtype=torch.complex128)
+    for b, z in enumerate(Zs):
+        psi[b, :z] = torch.complex(torch.randn(z, T, generator=g, dtype=torch.float64), torch.randn(z, T, generator=g, dtype=torch.float64)) * .4
+    psi = psi.to(cuda)
+    Zt = torch.tensor(Zs, dtype=torch.int32, device=cuda)
+
+    def expect(field, b):
+        z = Zs[b]
+        f = field[b, :z]
+        lz = (2 * math.pi / ks[b]) / z
+        lth = (2 * math.pi * P["radius"]) / T
+        dz = (f - torch.roll(f, 1, 0)) / lz
+        dth = (f - torch.roll(f, 1, 1)) / lth
+        p2 = f.real ** 2 + f.imag ** 2
+        cols = [p2, p2 ** 2, dz.real ** 2 + dz.imag ** 2, dth.real ** 2 + dth.imag ** 2, (f.conj() * dth).imag, p2.sqrt(), f.real, f.imag]
+        return torch.stack([c.sum(1) for c in cols], 1)
+
+    S = ops.row_moments(psi, Zt, par)
+    for b, z in enumerate(Zs):
+        torch.testing.assert_close(S[b, :z], expect(psi, b), rtol=1e-11, atol=1e-11)
+        assert (S[b, z:] == 0).all()
+    # plane wave added on the fly: same moments as those of the explicitly transformed field
+    qz, qth, c = 2 * math.pi, 6 * math.pi, .07 - .02j
+    moves = ops.make_moves(cuda, [ops.MOVE_WAVE, ops.MOVE_WAVE], B=2, c=[c, c], qz=[qz, qz], qth=[qth, qth])
+    Sm = ops.move_row_moments(psi, Zt, par, moves)
+    moved = psi.clone()
+    for b, z in enumerate(Zs):
+        i = torch.arange(z, device=cuda, dtype=torch.float64)[:, None]
+        j = torch.arange(T, device=cuda, dtype=torch.float64)[None, :]
+        moved[b, :z] += c * torch.exp(1j * (i * qz / z + j * qth / T))
+        torch.testing.assert_close(Sm[b, :z], expect(moved, b), rtol=1e-10, atol=1e-10)
+    if T % 2 == 0 and T >= 8:
+        ws = ops.HbmWorkspace(Zs[0], T, torch.complex128, cuda)
+        ws.pack(psi[0].contiguous())
+        torch.testing.assert_close(ws.row_moments(par[0:1]), expect(psi, 0), rtol=1e-11, atol=1e-11)
