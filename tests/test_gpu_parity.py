@@ -177,7 +177,7 @@ def test_smem_sweep_f64_matches_oracle(cuda, Z, T, variant, a, temp):
 def test_smem_sweep_with_amplitude_moves_matches_oracle(cuda, variant, Z, T):
     """Sweeps + global amplitude moves + measurement, fp64, vs the oracle: same amplitude trajectory end point,
     same accept counts, energies within 1e-10.  Sizes cover the column-mapped 2- and 3-colour site loops (T even) and the
-    generic ones (T odd): the energy is accumulated site by site inside those loops."""
+    generic ones (T odd), and with them the two forms of the energy pass that follows the colour passes (column pairs / a warp per row)."""
     import torch
     from cylinder_b200 import ops, _abi
     P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.3, intrinsic_curvature=0.2, alpha=-.8, u=1.2, C=.9, n=3, temperature=.3)
