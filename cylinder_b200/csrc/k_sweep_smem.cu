@@ -7,13 +7,15 @@
 //      the row weights of the field energy for a' are built one row per thread (fp64, fast reciprocals; those for the
 //      current amplitude are in place since the last accepted move) while warp 7 evaluates E_surf(a');
 //   1. site moves (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once; draws from
-//      Philox2x32-10 at counter (site, sweep) -- stateless, so a sweep can be re-run or resumed bit-identically.  The
-//      ENERGY is accumulated in the same pass: a site adds its own |psi|^2, |psi|^4 terms when it is finalised, and a
-//      bond (|dz|^2, |dth|^2, Im(conj(psi) dth)) is added by whichever endpoint is finalised LATER
-//      (its neighbour has the lower colour), dotted with the row weights for a and for (a' - a): the energy change of
-//      the amplitude move is accumulated directly, not as a difference of two large sums, and no second pass over the
-//      lattice is needed.  For even T the loops are column-mapped: a thread keeps its column pair and walks the rows with an
-//      even stride, so colour parity, theta wrap and addresses are loop constants (2 and 3 colours);
+//      Philox2x32-10 at counter (site, sweep) -- stateless, so a sweep can be re-run or resumed bit-identically.  For even T
+//      the loops are column-mapped: a thread keeps its column pair and walks down the rows with an even stride, so colour
+//      parity, theta wrap and the neighbour offsets are loop constants and site pointer, coefficient pointer and Philox
+//      counter advance by constants (2 and 3 colours);
+//  1b. the ENERGY pass over the swept lattice: per column pair the five moments (|psi|^2, |psi|^4, |dz|^2, |dth|^2,
+//      Im(conj(psi) dth)) of the two sites with their bonds upwards and to the left, dotted with the row
+//      weights for a and for (a' - a) -- the energy change of the amplitude move is accumulated directly, not as a difference
+//      of two large sums.  (Closing each bond inside the colour passes, by its later-finalised endpoint, saved the second
+//      pass over shared memory but cost more instructions: per-site bookkeeping, divergent with three colours.)
 //   2. warp-level sums of {accepts, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|}; the 8 partials are added by the
 //      threads that need them;
 //   3. on three threads of different warps: Robbins-Monro on sigma_site (On_lattice_simple.py:688-696, batched; cyl_site.cuh),
