@@ -876,7 +876,8 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
   const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
   double c_cur = 0.0, c_dif = 0.0;
   if (i < Z) {
-    // same arithmetic as the shared-memory kernel's weights phase
+    // same arithmetic as the shared-memory kernel's weights phase (k_sweep_smem.cu:row_weights): both weights are rounded to the
+    // working precision first, so the chain samples the model with the rounded weights on both paths
     const double ra = fast_radius_rescaled(p.radius, a), rn = try_move ? fast_radius_rescaled(p.radius, a_new) : ra;
     const int ip = (i + 1 == Z) ? 0 : i + 1;
     double s0, c0, sm, cm;
@@ -890,7 +891,10 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
     const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
     RowW<R> w;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) { w.cur[q] = (R)(Wc[q] * fold[q]); w.dif[q] = (R)((Wn[q] - Wc[q]) * fold[q]); }
+    for (int q = 0; q < 5; ++q) {                 // dif = difference of the two ROUNDED weights, as in k_sweep_smem.cu:row_weights
+      w.cur[q] = (R)(Wc[q] * fold[q]);
+      w.dif[q] = (R)(Wn[q] * fold[q]) - w.cur[q];
+    }
     w.pad[0] = w.pad[1] = R(0);
     roww[i] = w;
     c_cur = Wc[5];
