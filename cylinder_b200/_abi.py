@@ -11,13 +11,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcylinder_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "cylinder_b200.h")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # constants mirrored from the header (checked against it in tests/test_abi_cpu.py)
 VARIANT_SIMPLE, VARIANT_RESCALED_0TH, VARIANT_RESCALED_1ST, VARIANT_DECOUPLED = 0, 1, 2, 3
 VARIANTS = {"simple": VARIANT_SIMPLE, "rescaled_0thorder": VARIANT_RESCALED_0TH, "rescaled_1storder": VARIANT_RESCALED_1ST,
             "decoupled": VARIANT_DECOUPLED}
-SWEEP_ADAPT_SIGMA, SWEEP_AMP_MOVES, SWEEP_MEASURE = 1, 2, 4
+SWEEP_ADAPT_SIGMA, SWEEP_AMP_MOVES, SWEEP_MEASURE, SWEEP_INDEX_ORDER = 1, 2, 4, 8
+
+
+def sweep_tile_rows(n):
+    """CYL_SWEEP_TILE_ROWS(n): explicit tile height of the HBM path (32, 30, 28, 24), OR-ed into the sweep flags."""
+    return (int(n) & 0xFF) << 8
+
+
 CHAIN_DOUBLES, OBS_DOUBLES, NMOM = 16, 16, 8
 CH_AMPLITUDE, CH_SIGMA_SITE, CH_SIGMA_AMP, CH_E_FIELD, CH_E_SURF, CH_STEP_COUNTER = 0, 1, 2, 3, 4, 5
 CH_SITE_PROPOSED, CH_SITE_ACCEPTED, CH_AMP_PROPOSED, CH_AMP_ACCEPTED, CH_AMP_COUNTER, CH_FLAGS = 6, 7, 8, 9, 10, 11
@@ -51,6 +58,7 @@ _SIGNATURES = {
     "cyl_field_energy_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "cyl_sweep_smem_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
     "cyl_sweep_smem_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp],
+    "cyl_sweep_smem_bytes": [_i, _i, _i],
     "cyl_sweep_smem_series_f32": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
     "cyl_sweep_smem_series_f64": [_vp, _i, _vp, _i, _i, _vp, _vp, _u64, _i64, _u64, _i, _i, _u32, _vp, _vp, _vp, _vp],
     "cyl_hbm_layout": [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)],
@@ -67,7 +75,7 @@ _SIGNATURES = {
     "cyl_fourier_am_state_doubles": [_i, _i],
     "cyl_fourier_am_steps_f64": [_vp, _i, _i, _vp, _vp, _vp, _i, _u64, _i64, _u64, _i, _i, _i, _d, _d, _d, _i, _vp],
 }
-_RESTYPES = {"cyl_last_error": C.c_char_p}
+_RESTYPES = {"cyl_last_error": C.c_char_p, "cyl_sweep_smem_bytes": C.c_int64}
 
 _lib = None
 

@@ -78,25 +78,28 @@ __device__ __forceinline__ void moments_store(double (&m)[CYL_NMOM], int wpr, in
 // z_i / z_{i-1/2} for a_eval, g0r = metric at z_i for a_ref.  WITHOUT the global lz*lth factor.
 // O(u) fluctuation correction to the thermal background of the 1st-order variant, per cell
 // (On_lattice_rescaled_1storder.py:87-108; the reference's ValueError branches are its log arguments going <= 0)
-__device__ __forceinline__ double background_correction_1st(const CylParams& p, double area, int Z, int T) {
+__device__ __forceinline__ double background_correction_1st(double alpha, double C, double u, double temperature, double area, int Z, int T) {
   const double pi = 3.14159265358979323846;
   const double area_factor = 2.0 / sqrt(pi);                    // 1st:34
   const double upper = 1 * area_factor;                         // 1st:89
   const double lower = (1.0 / (double)max(Z, T)) * area_factor; // 1st:90
-  const double alpha_cell = p.alpha * area;                     // 1st:92
-  const double hi = p.C * (upper * upper) + alpha_cell;
-  double lo = p.C * (lower * lower) + alpha_cell;
+  const double alpha_cell = alpha * area;                       // 1st:92
+  const double hi = C * (upper * upper) + alpha_cell;
+  double lo = C * (lower * lower) + alpha_cell;
   double integral = 0.0;                                        // 1st:103-105
   if (hi > 0) {
     if (!(lo > 0)) {                                            // 1st:98-102
-      const double l2 = sqrt(fabs(alpha_cell) / p.C) + .0000001;
-      lo = p.C * (l2 * l2) + alpha_cell;
+      const double l2 = sqrt(fabs(alpha_cell) / C) + .0000001;
+      lo = C * (l2 * l2) + alpha_cell;
     }
-    integral = pi / p.C * (log(hi) - log(lo));                  // 1st:96
+    integral = pi / C * (log(hi) - log(lo));                    // 1st:96
   }
-  double correction = p.u * (p.temperature * p.temperature * p.temperature) * 4 * (integral * integral);   // 1st:106
+  double correction = u * (temperature * temperature * temperature) * 4 * (integral * integral);   // 1st:106
   correction /= (double)Z * (double)T;                          // 1st:107
   return correction;
+}
+__device__ __forceinline__ double background_correction_1st(const CylParams& p, double area, int Z, int T) {
+  return background_correction_1st(p.alpha, p.C, p.u, p.temperature, area, Z, T);
 }
 
 __device__ __forceinline__ void field_energy_weights(int variant, const CylParams& p, double lz, double lth, int Z, int T,
@@ -152,8 +155,10 @@ __device__ __forceinline__ double field_energy_row_eval(int variant, const CylPa
 // Energy accumulated on the fly by the sweep kernels (distributed over the sites as they are finalised)
 // ------------------------------------------------------------------------------------------------------
 // energy weights of a row: current amplitude, and (proposed - current); pixel-length factors folded in
+// cst = the row's constant term W[5] (background energy of the rescaled variants): {current, proposed - current}; the batched
+// kernel adds it once per row inside its energy pass, the HBM path keeps the constants in a side sum and leaves these 0.
 template <typename R>
-struct __align__(16) RowW { R cur[5]; R dif[5]; R pad[2]; };
+struct __align__(16) RowW { R cur[5]; R dif[5]; R cst[2]; };
 
 // energy accumulators of one thread: E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|
 template <typename R> struct EAcc { R ec, ed, s2, sa; };
@@ -161,10 +166,10 @@ __device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.
 __device__ __forceinline__ double sqrt_fast(double x) { return sqrt(x); }
 
 template <typename R, typename C>
-__device__ __forceinline__ void energy_own(EAcc<R>& e, const RowW<R>& w, C q, bool measure) {
+__device__ __forceinline__ void energy_own(EAcc<R>& e, const RowW<R>& w, C q, bool measure, bool with_abs = true) {
   const R p2 = q.x * q.x + q.y * q.y, p4 = p2 * p2;
   e.ed += w.dif[0] * p2 + w.dif[1] * p4;
-  if (measure) { e.ec += w.cur[0] * p2 + w.cur[1] * p4; e.s2 += p2; e.sa += sqrt_fast(p2); }
+  if (measure) { e.ec += w.cur[0] * p2 + w.cur[1] * p4; e.s2 += p2; if (with_abs) e.sa += sqrt_fast(p2); }
 }
 // z-bond between the site `hi` of a row and the site `lo` of the row above it; (wc, wd) = that row's |dz|^2 weights
 template <typename R, typename C>
@@ -176,7 +181,7 @@ __device__ __forceinline__ void energy_zbond(EAcc<R>& e, R wc, R wd, C hi, C lo,
 // Two adjacent sites a (column j), b (column j+1) of one row with the sites la, lb above them and wl left of a: their own terms,
 // their bonds upwards and the bonds (wl, a), (a, b).  The five moments are summed over the pair before the weights are applied.
 template <typename R, typename C>
-__device__ __forceinline__ void energy_pair(EAcc<R>& e, const RowW<R>& w, C a, C b, C la, C lb, C wl, bool measure) {
+__device__ __forceinline__ void energy_pair(EAcc<R>& e, const RowW<R>& w, C a, C b, C la, C lb, C wl, bool measure, bool with_abs = true) {
   const R p2a = a.x * a.x + a.y * a.y, p2b = b.x * b.x + b.y * b.y;
   const R s1 = p2a + p2b, s2 = p2a * p2a + p2b * p2b;
   const R zar = a.x - la.x, zai = a.y - la.y, zbr = b.x - lb.x, zbi = b.y - lb.y;
@@ -188,7 +193,7 @@ __device__ __forceinline__ void energy_pair(EAcc<R>& e, const RowW<R>& w, C a, C
   if (measure) {
     e.ec += w.cur[0] * s1 + w.cur[1] * s2 + w.cur[2] * m3 + w.cur[3] * m4 + w.cur[4] * m5;
     e.s2 += s1;
-    e.sa += sqrt_fast(p2a) + sqrt_fast(p2b);
+    if (with_abs) e.sa += sqrt_fast(p2a) + sqrt_fast(p2b);
   }
 }
 // theta-bond between the site `hi` (column j) and `lo` (column j-1) of one row

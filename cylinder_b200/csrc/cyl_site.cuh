@@ -41,72 +41,7 @@ struct __align__(16) RowCoef {
   R kfull;   // K (for energy bookkeeping)
 };
 
-// Build the coefficients of a row from the metric at z = lz*i (g0) and z -+ lz/2 (gm, gp), all at the current
-// amplitude.  The metric comes in fp64; the coefficient arithmetic runs in A = double for the fp64 kernels and in
-// A = float for the fp32 kernels (the results are stored as fp32 anyway; both fp32 kernels share this code, so their
-// tables are bit-identical) -- the rebuild after an accepted amplitude move is a latency-bound phase on Z threads.
-template <typename A> __device__ __forceinline__ A coef_rcp(A x);
-template <> __device__ __forceinline__ double coef_rcp<double>(double x) { return fast_rcp(x); }
-template <> __device__ __forceinline__ float coef_rcp<float>(float x) { return __frcp_rn(x); }
-
-template <typename R>
-__device__ __forceinline__ RowCoef<R> row_coef(const CylParams& p, int variant, double lz, double lth, const Geo& g0,
-                                               const Geo& gm, const Geo& gp) {
-  using A = R;
-  const A g0t = (A)g0.gth, g0z = (A)g0.gz, g0a = (A)g0.ath;
-  const A gmt = (A)gm.gth, gmz = (A)gm.gz, gma = (A)gm.ath;
-  const A gpt = (A)gp.gth, gpz = (A)gp.gz, gpa = (A)gp.ath;
-  const A C = (A)p.C, n = (A)p.n, alpha = (A)p.alpha;
-  const A sg = g0t * g0z;
-  const A Cn2 = C * n * n;
-  const A ilz2 = (A)(1.0 / (lz * lz)), ilth = (A)(1.0 / lth);
-  const A igzm = coef_rcp<A>(gmz), igzp = coef_rcp<A>(gpz);
-  A clz, crz, clt, crt, xl, xr, mass, sgmul;
-  if (variant == CYL_VARIANT_SIMPLE) {
-    const A igtm = coef_rcp<A>(gmt), igtp = coef_rcp<A>(gpt);
-    const A Rm = igtm * igtm, Rp = igtp * igtp;
-    clz = C * ilz2 * igzm * igzm;
-    crz = C * ilz2 * igzp * igzp;
-    clt = C * Rm * Rm * ilth * ilth;
-    crt = C * Rp * Rp * ilth * ilth;
-    xl = 2 * C * n * Rm * gma * ilth;
-    xr = 2 * C * n * Rp * gpa * ilth;
-    mass = alpha + Cn2 * Rm * gma * gma;
-    sgmul = A(1);
-  } else if (variant == CYL_VARIANT_RESCALED_1ST || variant == CYL_VARIANT_DECOUPLED) {
-    const bool first = variant == CYL_VARIANT_RESCALED_1ST;
-    const A igtm = coef_rcp<A>(gmt), igtp = coef_rcp<A>(gpt);
-    const A Rm = igtm * igtm, Rp = igtp * igtp;
-    clz = first ? C * ilz2 * igzm * igzm : C * ilz2;
-    crz = first ? C * ilz2 * igzp * igzp : C * ilz2;
-    clt = C * Rm * ilth * ilth;
-    crt = C * Rp * ilth * ilth;
-    xl = 2 * C * n * Rm * gma * ilth * (first ? igtm : A(1));
-    xr = 2 * C * n * Rp * gpa * ilth * (first ? igtp : A(1));
-    mass = alpha + Cn2 * Rm * gma * gma;
-    sgmul = sg;
-  } else {
-    const A igt0 = coef_rcp<A>(g0t);
-    const A R0 = igt0 * igt0, isg = igt0 * coef_rcp<A>(g0z);
-    clz = C * ilz2 * igzm * gmt * isg;                      // C/(lz^2 Gz(z-)^2) * sg(z-)/sg(z)
-    crz = C * ilz2 * igzp * gpt * isg;
-    clt = crt = C * R0 * ilth * ilth;
-    xl = xr = 2 * C * n * R0 * g0a * ilth;
-    mass = alpha + Cn2 * R0 * g0a * g0a;
-    sgmul = sg;
-  }
-  const A K = sg * (A)(lz * lth);
-  RowCoef<R> c;
-  c.kfull = (R)K;
-  c.kacc = (p.temperature > 0) ? (R)(K * (A)(1.4426950408889634 / p.temperature)) : (R)INFINITY;
-  c.mass = (R)mass;
-  c.csum = (R)(clz + crz + clt + crt);
-  c.hu = (R)(p.u / 2);
-  c.clz = (R)clz; c.crz = (R)crz; c.clt = (R)clt; c.crt = (R)crt;
-  c.xl = (R)xl; c.xr = (R)xr;
-  c.sgmul = (R)sgmul;
-  return c;
-}
+// (the rows are built by cyl_rowtab.cuh:coef_row, in the kernel's working precision)
 
 // dE / K for the move p -> p + d.
 template <typename R, typename C>
@@ -188,13 +123,6 @@ __host__ __device__ __forceinline__ int num_colours(int Z, int T) { return ((Z |
 // f = max(step_counter + n/2, 200): the reference's per-proposal rule (On_lattice_simple.py:688-696, m = 1, p* = .5,
 // ratio = 4) is sigma *= (1 + 2/f) on accept, (1 - 2/f) on reject; the batch applies the product.  The fp32 kernels
 // evaluate the exponent in fp32 (sigma is a tuning width, and both fp32 kernels share this code so they stay
-// bit-identical to each other); the fp64 kernels in fp64 (the oracle restates exactly that).
+// bit-identical to each other); the fp64 kernels in fp64 (the oracle restates exactly that).  Defined in cyl_rowtab.cuh
+// (rm_logs + rm_apply).
 template <typename R> __device__ __forceinline__ double rm_batch_update(double sigma, double step_counter, double n, double k);
-template <> __device__ __forceinline__ double rm_batch_update<double>(double sigma, double step_counter, double n, double k) {
-  const double f = fmax(step_counter + 0.5 * n, 200.0);
-  return sigma * exp(k * log1p(2.0 / f) + (n - k) * log1p(-2.0 / f));
-}
-template <> __device__ __forceinline__ double rm_batch_update<float>(double sigma, double step_counter, double n, double k) {
-  const float x = 2.0f / fmaxf((float)step_counter + 0.5f * (float)n, 200.0f);
-  return sigma * (double)expf((float)k * log1pf(x) + (float)(n - k) * log1pf(-x));
-}

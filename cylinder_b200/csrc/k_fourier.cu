@@ -420,6 +420,8 @@ extern "C" int cyl_fourier_am_steps_f64(const CylParams* params, int nz, int nth
   const int ncoef = (2 * nz + 1) * (2 * nth + 1);
   CYL_CHECK_ARG(ncoef <= FOURIER_MAX_COEF - 1, "cyl_fourier_am_steps_f64: %d coefficients > %d (one state component per lane)", ncoef,
                 FOURIER_MAX_COEF - 1);
+  const int layout = method & (CYL_FOURIER_LAYOUT_CTA | CYL_FOURIER_LAYOUT_WARP);
+  method &= ~(CYL_FOURIER_LAYOUT_CTA | CYL_FOURIER_LAYOUT_WARP);
   CYL_CHECK_ARG(method >= CYL_FOURIER_SEQUENTIAL && method <= CYL_FOURIER_NO_FIELD, "cyl_fourier_am_steps_f64: unknown method %d", method);
   if (n_steps == 0) return CYL_OK;
   // few chains: a CTA per chain (the energy quadrature shared by eight warps); many: a warp per chain
@@ -427,7 +429,7 @@ extern "C" int cyl_fourier_am_steps_f64(const CylParams* params, int nz, int nth
   CYL_CUDA(cudaGetDevice(&dev));
   CYL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   bool cta = B <= sms;
-  if (const char* mode = getenv("CYL_FOURIER_MODE")) cta = (mode[0] == 'c');      // "cta" / "warp": testing override
+  if (layout) cta = (layout & CYL_FOURIER_LAYOUT_CTA) != 0;                       // explicit layout (tests run both)
   const int warps = cta ? 8 : 4, dd = ncoef + 1;
   const size_t smem = sizeof(FourierTables) + (size_t)warps * (2 * ncoef * sizeof(double2) + (size_t)dd * dd * sizeof(double)) +
                       (size_t)warps * sizeof(double);

@@ -32,6 +32,7 @@
 #include "cyl_common.cuh"
 #include "cyl_energy.cuh"
 #include "cyl_site.cuh"
+#include "cyl_rowtab.cuh"
 #include "cyl_surface.cuh"
 
 #define HBM_NT 256
@@ -197,17 +198,13 @@ __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const doub
   const CylParams p = *params;
   const double a = chain[CYL_CH_AMPLITUDE];
   const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
-  // same arithmetic as the shared-memory kernel's tables (the two fp32 paths stay bit-identical)
-  const double ra = fast_radius_rescaled(p.radius, a);
-  const int ip = (i + 1 == Z) ? 0 : i + 1;
-  double s0, c0, sm, cm, sp, cp;
-  sincos(p.wavenumber * (lz * i), &s0, &c0);
-  sincos(p.wavenumber * (lz * (i - .5)), &sm, &cm);
-  sincos(p.wavenumber * (lz * (ip - .5)), &sp, &cp);
-  const Geo g0 = geo_from_sc(p.wavenumber, ra, a, s0, c0), gm = geo_from_sc(p.wavenumber, ra, a, sm, cm),
-            gp = geo_from_sc(p.wavenumber, ra, a, sp, cp);
-  coef[i] = row_coef<R>(p, variant, lz, lth, g0, gm, gp);
+  const double lz = (2 * pi / p.wavenumber) / Z;
+  // same functions as the shared-memory kernel's tables (cyl_rowtab.cuh): the two fp32 paths stay bit-identical
+  const RepConst<R> rc = make_rep_const<R>(p, Z, T, variant);
+  const AmpGeo<R> ag = amp_geo<R>(rc, a);
+  const RowTrig<R> t = row_trig<R>(p.wavenumber, lz, i), tp = row_trig<R>(p.wavenumber, lz, (i + 1 == Z) ? 0 : i + 1);
+  const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm), gp = geo_sc<R>(ag, tp.sm, tp.cm);
+  coef[i] = coef_row<R>(rc, g0, gm, gp);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -873,37 +870,31 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
   const int sel = hdr->coef_sel;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;
+  const double lz = (2 * pi / p.wavenumber) / Z;
   double c_cur = 0.0, c_dif = 0.0;
   if (i < Z) {
-    // same arithmetic as the shared-memory kernel's weights phase (k_sweep_smem.cu:row_weights): both weights are rounded to the
-    // working precision first, so the chain samples the model with the rounded weights on both paths
-    const double ra = fast_radius_rescaled(p.radius, a), rn = try_move ? fast_radius_rescaled(p.radius, a_new) : ra;
-    const int ip = (i + 1 == Z) ? 0 : i + 1;
-    double s0, c0, sm, cm;
-    sincos(p.wavenumber * (lz * i), &s0, &c0);
-    sincos(p.wavenumber * (lz * (i - .5)), &sm, &cm);
-    const Geo g0 = geo_from_sc(p.wavenumber, ra, a, s0, c0), gm = geo_from_sc(p.wavenumber, ra, a, sm, cm);
-    const Geo h0 = geo_from_sc(p.wavenumber, rn, a_new, s0, c0), hm = geo_from_sc(p.wavenumber, rn, a_new, sm, cm);
-    double Wc[6], Wn[6];
-    field_energy_weights(variant, p, lz, lth, Z, T, g0, gm, g0, Wc);
-    field_energy_weights(variant, p, lz, lth, Z, T, h0, hm, g0, Wn);              // a_ref = current amplitude (:75)
-    const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
+    // same functions as the shared-memory kernel's tables (cyl_rowtab.cuh, working precision): the current weights are the
+    // function of the amplitude the smem kernel stores on accept, the proposal's are evaluated with the current amplitude as
+    // metric reference (:75), and dif is the difference of the two -- the chain samples the model with these weights
+    const RepConst<R> rc = make_rep_const<R>(p, Z, T, variant);
+    const AmpGeo<R> ar = amp_geo<R>(rc, a), ae = amp_geo<R>(rc, a_new);
+    const RowTrig<R> t = row_trig<R>(p.wavenumber, lz, i);
+    const GeoT<R> g0 = geo_sc<R>(ar, t.s0, t.c0), gm = geo_sc<R>(ar, t.sm, t.cm);
+    const GeoT<R> h0 = geo_sc<R>(ae, t.s0, t.c0), hm = geo_sc<R>(ae, t.sm, t.cm);
+    R wc[6], wn[6];
+    weight_row<R>(rc, g0, gm, g0, wc);
+    weight_row<R>(rc, h0, hm, g0, wn);
     RowW<R> w;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {                 // dif = difference of the two ROUNDED weights, as in k_sweep_smem.cu:row_weights
-      w.cur[q] = (R)(Wc[q] * fold[q]);
-      w.dif[q] = (R)(Wn[q] * fold[q]) - w.cur[q];
-    }
-    w.pad[0] = w.pad[1] = R(0);
+    for (int q = 0; q < 5; ++q) { w.cur[q] = wc[q]; w.dif[q] = wn[q] - wc[q]; }
+    w.cst[0] = w.cst[1] = R(0);                       // the constants go through the side sums below
     roww[i] = w;
-    c_cur = Wc[5];
-    c_dif = Wn[5] - Wc[5];
+    c_cur = (double)wc[5];
+    c_dif = (double)(wn[5] - wc[5]);
     if (try_move) {
-      double sp, cp;
-      sincos(p.wavenumber * (lz * (ip - .5)), &sp, &cp);
-      const Geo hp = geo_from_sc(p.wavenumber, rn, a_new, sp, cp);
-      coef2[(size_t)(sel ^ 1) * Z + i] = row_coef<R>(p, variant, lz, lth, h0, hm, hp);
+      const RowTrig<R> tp = row_trig<R>(p.wavenumber, lz, (i + 1 == Z) ? 0 : i + 1);
+      const GeoT<R> hp = geo_sc<R>(ae, tp.sm, tp.cm);
+      coef2[(size_t)(sel ^ 1) * Z + i] = coef_row<R>(rc, h0, hm, hp);
     }
   }
   c_cur = block_sum<double>(c_cur, scr);
@@ -1101,8 +1092,9 @@ static int sweep_hbm_dispatch(const HbmGeom& g, void* work, int32_t* cur, const 
   CYL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int best = 32;
   double best_cost = 1e300;
-  const char* force = getenv("CYL_HBM_TILE_ROWS");                  // tuning / debugging override
-  if (force) best = atoi(force);
+  const int force = (int)((flags >> 8) & 0xFFu);                    // CYL_SWEEP_TILE_ROWS(n): explicit tile height
+  flags &= ~0xFF00u;
+  if (force) best = force;
   else { HBM_TRY_TH(32); HBM_TRY_TH(30); HBM_TRY_TH(28); HBM_TRY_TH(24); }
   switch (best) {
     HBM_RUN_TH(32);

@@ -1,50 +1,57 @@
 // Batched-replica checkerboard sweeps, lattice resident in shared memory.
 //
 // One CTA owns one replica for the whole launch (nsweeps sweeps): psi is read from HBM once, kept in shared
-// memory, written back once; the per-row metric coefficients, the amplitude-independent sin/cos tables and the
-// per-row energy weights live in shared memory too.  Per sweep:
-//   0. the amplitude proposal a' = a + sigma_amp N(0,1) is known up front (its draws are precomputed, counter-based);
-//      the row weights of the field energy for a' are built one row per thread (fp64, fast reciprocals; those for the
-//      current amplitude are in place since the last accepted move) while warp 7 evaluates E_surf(a');
+// memory, written back once; the per-row site-move coefficients, the amplitude-independent sin/cos tables and the
+// per-row energy weights live in shared memory too.  The replicas are the (alpha, C, n, kappa, k) parameter grid that
+// scripts/taskarray.sh farms out as separate CPU jobs in the reference.
+//
+// A sweep is organised so that only FOUR CTA-wide barriers lie on its critical path (colour 0, colour 1, energy, decision;
+// five with three colours, one more when an amplitude move is accepted) and no phase leaves the CTA to one or two threads
+// for long:
+//   T. proposal tables.  a' = a + sigma_amp N(0,1) is known up front (its draws are precomputed, counter-based).  Warps 0..6
+//      build the row weights of the field energy for a' (one row per thread, rows dealt round-robin to the warps) and store
+//      their DIFFERENCE to the current weights; warp 7 evaluates E_surf(a').  No barrier follows: nothing here is read before
+//      the energy pass, so every warp goes straight on to its sites.
 //   1. site moves (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once; draws from
 //      Philox2x32-10 at counter (site, sweep) -- stateless, so a sweep can be re-run or resumed bit-identically.  For even T
 //      the loops are column-mapped: a thread keeps its column pair and walks down the rows with an even stride, so colour
 //      parity, theta wrap and the neighbour offsets are loop constants and site pointer, coefficient pointer and Philox
-//      counter advance by constants (2 and 3 colours);
-//  1b. the ENERGY pass over the swept lattice: per column pair the five moments (|psi|^2, |psi|^4, |dz|^2, |dth|^2,
+//      counter advance by constants (2 and 3 colours).
+//   E. energy pass over the swept lattice: per column pair the five moments (|psi|^2, |psi|^4, |dz|^2, |dth|^2,
 //      Im(conj(psi) dth)) of the two sites with their bonds upwards and to the left, dotted with the row
 //      weights for a and for (a' - a) -- the energy change of the amplitude move is accumulated directly, not as a difference
-//      of two large sums.  (Closing each bond inside the colour passes, by its later-finalised endpoint, saved the second
-//      pass over shared memory but cost more instructions: per-site bookkeeping, divergent with three colours.)
-//   2. warp-level sums of {accepts, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|}; the 8 partials are added by the
-//      threads that need them;
-//   3. on three threads of different warps: Robbins-Monro on sigma_site (On_lattice_simple.py:688-696, batched; cyl_site.cuh),
-//      the measurement record, and the amplitude decision (Lattice.run :544-550 through engine.step_real_group; accept
-//      rule B.2; Robbins-Monro on sigma_amp);
-//   4. on accept, rebuild the row coefficients and the current weights from the sin/cos tables (no trigonometry);
-//   5. with CYL_SWEEP_MEASURE and a profile buffer: row sums of Lattice.measure (:121-131), one thread per row.
-// The replicas are the (alpha, C, n, kappa, k) parameter grid that scripts/taskarray.sh farms out as separate CPU
-// jobs in the reference.
+//      of two large sums; the rows' constant terms (background energy of the rescaled variants) ride in the same sums.  Then,
+//      with CYL_SWEEP_MEASURE and a profile buffer, the row sums of Lattice.measure (:121-131): two threads per row, each half
+//      a row of 16-byte loads.  Warp-level sums of {accepts, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|}.
+//   D. decisions on three threads of different warps, each a few dozen instructions: Robbins-Monro on sigma_site
+//      (On_lattice_simple.py:688-696, batched; its logarithms were taken in phase T), the measurement record, and the
+//      amplitude decision (Lattice.run :544-550 through engine.step_real_group; accept rule B.2 as T ln u <= -dE with T ln u
+//      precomputed; Robbins-Monro on sigma_amp).
+//   R. only when the move was accepted: coefficient rows and current weights of the new amplitude from the sin/cos tables
+//      (cyl_rowtab.cuh, working precision, no trigonometry), all eight warps, one barrier.
 #include <cstdlib>
 #include <type_traits>
 #include "cyl_common.cuh"
 #include "cyl_energy.cuh"
 #include "cyl_site.cuh"
+#include "cyl_rowtab.cuh"
 #include "cyl_surface.cuh"
 
 #define SWEEP_NT 256
 #define SWEEP_NWARP (SWEEP_NT / 32)
 
+template <typename R>
 struct SmemScalars {
-  double amp, amp_new, sigma_site, sigma_amp, e_field, e_surf, e_surf_new;
-  double cst;                       // sum over rows of the constant term W[5] of the energy at the current amplitude
+  RepConst<R> rc;
+  double amp, sigma_site, sigma_amp, e_field, e_surf, e_surf_new;
   double step_counter, site_proposed, site_accepted, amp_proposed, amp_accepted, amp_counter, flags;
   double obs[CYL_OBS_DOUBLES];      // observable sums of this launch, flushed once at the end
+  RmLogs<R> rm;                     // logarithms of this sweep's Robbins-Monro factors (phase T -> phase D)
   int amp_accept;
 };
 
 // Optional per-phase cycle accounting (build with CYL_EXTRA_NVCC_FLAGS=-DCYL_PHASE_TIMING): thread 0 accumulates
-// clock64() deltas into obs slots 10..15 = weights/surface, site moves + energy, reduction, decision, rebuild, profiles.
+// clock64() deltas into obs slots 10..15 = proposal tables, site moves, energy + profiles + reduction, decision, rebuild.
 #ifdef CYL_PHASE_TIMING
 #define PHASE_MARK(k) do { if (tid == 0) { const long long t__ = clock64(); sc->obs[10 + (k)] += (double)(t__ - t_phase); t_phase = t__; } } while (0)
 #else
@@ -63,10 +70,7 @@ struct SmemScalars {
 #define SMEM_WEIGHTS_ON true
 #endif
 #define SWEEP_FLAG_LONGEST_FIRST 0x80000000u   // set by the launcher, not part of the ABI: see the kernel prologue
-#define AMP_CHUNK 64                // amplitude-move draws are precomputed for this many sweeps at a time
-
-// sin/cos(k z) at z_i and z_{i-1/2}
-struct RowTrig { double s0, c0, sm, cm; };
+#define AMP_CHUNK 32                // amplitude-move draws are precomputed for this many sweeps at a time
 
 template <typename R>
 struct SweepSmemLayout {
@@ -76,87 +80,42 @@ struct SweepSmemLayout {
     size_t o = (size_t)Zmax * T * sizeof(C);
     o = (o + 15) & ~(size_t)15;
     off_coef = o; o += (size_t)Zmax * sizeof(RowCoef<R>);
-    off_trig = o; o += (size_t)Zmax * sizeof(RowTrig);
+    off_trig = o; o += (size_t)Zmax * sizeof(RowTrig<R>);
     off_w = o;    o += (size_t)Zmax * sizeof(RowW<R>);
     off_prof = o; o += (size_t)Zmax * 3 * sizeof(R);          // per-launch profile sums, flushed once at the end
     o = (o + 15) & ~(size_t)15;
-    off_amp = o;  o += 2 * AMP_CHUNK * sizeof(double);          // unit normal + accept uniform per sweep
+    off_amp = o;  o += 2 * AMP_CHUNK * sizeof(double);          // unit normal + T ln(u) per sweep
     off_scr = o;  o += 8 * SWEEP_NWARP * sizeof(double);
-    off_sc = o;   o += sizeof(SmemScalars);
+    off_sc = o;   o += sizeof(SmemScalars<R>);
     total = (o + 15) & ~(size_t)15;
   }
 };
 
+// Coefficient rows and current energy weights of every row at amplitude a (the accepted amplitude is the metric reference
+// too); dif <- 0.  All eight warps, rows dealt round-robin to the warps so that every warp runs the chain once.
 template <typename R>
-__device__ __forceinline__ void build_row_coefs(RowCoef<R>* coef, const RowTrig* trig, const CylParams& p, int variant,
-                                                double a, double lz, double lth, int Z) {
-  const double ra = fast_radius_rescaled(p.radius, a);
-  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
-    const RowTrig t = trig[i], tp = trig[i + 1 == Z ? 0 : i + 1];
-    const Geo g0 = geo_from_sc(p.wavenumber, ra, a, t.s0, t.c0);
-    const Geo gm = geo_from_sc(p.wavenumber, ra, a, t.sm, t.cm);
-    const Geo gp = geo_from_sc(p.wavenumber, ra, a, tp.sm, tp.cm);      // z_{i+1/2} = z_{(i+1)-1/2}, periodic
-    coef[i] = row_coef<R>(p, variant, lz, lth, g0, gm, gp);
-  }
-}
-
-// Energy weights of row `tr` at amplitude a_eval (metric reference a_ref), pixel lengths folded in, rounded to the working
-// precision; returns the row's constant term W[5] (kept in double: it only enters through a per-replica sum).
-// The weights a sweep uses are ALWAYS this function of the amplitude -- `cur` is refreshed from it when a move is accepted,
-// `dif` is the difference of two such roundings -- so the chain samples exactly the model with the rounded weights.
-template <typename R>
-__device__ __forceinline__ double row_weights(const CylParams& p, int variant, double lz, double lth, int Z, int T, const RowTrig& tr,
-                                              double ra_eval, double a_eval, double ra_ref, double a_ref, R (&wf)[5]) {
-  const Geo g0e = geo_from_sc(p.wavenumber, ra_eval, a_eval, tr.s0, tr.c0), gme = geo_from_sc(p.wavenumber, ra_eval, a_eval, tr.sm, tr.cm);
-  Geo g0r = g0e;                                                         // a_ref = current amplitude (:75); rescaled variants only
-  if (variant != CYL_VARIANT_SIMPLE && a_ref != a_eval) g0r = geo_from_sc(p.wavenumber, ra_ref, a_ref, tr.s0, tr.c0);
-  double W[6];
-  field_energy_weights(variant, p, lz, lth, Z, T, g0e, gme, g0r, W);
-  const double fold[5] = {1.0, 1.0, 1.0 / (lz * lz), 1.0 / (lth * lth), 1.0 / lth};   // pixel lengths of dz, dth
+__device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowW<R>* roww, const RowTrig<R>* trig, const RepConst<R>& rc,
+                                             double a, int Z, bool weights) {
+  const AmpGeo<R> ag = amp_geo<R>(rc, a);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = lane * SWEEP_NWARP + warp; i < Z; i += SWEEP_NT) {
+    const RowTrig<R> t = trig[i], tp = trig[i + 1 == Z ? 0 : i + 1];
+    const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm);
+    const GeoT<R> gp = geo_sc<R>(ag, tp.sm, tp.cm);                  // z_{i+1/2} = z_{(i+1)-1/2}, periodic
+    coef[i] = coef_row<R>(rc, g0, gm, gp);
+    if (weights) {
+      R wf[6];
+      weight_row<R>(rc, g0, gm, g0, wf);
+      RowW<R> w;
 #pragma unroll
-  for (int q = 0; q < 5; ++q) wf[q] = (R)(W[q] * fold[q]);
-  return W[5];
-}
-
-// cur <- weights at the current amplitude, dif <- 0, for every row; returns this thread's share of the constant term
-template <typename R>
-__device__ __forceinline__ double build_row_weights(RowW<R>* roww, const RowTrig* trig, const CylParams& p, int variant, double a,
-                                                    double lz, double lth, int Z, int T) {
-  const double ra = fast_radius_rescaled(p.radius, a);
-  double cst = 0.0;
-  for (int i = threadIdx.x; i < Z; i += blockDim.x) {
-    RowW<R> w;
-    cst += row_weights<R>(p, variant, lz, lth, Z, T, trig[i], ra, a, ra, a, w.cur);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) w.dif[q] = R(0);
-    w.pad[0] = w.pad[1] = R(0);
-    roww[i] = w;
+      for (int q = 0; q < 5; ++q) { w.cur[q] = wf[q]; w.dif[q] = R(0); }
+      w.cst[0] = wf[5]; w.cst[1] = R(0);
+      roww[i] = w;
+    }
   }
-  return cst;
 }
 
 __device__ __forceinline__ double surface_energy_of(const CylParams& p, double a) { return surface_energy_warp(p, a, nullptr, nullptr, true); }
-
-// Sum N doubles over the CTA (result in every thread).  scratch: N * SWEEP_NWARP doubles.
-template <int N>
-__device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int q = 0; q < N; ++q) v[q] = warp_sum(v[q]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < N; ++q) scratch[q * SWEEP_NWARP + warp] = v[q];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < SWEEP_NWARP; ++w) t += scratch[q * SWEEP_NWARP + w];
-    v[q] = t;
-  }
-}
 
 // one site move; returns the accept flag, `q` = the site's value after the move
 template <typename R, typename C>
@@ -191,13 +150,13 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const SweepSmemLayout<R> lay(Zmax, T);
   C* psi = reinterpret_cast<C*>(smem_raw);
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
-  RowTrig* trig = reinterpret_cast<RowTrig*>(smem_raw + lay.off_trig);
+  RowTrig<R>* trig = reinterpret_cast<RowTrig<R>*>(smem_raw + lay.off_trig);
   RowW<R>* roww = reinterpret_cast<RowW<R>*>(smem_raw + lay.off_w);
   R* prof_s = reinterpret_cast<R*>(smem_raw + lay.off_prof);
   double* ampz = reinterpret_cast<double*>(smem_raw + lay.off_amp);
-  double* ampu = ampz + AMP_CHUNK;
+  double* amplu = ampz + AMP_CHUNK;
   double* scr = reinterpret_cast<double*>(smem_raw + lay.off_scr);
-  SmemScalars* sc = reinterpret_cast<SmemScalars*>(smem_raw + lay.off_sc);
+  SmemScalars<R>* sc = reinterpret_cast<SmemScalars<R>*>(smem_raw + lay.off_sc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int b = blockIdx.x;
@@ -249,19 +208,26 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     __syncthreads();                                                       // the scratch is reused below
   }
   const int Z = Zs[b];
+  double* ch = chain + (size_t)b * CYL_CHAIN_DOUBLES;
+  if (Z < 1 || Z > Zmax) {
+    // a row count the shared-memory layout was not sized for (the host cannot validate a device array): leave the replica
+    // untouched and say so in its flags (bit 1)
+    if (tid == 0) ch[CYL_CH_FLAGS] = (double)((unsigned)ch[CYL_CH_FLAGS] | 2u);
+    return;
+  }
   const int nsite = Z * T;
   const CylParams p = params[b];
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z, lth = (2 * pi * p.radius) / T;     // On_lattice_simple.py:47,:49
   const uint32_t rep = (uint32_t)(replica0 + b);
   const SiteStream stream = site_stream(seed, (uint64_t)(replica0 + b));
-  double* ch = chain + (size_t)b * CYL_CHAIN_DOUBLES;
   C* psi_b = psi_g + (size_t)b * Zmax * T;
   constexpr bool extras = EXTRAS;
   const bool measure = (flags & CYL_SWEEP_MEASURE) != 0;
+  const bool profiles = measure && prof != nullptr;
+  const RepConst<R>& rc = sc->rc;
 
   // ---- prologue: state, lattice, tables ----
   if (tid == 0) {
+    sc->rc = make_rep_const<R>(p, Z, T, variant);
     sc->amp = ch[CYL_CH_AMPLITUDE];
     sc->sigma_site = ch[CYL_CH_SIGMA_SITE];
     sc->sigma_amp = ch[CYL_CH_SIGMA_AMP];
@@ -273,27 +239,22 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     sc->amp_counter = ch[CYL_CH_AMP_COUNTER];
     sc->flags = ch[CYL_CH_FLAGS];
     sc->e_field = ch[CYL_CH_E_FIELD];
+    sc->e_surf = ch[CYL_CH_E_SURF];
     sc->amp_accept = 0;
     for (int q = 0; q < CYL_OBS_DOUBLES; ++q) sc->obs[q] = 0.0;
   }
   for (int s = tid; s < nsite; s += SWEEP_NT) psi[s] = psi_b[s];
   for (int s = tid; s < 3 * Z; s += SWEEP_NT) prof_s[s] = R(0);
-  for (int i = tid; i < Z; i += SWEEP_NT) {
-    RowTrig t;
-    sincos(p.wavenumber * (lz * i), &t.s0, &t.c0);
-    sincos(p.wavenumber * (lz * (i - .5)), &t.sm, &t.cm);
-    trig[i] = t;
+  {
+    const double pi = 3.14159265358979323846;
+    const double lz = (2 * pi / p.wavenumber) / Z;                         // On_lattice_simple.py:47
+    for (int i = tid; i < Z; i += SWEEP_NT) trig[i] = row_trig<R>(p.wavenumber, lz, i);
   }
   __syncthreads();
-  build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
-  if (extras) {
-    double c0[1] = {build_row_weights<R>(roww, trig, p, variant, sc->amp, lz, lth, Z, T)};
-    block_sum_n<1>(c0, scr);
-    if (tid == 0) sc->cst = c0[0];
-    if (warp == 0) {
-      const double es = surface_energy_of(p, sc->amp);
-      if (lane == 0) sc->e_surf = es;
-    }
+  rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, extras);
+  if (extras && warp == 0) {
+    const double es = surface_energy_of(p, sc->amp);
+    if (lane == 0) sc->e_surf = es;
   }
   __syncthreads();
 
@@ -315,10 +276,14 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
     if (extras && (sw & (AMP_CHUNK - 1)) == 0) {
-      // draws of the next AMP_CHUNK amplitude moves, one sweep per thread (counter-based: any order, any thread)
+      // draws of the next AMP_CHUNK amplitude moves, one sweep per thread (counter-based: any order, any thread); the
+      // acceptance uniform is kept as T ln(u), so the decision is a comparison (accept rule B.2: u <= exp(-dE/T))
       if (tid < AMP_CHUNK && sw + tid < nsweeps) {
         const uint64_t s2 = sweep + (uint64_t)tid;
-        amp_draw(philox4x32_10(0u, rep, (uint32_t)s2, philox_c3(CYL_TAG_AMP, s2), keys), ampz[tid], ampu[tid]);
+        double z, u;
+        amp_draw(philox4x32_10(0u, rep, (uint32_t)s2, philox_c3(CYL_TAG_AMP, s2), keys), z, u);
+        ampz[tid] = z;
+        amplu[tid] = p.temperature * log(u);
       }
       __syncthreads();
     }
@@ -327,17 +292,13 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 #ifdef CYL_PHASE_TIMING
     long long t_phase = clock64();
 #endif
-    // The proposal a' = a + sigma_amp N(0,1) is known to every thread: the unit normal was drawn ahead of time, a and
-    // sigma_amp were fixed by the previous sweep's decision.
     // Chain scalars are read once here (the previous sweep ended with a barrier): during the decision phase several
     // threads work from these copies while thread 0 updates the shared ones.
     const double a = sc->amp, sig_amp = sc->sigma_amp, amp_cnt = sc->amp_counter, e_surf_cur = sc->e_surf;
     const double a_new = extras ? a + sig_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
     const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
-    double cst_new = 0.0;
 
-    // ---- 0. weights of the proposed amplitude on warps 0..6, one row per thread (the current amplitude's are in place since
-    //         the last accepted move); warp 7 meanwhile evaluates the surface energy of the proposal ----
+    // ---- T. tables of the proposal; no barrier: their first reader is the energy pass, two barriers from here ----
     if (extras) {
       if (try_move) {
         if (warp == SWEEP_NWARP - 1) {
@@ -345,32 +306,36 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const double es = surface_energy_of(p, a_new);
           if (lane == 0) sc->e_surf_new = es;
 #endif
-        } else if (warp * 32 < Z && SMEM_WEIGHTS_ON) {
-          const double ra = fast_radius_rescaled(p.radius, a), rn = fast_radius_rescaled(p.radius, a_new);
-          for (int i = tid; i < Z; i += SWEEP_NT - 32) {
-            R wn[5];
-            cst_new += row_weights<R>(p, variant, lz, lth, Z, T, trig[i], rn, a_new, ra, a, wn);
+        } else if (SMEM_WEIGHTS_ON) {
+          const AmpGeo<R> ae = amp_geo<R>(rc, a_new), ar = amp_geo<R>(rc, a);
+          const bool needs_ref = variant == CYL_VARIANT_RESCALED_0TH || variant == CYL_VARIANT_RESCALED_1ST;
+          for (int i = lane * (SWEEP_NWARP - 1) + warp; i < Z; i += SWEEP_NT - 32) {
+            const RowTrig<R> t = trig[i];
+            const GeoT<R> g0e = geo_sc<R>(ae, t.s0, t.c0), gme = geo_sc<R>(ae, t.sm, t.cm);
+            const GeoT<R> g0r = needs_ref ? geo_sc<R>(ar, t.s0, t.c0) : g0e;     // a_ref = current amplitude (:75)
+            R wf[6];
+            weight_row<R>(rc, g0e, gme, g0r, wf);
             RowW<R>& w = roww[i];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) w.dif[q] = wn[q] - w.cur[q];
+            for (int q = 0; q < 5; ++q) w.dif[q] = wf[q] - w.cur[q];
+            w.cst[1] = wf[5] - w.cst[0];
           }
         }
       }
-      __syncthreads();
+      if (tid == 64 && (flags & CYL_SWEEP_ADAPT_SIGMA)) sc->rm = rm_logs<R>(sc->step_counter, (double)nsite);
     }
     PHASE_MARK(0);
 
     // ---- 1. site moves ----
     int nacc = 0;
     EAcc<R> e = {R(0), R(0), R(0), R(0)};
-    // one site of row i (row = i*T; up / dn = offsets of the rows above / below)
     // (mapped loops) `o` points at the site, the neighbours sit at element offsets oL / oR (rows above / below, periodic) and
     // oW / oE (columns left / right, fixed per thread and pass); a thread walks down its rows by advancing o, the coefficient
     // pointer and the Philox site counter by constants
-    auto visit = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rc, uint32_t site) {
+    auto visit = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rcf, uint32_t site) {
       const C L = o[oL], Rz = o[oR], W = o[oW], E = o[oE];
       C q;
-      site_move<R, C>(o, 0, L, Rz, W, E, *rc, sigma, site, c1, stream.key, q, nacc);
+      site_move<R, C>(o, 0, L, Rz, W, E, *rcf, sigma, site, c1, stream.key, q, nacc);
     };
     if (mapped && ncol == 2) {
       // both lengths even: colour = (i + j) & 1
@@ -381,10 +346,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const int j = 2 * cj + ((colour + rg) & 1);
           const int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
           C* o = psi + rg * T + j;
-          const RowCoef<R>* rc = coef + rg;
+          const RowCoef<R>* rcf = coef + rg;
           uint32_t site = (uint32_t)(rg * T + j);
-          for (int i = rg; i < Z; i += RGe, o += step, rc += RGe, site += (uint32_t)step)
-            visit(o, (i == 0 ? nsite : 0) - T, (i == Z - 1 ? -nsite : 0) + T, oW, oE, rc, site);
+          for (int i = rg; i < Z; i += RGe, o += step, rcf += RGe, site += (uint32_t)step)
+            visit(o, (i == 0 ? nsite : 0) - T, (i == Z - 1 ? -nsite : 0) + T, oW, oE, rcf, site);
         }
         __syncthreads();
       }
@@ -397,28 +362,28 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       for (int colour = 0; colour < 3; ++colour) {
         if (col_active) {
           if (colour == 1) {
-            const int b = (rg & 1) ? 0 : 1;                                // rows keep their parity: the step is even
-            const int j = 2 * cj + b, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            const int bb = (rg & 1) ? 0 : 1;                               // rows keep their parity: the step is even
+            const int j = 2 * cj + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
             const int step = RGe * T;
             C* o = psi + rg * T + j;
-            const RowCoef<R>* rc = coef + rg;
+            const RowCoef<R>* rcf = coef + rg;
             uint32_t site = (uint32_t)(rg * T + j);
-            for (int i = rg; i < Z - 1; i += RGe, o += step, rc += RGe, site += (uint32_t)step)
-              visit(o, (i == 0 ? nsite : 0) - T, T, oW, oE, rc, site);
+            for (int i = rg; i < Z - 1; i += RGe, o += step, rcf += RGe, site += (uint32_t)step)
+              visit(o, (i == 0 ? nsite : 0) - T, T, oW, oE, rcf, site);
           } else {
-            const int b = colour ? 1 : 0;
-            const int j = 2 * cj + b, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            const int bb = colour ? 1 : 0;
+            const int j = 2 * cj + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
             const int step = 2 * RGe * T;                                  // even rows in pass 0, odd rows in pass 2
-            C* o = psi + (2 * rg + b) * T + j;
-            const RowCoef<R>* rc = coef + (2 * rg + b);
-            uint32_t site = (uint32_t)((2 * rg + b) * T + j);
-            for (int ii = rg; ii < half; ii += RGe, o += step, rc += 2 * RGe, site += (uint32_t)step)
-              visit(o, (ii == 0 && b == 0 ? nsite : 0) - T, T, oW, oE, rc, site);
+            C* o = psi + (2 * rg + bb) * T + j;
+            const RowCoef<R>* rcf = coef + (2 * rg + bb);
+            uint32_t site = (uint32_t)((2 * rg + bb) * T + j);
+            for (int ii = rg; ii < half; ii += RGe, o += step, rcf += 2 * RGe, site += (uint32_t)step)
+              visit(o, (ii == 0 && bb == 0 ? nsite : 0) - T, T, oW, oE, rcf, site);
           }
         }
         if (colour != 1 && tid >= SWEEP_NT - Th) {                         // the last row, from the top of the CTA (those
-          const int b = colour ? 0 : 1;                                    // threads have the fewest rows above)
-          const int j = 2 * (tid - (SWEEP_NT - Th)) + b, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+          const int bb = colour ? 0 : 1;                                   // threads have the fewest rows above)
+          const int j = 2 * (tid - (SWEEP_NT - Th)) + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
           const int row = (Z - 1) * T;
           visit(psi + row + j, -T, -row, oW, oE, coef + (Z - 1), (uint32_t)(row + j));
         }
@@ -474,10 +439,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     PHASE_MARK(1);
 
-    // ---- 1b. field energy of the swept lattice under the current weights and its change under the proposal's: every site's
-    //          own terms and its bonds to the row above and to the column on its left (each bond once).  A separate pass over
-    //          the final field costs fewer instructions than closing bonds inside the colour passes, where the bookkeeping of
-    //          who closes which bond is per site (and divergent with three colours). ----
+    // ---- E. field energy of the swept lattice under the current weights and its change under the proposal's: every site's
+    //         own terms and its bonds to the row above and to the column on its left (each bond once), plus the rows'
+    //         constant terms.  A separate pass over the final field costs fewer instructions than closing bonds inside the
+    //         colour passes, where the bookkeeping of who closes which bond is per site (and divergent with three colours).
+    //         With profiles on, sum |psi| comes from the profile pass below instead. ----
     if (extras && SMEM_ENERGY_ON) {
       if (mapped) {
         if (col_active) {
@@ -486,17 +452,23 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const C* o = psi + rg * T + j0;                                  // walks down the thread's rows, as in the site loops
           const RowW<R>* pw = roww + rg;
           int oL = (rg == 0 ? nsite : 0) - T;                              // periodic wrap upwards: first row of group 0 only
-          auto rows = [&](auto meas) {                                     // the measurement terms compiled in or out
+          auto rows = [&](auto meas, auto with_abs) {                      // the measurement terms compiled in or out
 #pragma unroll 1
             for (int i = rg; i < Z; i += RGe, o += step, pw += RGe) {
               const RowW<R> w = *pw;
               const Pair q = *reinterpret_cast<const Pair*>(o), l = *reinterpret_cast<const Pair*>(o + oL);
               const C wl = o[oW];
               oL = -T;
-              energy_pair<R, C>(e, w, q.a, q.b, l.a, l.b, wl, decltype(meas)::value);
+              energy_pair<R, C>(e, w, q.a, q.b, l.a, l.b, wl, decltype(meas)::value, decltype(with_abs)::value);
+              if (cj == 0) {
+                e.ed += w.cst[1];
+                if (decltype(meas)::value) e.ec += w.cst[0];
+              }
             }
           };
-          if (measure) rows(std::true_type{}); else rows(std::false_type{});
+          if (!measure) rows(std::false_type{}, std::false_type{});
+          else if (profiles) rows(std::true_type{}, std::false_type{});
+          else rows(std::true_type{}, std::true_type{});
         }
       } else {
         for (int i = warp; i < Z; i += SWEEP_NWARP) {                      // T odd or wide: a warp per row
@@ -504,28 +476,64 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           const RowW<R> w = roww[i];
           for (int j = lane; j < T; j += 32) {
             const C q = psi[row + j], l = psi[up + j], wl = psi[row + (j == 0 ? T : j) - 1];
-            energy_own<R, C>(e, w, q, measure);
+            energy_own<R, C>(e, w, q, measure, !profiles);
             energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, l, measure);
             energy_tbond<R, C>(e, w, q, wl, measure);
+          }
+          if (lane == 0) {
+            e.ed += w.cst[1];
+            if (measure) e.ec += w.cst[0];
           }
         }
       }
     }
+    // profiles of Lattice.measure (:121-131), read-only like the energy pass, so no barrier in between.  Even T: two
+    // adjacent threads per row, each half a row of 16-byte loads (rows on consecutive lane pairs: conflict-free), combined by
+    // one shuffle; every thread keeps its own share of sum |psi|.
+    if (profiles) {
+      if ((T & 1) == 0) {
+        struct __align__(16) Pair { C a, b; };
+        const int npair = T >> 1, h0 = npair >> 1, half = tid & 1;
+        const int p0 = half ? h0 : 0, p1 = half ? npair : h0;
+        for (int i = tid >> 1; i < ((Z + SWEEP_NT / 2 - 1) / (SWEEP_NT / 2)) * (SWEEP_NT / 2); i += SWEEP_NT / 2) {
+          R sa = 0, sre = 0, sim = 0;
+          if (i < Z) {
+            const Pair* rowp = reinterpret_cast<const Pair*>(psi + i * T);
+            for (int k = p0; k < p1; ++k) {
+              const Pair v = rowp[k];
+              sre += v.a.x + v.b.x; sim += v.a.y + v.b.y;
+              sa += sqrt_fast(v.a.x * v.a.x + v.a.y * v.a.y) + sqrt_fast(v.b.x * v.b.x + v.b.y * v.b.y);
+            }
+          }
+          e.sa += sa;
+          sre += __shfl_xor_sync(0xffffffffu, sre, 1); sim += __shfl_xor_sync(0xffffffffu, sim, 1); sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+          if (i < Z && half == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa; }
+        }
+      } else {
+        for (int i = tid; i < Z; i += SWEEP_NT) {
+          R sa = 0, sre = 0, sim = 0;
+          for (int j = 0; j < T; ++j) {
+            const C v = psi[i * T + j];
+            sre += v.x; sim += v.y; sa += sqrt_fast(v.x * v.x + v.y * v.y);
+          }
+          e.sa += sa;
+          prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa;
+        }
+      }
+    }
 
-    // ---- 2. reduction: sums within a warp (working precision), the eight partials are added by whoever needs them ----
+    // ---- reduction: sums within a warp (working precision), the eight partials are added by whoever needs them ----
     {
       const int wacc = __reduce_add_sync(0xffffffffu, nacc);
       R v[4] = {e.ec, e.ed, e.s2, e.sa};
-      double wc = 0.0;
       if (extras) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
-        if (try_move) wc = warp_sum(cst_new);
       }
       if (lane == 0) {
         double* s = scr + warp * 8;
         s[0] = (double)wacc;
-        if (extras) { s[1] = (double)v[0]; s[2] = (double)v[1]; s[3] = (double)v[2]; s[4] = (double)v[3]; s[5] = wc; }
+        if (extras) { s[1] = (double)v[0]; s[2] = (double)v[1]; s[3] = (double)v[2]; s[4] = (double)v[3]; }
       }
     }
     __syncthreads();
@@ -537,21 +545,23 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       return t;
     };
 
-    // ---- 3. decisions, spread over threads of different warps: Robbins-Monro on sigma_site (warp 2), the measurement record
+    // ---- D. decisions, spread over threads of different warps: Robbins-Monro on sigma_site (warp 2), the measurement record
     //         (warp 1), the amplitude move (warp 0) ----
     // optional time series: one record of CYL_SERIES_DOUBLES per measured sweep and replica (the engine's me.df)
     double* rec = (SERIES && extras && measure && series) ? series + ((size_t)b * nsweeps + sw) * CYL_SERIES_DOUBLES : nullptr;
     if (tid == 64) {
       const double nac = total(0);
       if (rec) rec[CYL_TS_SITE_ACCEPTANCE] = nac * inv_nsite;
-      if (flags & CYL_SWEEP_ADAPT_SIGMA)
-        sc->sigma_site = rm_batch_update<R>(sc->sigma_site, sc->step_counter, (double)nsite, nac);
+      if (flags & CYL_SWEEP_ADAPT_SIGMA) {
+        const RmLogs<R> l = extras ? sc->rm : rm_logs<R>(sc->step_counter, (double)nsite);
+        sc->sigma_site = rm_apply(sc->sigma_site, l, (double)nsite, nac);
+      }
       sc->step_counter += nsite;
       sc->site_proposed += nsite;
       sc->site_accepted += nac;
     }
     if (extras && measure && tid == 32) {                                // measure_avgs :135-156 + engine record
-      const double e_cur = (total(1) + sc->cst) * lz * lth;              // :213
+      const double e_cur = total(1) * rc.lzlth_d;                        // :213
       sc->e_field = e_cur;
       double* o = sc->obs;
       o[CYL_OB_COUNT] += 1.0;
@@ -577,12 +587,10 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       int accept = 0;
       if (flags & CYL_SWEEP_AMP_MOVES) {
         if (try_move) {
-          const double e_dif = (total(2) + (total(5) - sc->cst)) * lz * lth;
+          const double e_dif = total(2) * rc.lzlth_d;
           const double dE = (sc->e_surf_new - e_surf_cur) + e_dif;
           if (!isfinite(dE)) sc->flags = (double)((unsigned)sc->flags | 1u);
-          if (dE <= 0) accept = 1;                                       // accept rule B.2
-          else if (p.temperature == 0) accept = 0;
-          else accept = (ampu[sw & (AMP_CHUNK - 1)] <= exp(-dE / p.temperature));
+          accept = (amplu[sw & (AMP_CHUNK - 1)] <= -dE);                 // accept rule B.2 (T ln u <= 0: any dE <= 0 passes)
         }
         // Robbins-Monro on sigma_amp (engine, SURVEY.md B.3: m = 1, target p*)
         sc->amp_counter = amp_cnt + 1;
@@ -602,48 +610,19 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     __syncthreads();
     PHASE_MARK(3);
-    // ---- 4. metric tables follow the amplitude ----
+    // ---- R. metric tables follow the amplitude: the accepted amplitude becomes the metric reference too (rescaled
+    //         variants), so the weights are rebuilt rather than taken from the proposal's ----
     if (extras && sc->amp_accept) {
-      // the accepted amplitude becomes the metric reference too (rescaled variants), so the weights are rebuilt rather
-      // than taken from the proposal's
-      build_row_coefs<R>(coef, trig, p, variant, sc->amp, lz, lth, Z);
-      double c0[1] = {build_row_weights<R>(roww, trig, p, variant, sc->amp, lz, lth, Z, T)};
-      block_sum_n<1>(c0, scr);
-      if (tid == 0) sc->cst = c0[0];
+      rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, true);
       __syncthreads();
     }
     PHASE_MARK(4);
-    // ---- 5. profiles of Lattice.measure (:121-131): one THREAD per row, taken from the top of the CTA so that they run
-    //         beside the next sweep's weight phase (threads from the bottom); that phase ends with a barrier before any
-    //         site is written again ----
-    if (measure && prof) {
-      struct __align__(16) Pair { C a, b; };
-      for (int i = (SWEEP_NT - 33) - tid; i >= 0 && i < Z; i += SWEEP_NT - 32) {
-        const int row = i * T;
-        R sa = 0, sre = 0, sim = 0;
-        int j = 0;
-        if ((T & 1) == 0) {
-          for (; j < T; j += 2) {
-            const Pair v = *reinterpret_cast<const Pair*>(psi + row + j);
-            sre += v.a.x + v.b.x; sim += v.a.y + v.b.y;
-            sa += sqrt_fast(v.a.x * v.a.x + v.a.y * v.a.y) + sqrt_fast(v.b.x * v.b.x + v.b.y * v.b.y);
-          }
-        } else {
-          for (; j < T; ++j) {
-            const C v = psi[row + j];
-            sre += v.x; sim += v.y; sa += sqrt_fast(v.x * v.x + v.y * v.y);
-          }
-        }
-        prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa;
-      }
-    }
-    PHASE_MARK(5);
   }
 
   // ---- epilogue ----
   __syncthreads();
   for (int s = tid; s < nsite; s += SWEEP_NT) psi_b[s] = psi[s];
-  if (measure && prof) {
+  if (profiles) {
     double* pr = prof + (size_t)b * Zmax * 3;
     for (int s = tid; s < 3 * Z; s += SWEEP_NT) pr[s] += (double)prof_s[s];
   }
@@ -685,16 +664,22 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
   auto kern = !extras ? sweep_smem_kernel<R, false, false> : (series ? sweep_smem_kernel<R, true, true> : sweep_smem_kernel<R, true, false>);
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const PhiloxKeys keys = philox_expand(seed);
-  // longest-first assignment pays when the grid runs in several waves and a CTA lives long enough to amortise the search
+  // longest-first assignment pays when the grid runs in several waves and a CTA lives long enough to amortise the search;
+  // CYL_SWEEP_INDEX_ORDER keeps block b on replica b
   int sms = 0;
   CYL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  flags &= ~SWEEP_FLAG_LONGEST_FIRST;
-  const char* lf = getenv("CYL_SMEM_LONGEST_FIRST");                        // "0": keep the index order (tests compare the two)
-  if (B > 8 * sms && nsweeps >= 32 && !(lf && lf[0] == '0')) flags |= SWEEP_FLAG_LONGEST_FIRST;
+  uint32_t kflags = flags & ~(SWEEP_FLAG_LONGEST_FIRST | CYL_SWEEP_INDEX_ORDER);
+  if (B > 8 * sms && nsweeps >= 32 && !(flags & CYL_SWEEP_INDEX_ORDER)) kflags |= SWEEP_FLAG_LONGEST_FIRST;
   kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,
-                                                      seed, replica0, sweep0, nsweeps, variant, flags, obs, prof, series);
+                                                      seed, replica0, sweep0, nsweeps, variant, kflags, obs, prof, series);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
+}
+
+/* shared-memory bytes one replica of Zmax x T needs (the caller decides between this path and the HBM path from it) */
+extern "C" int64_t cyl_sweep_smem_bytes(int Zmax, int T, int is_f64) {
+  if (Zmax <= 0 || T <= 0) return -1;
+  return (int64_t)(is_f64 ? SweepSmemLayout<double>(Zmax, T).total : SweepSmemLayout<float>(Zmax, T).total);
 }
 
 extern "C" int cyl_sweep_smem_f32(void* psi, int B, const int32_t* Z, int Zmax, int T, const CylParams* params,

@@ -43,15 +43,19 @@ class FourierChains:
         st[:, HDR + self.d:] = torch.eye(self.d, dtype=torch.float64).reshape(1, -1)
         self.state = st.to(self.device)
 
-    def run(self, n_steps, measure_every=1, fieldsteps_per_ampstep=1, method="sequential"):
+    LAYOUTS = {None: 0, "cta": 0x100, "warp": 0x200}          # CYL_FOURIER_LAYOUT_* (default: chosen from the chain count)
+
+    def run(self, n_steps, measure_every=1, fieldsteps_per_ampstep=1, method="sequential", layout=None):
         """n_steps measurements, each after measure_every iterations of the chosen driver (run.py:286-317).  A chain keeps
-        one method for its whole life (the Philox move index advances by the method's moves per iteration)."""
+        one method for its whole life (the Philox move index advances by the method's moves per iteration).  `layout`
+        ("cta" / "warp") forces the execution layout; results do not depend on it."""
         m = METHODS[method]
         # Robbins-Monro constants: m = 1 for the amplitude, m = ncoef for the coefficient group, m = d for the joint move
         ratio_real = robbins_monro_ratio(self.target, self.d if m == 1 else 1)
         call("cyl_fourier_am_steps_f64", self.device.index, ptr(self.params), self.nz, self.nth, ptr(self.amp), ptr(self.coeffs),
              ptr(self.state), self.B, self.seed, self.chain0, self.steps_done, int(n_steps), int(measure_every),
-             int(fieldsteps_per_ampstep), self.target, ratio_real, robbins_monro_ratio(self.target, max(1, self.ncoef)), m, stream())
+             int(fieldsteps_per_ampstep), self.target, ratio_real, robbins_monro_ratio(self.target, max(1, self.ncoef)),
+             m | self.LAYOUTS[layout], stream())
         self.steps_done += int(n_steps)
         return self
 

@@ -67,11 +67,13 @@ class ReplicaBatch:
         """Site-updates per sweep summed over the batch."""
         return int(self.Z_host.astype(np.int64).sum()) * self.T
 
-    def run(self, nsweeps, amp_moves=True, measure=True, adapt=True, series=False):
+    def run(self, nsweeps, amp_moves=True, measure=True, adapt=True, series=False, index_order=False):
         """nsweeps sweeps of every replica in one launch.  series=True (with measure): also returns the per-sweep records
         [B, nsweeps, 8] (ops.SERIES_NAMES: amplitude, energies, <|psi|^2>, <|psi|>, width, accept flags) -- the engine's time
         series (me.df, run.py:324-326) for every replica at once."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
+        if index_order:                      # CTA b works on replica b (default: longest replicas first; same results)
+            flags |= _abi.SWEEP_INDEX_ORDER
         ts = torch.zeros(self.B, int(nsweeps), len(ops.SERIES_NAMES), dtype=torch.float64, device=self.device) if (series and measure) else None
         ops.sweep_smem(self.psi, self.Z, self.params, self.chain, self.seed, self.sweeps_done, nsweeps, self.variant, flags,
                        self.replica0, self.obs, self.prof, series=ts)

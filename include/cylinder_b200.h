@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CYL_ABI_VERSION 6
+#define CYL_ABI_VERSION 7
 
 /* error codes */
 #define CYL_OK             0
@@ -44,6 +44,12 @@ extern "C" {
 #define CYL_SWEEP_ADAPT_SIGMA   1u    /* Robbins-Monro width adaptation (On_lattice_simple.py:688-696) */
 #define CYL_SWEEP_AMP_MOVES     2u    /* one global amplitude move per sweep (run_lattice.py:72-90)     */
 #define CYL_SWEEP_MEASURE       4u    /* accumulate observables after every sweep (:121-156)            */
+/* Execution options (they never change results, only how the work is laid out; the library reads no environment
+ * variables and keeps no global option state): */
+#define CYL_SWEEP_INDEX_ORDER   8u    /* cyl_sweep_smem_*: CTA b takes replica b (default: CTAs take the replicas in
+                                         descending row count when the launch is large enough for that to pay)      */
+#define CYL_SWEEP_TILE_ROWS(n)  (((uint32_t)(n) & 0xFFu) << 8)   /* cyl_sweep_hbm_*: tile height 32, 30, 28 or 24
+                                         (default 0: chosen per lattice so that the wave count is near-integral)     */
 
 /* Physical parameters of one replica = constructor arguments of the reference's
  * Cylinder (system_cylinder.py:15) and Lattice (On_lattice_simple.py:18-19). 12 doubles. */
@@ -73,7 +79,7 @@ typedef struct CylParams {
 #define CYL_CH_AMP_PROPOSED  8
 #define CYL_CH_AMP_ACCEPTED  9
 #define CYL_CH_AMP_COUNTER  10   /* Robbins-Monro step counter of the amplitude moves                   */
-#define CYL_CH_FLAGS        11   /* bit0: non-finite energy seen                                         */
+#define CYL_CH_FLAGS        11   /* bit0: non-finite energy seen; bit1: Z[b] outside [1, Zmax] (replica skipped) */
 
 /* Per-replica observable accumulators (sums over measurements), CYL_OBS_DOUBLES doubles. */
 #define CYL_OBS_DOUBLES 16
@@ -189,6 +195,11 @@ int cyl_sweep_smem_f64(void* psi, int B, const int32_t* Z, int Zmax, int T, cons
                        double* chain, uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps,
                        int variant, uint32_t flags, double* obs, double* prof, void* stream);
 
+/* Shared-memory bytes per replica the batched path needs for a Zmax x T lattice (negative: bad arguments); compare with
+ * cyl_device_info's max_smem_optin to choose between this path and the HBM path.  Precondition of cyl_sweep_smem_*:
+ * 1 <= Z[b] <= Zmax for every replica (device array; a violating replica is skipped and flagged in CYL_CH_FLAGS bit 1). */
+int64_t cyl_sweep_smem_bytes(int Zmax, int T, int is_f64);
+
 /* The same sweeps with a time series (the engine's me.df / save_time_series, run.py:324-326): one record per measured
  * sweep and replica, series [B][nsweeps][CYL_SERIES_DOUBLES]; requires CYL_SWEEP_MEASURE. */
 #define CYL_SERIES_DOUBLES 8
@@ -264,6 +275,10 @@ int cyl_fourier_surface_energy_f64(const CylParams* params, const double* amp, i
 #define CYL_FOURIER_SIMULTANEOUS    1   /* run.py:295-304: one joint move of [|a|, |c_i|] (engine step_all)           */
 #define CYL_FOURIER_FIXED_AMPLITUDE 2   /* run.py:305-312: coefficient moves only                                     */
 #define CYL_FOURIER_NO_FIELD        3   /* run.py:313-318: amplitude moves on the bare surface energy                 */
+/* execution layout, OR-ed into `method` (default 0: one CTA per chain when B <= SM count, else one warp per chain;
+ * results do not depend on it) */
+#define CYL_FOURIER_LAYOUT_CTA   0x100
+#define CYL_FOURIER_LAYOUT_WARP  0x200
 
 /* Batched adaptive Metropolis over the Fourier model: run.py:286-317 with the engine arithmetic
  * of SURVEY.md Appendix B (real-group / complex-group moves, Robbins-Monro widths, recursive mean and covariance, proposals

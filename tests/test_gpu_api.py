@@ -167,12 +167,11 @@ def test_single_run_lattice_and_fourier(cuda, tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", ["cta", "warp"])
-def test_batched_fourier_chains_match_oracle(cuda, mode, monkeypatch):
+def test_batched_fourier_chains_match_oracle(cuda, mode):
     """cyl_fourier_am_steps_f64 (amplitude + coefficient moves, Robbins-Monro widths, recursive mean and covariance with
     re-factorisation after measurement 50) vs the numpy restatement on the same Philox draws, in both layouts: one CTA per chain
     (few chains: the energy quadrature shared by eight warps) and one warp per chain (many chains)."""
     import torch
-    monkeypatch.setenv("CYL_FOURIER_MODE", mode)
     from cylinder_b200.fourier_chains import FourierChains
     from oracle import fourier_am_oracle as fa
     B, nfc = 3, (1, 1)
@@ -181,8 +180,8 @@ def test_batched_fourier_chains_match_oracle(cuda, mode, monkeypatch):
     rng = np.random.RandomState(3)
     c0 = rng.normal(0, .15, (B, 9)) + 1j * rng.normal(0, .15, (B, 9))
     fc = FourierChains(P, num_field_coeffs=nfc, amplitude=.05, field_coeffs=c0, seed=99, chain0=10)
-    fc.run(40, measure_every=2, fieldsteps_per_ampstep=2)
-    fc.run(25, measure_every=2, fieldsteps_per_ampstep=2)          # resumes; crosses measurement 50 (covariance adaptation on)
+    fc.run(40, measure_every=2, fieldsteps_per_ampstep=2, layout=mode)
+    fc.run(25, measure_every=2, fieldsteps_per_ampstep=2, layout=mode)          # resumes; crosses measurement 50 (covariance adaptation on)
     for b in range(B):
         Pb = {k: (v[b] if isinstance(v, list) else v) for k, v in P.items()}
         ch = fa.Chain(Pb, 1, 1, .05, c0[b], bound=.99)

@@ -115,9 +115,9 @@ def test_c3_batch_is_independent_of_batching(cuda):
     assert int(full.Z_host.min()) == 40 and int(full.Z_host.max()) == 100 and (full.Z_host % 2 == 1).any()
 
 
-def test_c3_longest_first_assignment_changes_nothing(cuda, monkeypatch):
+def test_c3_longest_first_assignment_changes_nothing(cuda):
     """A launch of many replicas and >= 32 sweeps hands the replicas to the CTAs in descending row count (the kernel's own
-    ranking of Z); CYL_SMEM_LONGEST_FIRST=0, a small shard or a short launch keep the index order.  Same results either
+    ranking of Z); CYL_SWEEP_INDEX_ORDER, a small shard or a short launch keep the index order.  Same results either
     way, replica by replica -- lattice, chain, observables and profiles each in the replica's own slot."""
     import sys, os
     import torch
@@ -127,10 +127,8 @@ def test_c3_longest_first_assignment_changes_nothing(cuda, monkeypatch):
     B = 2000                                                             # > 8 x SM count: ranked launch
     ranked = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11)
     ranked.run(40)
-    monkeypatch.setenv("CYL_SMEM_LONGEST_FIRST", "0")
     plain = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11)
-    plain.run(40)
-    monkeypatch.delenv("CYL_SMEM_LONGEST_FIRST")
+    plain.run(40, index_order=True)
     assert torch.equal(ranked.psi, plain.psi) and torch.equal(ranked.chain, plain.chain)
     assert torch.equal(ranked.obs, plain.obs) and torch.equal(ranked.prof, plain.prof)
     short = ReplicaBatch(bench.grid_params(B, 0), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=11)

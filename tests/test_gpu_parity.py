@@ -523,17 +523,12 @@ def test_hbm_thin_last_tile_matches_oracle(cuda, Z, T):
     psi0 = rng.normal(0, .3, (Z, T)) + 1j * rng.normal(0, .3, (Z, T))
     st = _oracle_state(psi0.copy(), P, lo.SIMPLE, .05)
     par = _params(ops, cuda, P)
-    for th in ("32", "24"):
-        import os
-        os.environ["CYL_HBM_TILE_ROWS"] = th
-        try:
-            st = _oracle_state(psi0.copy(), P, lo.SIMPLE, .05)
-            ws = ops.HbmWorkspace(Z, T, torch.complex128, cuda)
-            ws.pack(torch.tensor(psi0, dtype=torch.complex128, device=cuda))
-            chain = ops.new_chain(1, cuda, amplitude=a, sigma_site=.05)
-            ws.sweep(par, chain[0], 123, 0, 2, lo.SIMPLE, _abi.SWEEP_ADAPT_SIGMA, replica=1)
-        finally:
-            del os.environ["CYL_HBM_TILE_ROWS"]
+    for th in (32, 24):
+        st = _oracle_state(psi0.copy(), P, lo.SIMPLE, .05)
+        ws = ops.HbmWorkspace(Z, T, torch.complex128, cuda)
+        ws.pack(torch.tensor(psi0, dtype=torch.complex128, device=cuda))
+        chain = ops.new_chain(1, cuda, amplitude=a, sigma_site=.05)
+        ws.sweep(par, chain[0], 123, 0, 2, lo.SIMPLE, _abi.SWEEP_ADAPT_SIGMA | _abi.sweep_tile_rows(th), replica=1)
         for s in range(2):
             cb.sweep(st, a, 123, 1, s)
         np.testing.assert_allclose(ws.unpack().cpu().numpy(), st.psi, rtol=0, atol=1e-11)

@@ -85,3 +85,105 @@ def test_amplitude_distribution_matches_oracle(cuda):
     assert abs(g.mean() - abs_a.mean()) < 5 * err, (g.mean(), abs_a.mean(), err)
     assert obs["amplitude_acceptance"].mean().item() == pytest.approx(.3, abs=.06)
     assert (batch.chain[:, 0].abs() < .8).all()
+
+
+# ------------------------------------------------------------------------------------------------------
+# BASELINE config C1 / one point of C3's grid at full size: 50 x 50 base lattice, T = 0.01, alpha = -1, u = 1, C = 1, n = 6
+# (infile.txt:1-19), fp32 storage -- the kernel instantiation and the shapes bench.py times.
+#
+# At this temperature the slow modes of the field need > 10^4 sweeps to equilibrate (the sequential reference does ~5 x 10^4
+# proposals/s/core: 20 sweeps a second), so "run both to equilibrium and compare" is not affordable for the CPU side.  Two
+# tests instead:
+#   (A) paired continuation.  The GPU equilibrates 512 replicas (2 x 10^4 sweeps); the final lattices of 16 of them are
+#       handed to 16 sequential reference chains (oracle, one per host core, random-site order, per-proposal Robbins-Monro),
+#       and BOTH samplers continue from these states for the same number of sweeps.  If the stationary distributions agree,
+#       the start states are draws from it for both and every expectation agrees; the slow modes are shared by each pair, so
+#       the paired differences are sharp.  A bias of the fp32 / checkerboard / 23-bit-draw sampler in any mode that relaxes
+#       within the window (|psi|^2, acceptance, the z-profile <|psi|>(z)) shows up as a non-zero mean difference.
+#   (B) independent chains.  8 reference chains and 512 GPU replicas from the same distribution of random starts
+#       (On_lattice_simple.py:159-182), same schedule; ensemble means within 5 sigma of the (larger) reference scatter.
+# ------------------------------------------------------------------------------------------------------
+C1 = dict(radius=1.0, gamma=1.0, kappa=0.0, intrinsic_curvature=0.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=.01,
+          amp_bound=.8, amp_target_acceptance=.3)
+
+
+def _paired(o, g):
+    """mean and standard error of the paired differences"""
+    d = np.asarray(o) - np.asarray(g)
+    return d.mean(0), d.std(0, ddof=1) / math.sqrt(d.shape[0])
+
+
+@pytest.mark.parametrize("k,variant,amp_moves", [(1.0, "simple", False), (0.55, "simple", False), (1.0, "rescaled_0thorder", False),
+                                                 (1.0, "simple", True)])
+def test_c1_paired_continuation_matches_sequential_reference(cuda, k, variant, amp_moves):
+    import torch
+    from cylinder_b200 import _abi
+    from cylinder_b200.replicas import ReplicaBatch
+    from oracle import sequential_runs as sr
+    B, NP, NSW = 512, 16, 120
+    P = dict(C1, wavenumber=k)
+    batch = ReplicaBatch(dict(P, wavenumber=np.full(B, k)), dims=(50, 50), variant=variant, dtype=torch.complex64, device=cuda,
+                         seed=0xC1, amplitude=0.0 if amp_moves else 0.3)
+    Z, T = int(batch.Z_host[0]), batch.T
+    assert (Z, T) == ((50, 50) if k == 1.0 else (91, 50))
+    batch.run(20000, amp_moves=amp_moves, measure=False)
+    ch0 = batch.chain[:NP].cpu().numpy().copy()
+    starts = batch.psi[:NP, :Z].cpu().numpy().astype(np.complex128)
+    batch.reset_observables()
+    batch.run(NSW, amp_moves=amp_moves, measure=True)
+    ch1 = batch.chain[:NP].cpu().numpy()
+    obs = batch.obs[:NP].cpu().numpy()
+    g_psi2, g_abs = obs[:, _abi.OB_PSI2] / NSW, obs[:, _abi.OB_ABSPSI] / NSW
+    g_acc = (ch1[:, _abi.CH_SITE_ACCEPTED] - ch0[:, _abi.CH_SITE_ACCEPTED]) / (NSW * Z * T)
+    g_prof = batch.prof[:NP, :Z, 2].cpu().numpy() / (NSW * T)
+    tasks = [dict(psi0=starts[i], P=P, variant=lo.VARIANTS[variant], amplitude=ch0[i, _abi.CH_AMPLITUDE],
+                  sigma=ch0[i, _abi.CH_SIGMA_SITE], step_counter=int(ch0[i, _abi.CH_STEP_COUNTER]), nsweeps=NSW, seed=1000 + i,
+                  amp_moves=amp_moves, sigma_amp=ch0[i, _abi.CH_SIGMA_AMP], amp_counter=int(ch0[i, _abi.CH_AMP_COUNTER]))
+             for i in range(NP)]
+    res = sr.run_chains(tasks)
+    for name, o, g in (("psi2", [r["psi2"] for r in res], g_psi2), ("abs_psi", [r["abs_psi"] for r in res], g_abs),
+                       ("acceptance", [r["acceptance"] for r in res], g_acc)):
+        m, se = _paired(o, g)
+        assert abs(m) < 5 * se, (name, m, se, np.mean(o), np.mean(g))
+    # field profile <|psi|>(z), row by row: pooled standard error over the rows (the rows' scatters are alike)
+    m, se = _paired(np.stack([r["profile_abs"] for r in res]), g_prof)
+    pooled = math.sqrt(float(np.mean(se ** 2)))
+    assert np.all(np.abs(m) < 5 * pooled), (float(np.abs(m).max()), pooled)
+    assert g_prof.max() > 1.3 * g_prof.min(), "the profile should be non-trivial at this amplitude"
+    # the paired differences are small compared with the observable itself (the test has power)
+    assert pooled < .05 * float(g_prof.mean())
+    if amp_moves:
+        g_amp_acc = (ch1[:, _abi.CH_AMP_ACCEPTED] - ch0[:, _abi.CH_AMP_ACCEPTED]) / NSW
+        m, se = _paired([r["amp_acceptance"] for r in res], g_amp_acc)
+        assert abs(m) < 5 * se, ("amp_acceptance", m, se)
+        m, se = _paired([r["abs_a"] for r in res], obs[:, _abi.OB_ABS_A] / NSW)
+        assert abs(m) < 5 * se, ("abs_a", m, se)
+        # and the whole ensemble's amplitude acceptance sits at the Robbins-Monro target
+        assert batch.observables()["amplitude_acceptance"].mean().item() == pytest.approx(.3, abs=.03)
+
+
+def test_c1_independent_chains_match_sequential_reference(cuda):
+    import torch
+    from oracle import checkerboard_oracle as cb
+    from oracle import sequential_runs as sr
+    from cylinder_b200.replicas import ReplicaBatch
+    B, NC, BURN, NSW, a = 512, 8, 80, 120, 0.3
+    P = dict(C1, wavenumber=1.0)
+    batch = ReplicaBatch(dict(P, wavenumber=np.full(B, 1.0)), dims=(50, 50), dtype=torch.complex64, device=cuda, seed=77, amplitude=a)
+    batch.run(BURN, amp_moves=False, measure=False)
+    batch.run(NSW, amp_moves=False, measure=True)
+    g = batch.observables()
+    g_psi2 = g["psi_squared"].cpu().numpy()
+    g_prof = (batch.prof[:, :, 2] / (NSW * 50)).cpu().numpy()
+    tasks = [dict(psi0=cb.random_initialize(50, 50, .1, 77, 100000 + i), P=P, amplitude=a, sigma=.005, nsweeps=NSW, burn=BURN, seed=500 + i)
+             for i in range(NC)]
+    res = sr.run_chains(tasks)
+    o_psi2 = np.array([r["psi2"] for r in res])
+    err = math.hypot(o_psi2.std(ddof=1) / math.sqrt(NC), g_psi2.std(ddof=1) / math.sqrt(B))
+    assert abs(o_psi2.mean() - g_psi2.mean()) < 5 * err, (o_psi2.mean(), g_psi2.mean(), err)
+    o_acc = np.array([r["acceptance"] for r in res])
+    assert o_acc.mean() == pytest.approx(g["site_acceptance"].mean().item(), abs=.01)
+    o_prof = np.stack([r["profile_abs"] for r in res])
+    perr = np.hypot(o_prof.std(0, ddof=1) / math.sqrt(NC), g_prof.std(0, ddof=1) / math.sqrt(B))
+    pooled = math.sqrt(float(np.mean(perr ** 2)))
+    assert np.all(np.abs(o_prof.mean(0) - g_prof.mean(0)) < 5 * pooled), (float(np.abs(o_prof.mean(0) - g_prof.mean(0)).max()), pooled)
