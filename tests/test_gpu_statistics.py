@@ -149,7 +149,8 @@ def test_c1_paired_continuation_matches_sequential_reference(cuda, k, variant, a
     m, se = _paired(np.stack([r["profile_abs"] for r in res]), g_prof)
     pooled = math.sqrt(float(np.mean(se ** 2)))
     assert np.all(np.abs(m) < 5 * pooled), (float(np.abs(m).max()), pooled)
-    assert g_prof.max() > 1.3 * g_prof.min(), "the profile should be non-trivial at this amplitude"
+    if not amp_moves:                           # a = 0.3: the order parameter is suppressed where n A_theta is large
+        assert g_prof.max() > 1.3 * g_prof.min(), "the profile should be non-trivial at this amplitude"
     # the paired differences are small compared with the observable itself (the test has power)
     assert pooled < .05 * float(g_prof.mean())
     if amp_moves:
