@@ -178,24 +178,6 @@ __device__ __forceinline__ void energy_zbond(EAcc<R>& e, R wc, R wd, C hi, C lo,
   e.ed += wd * m;
   if (measure) e.ec += wc * m;
 }
-// Two adjacent sites a (column j), b (column j+1) of one row with the sites la, lb above them and wl left of a: their own terms,
-// their bonds upwards and the bonds (wl, a), (a, b).  The five moments are summed over the pair before the weights are applied.
-template <typename R, typename C>
-__device__ __forceinline__ void energy_pair(EAcc<R>& e, const RowW<R>& w, C a, C b, C la, C lb, C wl, bool measure, bool with_abs = true) {
-  const R p2a = a.x * a.x + a.y * a.y, p2b = b.x * b.x + b.y * b.y;
-  const R s1 = p2a + p2b, s2 = p2a * p2a + p2b * p2b;
-  const R zar = a.x - la.x, zai = a.y - la.y, zbr = b.x - lb.x, zbi = b.y - lb.y;
-  const R m3 = zbi * zbi + (zbr * zbr + (zai * zai + zar * zar));
-  const R tar = a.x - wl.x, tai = a.y - wl.y, tbr = b.x - a.x, tbi = b.y - a.y;
-  const R m4 = tbi * tbi + (tbr * tbr + (tai * tai + tar * tar));
-  const R m5 = (a.x * tai - a.y * tar) + (b.x * tbi - b.y * tbr);         // Im(conj(psi) dth)
-  e.ed += w.dif[0] * s1 + w.dif[1] * s2 + w.dif[2] * m3 + w.dif[3] * m4 + w.dif[4] * m5;
-  if (measure) {
-    e.ec += w.cur[0] * s1 + w.cur[1] * s2 + w.cur[2] * m3 + w.cur[3] * m4 + w.cur[4] * m5;
-    e.s2 += s1;
-    if (with_abs) e.sa += sqrt_fast(p2a) + sqrt_fast(p2b);
-  }
-}
 // theta-bond between the site `hi` (column j) and `lo` (column j-1) of one row
 template <typename R, typename C>
 __device__ __forceinline__ void energy_tbond(EAcc<R>& e, const RowW<R>& w, C hi, C lo, bool measure) {

@@ -102,6 +102,105 @@ template <> struct Draw<float> {
   }
 };
 
+// ------------------------------------------------------------------------------------------------------
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2, PTX *.f32x2): a complex number IS a (re, im) pair, so the linear part of
+// dE runs two lanes per instruction.  ptxas folds the packing moves, lane swaps, per-lane negations and scalar broadcasts
+// below into operand modifiers of the packed instruction (R.F32x2.LO_HI, .NP, R.F32), so none of them costs an instruction.
+// These kernels are bound by instruction issue (profiles/r02_*): the packed form of a site move is ~17 instructions shorter.
+// ------------------------------------------------------------------------------------------------------
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 pk2(float x, float y) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ F2 pk2(float2 a) { return pk2(a.x, a.y); }
+__device__ __forceinline__ float2 up2(F2 a) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a.v)); return r; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return d; }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v)); return d; }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v)); return d; }
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) { F2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v)); return d; }
+__device__ __forceinline__ F2 fma2s(float s, F2 b, F2 c) { return fma2(pk2(s, s), b, c); }       // scalar * pair + pair
+__device__ __forceinline__ F2 mul2s(float s, F2 b) { return mul2(pk2(s, s), b); }
+__device__ __forceinline__ F2 neg2(F2 a) { const float2 t = up2(a); return pk2(-t.x, -t.y); }
+__device__ __forceinline__ float hsum2(F2 a) { const float2 t = up2(a); return t.x + t.y; }
+
+// The same pair operations for either working precision: Pk<float> = packed FFMA2 lanes, Pk<double> = two scalars.  Used by
+// code that is written once for both instantiations (the row-serial energy pass of the batched kernel).
+template <typename R> struct Pk;
+template <> struct Pk<float> {
+  using T = F2;
+  static __device__ __forceinline__ T make(float2 a) { return pk2(a); }
+  static __device__ __forceinline__ T zero() { return pk2(0.0f, 0.0f); }
+  static __device__ __forceinline__ T fma(T a, T b, T c) { return fma2(a, b, c); }
+  static __device__ __forceinline__ T add(T a, T b) { return add2(a, b); }
+  static __device__ __forceinline__ T sub(T a, T b) { return sub2(a, b); }
+  static __device__ __forceinline__ T rot(T a) { const float2 t = up2(a); return pk2(-t.y, t.x); }     // i a
+  static __device__ __forceinline__ float hsum(T a) { return hsum2(a); }
+  static __device__ __forceinline__ float2 get(T a) { return up2(a); }
+};
+template <> struct Pk<double> {
+  struct T { double x, y; };
+  static __device__ __forceinline__ T make(double2 a) { return T{a.x, a.y}; }
+  static __device__ __forceinline__ T zero() { return T{0.0, 0.0}; }
+  static __device__ __forceinline__ T fma(T a, T b, T c) { return T{::fma(a.x, b.x, c.x), ::fma(a.y, b.y, c.y)}; }
+  static __device__ __forceinline__ T add(T a, T b) { return T{a.x + b.x, a.y + b.y}; }
+  static __device__ __forceinline__ T sub(T a, T b) { return T{a.x - b.x, a.y - b.y}; }
+  static __device__ __forceinline__ T rot(T a) { return T{-a.y, a.x}; }
+  static __device__ __forceinline__ double hsum(T a) { return a.x + a.y; }
+  static __device__ __forceinline__ double2 get(T a) { return make_double2(a.x, a.y); }
+};
+
+// dE / K of the move p -> p + d, packed (same polynomial as site_delta_over_k, regrouped so that the (re, im) lanes stay
+// together until two horizontal sums):
+//   quad = Re(conj(d) (csum d + 2 g)) + Re(conj(-i d) v),   g = csum p - (clz L + crz Rz + clt W + crt E),  v = xl W - xr E
+//   s    = Re(conj(d) (d + 2 p))
+// (Re(conj(d) i v) = Re(conj(-i d) v): the rotation sits on d, where it is a lane swap with one negation -- an operand modifier.)
+__device__ __forceinline__ float site_delta_over_k_packed(const RowCoef<float>& c, float2 p, float2 L, float2 Rz, float2 W, float2 E, F2 d) {
+  const F2 pp = pk2(p);
+  F2 n = mul2s(c.clz, pk2(L));
+  n = fma2s(c.crz, pk2(Rz), n);
+  n = fma2s(c.clt, pk2(W), n);
+  n = fma2s(c.crt, pk2(E), n);
+  const F2 g = fma2s(c.csum, pp, neg2(n));
+  F2 v = mul2s(c.xl, pk2(W));
+  v = fma2s(-c.xr, pk2(E), v);
+  const F2 two = pk2(2.0f, 2.0f);
+  const float2 dd = up2(d);
+  F2 m = mul2(d, fma2(g, two, mul2s(c.csum, d)));
+  m = fma2(pk2(-dd.y, dd.x), neg2(v), m);                   // (d.y, -d.x) . v
+  const float quad = hsum2(m);
+  const float s = hsum2(mul2(d, fma2(pp, two, d)));
+  const float p2 = __fmaf_rn(p.x, p.x, p.y * p.y);
+  return __fmaf_rn(c.mass, s, __fmaf_rn(c.hu * s, __fmaf_rn(2.0f, p2, s), quad));
+}
+
+// One proposal of Lattice.step_lattice_loc at a site with value pv and neighbours L, Rz (rows above / below), W, E (columns
+// left / right): draws from the Philox block x, d = sigma sgmul (z_re, z_im), dE/K, accept rule.  q = the site's value after
+// the move.  EVERY sweep kernel goes through this function, so the fp32 paths take bit-identical decisions.
+template <typename R, typename C>
+__device__ __forceinline__ bool site_propose(const RowCoef<R>& rc, C pv, C L, C Rz, C W, C E, R sigma, uint2 x, C& q) {
+  R zre, zim;
+  Draw<R>::normals(x.x, x.y, zre, zim);
+  const R w = sigma * rc.sgmul;
+  const R dre = w * zre, dim = w * zim;
+  const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
+  const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
+  q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+  return acc;
+}
+#ifndef CYL_NO_PACKED_F32
+template <>
+__device__ __forceinline__ bool site_propose<float, float2>(const RowCoef<float>& rc, float2 pv, float2 L, float2 Rz, float2 W, float2 E,
+                                                            float sigma, uint2 x, float2& q) {
+  float rad;                                                                  // as Draw<float>::normals
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg2_fast(u01_f32(x.x))));
+  float s, c;
+  __sincosf(6.283185307179586f * u16_f32(__byte_perm(x.x, x.y, 0x0004) & 0xFFFFu), &s, &c);
+  const F2 d = mul2s(rad * (sigma * rc.sgmul), pk2(c, s));
+  const float den = site_delta_over_k_packed(rc, pv, L, Rz, W, E, d);
+  const bool acc = Draw<float>::accept(x.y, den, rc.kacc);
+  q = acc ? up2(add2(pk2(pv), d)) : pv;
+  return acc;
+}
+#endif
+
 // draws of one global amplitude move from one Philox4x32-10 block: (x.x, x.y) -> unit normal, x.z -> acceptance uniform
 __device__ __forceinline__ void amp_draw(uint4 x, double& z, double& u) {
   double s, c;

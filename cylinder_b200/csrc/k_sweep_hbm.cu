@@ -432,13 +432,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const RowCoef<R> rc = coef[r];
       const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
       const uint2 x = philox2x32_10(site, c1, kc, kr);
-      R zre, zim;
-      Draw<R>::normals(x.x, x.y, zre, zim);
-      const R w = sigma * rc.sgmul;
-      const R dre = w * zre, dim = w * zim;
-      const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-      const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-      const C q = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+      C q;
+      const bool acc = site_propose<R, C>(rc, pv, Ln, Rz, W, E, sigma, x, q);
       if (acc) own[0] = q;
       nacc += (acc && counted);
       if (EXTRAS && HBM_ENERGY_ON && counted) {
@@ -503,13 +498,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const C W = oth[r * SWH + colW], E = oth[r * SWH + colE];
       const RowCoef<R> rc = coef[r];
       const uint2 x = philox2x32_10((uint32_t)(gi * g.T + gj), c1, kc, kr);
-      R zre, zim;
-      Draw<R>::normals(x.x, x.y, zre, zim);
-      const R w = sigma * rc.sgmul;
-      const R dre = w * zre, dim = w * zim;
-      const R den = site_delta_over_k<R, C>(rc, pv, Ln, Rz, W, E, dre, dim);
-      const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-      const C qv = acc ? Real<R>::make(pv.x + dre, pv.y + dim) : pv;
+      C qv;
+      const bool acc = site_propose<R, C>(rc, pv, Ln, Rz, W, E, sigma, x, qv);
       if (acc) own[r * SWH + col] = qv;
       const int li = r - NCOL, lj = q - HS;
       const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);

@@ -92,13 +92,13 @@ struct SweepSmemLayout {
 };
 
 // Coefficient rows and current energy weights of every row at amplitude a (the accepted amplitude is the metric reference
-// too); dif <- 0.  All eight warps, rows dealt round-robin to the warps so that every warp runs the chain once.
+// too); dif <- 0.  Row i on thread i: the rows fill whole warps (the kernel is bound by instruction issue, and a warp with
+// eight active lanes issues as many instructions as a full one; the chain's latency is the same either way).
 template <typename R>
 __device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowW<R>* roww, const RowTrig<R>* trig, const RepConst<R>& rc,
                                              double a, int Z, bool weights) {
   const AmpGeo<R> ag = amp_geo<R>(rc, a);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = lane * SWEEP_NWARP + warp; i < Z; i += SWEEP_NT) {
+  for (int i = threadIdx.x; i < Z; i += SWEEP_NT) {
     const RowTrig<R> t = trig[i], tp = trig[i + 1 == Z ? 0 : i + 1];
     const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm);
     const GeoT<R> gp = geo_sc<R>(ag, tp.sm, tp.cm);                  // z_{i+1/2} = z_{(i+1)-1/2}, periodic
@@ -117,20 +117,50 @@ __device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowW<R>* roww, co
 
 __device__ __forceinline__ double surface_energy_of(const CylParams& p, double a) { return surface_energy_warp(p, a, nullptr, nullptr, true); }
 
+// The five moments of the field energy (sum |psi|^2, sum |psi|^4, sum |dz psi|^2, sum |dth psi|^2,
+// sum Im(conj(psi) dth psi); differences not divided by the pixel lengths) and the profile sums of Lattice.measure
+// (On_lattice_simple.py:121-131: sum psi, sum |psi|) over the column pairs [p0, p1) of ONE row, walking along theta: the left
+// neighbour is the previous iteration's site, the row above comes by 16-byte loads like the row itself, and the row weights
+// are applied once per half row by the caller instead of once per site.  (re, im) lanes stay packed (FFMA2) until the end.
+template <typename R, typename C, bool MEAS>
+__device__ __forceinline__ void half_row_moments(const C* __restrict__ row, const C* __restrict__ up, int p0, int p1, int T,
+                                                 R (&S)[5], R& sre, R& sim, R& sabs) {
+  using P = Pk<R>;
+  using V = typename P::T;
+  struct __align__(16) Quad { C a, b; };
+  const Quad* rq = reinterpret_cast<const Quad*>(row);
+  const Quad* uq = reinterpret_cast<const Quad*>(up);
+  V wl = P::make(row[(p0 == 0 ? T : 2 * p0) - 1]);
+  R s2 = 0, s4 = 0, sa = 0;
+  V dz = P::zero(), dt = P::zero(), im = P::zero(), sp = P::zero();
+#pragma unroll 2
+  for (int k = p0; k < p1; ++k) {
+    const Quad q = rq[k], l = uq[k];
+    const V A = P::make(q.a), B = P::make(q.b);
+    const R p2a = q.a.x * q.a.x + q.a.y * q.a.y, p2b = q.b.x * q.b.x + q.b.y * q.b.y;
+    s2 += p2a + p2b;
+    s4 += p2a * p2a + p2b * p2b;
+    if (MEAS) { sa += sqrt_fast(p2a) + sqrt_fast(p2b); sp = P::add(sp, P::add(A, B)); }
+    const V za = P::sub(A, P::make(l.a)), zb = P::sub(B, P::make(l.b));
+    dz = P::fma(za, za, dz); dz = P::fma(zb, zb, dz);
+    const V ta = P::sub(A, wl), tb = P::sub(B, A);
+    dt = P::fma(ta, ta, dt); dt = P::fma(tb, tb, dt);
+    im = P::fma(P::rot(A), ta, im); im = P::fma(P::rot(B), tb, im);   // (-a.y, a.x) . t = Im(conj(a) t)
+    wl = B;
+  }
+  S[0] = s2; S[1] = s4; S[2] = P::hsum(dz); S[3] = P::hsum(dt); S[4] = P::hsum(im);
+  const C spc = P::get(sp);
+  sre = spc.x; sim = spc.y; sabs = sa;
+}
+
 // one site move; returns the accept flag, `q` = the site's value after the move
 template <typename R, typename C>
 __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz, const C W, const C E, const RowCoef<R>& rc,
                                           R sigma, uint32_t site, uint32_t c1, uint32_t key, C& q, int& nacc) {
   const C pv = psi[idx];
   const uint2 x = philox2x32_10(site, c1, key);
-  R zre, zim;
-  Draw<R>::normals(x.x, x.y, zre, zim);
-  const R w = sigma * rc.sgmul;
-  const R dre = w * zre, dim = w * zim;
-  const R den = site_delta_over_k<R, C>(rc, pv, L, Rz, W, E, dre, dim);
-  const bool acc = Draw<R>::accept(x.y, den, rc.kacc);
-  q = pv;
-  if (acc) { q = Real<R>::make(pv.x + dre, pv.y + dim); psi[idx] = q; ++nacc; }
+  const bool acc = site_propose<R, C>(rc, pv, L, Rz, W, E, sigma, x, q);
+  if (acc) { psi[idx] = q; ++nacc; }
   return acc;
 }
 
@@ -309,7 +339,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         } else if (SMEM_WEIGHTS_ON) {
           const AmpGeo<R> ae = amp_geo<R>(rc, a_new), ar = amp_geo<R>(rc, a);
           const bool needs_ref = variant == CYL_VARIANT_RESCALED_0TH || variant == CYL_VARIANT_RESCALED_1ST;
-          for (int i = lane * (SWEEP_NWARP - 1) + warp; i < Z; i += SWEEP_NT - 32) {
+          for (int i = tid; i < Z; i += SWEEP_NT - 32) {                   // row i on thread i: full warps
             const RowTrig<R> t = trig[i];
             const GeoT<R> g0e = geo_sc<R>(ae, t.s0, t.c0), gme = geo_sc<R>(ae, t.sm, t.cm);
             const GeoT<R> g0r = needs_ref ? geo_sc<R>(ar, t.s0, t.c0) : g0e;     // a_ref = current amplitude (:75)
@@ -439,85 +469,72 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     PHASE_MARK(1);
 
-    // ---- E. field energy of the swept lattice under the current weights and its change under the proposal's: every site's
-    //         own terms and its bonds to the row above and to the column on its left (each bond once), plus the rows'
-    //         constant terms.  A separate pass over the final field costs fewer instructions than closing bonds inside the
-    //         colour passes, where the bookkeeping of who closes which bond is per site (and divergent with three colours).
-    //         With profiles on, sum |psi| comes from the profile pass below instead. ----
-    if (extras && SMEM_ENERGY_ON) {
-      if (mapped) {
-        if (col_active) {
-          struct __align__(16) Pair { C a, b; };
-          const int j0 = 2 * cj, oW = (j0 == 0 ? T : 0) - 1, step = RGe * T;
-          const C* o = psi + rg * T + j0;                                  // walks down the thread's rows, as in the site loops
-          const RowW<R>* pw = roww + rg;
-          int oL = (rg == 0 ? nsite : 0) - T;                              // periodic wrap upwards: first row of group 0 only
-          auto rows = [&](auto meas, auto with_abs) {                      // the measurement terms compiled in or out
-#pragma unroll 1
-            for (int i = rg; i < Z; i += RGe, o += step, pw += RGe) {
-              const RowW<R> w = *pw;
-              const Pair q = *reinterpret_cast<const Pair*>(o), l = *reinterpret_cast<const Pair*>(o + oL);
-              const C wl = o[oW];
-              oL = -T;
-              energy_pair<R, C>(e, w, q.a, q.b, l.a, l.b, wl, decltype(meas)::value, decltype(with_abs)::value);
-              if (cj == 0) {
-                e.ed += w.cst[1];
-                if (decltype(meas)::value) e.ec += w.cst[0];
-              }
-            }
-          };
-          if (!measure) rows(std::false_type{}, std::false_type{});
-          else if (profiles) rows(std::true_type{}, std::false_type{});
-          else rows(std::true_type{}, std::true_type{});
-        }
-      } else {
-        for (int i = warp; i < Z; i += SWEEP_NWARP) {                      // T odd or wide: a warp per row
-          const int row = i * T, up = (i == 0 ? nsite : row) - T;
-          const RowW<R> w = roww[i];
-          for (int j = lane; j < T; j += 32) {
-            const C q = psi[row + j], l = psi[up + j], wl = psi[row + (j == 0 ? T : j) - 1];
-            energy_own<R, C>(e, w, q, measure, !profiles);
-            energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, l, measure);
-            energy_tbond<R, C>(e, w, q, wl, measure);
-          }
-          if (lane == 0) {
-            e.ed += w.cst[1];
-            if (measure) e.ec += w.cst[0];
-          }
-        }
-      }
-    }
-    // profiles of Lattice.measure (:121-131), read-only like the energy pass, so no barrier in between.  Even T: two
-    // adjacent threads per row, each half a row of 16-byte loads (rows on consecutive lane pairs: conflict-free), combined by
-    // one shuffle; every thread keeps its own share of sum |psi|.
-    if (profiles) {
+    // ---- E. field energy of the swept lattice under the current weights and its change under the proposal's, and the row
+    //         sums of Lattice.measure (:121-131), in ONE read-only pass over the final field.  Even T: two adjacent threads per
+    //         row, each walking half the row along theta (half_row_moments: every site's own terms, its bond to the row above
+    //         and to the column on its left -- each bond once); the weights for a and for (a' - a) are applied once per half
+    //         row, the rows' constant terms (background energy of the rescaled variants) ride in the same sums, and the two
+    //         halves' profile sums meet in one shuffle.  Rows on consecutive lane pairs: conflict-free 16-byte loads.  A
+    //         separate pass costs fewer instructions than closing bonds inside the colour passes, where the bookkeeping of who
+    //         closes which bond is per site (and divergent with three colours). ----
+    bool has_rows = false;                                                 // warp-uniform: did this warp accumulate anything?
+    if ((extras && SMEM_ENERGY_ON) || profiles) {
       if ((T & 1) == 0) {
-        struct __align__(16) Pair { C a, b; };
         const int npair = T >> 1, h0 = npair >> 1, half = tid & 1;
         const int p0 = half ? h0 : 0, p1 = half ? npair : h0;
-        for (int i = tid >> 1; i < ((Z + SWEEP_NT / 2 - 1) / (SWEEP_NT / 2)) * (SWEEP_NT / 2); i += SWEEP_NT / 2) {
-          R sa = 0, sre = 0, sim = 0;
-          if (i < Z) {
-            const Pair* rowp = reinterpret_cast<const Pair*>(psi + i * T);
-            for (int k = p0; k < p1; ++k) {
-              const Pair v = rowp[k];
-              sre += v.a.x + v.b.x; sim += v.a.y + v.b.y;
-              sa += sqrt_fast(v.a.x * v.a.x + v.a.y * v.a.y) + sqrt_fast(v.b.x * v.b.x + v.b.y * v.b.y);
+        has_rows = (tid & ~31) < 2 * Z;
+        auto rows = [&](auto meas) {
+          constexpr bool MEAS = decltype(meas)::value;
+          for (int ib = (tid & ~31) >> 1; ib < Z; ib += SWEEP_NT / 2) {    // warp-uniform trip count (shuffle below)
+            const int i = ib + (lane >> 1);
+            R S[5] = {R(0), R(0), R(0), R(0), R(0)}, sre = R(0), sim = R(0), sabs = R(0);
+            if (i < Z) {
+              half_row_moments<R, C, MEAS>(psi + i * T, psi + (i == 0 ? nsite : i * T) - T, p0, p1, T, S, sre, sim, sabs);
+              const RowW<R> w = roww[i];
+              R ed = w.dif[0] * S[0] + w.dif[1] * S[1] + w.dif[2] * S[2] + w.dif[3] * S[3] + w.dif[4] * S[4];
+              if (half == 0) ed += w.cst[1];
+              e.ed += ed;
+              if (MEAS) {
+                R ec = w.cur[0] * S[0] + w.cur[1] * S[1] + w.cur[2] * S[2] + w.cur[3] * S[3] + w.cur[4] * S[4];
+                if (half == 0) ec += w.cst[0];
+                e.ec += ec; e.s2 += S[0]; e.sa += sabs;
+              }
+            }
+            if (MEAS && profiles) {
+              sre += __shfl_xor_sync(0xffffffffu, sre, 1); sim += __shfl_xor_sync(0xffffffffu, sim, 1); sabs += __shfl_xor_sync(0xffffffffu, sabs, 1);
+              if (i < Z && half == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sabs; }
             }
           }
-          e.sa += sa;
-          sre += __shfl_xor_sync(0xffffffffu, sre, 1); sim += __shfl_xor_sync(0xffffffffu, sim, 1); sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-          if (i < Z && half == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa; }
-        }
+        };
+        if (measure) rows(std::true_type{}); else rows(std::false_type{});
       } else {
-        for (int i = tid; i < Z; i += SWEEP_NT) {
-          R sa = 0, sre = 0, sim = 0;
-          for (int j = 0; j < T; ++j) {
-            const C v = psi[i * T + j];
-            sre += v.x; sim += v.y; sa += sqrt_fast(v.x * v.x + v.y * v.y);
+        has_rows = true;
+        if (extras && SMEM_ENERGY_ON) {
+          for (int i = warp; i < Z; i += SWEEP_NWARP) {                    // T odd: a warp per row
+            const int row = i * T, up = (i == 0 ? nsite : row) - T;
+            const RowW<R> w = roww[i];
+            for (int j = lane; j < T; j += 32) {
+              const C q = psi[row + j], l = psi[up + j], wl = psi[row + (j == 0 ? T : j) - 1];
+              energy_own<R, C>(e, w, q, measure, !profiles);
+              energy_zbond<R, C>(e, w.cur[2], w.dif[2], q, l, measure);
+              energy_tbond<R, C>(e, w, q, wl, measure);
+            }
+            if (lane == 0) {
+              e.ed += w.cst[1];
+              if (measure) e.ec += w.cst[0];
+            }
           }
-          e.sa += sa;
-          prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa;
+        }
+        if (profiles) {
+          for (int i = tid; i < Z; i += SWEEP_NT) {
+            R sa = 0, sre = 0, sim = 0;
+            for (int j = 0; j < T; ++j) {
+              const C v = psi[i * T + j];
+              sre += v.x; sim += v.y; sa += sqrt_fast(v.x * v.x + v.y * v.y);
+            }
+            e.sa += sa;
+            prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sa;
+          }
         }
       }
     }
@@ -526,7 +543,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     {
       const int wacc = __reduce_add_sync(0xffffffffu, nacc);
       R v[4] = {e.ec, e.ed, e.s2, e.sa};
-      if (extras) {
+      if (extras && has_rows) {                                            // the other warps hold zeros
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
       }
