@@ -189,11 +189,12 @@ __device__ __forceinline__ bool site_propose(const RowCoef<R>& rc, C pv, C L, C 
 template <>
 __device__ __forceinline__ bool site_propose<float, float2>(const RowCoef<float>& rc, float2 pv, float2 L, float2 Rz, float2 W, float2 E,
                                                             float sigma, uint2 x, float2& q) {
-  float rad;                                                                  // as Draw<float>::normals
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg2_fast(u01_f32(x.x))));
+  // Box-Muller as Draw<float>::normals, with the constant of sqrt(-2 ln u) = sqrt(2 ln 2) sqrt(-lg2 u) folded into the width
+  float rad;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-lg2_fast(u01_f32(x.x))));
   float s, c;
   __sincosf(6.283185307179586f * u16_f32(__byte_perm(x.x, x.y, 0x0004) & 0xFFFFu), &s, &c);
-  const F2 d = mul2s(rad * (sigma * rc.sgmul), pk2(c, s));
+  const F2 d = mul2s(rad * ((1.1774100225154747f * sigma) * rc.sgmul), pk2(c, s));
   const float den = site_delta_over_k_packed(rc, pv, L, Rz, W, E, d);
   const bool acc = Draw<float>::accept(x.y, den, rc.kacc);
   q = acc ? up2(add2(pk2(pv), d)) : pv;

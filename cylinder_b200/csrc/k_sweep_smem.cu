@@ -48,7 +48,8 @@ struct SmemScalars {
   double obs[CYL_OBS_DOUBLES];      // observable sums of this launch, flushed once at the end
   RmLogs<R> rm;                     // logarithms of this sweep's Robbins-Monro factors (phase T -> phase D)
   int amp_accept;
-};
+  alignas(16) uint32_t keys[12];    // the ten Philox round keys of this replica's site stream: three loads per colour pass
+};                                  // instead of re-deriving the Weyl sequence (18 instructions) in every warp
 
 // Optional per-phase cycle accounting (build with CYL_EXTRA_NVCC_FLAGS=-DCYL_PHASE_TIMING): thread 0 accumulates
 // clock64() deltas into obs slots 10..15 = proposal tables, site moves, energy + profiles + reduction, decision, rebuild.
@@ -72,6 +73,12 @@ struct SmemScalars {
 #define SWEEP_FLAG_LONGEST_FIRST 0x80000000u   // set by the launcher, not part of the ABI: see the kernel prologue
 #define AMP_CHUNK 32                // amplitude-move draws are precomputed for this many sweeps at a time
 
+// Energy weights of a row in this kernel: for the current amplitude, and for the proposal (their DIFFERENCE is taken where
+// it is used, in working precision, so the chain samples exactly the model with the rounded weights); cst = the rows'
+// constant terms (background energy of the rescaled variants) for {current, proposal}.
+template <typename R>
+struct __align__(16) RowWS { R cur[5]; R nxt[5]; R cst[2]; };
+
 template <typename R>
 struct SweepSmemLayout {
   using C = typename Real<R>::complex_t;
@@ -81,7 +88,7 @@ struct SweepSmemLayout {
     o = (o + 15) & ~(size_t)15;
     off_coef = o; o += (size_t)Zmax * sizeof(RowCoef<R>);
     off_trig = o; o += (size_t)Zmax * sizeof(RowTrig<R>);
-    off_w = o;    o += (size_t)Zmax * sizeof(RowW<R>);
+    off_w = o;    o += (size_t)Zmax * sizeof(RowWS<R>);
     off_prof = o; o += (size_t)Zmax * 3 * sizeof(R);          // per-launch profile sums, flushed once at the end
     o = (o + 15) & ~(size_t)15;
     off_amp = o;  o += 2 * AMP_CHUNK * sizeof(double);          // unit normal + T ln(u) per sweep
@@ -91,25 +98,55 @@ struct SweepSmemLayout {
   }
 };
 
-// Coefficient rows and current energy weights of every row at amplitude a (the accepted amplitude is the metric reference
-// too); dif <- 0.  Row i on thread i: the rows fill whole warps (the kernel is bound by instruction issue, and a warp with
-// eight active lanes issues as many instructions as a full one; the chain's latency is the same either way).
 template <typename R>
-__device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowW<R>* roww, const RowTrig<R>* trig, const RepConst<R>& rc,
-                                             double a, int Z, bool weights) {
+__device__ __forceinline__ bool weights_need_ref(int variant) { return variant == CYL_VARIANT_RESCALED_0TH || variant == CYL_VARIANT_RESCALED_1ST; }
+
+// Tables of an accepted amplitude a (the accepted amplitude becomes the metric reference too).  Coefficient row i on thread i;
+// the current weights of row i on thread NT/2 + i, i.e. on other warps, so the two chains run side by side (this phase has
+// one barrier behind it and nothing else to do).  `weights` = evaluate the weights; otherwise `adopt` = take the proposal's
+// (variants whose weights do not involve the reference amplitude: they were evaluated for exactly this amplitude).
+// Rows fill whole warps: the kernel is bound by instruction issue, and a warp with eight active lanes issues as many
+// instructions as a full one.
+template <typename R>
+__device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowWS<R>* roww, const RowTrig<R>* trig, const RepConst<R>& rc,
+                                             double a, int Z, bool weights, bool adopt) {
   const AmpGeo<R> ag = amp_geo<R>(rc, a);
-  for (int i = threadIdx.x; i < Z; i += SWEEP_NT) {
+  const int tid = threadIdx.x;
+  const bool split = 2 * Z <= SWEEP_NT;                                  // weights on the upper half of the CTA
+  for (int i = tid; i < Z; i += SWEEP_NT) {
     const RowTrig<R> t = trig[i], tp = trig[i + 1 == Z ? 0 : i + 1];
     const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm);
     const GeoT<R> gp = geo_sc<R>(ag, tp.sm, tp.cm);                  // z_{i+1/2} = z_{(i+1)-1/2}, periodic
     coef[i] = coef_row<R>(rc, g0, gm, gp);
-    if (weights) {
+    if (weights && !split) {
       R wf[6];
       weight_row<R>(rc, g0, gm, g0, wf);
-      RowW<R> w;
+      RowWS<R> w;
 #pragma unroll
-      for (int q = 0; q < 5; ++q) { w.cur[q] = wf[q]; w.dif[q] = R(0); }
-      w.cst[0] = wf[5]; w.cst[1] = R(0);
+      for (int q = 0; q < 5; ++q) { w.cur[q] = wf[q]; w.nxt[q] = wf[q]; }
+      w.cst[0] = wf[5]; w.cst[1] = wf[5];
+      roww[i] = w;
+    }
+  }
+  if (weights && split) {
+    const int i = tid - SWEEP_NT / 2;
+    if (i >= 0 && i < Z) {
+      const RowTrig<R> t = trig[i];
+      const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm);
+      R wf[6];
+      weight_row<R>(rc, g0, gm, g0, wf);
+      RowWS<R> w;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) { w.cur[q] = wf[q]; w.nxt[q] = wf[q]; }
+      w.cst[0] = wf[5]; w.cst[1] = wf[5];
+      roww[i] = w;
+    }
+  } else if (!weights && adopt) {
+    for (int i = SWEEP_NT - 1 - tid; i < Z; i += SWEEP_NT) {             // from the top of the CTA: not the coefficient threads
+      RowWS<R> w = roww[i];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) w.cur[q] = w.nxt[q];
+      w.cst[0] = w.cst[1];
       roww[i] = w;
     }
   }
@@ -181,7 +218,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   C* psi = reinterpret_cast<C*>(smem_raw);
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
   RowTrig<R>* trig = reinterpret_cast<RowTrig<R>*>(smem_raw + lay.off_trig);
-  RowW<R>* roww = reinterpret_cast<RowW<R>*>(smem_raw + lay.off_w);
+  RowWS<R>* roww = reinterpret_cast<RowWS<R>*>(smem_raw + lay.off_w);
   R* prof_s = reinterpret_cast<R*>(smem_raw + lay.off_prof);
   double* ampz = reinterpret_cast<double*>(smem_raw + lay.off_amp);
   double* amplu = ampz + AMP_CHUNK;
@@ -273,6 +310,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     sc->amp_accept = 0;
     for (int q = 0; q < CYL_OBS_DOUBLES; ++q) sc->obs[q] = 0.0;
   }
+  if (tid >= 32 && tid < 42) sc->keys[tid - 32] = stream.key + (uint32_t)(tid - 32) * PHILOX_W0;
   for (int s = tid; s < nsite; s += SWEEP_NT) psi[s] = psi_b[s];
   for (int s = tid; s < 3 * Z; s += SWEEP_NT) prof_s[s] = R(0);
   {
@@ -281,13 +319,14 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     for (int i = tid; i < Z; i += SWEEP_NT) trig[i] = row_trig<R>(p.wavenumber, lz, i);
   }
   __syncthreads();
-  rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, extras);
+  rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, extras, false);
   if (extras && warp == 0) {
     const double es = surface_energy_of(p, sc->amp);
     if (lane == 0) sc->e_surf = es;
   }
   __syncthreads();
 
+  const bool needs_ref = weights_need_ref<R>(variant);
   const double amp_pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
   const double amp_ratio = 1.0 / (amp_pt * (1.0 - amp_pt));
   const double inv_nsite = 1.0 / nsite;
@@ -338,17 +377,18 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 #endif
         } else if (SMEM_WEIGHTS_ON) {
           const AmpGeo<R> ae = amp_geo<R>(rc, a_new), ar = amp_geo<R>(rc, a);
-          const bool needs_ref = variant == CYL_VARIANT_RESCALED_0TH || variant == CYL_VARIANT_RESCALED_1ST;
-          for (int i = tid; i < Z; i += SWEEP_NT - 32) {                   // row i on thread i: full warps
+          // row i on thread NT - 33 - i: whole warps, counted down from warp 6 -- the low warps carry the extra row of the
+          // site loops when Z is not a multiple of the row groups, so the table chain goes to the others
+          for (int i = (SWEEP_NT - 33) - tid; i < Z; i += SWEEP_NT - 32) {
             const RowTrig<R> t = trig[i];
             const GeoT<R> g0e = geo_sc<R>(ae, t.s0, t.c0), gme = geo_sc<R>(ae, t.sm, t.cm);
             const GeoT<R> g0r = needs_ref ? geo_sc<R>(ar, t.s0, t.c0) : g0e;     // a_ref = current amplitude (:75)
             R wf[6];
             weight_row<R>(rc, g0e, gme, g0r, wf);
-            RowW<R>& w = roww[i];
+            RowWS<R>& w = roww[i];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) w.dif[q] = wf[q] - w.cur[q];
-            w.cst[1] = wf[5] - w.cst[0];
+            for (int q = 0; q < 5; ++q) w.nxt[q] = wf[q];
+            w.cst[1] = wf[5];
           }
         }
       }
@@ -362,16 +402,30 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     // (mapped loops) `o` points at the site, the neighbours sit at element offsets oL / oR (rows above / below, periodic) and
     // oW / oE (columns left / right, fixed per thread and pass); a thread walks down its rows by advancing o, the coefficient
     // pointer and the Philox site counter by constants
-    auto visit = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rcf, uint32_t site) {
-      const C L = o[oL], Rz = o[oR], W = o[oW], E = o[oE];
+    // (Starting the NEXT row's Philox block before the current row's move -- a second independent chain per warp -- measured
+    // 6 % slower: the loops are bound by pipe throughput, not by dependency latency.)
+    uint32_t kr[10], kc = 0;                                               // round keys: reloaded at the top of every mapped pass
+    auto load_keys = [&]() {
+      const uint4 k0 = *reinterpret_cast<const uint4*>(&sc->keys[0]), k1 = *reinterpret_cast<const uint4*>(&sc->keys[4]);
+      const uint2 k2 = *reinterpret_cast<const uint2*>(&sc->keys[8]);
+      kr[0] = k0.x; kr[1] = k0.y; kr[2] = k0.z; kr[3] = k0.w; kr[4] = k1.x; kr[5] = k1.y; kr[6] = k1.z; kr[7] = k1.w; kr[8] = k2.x; kr[9] = k2.y;
+      kc = kr[0] ^ c1;
+    };
+    auto draw = [&](uint32_t site) { return philox2x32_10(site, c1, kc, kr); };
+    auto visit_x = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rcf, uint2 x) {
+      const C L = o[oL], Rz = o[oR], W = o[oW], E = o[oE], pv = o[0];
       C q;
-      site_move<R, C>(o, 0, L, Rz, W, E, *rcf, sigma, site, c1, stream.key, q, nacc);
+      if (site_propose<R, C>(*rcf, pv, L, Rz, W, E, sigma, x, q)) { o[0] = q; ++nacc; }
+    };
+    auto visit = [&](C* o, int oL, int oR, int oW, int oE, const RowCoef<R>* rcf, uint32_t site) {
+      visit_x(o, oL, oR, oW, oE, rcf, draw(site));
     };
     if (mapped && ncol == 2) {
       // both lengths even: colour = (i + j) & 1
       const int step = RGe * T;
 #pragma unroll 1
       for (int colour = 0; colour < 2; ++colour) {
+        load_keys();
         if (col_active) {
           const int j = 2 * cj + ((colour + rg) & 1);
           const int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
@@ -390,6 +444,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       const int half = (Z - 1) >> 1;
 #pragma unroll 1
       for (int colour = 0; colour < 3; ++colour) {
+        load_keys();
         if (col_active) {
           if (colour == 1) {
             const int bb = (rg & 1) ? 0 : 1;                               // rows keep their parity: the step is even
@@ -480,29 +535,33 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     bool has_rows = false;                                                 // warp-uniform: did this warp accumulate anything?
     if ((extras && SMEM_ENERGY_ON) || profiles) {
       if ((T & 1) == 0) {
-        const int npair = T >> 1, h0 = npair >> 1, half = tid & 1;
-        const int p0 = half ? h0 : 0, p1 = half ? npair : h0;
-        has_rows = (tid & ~31) < 2 * Z;
+        // 2 threads per row; a thread walks its half of the row's column pairs
+        constexpr int lg = 1, nsplit = 2;                                  // (4 threads per row for Z <= NT/4 measured no faster)
+        const int part = tid & 1;
+        const int npair = T >> 1, p0 = (part * npair) >> lg, p1 = ((part + 1) * npair) >> lg;
+        const int rows_per_warp = 32 >> lg, rows_per_round = SWEEP_NT >> lg;
+        has_rows = ((tid & ~31) >> lg) < Z;
         auto rows = [&](auto meas) {
           constexpr bool MEAS = decltype(meas)::value;
-          for (int ib = (tid & ~31) >> 1; ib < Z; ib += SWEEP_NT / 2) {    // warp-uniform trip count (shuffle below)
-            const int i = ib + (lane >> 1);
+          for (int ib = warp * rows_per_warp; ib < Z; ib += rows_per_round) {   // warp-uniform trip count (shuffles below)
+            const int i = ib + (lane >> lg);
             R S[5] = {R(0), R(0), R(0), R(0), R(0)}, sre = R(0), sim = R(0), sabs = R(0);
             if (i < Z) {
               half_row_moments<R, C, MEAS>(psi + i * T, psi + (i == 0 ? nsite : i * T) - T, p0, p1, T, S, sre, sim, sabs);
-              const RowW<R> w = roww[i];
-              R ed = w.dif[0] * S[0] + w.dif[1] * S[1] + w.dif[2] * S[2] + w.dif[3] * S[3] + w.dif[4] * S[4];
-              if (half == 0) ed += w.cst[1];
+              const RowWS<R> w = roww[i];
+              R ed = (w.nxt[0] - w.cur[0]) * S[0] + (w.nxt[1] - w.cur[1]) * S[1] + (w.nxt[2] - w.cur[2]) * S[2] +
+                     (w.nxt[3] - w.cur[3]) * S[3] + (w.nxt[4] - w.cur[4]) * S[4];
+              if (part == 0) ed += w.cst[1] - w.cst[0];
               e.ed += ed;
               if (MEAS) {
                 R ec = w.cur[0] * S[0] + w.cur[1] * S[1] + w.cur[2] * S[2] + w.cur[3] * S[3] + w.cur[4] * S[4];
-                if (half == 0) ec += w.cst[0];
+                if (part == 0) ec += w.cst[0];
                 e.ec += ec; e.s2 += S[0]; e.sa += sabs;
               }
             }
             if (MEAS && profiles) {
               sre += __shfl_xor_sync(0xffffffffu, sre, 1); sim += __shfl_xor_sync(0xffffffffu, sim, 1); sabs += __shfl_xor_sync(0xffffffffu, sabs, 1);
-              if (i < Z && half == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sabs; }
+              if (i < Z && part == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sabs; }
             }
           }
         };
@@ -512,7 +571,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         if (extras && SMEM_ENERGY_ON) {
           for (int i = warp; i < Z; i += SWEEP_NWARP) {                    // T odd: a warp per row
             const int row = i * T, up = (i == 0 ? nsite : row) - T;
-            const RowW<R> w = roww[i];
+            const RowWS<R> ws = roww[i];
+            RowW<R> w;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { w.cur[q] = ws.cur[q]; w.dif[q] = ws.nxt[q] - ws.cur[q]; }
+            w.cst[0] = ws.cst[0]; w.cst[1] = ws.cst[1] - ws.cst[0];
             for (int j = lane; j < T; j += 32) {
               const C q = psi[row + j], l = psi[up + j], wl = psi[row + (j == 0 ? T : j) - 1];
               energy_own<R, C>(e, w, q, measure, !profiles);
@@ -562,22 +625,13 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
       return t;
     };
 
-    // ---- D. decisions, spread over threads of different warps: Robbins-Monro on sigma_site (warp 2), the measurement record
-    //         (warp 1), the amplitude move (warp 0) ----
+    // ---- D. decisions, on threads of different warps: Robbins-Monro on sigma_site (warp 2), the amplitude move (warp 0) ----
     // optional time series: one record of CYL_SERIES_DOUBLES per measured sweep and replica (the engine's me.df)
     double* rec = (SERIES && extras && measure && series) ? series + ((size_t)b * nsweeps + sw) * CYL_SERIES_DOUBLES : nullptr;
-    if (tid == 64) {
-      const double nac = total(0);
-      if (rec) rec[CYL_TS_SITE_ACCEPTANCE] = nac * inv_nsite;
-      if (flags & CYL_SWEEP_ADAPT_SIGMA) {
-        const RmLogs<R> l = extras ? sc->rm : rm_logs<R>(sc->step_counter, (double)nsite);
-        sc->sigma_site = rm_apply(sc->sigma_site, l, (double)nsite, nac);
-      }
-      sc->step_counter += nsite;
-      sc->site_proposed += nsite;
-      sc->site_accepted += nac;
-    }
-    if (extras && measure && tid == 32) {                                // measure_avgs :135-156 + engine record
+    // The measurement record (measure_avgs :135-156 + the engine's record) is not needed by anybody inside the launch, so it
+    // is taken AFTER the decision barrier, off the critical path, by a thread of a warp that carries neither table rows nor
+    // the extra site row; the partial sums it reads are next written two barriers from here.
+    auto measure_record = [&]() {
       const double e_cur = total(1) * rc.lzlth_d;                        // :213
       sc->e_field = e_cur;
       double* o = sc->obs;
@@ -599,6 +653,18 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         rec[CYL_TS_ABSPSI] = total(4) * inv_nsite;
         rec[CYL_TS_SIGMA_SITE] = (double)sigma;
       }
+    };
+#define MEASURE_RECORD(t) if (extras && measure && tid == (t)) measure_record();
+    if (tid == 64) {
+      const double nac = total(0);
+      if (rec) rec[CYL_TS_SITE_ACCEPTANCE] = nac * inv_nsite;
+      if (flags & CYL_SWEEP_ADAPT_SIGMA) {
+        const RmLogs<R> l = extras ? sc->rm : rm_logs<R>(sc->step_counter, (double)nsite);
+        sc->sigma_site = rm_apply(sc->sigma_site, l, (double)nsite, nac);
+      }
+      sc->step_counter += nsite;
+      sc->site_proposed += nsite;
+      sc->site_accepted += nac;
     }
     if (extras && tid == 0) {
       int accept = 0;
@@ -627,10 +693,11 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     }
     __syncthreads();
     PHASE_MARK(3);
+    MEASURE_RECORD(96)
     // ---- R. metric tables follow the amplitude: the accepted amplitude becomes the metric reference too (rescaled
     //         variants), so the weights are rebuilt rather than taken from the proposal's ----
     if (extras && sc->amp_accept) {
-      rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, true);
+      rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, needs_ref, true);
       __syncthreads();
     }
     PHASE_MARK(4);

@@ -12,7 +12,7 @@ batch = ReplicaBatch(bench.grid_params(8192, 0), dims=(50, 50), dtype=torch.comp
 batch.run(50); batch.reset_observables(); batch.run(50)
 torch.cuda.synchronize()
 ph = batch.obs[:, 10:16].sum(0).cpu().numpy()
-names = ["weights/surface", "site moves + energy", "reduction", "decision", "rebuild", "profiles"]
+names = ["proposal tables (thread 0)", "site moves incl. barriers", "energy + profiles + reduction", "decision", "rebuild", "-"]
 tot = ph.sum()
 for n, v in zip(names, ph):
-    print("%-16s %6.1f%%  %8.0f cycles per CTA-sweep" % (n, 100 * v / tot, v / (8192 * 50)))
+    print("%-30s %6.1f%%  %8.0f cycles per CTA-sweep" % (n, 100 * v / tot, v / (8192 * 50)))
