@@ -14,8 +14,16 @@ Legs, all in one run and one JSON line:
              D2H of lattice + observable records, every step
   roofline   config C4: one 4096 x 4096 fp32 lattice streamed from HBM by the TMA-tiled kernel, timed alone with
              CUDA events; achieved = 24 B x site-updates / time against MEASURED_PEAKS.json hbm_gbs
+  roofline_value  the kernel the headline times (sweep_smem_kernel<float>): warp-instructions of one step (ncu
+             smsp__inst_executed.sum of exactly this launch, kept with the hash of the kernel sources in
+             profiles/r02_counters.json) / step time, against SMs x 4 issue slots x the SM clock sampled during the run
+  sustained  the value leg repeated for >= --sustained-seconds with one CUDA event per step: rate of the first and of the
+             last second (clock droop under sustained load would show here)
   cpu_baseline  the oracle's sequential restatement of the reference's per-site Python loop, one independent replica
              per host core for a bounded wall time (rank 0, N = 1 only)
+  aux        N = 1 only: the same full path in fp64 (the reference's precision), config C1 through Lattice.run, config C3
+             (4096 replicas x 1000 sweeps), config C2 (Fourier model)
+--scaling strong: config C5's 65536 replicas in total, split over the ranks (default weak: 8192 per GPU).
 """
 import argparse
 import json
@@ -41,7 +49,23 @@ PER_SWEEP = "site moves + Robbins-Monro + row moments/measure + 1 amplitude move
 CPU_SAMPLE = ("%d replicas of the same grid, one per host core, whole sweeps of the reference algorithm (Z*T random-site proposals "
               "with per-proposal Robbins-Monro + 1 amplitude move + 1 measurement per sweep)")
 ALG_BYTES_PER_UPDATE_F32 = 24.0      # 2 reads + 1 write of an 8-byte site per full sweep
-NCU_HBM_TRAFFIC_BYTES = 135.629e6 + 87.912e6   # sweep_hbm_kernel<float,2,32,0>, 4096x4096, one launch (profiles/r01_ncu_full_d.md)
+COUNTERS = os.path.join(ROOT, "profiles", "r02_counters.json")   # written by scripts/ncu_counters.py from the .ncu-rep files
+STRONG_TOTAL = 65536
+
+
+def profiler_counters():
+    """ncu counters of the two hot kernels with the hash of the kernel sources they were measured on.  Returns
+    (counters or None, note): counters of another source state are refused (the leg then reports no fraction)."""
+    from cylinder_b200.build import source_sha
+    try:
+        with open(COUNTERS) as f:
+            c = json.load(f)
+    except (OSError, ValueError):
+        return None, "profiles/r02_counters.json missing"
+    sha = source_sha()
+    if c.get("source_sha") != sha:
+        return None, "profiles/r02_counters.json was measured on kernel sources %s, this build is %s: re-profile" % (c.get("source_sha"), sha)
+    return c, "profiles/r02_counters.json (kernel sources %s)" % sha
 
 
 def grid_params(n_replicas, replica0=0):
@@ -128,7 +152,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD % args.replicas_per_gpu, "per_sweep": PER_SWEEP,
+            "config": {"workload": WORKLOAD % (STRONG_TOTAL // max(1, args.gpus) if args.scaling == "strong" else args.replicas_per_gpu), "per_sweep": PER_SWEEP,
                        "sample": "reference algorithm on the host cores: " + sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -200,6 +224,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--sustained-seconds", type=float, default=10.0)
+    ap.add_argument("--no-sustained", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -232,8 +259,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    Bg, nsw, K, W = args.replicas_per_gpu, args.sweeps_per_step, args.steps, max(args.warmup, 0)
-    replica0 = rank * Bg
+    from cylinder_b200.replicas import shard_range
+    nsw, K, W = args.sweeps_per_step, args.steps, max(args.warmup, 0)
+    if args.scaling == "strong":                                   # config C5 in total, whatever the number of GPUs
+        replica0, hi = shard_range(STRONG_TOTAL, rank, world)
+        Bg = hi - replica0
+    else:
+        Bg = args.replicas_per_gpu
+        replica0 = rank * Bg
     batch = ReplicaBatch(grid_params(Bg, replica0), dims=DIMS, variant="simple", dtype=torch.complex64, device=dev, seed=SEED,
                          replica0=replica0, amplitude=0.0)
     sites_per_sweep = batch.sites
@@ -241,8 +274,8 @@ def main():
 
     def step_device():
         batch.run(nsw, amp_moves=True, measure=True, adapt=True)
-        if world > 1:                      # the path's one exchange: observable records of every replica on every rank
-            batch.gather_records()
+        if world > 1:                      # the path's one exchange: observable records of every replica on every rank --
+            batch.gather_start()           # snapshot + all-gather on a side stream, overlapped by the next step's sweeps
 
     # ---- value leg ----
     sampler = ClockSampler(local) if rank == 0 else None      # started before warm-up so that samples exist from the first timed ms
@@ -254,10 +287,40 @@ def main():
     e0.record()
     for _ in range(K):
         step_device()
+    if world > 1:
+        batch.gather_finish()              # the last exchange is inside the timed region
     e1.record()
     barrier()
     t_wall1 = time.perf_counter()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    # ---- sustained leg: the same steps for >= S seconds, one event per step ----
+    sustained = None
+    if not args.no_sustained and args.sustained_seconds > 0:
+        n_sus = max(K, int(args.sustained_seconds * 1e3 / (ms_total / K)) + 1)
+        if world > 1:
+            t = torch.tensor([n_sus], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_sus = int(t.item())
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus + 1)]
+        evs[0].record()
+        for i in range(n_sus):
+            step_device()
+            evs[i + 1].record()
+        barrier()
+        t_wall1 = time.perf_counter()
+        ts = [evs[0].elapsed_time(e) for e in evs[1:]]                     # ms since the start, per step
+        per_step_local = float(sites_per_sweep) * nsw
+
+        def window_rate(lo_ms, hi_ms):
+            idx = [i for i, t in enumerate(ts) if lo_ms < t <= hi_ms]
+            if not idx:
+                return None
+            t_first = ts[idx[0] - 1] if idx[0] > 0 else 0.0
+            return per_step_local * len(idx) / ((ts[idx[-1]] - t_first) * 1e-3)
+        total_ms = max_over_ranks(ts[-1])
+        sustained = {"seconds": total_ms * 1e-3, "steps": n_sus, "rate_first_second_this_rank": window_rate(0.0, 1000.0),
+                     "rate_last_second_this_rank": window_rate(ts[-1] - 1000.0, ts[-1]),
+                     "min_step_ms": min(b - a for a, b in zip([0.0] + ts[:-1], ts)), "max_step_ms": max(b - a for a, b in zip([0.0] + ts[:-1], ts))}
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     updates_per_step_all = float(sites_per_sweep) * nsw
     if world > 1:
@@ -265,7 +328,35 @@ def main():
         dist.all_reduce(t)
         updates_per_step_all = float(t.item())
     value = updates_per_step_all * K / (ms_total * 1e-3)
+    if sustained is not None:
+        sustained["rate"] = updates_per_step_all * sustained["steps"] / sustained["seconds"]
+        sustained["unit"] = UNIT
+        sustained["vs_value"] = sustained["rate"] / value
     acc = float(batch.observables()["site_acceptance"].mean().item())
+
+    # ---- roofline of the kernel the headline times: instruction issue ----
+    counters, counters_note = profiler_counters()
+    roofline_value = None
+    if rank == 0:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+        kc = (counters or {}).get("sweep_smem_kernel<float,extras>")
+        same = kc is not None and kc.get("replicas") == Bg and kc.get("sweeps") == nsw and args.scaling == "weak"
+        roofline_value = {"bound": "sm_issue", "unit": "warp-instructions/s", "kernel": "sweep_smem_kernel<float, extras>",
+                          "peak": (sms * 4 * sm_mhz * 1e6) if sm_mhz else None,
+                          "peak_source": "%d SMs x 4 issue slots x %.0f MHz (median SM clock sampled during the timed region)" % (sms, sm_mhz or 0),
+                          "counters": counters_note}
+        if same and sm_mhz:
+            inst = float(kc["smsp__inst_executed.sum"])
+            roofline_value.update({"achieved": inst / (ms_total / K * 1e-3), "frac": inst / (ms_total / K * 1e-3) / roofline_value["peak"],
+                                   "warp_instructions_per_step": inst,
+                                   "thread_instruction_slots_per_site_update": inst * 32.0 / (float(sites_per_sweep) * nsw),
+                                   "ncu": {k: kc.get(k) for k in ("gpu__time_duration_ms", "issue_active_pct", "top_stalls", "site_loop_sass_instructions")},
+                                   "note": "issue slots are not all usable by this mix: on this GPU FFMA with three register sources issues "
+                                           "every 1.9 cycles per sub-partition, FFMA2 every 3.0, IMAD.WIDE / LOP3 / IMAD every 2.0-2.4, MUFU every 8 "
+                                           "(scripts/micro/pipes.cu, profiles/r02_pipes.md)"})
+        else:
+            roofline_value.update({"achieved": None, "frac": None, "why": counters_note if kc is None else "counters are for %s replicas x %s sweeps, weak" % (kc.get("replicas"), kc.get("sweeps"))})
 
     # ---- e2e leg: host buffers in, host buffers out, every step ----
     e2e = None
@@ -281,14 +372,15 @@ def main():
             # pipelined over 4 slices of the batch, returns when the host buffers are complete
             batch.step_host(psi_h, chain_h, psi_out_h, rec_h, nsw, nchunks=args.e2e_chunks)
             if world > 1:
-                batch.gather_records()
-                torch.cuda.current_stream().synchronize()
+                batch.gather_start()
         for _ in range(min(W, 2)):
             step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
             step_e2e()
+        if world > 1:
+            batch.gather_finish()
         barrier()
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
         h2d = psi_h.numel() * psi_h.element_size() + chain_h.numel() * 8
@@ -332,9 +424,10 @@ def main():
         peak, peak_src = measured_peak_hbm()
         upd = float(n) * n * args.hbm_sweeps
         achieved = upd * ALG_BYTES_PER_UPDATE_F32 / (ms_hbm * 1e-3) / 1e9
-        traffic = NCU_HBM_TRAFFIC_BYTES if (n == 4096) else None
+        kh = (counters or {}).get("sweep_hbm_kernel<float,2,32,false>")
+        traffic = (kh["dram__bytes_read.sum"] + kh["dram__bytes_write.sum"]) if (kh and kh.get("n") == n) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_ncu_full_d.md "
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, " + counters_note + " "
                                       "(below the 24 B/update algorithmic figure: the kernel updates all colours per pass, 8.1 B read + "
                                       "8 B written per site; part of the writes is still dirty in the 126 MB L2 when the kernel ends)",
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE_F32 * n * n,
@@ -371,6 +464,44 @@ def main():
                                            "CPU core (SURVEY.md section 6)"}}
         del fc
 
+        def timed(fn):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e-3
+        # the headline's full per-sweep path in the reference's own precision (complex128 psi, fp64 arithmetic throughout)
+        B64, nsw64 = 2368, 100
+        b64 = ReplicaBatch(grid_params(B64, 0), dims=DIMS, variant="simple", dtype=torch.complex128, device=dev, seed=SEED, amplitude=0.0)
+        b64.run(20)
+        t64 = timed(lambda: b64.run(nsw64))
+        aux["fp64"] = {"site_updates_per_s": b64.sites * nsw64 / t64, "replicas": B64, "sweeps": nsw64, "dtype": "f64",
+                       "config": "same grid and per-sweep path as the headline, psi complex128 (the reference's precision); 2 CTAs/SM"}
+        del b64
+        # config C3 as SURVEY 8d states it: 4096 replicas (one per grid point) x 1000 sweeps
+        b3 = ReplicaBatch(grid_params(4096, 0), dims=DIMS, variant="simple", dtype=torch.complex64, device=dev, seed=SEED, amplitude=0.0)
+        b3.run(50)
+        t3 = timed(lambda: b3.run(1000))
+        aux["c3"] = {"site_updates_per_s": b3.sites * 1000 / t3, "replicas": 4096, "sweeps": 1000, "seconds": t3, "dtype": "f32"}
+        del b3
+        # config C1: the reference's own single-replica case through the drop-in class (one 50 x 50 lattice = ONE CTA of the GPU)
+        import random
+        import cylinder_b200
+        random.seed(12345)
+        lat = cylinder_b200.Lattice(amplitude=0, wavenumber=1, radius=1, gamma=1, kappa=0, intrinsic_curvature=0, alpha=-1, u=1, C=1, n=6,
+                                    temperature=.01, temperature_final=.01, dims=(50, 50), fieldsteps_per_ampstep=50)
+        lat.run(10, 50)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        n_steps_c1, sps_c1 = 2000, 5
+        lat.run(n_steps_c1, 50, sweeps_per_step=sps_c1)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter() - w0
+        aux["c1"] = {"seconds": w1, "sweeps": n_steps_c1 * sps_c1, "site_updates_per_s": n_steps_c1 * sps_c1 * 2500 / w1,
+                     "config": "Lattice(dims=(50,50), T=.01, alpha=-1, u=1, C=1, n=6).run(2000 steps of 5 sweeps + 1 amplitude move + "
+                               "measurement = 1e4 sweeps), wall clock incl. the class's own burn-in sweeps and per-step host round trips",
+                     "reference": "~20 min for the same number of proposals at ~2e4 proposals/s (SURVEY.md section 6)"}
+        del lat
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -381,7 +512,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD % Bg + ", fp32 psi resident in shared memory",
                            "sweeps_per_step": nsw, "per_sweep": PER_SWEEP,
@@ -389,7 +520,8 @@ def main():
                            "l2_policy": "state re-read from HBM once per step (%.0f MB/GPU > L2 not required: lattices live in "
                                         "shared memory during a step)" % (Bg * batch.Zmax * batch.T * 8 / 1e6),
                            "mean_site_acceptance": acc},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu, "aux": aux}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "roofline_value": roofline_value,
+                "sustained": sustained, "cpu_baseline": cpu, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -133,13 +133,25 @@ def ptr(t):
     return t.data_ptr()
 
 
+class _CurrentStream:
+    """Placeholder for "the current torch stream of the device this call runs on" (resolved inside call())."""
+
+
+_CUR = _CurrentStream()
+
+
 def call(name, device, *args):
-    """Set the device for this thread, call `name`, raise on a non-zero return code."""
+    """Call `name` on `device` (index of the tensors' GPU): the CUDA device is set for the duration of the call only (torch's
+    device guard, so the caller's current device is restored) and the stream handle is the current torch stream OF THAT
+    device, not of whatever device happens to be current.  Raises on a non-zero return code."""
+    import torch
     L = lib()
-    if device is not None:
-        check(L.cyl_set_device(int(device)), "cyl_set_device")
-    check(getattr(L, name)(*args), name)
+    if device is None:
+        device = torch.cuda.current_device()
+    with torch.cuda.device(int(device)):
+        sh = torch.cuda.current_stream(int(device)).cuda_stream
+        check(getattr(L, name)(*[sh if a is _CUR else a for a in args]), name)
 
 
 def stream():
-    return _stream()
+    return _CUR

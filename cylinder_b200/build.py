@@ -45,6 +45,20 @@ def _newest_header_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
+def source_sha():
+    """sha256 over the kernel sources (csrc/*.cu, *.cuh and the C header): ties profiler counters kept under profiles/ to the
+    build they were taken from (bench.py refuses counters of another source state)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    files.append(os.path.join(HERE, "..", "include", "cylinder_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def lib_path():
     return os.path.join(LIBDIR, LIBNAME)
 

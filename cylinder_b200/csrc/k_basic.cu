@@ -104,8 +104,10 @@ extern "C" int cyl_philox2x32_10(const uint32_t* ctr, const uint32_t* key, int64
 template <typename R>
 __global__ void lattice_init_kernel(typename Real<R>::complex_t* __restrict__ psi, int B, const int32_t* __restrict__ Z,
                                     int Zmax, int T, double mag_max, uint64_t seed, int64_t replica0) {
-  const int b = blockIdx.y;
-  const int site = blockIdx.x * blockDim.x + threadIdx.x;
+  // the batch index rides in grid.x (grid.y is limited to 65535; config C5 on one GPU has 65536 replicas)
+  const int per = (Zmax * T + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int b = blockIdx.x / per;
+  const int site = (blockIdx.x - b * per) * blockDim.x + threadIdx.x;
   if (site >= Zmax * T) return;
   const int i = site / T;
   typename Real<R>::complex_t v = Real<R>::make(R(0), R(0));
@@ -125,8 +127,9 @@ template <typename R>
 static int lattice_init(void* psi, int B, const int32_t* Z, int Zmax, int T, double mag_max, uint64_t seed,
                         int64_t replica0, void* stream) {
   CYL_CHECK_ARG(psi && Z && B > 0 && Zmax > 0 && T > 0, "cyl_lattice_init: bad arguments");
-  dim3 grid((Zmax * T + 255) / 256, B);
-  lattice_init_kernel<R><<<grid, 256, 0, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, mag_max,
+  const long long nblk = (long long)((Zmax * T + 255) / 256) * B;
+  CYL_CHECK_ARG(nblk <= 2147483647LL, "cyl_lattice_init: batch too large for one launch");
+  lattice_init_kernel<R><<<(unsigned)nblk, 256, 0, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, mag_max,
                                                              seed, replica0);
   CYL_LAUNCH_CHECK();
   return CYL_OK;

@@ -138,6 +138,7 @@ static int move_row_moments(const void* psi, int B, const int32_t* Z, int Zmax, 
   if (rc) return rc;
   CYL_CHECK_ARG(params && S, "cyl_move_row_moments: bad arguments");
   const int rows_per_cta = CYL_MOM_WARPS / moments_warps_per_row(T);
+  if (B > 65535) { cyl_set_error("cyl_move_row_moments: at most 65535 replicas per call (got %d); split the batch", B); return CYL_E_UNSUPPORTED; }
   dim3 grid((Zmax + rows_per_cta - 1) / rows_per_cta, B);
   move_row_moments_kernel<R><<<grid, CYL_MOM_WARPS * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params,
                                                                          moves, S);
@@ -150,6 +151,7 @@ static int move_apply(void* psi, int B, const int32_t* Z, int Zmax, int T, const
   int rc = check_moves(psi, B, Z, Zmax, T, moves, "cyl_move_apply");
   if (rc) return rc;
   const int per = (Zmax * T + 255) / 256;
+  if (B > 65535) { cyl_set_error("cyl_move_apply: at most 65535 replicas per call (got %d); split the batch", B); return CYL_E_UNSUPPORTED; }
   dim3 grid(per < 64 ? per : 64, B);
   move_apply_kernel<R><<<grid, 256, 0, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, moves, accept);
   CYL_LAUNCH_CHECK();

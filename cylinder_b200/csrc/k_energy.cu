@@ -12,11 +12,13 @@ __global__ void row_moments_kernel(const typename Real<R>::complex_t* __restrict
                                    const CylParams* __restrict__ params, double* __restrict__ S) {
   using C = typename Real<R>::complex_t;
   __shared__ double red[CYL_MOM_WARPS][CYL_NMOM];
-  const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpr = moments_warps_per_row(T), rows_per_cta = CYL_MOM_WARPS / wpr;
+  // the batch index rides in grid.x (grid.y is limited to 65535)
+  const int per = (Zmax + rows_per_cta - 1) / rows_per_cta;
+  const int b = blockIdx.x / per;
   const int row_in_cta = warp / wpr, seg = warp - row_in_cta * wpr;
-  const int i = blockIdx.x * rows_per_cta + row_in_cta;
+  const int i = (blockIdx.x - b * per) * rows_per_cta + row_in_cta;
   const int Z = Zs[b];
   double* out = (i < Zmax) ? S + ((size_t)b * Zmax + i) * CYL_NMOM : nullptr;
   double m[CYL_NMOM];
@@ -43,8 +45,9 @@ static int row_moments(const void* psi, int B, const int32_t* Z, int Zmax, int T
                        void* stream) {
   CYL_CHECK_ARG(psi && Z && params && S && B > 0 && Zmax > 0 && T > 0, "cyl_row_moments: bad arguments");
   const int rows_per_cta = CYL_MOM_WARPS / moments_warps_per_row(T);
-  dim3 grid((Zmax + rows_per_cta - 1) / rows_per_cta, B);
-  row_moments_kernel<R><<<grid, CYL_MOM_WARPS * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T,
+  const long long nblk = (long long)((Zmax + rows_per_cta - 1) / rows_per_cta) * B;
+  CYL_CHECK_ARG(nblk <= 2147483647LL, "cyl_row_moments: batch too large for one launch");
+  row_moments_kernel<R><<<(unsigned)nblk, CYL_MOM_WARPS * 32, 0, as_stream(stream)>>>((const typename Real<R>::complex_t*)psi, B, Z, Zmax, T,
                                                                             (int64_t)T, (int64_t)Zmax * T, params, S);
   CYL_LAUNCH_CHECK();
   return CYL_OK;

@@ -295,7 +295,11 @@ class Lattice:
 
     # ---- production path: checkerboard sweeps on the device --------------------------------------------
     def _fits_shared_memory(self):
-        return self.z_len * self.th_len * self._psi_store.element_size() <= 160 * 1024
+        """The batched kernel keeps the lattice AND its per-row tables in shared memory: ask the library for the real layout
+        (cyl_sweep_smem_bytes) instead of guessing from the lattice alone, so tall narrow lattices take the HBM path."""
+        need = _abi.lib().cyl_sweep_smem_bytes(int(self.z_len), int(self.th_len), int(self._psi_store.element_size() == 16))
+        limit = torch.cuda.get_device_properties(self.device).shared_memory_per_block_optin
+        return 0 < need <= limit
 
     def _push_chain(self):
         c = self._chain_host

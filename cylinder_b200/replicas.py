@@ -161,12 +161,33 @@ class ReplicaBatch:
         return torch.cat([self.obs, self.chain, self.prof.reshape(self.B, -1)], dim=1).contiguous()
 
     def gather_records(self, group=None):
-        """All ranks' records, concatenated in replica order, on every rank (one NCCL all-gather; gloo on CPU tests)."""
+        """All ranks' records, concatenated in replica order, on every rank (fp64 [sum B_r, 32 + 3 Zmax]).  Blocking form:
+        gather_start() + gather_finish()."""
+        self.gather_start(group)
+        return self.gather_finish()
+
+    def gather_start(self, group=None):
+        """Start the exchange of the per-replica records and return at once.  The records are snapshotted on the compute
+        stream (one small copy), the all-gather runs on a side stream into buffers allocated once -- the shapes were exchanged
+        when the exchange was built -- so the next launch of sweeps overlaps it: the gather is never on the critical path
+        (SURVEY.md 8e).  Profiles travel as fp32 (they are sums of O(10^4) terms of O(1): 1e-7 relative is far below their
+        statistical error); obs | chain stay fp64."""
         import torch.distributed as dist
-        rec = self.record()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return rec
-        return gather_ragged(rec, group)
+            self._gather_local = True
+            return self
+        self._gather_local = False
+        if getattr(self, "_exchange", None) is None or self._exchange.group is not group:
+            self._exchange = RecordExchange(self.B, self.obs.shape[1] + self.chain.shape[1], 3 * self.Zmax, self.device, group)
+        self._exchange.start(torch.cat([self.obs, self.chain], dim=1), self.prof.reshape(self.B, -1))
+        return self
+
+    def gather_finish(self):
+        """Wait (on the current stream, not the host) for the exchange started by gather_start; returns the records."""
+        if self._gather_local:
+            return self.record()
+        r64, r32 = self._exchange.finish()
+        return torch.cat([r64, r32.to(torch.float64)], dim=1)
 
     # ---- host round trips ------------------------------------------------------------------------------
     @property
@@ -219,6 +240,60 @@ class ReplicaBatch:
         self.obs.copy_(sd["obs"])
         self.prof.copy_(sd["prof"])
         self.seed, self.replica0, self.sweeps_done = int(sd["seed"]), int(sd["replica0"]), int(sd["sweeps_done"])
+
+
+class RecordExchange:
+    """All-gather of fixed-size per-replica records, [n_r, w64] float64 + [n_r, w32] float32 per rank, built for repetition:
+    the ranks exchange their (n_r, w64, w32) ONCE here, the padded send / receive buffers are allocated once, and every
+    start() is a snapshot copy on the caller's stream plus two all_gather_into_tensor calls on a side stream (CUDA; on CPU
+    tensors -- the gloo tests -- it runs inline).  finish() makes the caller's stream wait and returns the records of all
+    ranks concatenated in rank (= replica) order, trimmed to each rank's own shape."""
+
+    def __init__(self, n_local, w64, w32, device, group=None):
+        import torch.distributed as dist
+        self.group, self.device = group, torch.device(device)
+        self.world = dist.get_world_size(group)
+        mine = torch.tensor([n_local, w64, w32], dtype=torch.int64, device=self.device)
+        shapes = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(shapes, mine, group=group)
+        self.shapes = [tuple(int(v) for v in sh.tolist()) for sh in shapes]          # the only host sync, once
+        self.n, self.w64, self.w32 = n_local, w64, w32
+        nmax = max(sh[0] for sh in self.shapes)
+        m64, m32 = max(sh[1] for sh in self.shapes), max(sh[2] for sh in self.shapes)
+        self.send64 = torch.zeros(nmax, m64, dtype=torch.float64, device=self.device)
+        self.send32 = torch.zeros(nmax, m32, dtype=torch.float32, device=self.device)
+        self.recv64 = torch.empty(self.world, nmax, m64, dtype=torch.float64, device=self.device)
+        self.recv32 = torch.empty(self.world, nmax, m32, dtype=torch.float32, device=self.device)
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.pending = False
+
+    def start(self, rec64, rec32):
+        import torch.distributed as dist
+        if self.cuda:
+            main = torch.cuda.current_stream(self.device)
+            main.wait_stream(self.stream)                    # the previous exchange has read the send buffers (a step ago)
+        self.send64[: self.n, : self.w64].copy_(rec64)
+        self.send32[: self.n, : self.w32].copy_(rec32)
+        if self.cuda:
+            self.stream.wait_stream(main)
+            with torch.cuda.stream(self.stream):
+                dist.all_gather_into_tensor(self.recv64.view(-1), self.send64.view(-1), group=self.group)
+                dist.all_gather_into_tensor(self.recv32.view(-1), self.send32.view(-1), group=self.group)
+        else:
+            dist.all_gather(list(self.recv64.unbind(0)), self.send64, group=self.group)
+            dist.all_gather(list(self.recv32.unbind(0)), self.send32, group=self.group)
+        self.pending = True
+
+    def finish(self):
+        assert self.pending, "RecordExchange.finish() without start()"
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self.pending = False
+        m32 = self.recv32.shape[2]
+        r64 = torch.cat([self.recv64[r, :sh[0]] for r, sh in enumerate(self.shapes)], dim=0)
+        r32 = torch.cat([self.recv32[r, :sh[0]] for r, sh in enumerate(self.shapes)], dim=0)
+        return r64, r32
 
 
 def gather_ragged(rec, group=None):

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cylinder_b200.replicas import gather_ragged, parameter_grid, shard_range
+from cylinder_b200.replicas import RecordExchange, gather_ragged, parameter_grid, shard_range
 
 
 def test_shard_range_partitions():
@@ -37,7 +37,17 @@ def _worker(rank, world, port, q):
     rec[:, 0] = torch.arange(lo, hi, dtype=torch.float64)
     rec[:, 1:] = rank + 1
     out = gather_ragged(rec)
-    q.put((rank, out.numpy()))
+    # the repeated exchange with shapes fixed at construction: two rounds through the same buffers
+    ex = RecordExchange(hi - lo, 3, 4 + rank, "cpu")
+    rounds = []
+    for it in range(2):
+        r64 = torch.full((hi - lo, 3), float(10 * it + rank), dtype=torch.float64)
+        r64[:, 0] = torch.arange(lo, hi, dtype=torch.float64)
+        r32 = torch.full((hi - lo, 4 + rank), float(it) + .5, dtype=torch.float32)
+        ex.start(r64, r32)
+        a, b = ex.finish()
+        rounds.append((a.numpy().copy(), b.numpy().copy()))
+    q.put((rank, (out.numpy(), rounds)))
     dist.destroy_process_group()
 
 
@@ -53,7 +63,13 @@ def test_gather_ragged_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     for r in range(world):
-        out = res[r]
+        out, rounds = res[r]
+        for it, (a, b) in enumerate(rounds):
+            assert a.shape == (11, 3) and b.shape == (11, 5)
+            assert a[:, 0].tolist() == list(range(11))
+            lo0, hi0 = shard_range(11, 0, world)
+            assert np.all(a[lo0:hi0, 1:] == 10 * it) and np.all(a[hi0:, 1:] == 10 * it + 1)
+            assert np.all(b[lo0:hi0, :4] == it + .5) and np.all(b[hi0:, :5] == it + .5)
         assert out.shape == (11, 6)
         assert out[:, 0].tolist() == list(range(11))            # replica order preserved on every rank
         lo, hi = shard_range(11, 0, world)
