@@ -79,22 +79,26 @@ struct SmemScalars {
 template <typename R>
 struct __align__(16) RowWS { R cur[5]; R nxt[5]; R cst[2]; };
 
+// Shared memory of one CTA.  The chain scalars, the reduction scratch and the amplitude draws sit at FIXED offsets at the front
+// (their addresses are compile-time constants relative to the window: before, every use re-derived the variable offsets from
+// Zmax and T, a dozen instructions each time); the lattice and the row tables follow, at offsets the host computes once and
+// passes as a kernel parameter (constant-bank operands).
 template <typename R>
 struct SweepSmemLayout {
   using C = typename Real<R>::complex_t;
-  size_t off_coef, off_trig, off_w, off_prof, off_amp, off_scr, off_sc, total;
+  static constexpr uint32_t off_sc = 0;
+  static constexpr uint32_t off_scr = (uint32_t)((sizeof(SmemScalars<R>) + 15) & ~(size_t)15);
+  static constexpr uint32_t off_amp = off_scr + 8 * SWEEP_NWARP * (uint32_t)sizeof(double);   // unit normal + T ln(u) per sweep
+  static constexpr uint32_t off_psi = off_amp + 2 * AMP_CHUNK * (uint32_t)sizeof(double);
+  uint32_t off_coef, off_trig, off_w, off_prof, total;
   __host__ __device__ SweepSmemLayout(int Zmax, int T) {
-    size_t o = (size_t)Zmax * T * sizeof(C);
+    size_t o = off_psi + (size_t)(Zmax + 2) * T * sizeof(C);              // the lattice between two periodic halo rows
     o = (o + 15) & ~(size_t)15;
-    off_coef = o; o += (size_t)Zmax * sizeof(RowCoef<R>);
-    off_trig = o; o += (size_t)Zmax * sizeof(RowTrig<R>);
-    off_w = o;    o += (size_t)Zmax * sizeof(RowWS<R>);
-    off_prof = o; o += (size_t)Zmax * 3 * sizeof(R);          // per-launch profile sums, flushed once at the end
-    o = (o + 15) & ~(size_t)15;
-    off_amp = o;  o += 2 * AMP_CHUNK * sizeof(double);          // unit normal + T ln(u) per sweep
-    off_scr = o;  o += 8 * SWEEP_NWARP * sizeof(double);
-    off_sc = o;   o += sizeof(SmemScalars<R>);
-    total = (o + 15) & ~(size_t)15;
+    off_coef = (uint32_t)o; o += (size_t)Zmax * sizeof(RowCoef<R>);
+    off_trig = (uint32_t)o; o += (size_t)Zmax * sizeof(RowTrig<R>);
+    off_w = (uint32_t)o;    o += (size_t)Zmax * sizeof(RowWS<R>);
+    off_prof = (uint32_t)o; o += (size_t)Zmax * 3 * sizeof(R);          // per-launch profile sums, flushed once at the end
+    total = (uint32_t)((o + 15) & ~(size_t)15);
   }
 };
 
@@ -206,16 +210,21 @@ __device__ __forceinline__ bool site_move(C* psi, int idx, const C L, const C Rz
 #ifndef SMEM_MINB_EXTRAS
 #define SMEM_MINB_EXTRAS 4
 #endif
-template <typename R, bool EXTRAS, bool SERIES>
+// TT = the row length as a compile-time constant (50: the reference's default dims, every lattice of the benchmark grid), or 0
+// = any row length (run-time T_arg).  With TT known the neighbour offsets in z, the row-table and Philox-counter strides and the
+// thread map are immediates.
+template <typename R, bool EXTRAS, bool SERIES, int TT>
 __global__ void __launch_bounds__(SWEEP_NT, (sizeof(R) == 4 ? (EXTRAS ? SMEM_MINB_EXTRAS : 4) : 2))
-sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T,
+sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const int32_t* __restrict__ Zs, int Zmax, int T_arg,
                   const CylParams* __restrict__ params, double* __restrict__ chain, const __grid_constant__ PhiloxKeys keys,
                   uint64_t seed, int64_t replica0, uint64_t sweep0, int nsweeps, int variant, uint32_t flags, double* __restrict__ obs,
-                  double* __restrict__ prof, double* __restrict__ series) {
+                  double* __restrict__ prof, double* __restrict__ series, const __grid_constant__ SweepSmemLayout<R> lay) {
   using C = typename Real<R>::complex_t;
+  const int T = TT ? TT : T_arg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SweepSmemLayout<R> lay(Zmax, T);
-  C* psi = reinterpret_cast<C*>(smem_raw);
+  // psi[-T .. -1] and psi[Z*T .. (Z+1)*T - 1] are halo rows (periodic copies of rows Z-1 and 0), kept current by the
+  // column-mapped site loops, whose neighbour offsets in z are then the constants -T and +T
+  C* psi = reinterpret_cast<C*>(smem_raw + lay.off_psi) + T;
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
   RowTrig<R>* trig = reinterpret_cast<RowTrig<R>*>(smem_raw + lay.off_trig);
   RowWS<R>* roww = reinterpret_cast<RowWS<R>*>(smem_raw + lay.off_w);
@@ -232,7 +241,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     // of rank j in descending row count (ties in index order): the replicas still running when the grid drains are the
     // short ones.  Every CTA finds its replica by itself -- a histogram of Z, then the k-th replica of its bin -- in scratch
     // borrowed from the lattice region; no buffer, no extra launch, and the results do not depend on the assignment.
-    int* hist = reinterpret_cast<int*>(smem_raw);                          // (Zmax + 1) ints <= Zmax * T * sizeof(C)
+    int* hist = reinterpret_cast<int*>(smem_raw + lay.off_psi);            // (Zmax + 1) ints <= Zmax * T * sizeof(C)
     int* res = reinterpret_cast<int*>(scr);                                // [0] bin, [1] rank inside the bin, [2] replica, [8..15] warp sums
     for (int z = tid; z <= Zmax; z += SWEEP_NT) hist[z] = 0;
     __syncthreads();
@@ -319,6 +328,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     for (int i = tid; i < Z; i += SWEEP_NT) trig[i] = row_trig<R>(p.wavenumber, lz, i);
   }
   __syncthreads();
+  for (int j = tid; j < T; j += SWEEP_NT) { psi[j - T] = psi[(Z - 1) * T + j]; psi[Z * T + j] = psi[j]; }
   rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, extras, false);
   if (extras && warp == 0) {
     const double es = surface_energy_of(p, sc->amp);
@@ -341,6 +351,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const bool mapped = RGe >= 2;
   const int rg = mapped ? tid / Th : 0, cj = mapped ? tid - rg * Th : 0;
   const bool col_active = mapped && rg < RGe;
+  const int rg_last = mapped ? (Z - 1) % RGe : 0;                          // the row group that holds row Z-1 (2-colour loops)
 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
@@ -428,12 +439,17 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         load_keys();
         if (col_active) {
           const int j = 2 * cj + ((colour + rg) & 1);
-          const int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+          int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+          asm volatile("" : "+r"(oW), "+r"(oE));                        // keep them as offsets in registers (one add per load)
           C* o = psi + rg * T + j;
+          const C* oend = psi + nsite;
           const RowCoef<R>* rcf = coef + rg;
           uint32_t site = (uint32_t)(rg * T + j);
-          for (int i = rg; i < Z; i += RGe, o += step, rcf += RGe, site += (uint32_t)step)
-            visit(o, (i == 0 ? nsite : 0) - T, (i == Z - 1 ? -nsite : 0) + T, oW, oE, rcf, site);
+          for (; o < oend; o += step, rcf += RGe, site += (uint32_t)step)
+            visit(o, -T, T, oW, oE, rcf, site);
+          // halo rows: whoever moved row 0 / row Z-1 refreshes its copy (its own writes: no barrier needed in between)
+          if (rg == 0) psi[nsite + j] = psi[j];
+          if (rg == rg_last) psi[j - T] = psi[nsite - T + j];
         }
         __syncthreads();
       }
@@ -448,29 +464,38 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         if (col_active) {
           if (colour == 1) {
             const int bb = (rg & 1) ? 0 : 1;                               // rows keep their parity: the step is even
-            const int j = 2 * cj + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            const int j = 2 * cj + bb;
+            int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            asm volatile("" : "+r"(oW), "+r"(oE));
             const int step = RGe * T;
             C* o = psi + rg * T + j;
+            const C* oend = psi + nsite - T;                                // rows 0 .. Z-2
             const RowCoef<R>* rcf = coef + rg;
             uint32_t site = (uint32_t)(rg * T + j);
-            for (int i = rg; i < Z - 1; i += RGe, o += step, rcf += RGe, site += (uint32_t)step)
-              visit(o, (i == 0 ? nsite : 0) - T, T, oW, oE, rcf, site);
+            for (; o < oend; o += step, rcf += RGe, site += (uint32_t)step)
+              visit(o, -T, T, oW, oE, rcf, site);
+            if (rg == 0) psi[nsite + j] = psi[j];
           } else {
             const int bb = colour ? 1 : 0;
-            const int j = 2 * cj + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            const int j = 2 * cj + bb;
+            int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
+            asm volatile("" : "+r"(oW), "+r"(oE));
             const int step = 2 * RGe * T;                                  // even rows in pass 0, odd rows in pass 2
             C* o = psi + (2 * rg + bb) * T + j;
+            const C* oend = psi + nsite - T;                                // rows 2 ii + bb, ii < (Z-1)/2: below the last row
             const RowCoef<R>* rcf = coef + (2 * rg + bb);
             uint32_t site = (uint32_t)((2 * rg + bb) * T + j);
-            for (int ii = rg; ii < half; ii += RGe, o += step, rcf += 2 * RGe, site += (uint32_t)step)
-              visit(o, (ii == 0 && bb == 0 ? nsite : 0) - T, T, oW, oE, rcf, site);
+            for (; o < oend; o += step, rcf += 2 * RGe, site += (uint32_t)step)
+              visit(o, -T, T, oW, oE, rcf, site);
+            if (rg == 0 && bb == 0) psi[nsite + j] = psi[j];
           }
         }
         if (colour != 1 && tid >= SWEEP_NT - Th) {                         // the last row, from the top of the CTA (those
           const int bb = colour ? 0 : 1;                                   // threads have the fewest rows above)
           const int j = 2 * (tid - (SWEEP_NT - Th)) + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
           const int row = (Z - 1) * T;
-          visit(psi + row + j, -T, -row, oW, oE, coef + (Z - 1), (uint32_t)(row + j));
+          visit(psi + row + j, -T, T, oW, oE, coef + (Z - 1), (uint32_t)(row + j));
+          psi[j - T] = psi[row + j];
         }
         __syncthreads();
       }
@@ -745,7 +770,10 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
     return CYL_E_UNSUPPORTED;
   }
   const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
-  auto kern = !extras ? sweep_smem_kernel<R, false, false> : (series ? sweep_smem_kernel<R, true, true> : sweep_smem_kernel<R, true, false>);
+  auto kern = !extras ? sweep_smem_kernel<R, false, false, 0> : (series ? sweep_smem_kernel<R, true, true, 0> : sweep_smem_kernel<R, true, false, 0>);
+  // the compile-time row length pays in the plain-sweep instance (-2 %); with the amplitude machinery compiled in, the 64
+  // registers are exhausted either way and the specialised instance measured 2.6 % slower (more spills around the phases)
+  if (T == 50 && !extras) kern = sweep_smem_kernel<R, false, false, 50>;
   CYL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const PhiloxKeys keys = philox_expand(seed);
   // longest-first assignment pays when the grid runs in several waves and a CTA lives long enough to amortise the search;
@@ -755,7 +783,7 @@ static int sweep_smem(void* psi, int B, const int32_t* Z, int Zmax, int T, const
   uint32_t kflags = flags & ~(SWEEP_FLAG_LONGEST_FIRST | CYL_SWEEP_INDEX_ORDER);
   if (B > 8 * sms && nsweeps >= 32 && !(flags & CYL_SWEEP_INDEX_ORDER)) kflags |= SWEEP_FLAG_LONGEST_FIRST;
   kern<<<B, SWEEP_NT, lay.total, as_stream(stream)>>>((typename Real<R>::complex_t*)psi, B, Z, Zmax, T, params, chain, keys,
-                                                      seed, replica0, sweep0, nsweeps, variant, kflags, obs, prof, series);
+                                                      seed, replica0, sweep0, nsweeps, variant, kflags, obs, prof, series, lay);
   CYL_LAUNCH_CHECK();
   return CYL_OK;
 }

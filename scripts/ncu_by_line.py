@@ -139,3 +139,12 @@ if os.environ.get("CYL_CLASSES"):
     print()
     for ie, (n, w) in sorted(cl.items(), key=lambda kv: -kv[1][1])[:40]:
         print("exec=%10.4g  n=%5d  warp-inst=%9.3g %6.2f%%" % (ie, n, w, 100.0 * w / tot[0]))
+
+# CYL_EXEC="count": dump every instruction executed exactly `count` times (e.g. once per warp per sweep), with source lines
+if os.environ.get("CYL_EXEC"):
+    want = float(os.environ["CYL_EXEC"])
+    print()
+    for i, ((ln, ins), row) in enumerate(zip(fn, k["rows"])):
+        ie = int(row[h["Instructions Executed"]])
+        if abs(ie - want) <= 0.002 * want:
+            print("%5d %-18s %s" % (i, "%s:%d" % (ln[0].replace("k_sweep_", "").replace("cyl_", ""), ln[1]) if ln else "?", ins))
