@@ -193,7 +193,9 @@ __device__ __forceinline__ bool site_propose<float, float2>(const RowCoef<float>
   float rad;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-lg2_fast(u01_f32(x.x))));
   float s, c;
-  __sincosf(6.283185307179586f * u16_f32(__byte_perm(x.x, x.y, 0x0004) & 0xFFFFu), &s, &c);
+  // angle 2 pi (k + 1/2) / 65536 from the [1,2) mantissa trick of u16_f32 with its subtraction folded into the scaling (one FFMA)
+  const uint32_t k16 = __byte_perm(x.x, x.y, 0x0004) & 0xFFFFu;
+  __sincosf(__fmaf_rn(__uint_as_float(0x3F800000u | (k16 << 7)), 6.283185307179586f, -6.283137370279965f), &s, &c);
   const F2 d = mul2s(rad * ((1.1774100225154747f * sigma) * rc.sgmul), pk2(c, s));
   const float den = site_delta_over_k_packed(rc, pv, L, Rz, W, E, d);
   const bool acc = Draw<float>::accept(x.y, den, rc.kacc);

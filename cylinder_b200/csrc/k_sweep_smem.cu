@@ -48,6 +48,8 @@ struct SmemScalars {
   double obs[CYL_OBS_DOUBLES];      // observable sums of this launch, flushed once at the end
   RmLogs<R> rm;                     // logarithms of this sweep's Robbins-Monro factors (phase T -> phase D)
   int amp_accept;
+  CylParams p;                      // the replica's parameters: read where they are used (fixed shared-memory address) instead of
+                                    // a 96-byte copy per thread that the register allocator has to carry or spill
   alignas(16) uint32_t keys[12];    // the ten Philox round keys of this replica's site stream: three loads per colour pass
 };                                  // instead of re-deriving the Weyl sequence (18 instructions) in every warp
 
@@ -92,7 +94,7 @@ struct SweepSmemLayout {
   static constexpr uint32_t off_psi = off_amp + 2 * AMP_CHUNK * (uint32_t)sizeof(double);
   uint32_t off_coef, off_trig, off_w, off_prof, total;
   __host__ __device__ SweepSmemLayout(int Zmax, int T) {
-    size_t o = off_psi + (size_t)(Zmax + 2) * T * sizeof(C);              // the lattice between two periodic halo rows
+    size_t o = off_psi + (size_t)Zmax * T * sizeof(C);
     o = (o + 15) & ~(size_t)15;
     off_coef = (uint32_t)o; o += (size_t)Zmax * sizeof(RowCoef<R>);
     off_trig = (uint32_t)o; o += (size_t)Zmax * sizeof(RowTrig<R>);
@@ -105,15 +107,18 @@ struct SweepSmemLayout {
 template <typename R>
 __device__ __forceinline__ bool weights_need_ref(int variant) { return variant == CYL_VARIANT_RESCALED_0TH || variant == CYL_VARIANT_RESCALED_1ST; }
 
-// Tables of an accepted amplitude a (the accepted amplitude becomes the metric reference too).  Coefficient row i on thread i;
-// the current weights of row i on thread NT/2 + i, i.e. on other warps, so the two chains run side by side (this phase has
-// one barrier behind it and nothing else to do).  `weights` = evaluate the weights; otherwise `adopt` = take the proposal's
-// (variants whose weights do not involve the reference amplitude: they were evaluated for exactly this amplitude).
-// Rows fill whole warps: the kernel is bound by instruction issue, and a warp with eight active lanes issues as many
-// instructions as a full one.
+// Tables of an accepted amplitude a (the accepted amplitude becomes the metric reference too): coefficient row i on thread i,
+// the current weights of row i on thread NT/2 + i, i.e. on other warps, so the two chains run side by side (this phase has one
+// barrier behind it and nothing else to do).  Rows fill whole warps: the kernel is bound by instruction issue, and a warp with
+// eight active lanes issues as many instructions as a full one.
+// NOT inlined on purpose: the prologue of a launch and the accepted move inside a launch must produce bit-identical tables
+// (a run of 40 sweeps equals two runs of 20: tests/test_gpu_fullsize.py), and two inlined copies of a floating-point
+// expression are only equal as long as the compiler happens to contract them alike.  The proposal's weights (phase T) feed
+// nothing but the energy difference of that proposal, so they are never adopted as the current ones.
 template <typename R>
-__device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowWS<R>* roww, const RowTrig<R>* trig, const RepConst<R>& rc,
-                                             double a, int Z, bool weights, bool adopt) {
+__device__ __noinline__ void rebuild_rows(RowCoef<R>* coef, RowWS<R>* roww, const RowTrig<R>* trig, const RepConst<R>* rcp,
+                                          double a, int Z, bool weights) {
+  const RepConst<R>& rc = *rcp;
   const AmpGeo<R> ag = amp_geo<R>(rc, a);
   const int tid = threadIdx.x;
   const bool split = 2 * Z <= SWEEP_NT;                                  // weights on the upper half of the CTA
@@ -122,19 +127,9 @@ __device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowWS<R>* roww, c
     const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm);
     const GeoT<R> gp = geo_sc<R>(ag, tp.sm, tp.cm);                  // z_{i+1/2} = z_{(i+1)-1/2}, periodic
     coef[i] = coef_row<R>(rc, g0, gm, gp);
-    if (weights && !split) {
-      R wf[6];
-      weight_row<R>(rc, g0, gm, g0, wf);
-      RowWS<R> w;
-#pragma unroll
-      for (int q = 0; q < 5; ++q) { w.cur[q] = wf[q]; w.nxt[q] = wf[q]; }
-      w.cst[0] = wf[5]; w.cst[1] = wf[5];
-      roww[i] = w;
-    }
   }
-  if (weights && split) {
-    const int i = tid - SWEEP_NT / 2;
-    if (i >= 0 && i < Z) {
+  if (weights) {
+    for (int i = split ? tid - SWEEP_NT / 2 : tid; i >= 0 && i < Z; i += SWEEP_NT) {
       const RowTrig<R> t = trig[i];
       const GeoT<R> g0 = geo_sc<R>(ag, t.s0, t.c0), gm = geo_sc<R>(ag, t.sm, t.cm);
       R wf[6];
@@ -143,14 +138,6 @@ __device__ __forceinline__ void rebuild_rows(RowCoef<R>* coef, RowWS<R>* roww, c
 #pragma unroll
       for (int q = 0; q < 5; ++q) { w.cur[q] = wf[q]; w.nxt[q] = wf[q]; }
       w.cst[0] = wf[5]; w.cst[1] = wf[5];
-      roww[i] = w;
-    }
-  } else if (!weights && adopt) {
-    for (int i = SWEEP_NT - 1 - tid; i < Z; i += SWEEP_NT) {             // from the top of the CTA: not the coefficient threads
-      RowWS<R> w = roww[i];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) w.cur[q] = w.nxt[q];
-      w.cst[0] = w.cst[1];
       roww[i] = w;
     }
   }
@@ -222,9 +209,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   using C = typename Real<R>::complex_t;
   const int T = TT ? TT : T_arg;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // psi[-T .. -1] and psi[Z*T .. (Z+1)*T - 1] are halo rows (periodic copies of rows Z-1 and 0), kept current by the
-  // column-mapped site loops, whose neighbour offsets in z are then the constants -T and +T
-  C* psi = reinterpret_cast<C*>(smem_raw + lay.off_psi) + T;
+  C* psi = reinterpret_cast<C*>(smem_raw + lay.off_psi);
   RowCoef<R>* coef = reinterpret_cast<RowCoef<R>*>(smem_raw + lay.off_coef);
   RowTrig<R>* trig = reinterpret_cast<RowTrig<R>*>(smem_raw + lay.off_trig);
   RowWS<R>* roww = reinterpret_cast<RowWS<R>*>(smem_raw + lay.off_w);
@@ -292,7 +277,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     return;
   }
   const int nsite = Z * T;
-  const CylParams p = params[b];
+  const CylParams& pg = params[b];                                        // prologue reads; the sweeps use the copy in sc->p
   const uint32_t rep = (uint32_t)(replica0 + b);
   const SiteStream stream = site_stream(seed, (uint64_t)(replica0 + b));
   C* psi_b = psi_g + (size_t)b * Zmax * T;
@@ -303,7 +288,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
 
   // ---- prologue: state, lattice, tables ----
   if (tid == 0) {
-    sc->rc = make_rep_const<R>(p, Z, T, variant);
+    sc->p = pg;
+    sc->rc = make_rep_const<R>(pg, Z, T, variant);
     sc->amp = ch[CYL_CH_AMPLITUDE];
     sc->sigma_site = ch[CYL_CH_SIGMA_SITE];
     sc->sigma_amp = ch[CYL_CH_SIGMA_AMP];
@@ -324,19 +310,20 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   for (int s = tid; s < 3 * Z; s += SWEEP_NT) prof_s[s] = R(0);
   {
     const double pi = 3.14159265358979323846;
-    const double lz = (2 * pi / p.wavenumber) / Z;                         // On_lattice_simple.py:47
-    for (int i = tid; i < Z; i += SWEEP_NT) trig[i] = row_trig<R>(p.wavenumber, lz, i);
+    const double kk = pg.wavenumber;
+    const double lz = (2 * pi / kk) / Z;                                   // On_lattice_simple.py:47
+    for (int i = tid; i < Z; i += SWEEP_NT) trig[i] = row_trig<R>(kk, lz, i);
   }
   __syncthreads();
-  for (int j = tid; j < T; j += SWEEP_NT) { psi[j - T] = psi[(Z - 1) * T + j]; psi[Z * T + j] = psi[j]; }
-  rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, extras, false);
+  rebuild_rows<R>(coef, roww, trig, &sc->rc, sc->amp, Z, extras);
   if (extras && warp == 0) {
-    const double es = surface_energy_of(p, sc->amp);
+    const double es = surface_energy_of(sc->p, sc->amp);
     if (lane == 0) sc->e_surf = es;
   }
   __syncthreads();
 
   const bool needs_ref = weights_need_ref<R>(variant);
+  const CylParams& p = sc->p;
   const double amp_pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
   const double amp_ratio = 1.0 / (amp_pt * (1.0 - amp_pt));
   const double inv_nsite = 1.0 / nsite;
@@ -351,7 +338,6 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
   const bool mapped = RGe >= 2;
   const int rg = mapped ? tid / Th : 0, cj = mapped ? tid - rg * Th : 0;
   const bool col_active = mapped && rg < RGe;
-  const int rg_last = mapped ? (Z - 1) % RGe : 0;                          // the row group that holds row Z-1 (2-colour loops)
 
   for (int sw = 0; sw < nsweeps; ++sw) {
     const uint64_t sweep = sweep0 + (uint64_t)sw;
@@ -378,33 +364,39 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     const double a_new = extras ? a + sig_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
     const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
 
-    // ---- T. tables of the proposal; no barrier: their first reader is the energy pass, two barriers from here ----
+    // ---- T. tables of the proposal: row weights for a' on whole warps counted down from warp 6, E_surf(a') on warp 7, the
+    //         Robbins-Monro logarithms on one thread.  No barrier: their first reader is the energy pass, two barriers from
+    //         here.  (Running them DURING the first half of the energy pass, on the warps that hold no rows there, with one
+    //         more barrier before the weights are applied, measured 0.7 % slower.) ----
+    auto proposal_tables = [&]() {
     if (extras) {
-      if (try_move) {
-        if (warp == SWEEP_NWARP - 1) {
+        if (try_move) {
+          if (warp == SWEEP_NWARP - 1) {
 #ifndef SMEM_ABL_NO_ESURF
-          const double es = surface_energy_of(p, a_new);
-          if (lane == 0) sc->e_surf_new = es;
+            const double es = surface_energy_of(p, a_new);
+            if (lane == 0) sc->e_surf_new = es;
 #endif
-        } else if (SMEM_WEIGHTS_ON) {
-          const AmpGeo<R> ae = amp_geo<R>(rc, a_new), ar = amp_geo<R>(rc, a);
-          // row i on thread NT - 33 - i: whole warps, counted down from warp 6 -- the low warps carry the extra row of the
-          // site loops when Z is not a multiple of the row groups, so the table chain goes to the others
-          for (int i = (SWEEP_NT - 33) - tid; i < Z; i += SWEEP_NT - 32) {
-            const RowTrig<R> t = trig[i];
-            const GeoT<R> g0e = geo_sc<R>(ae, t.s0, t.c0), gme = geo_sc<R>(ae, t.sm, t.cm);
-            const GeoT<R> g0r = needs_ref ? geo_sc<R>(ar, t.s0, t.c0) : g0e;     // a_ref = current amplitude (:75)
-            R wf[6];
-            weight_row<R>(rc, g0e, gme, g0r, wf);
-            RowWS<R>& w = roww[i];
+          } else if (SMEM_WEIGHTS_ON) {
+            const AmpGeo<R> ae = amp_geo<R>(rc, a_new), ar = amp_geo<R>(rc, a);
+            // row i on thread NT - 33 - i: whole warps, counted down from warp 6 -- the low warps carry the extra row of the
+            // site loops when Z is not a multiple of the row groups, so the table chain goes to the others
+            for (int i = (SWEEP_NT - 33) - tid; i < Z; i += SWEEP_NT - 32) {
+              const RowTrig<R> t = trig[i];
+              const GeoT<R> g0e = geo_sc<R>(ae, t.s0, t.c0), gme = geo_sc<R>(ae, t.sm, t.cm);
+              const GeoT<R> g0r = needs_ref ? geo_sc<R>(ar, t.s0, t.c0) : g0e;     // a_ref = current amplitude (:75)
+              R wf[6];
+              weight_row<R>(rc, g0e, gme, g0r, wf);
+              RowWS<R>& w = roww[i];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) w.nxt[q] = wf[q];
-            w.cst[1] = wf[5];
+              for (int q = 0; q < 5; ++q) w.nxt[q] = wf[q];
+              w.cst[1] = wf[5];
+            }
           }
         }
+        if (tid == 64 && (flags & CYL_SWEEP_ADAPT_SIGMA)) sc->rm = rm_logs<R>(sc->step_counter, (double)nsite);
       }
-      if (tid == 64 && (flags & CYL_SWEEP_ADAPT_SIGMA)) sc->rm = rm_logs<R>(sc->step_counter, (double)nsite);
-    }
+    };
+    proposal_tables();
     PHASE_MARK(0);
 
     // ---- 1. site moves ----
@@ -439,17 +431,12 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         load_keys();
         if (col_active) {
           const int j = 2 * cj + ((colour + rg) & 1);
-          int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
-          asm volatile("" : "+r"(oW), "+r"(oE));                        // keep them as offsets in registers (one add per load)
+          const int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
           C* o = psi + rg * T + j;
-          const C* oend = psi + nsite;
           const RowCoef<R>* rcf = coef + rg;
           uint32_t site = (uint32_t)(rg * T + j);
-          for (; o < oend; o += step, rcf += RGe, site += (uint32_t)step)
-            visit(o, -T, T, oW, oE, rcf, site);
-          // halo rows: whoever moved row 0 / row Z-1 refreshes its copy (its own writes: no barrier needed in between)
-          if (rg == 0) psi[nsite + j] = psi[j];
-          if (rg == rg_last) psi[j - T] = psi[nsite - T + j];
+          for (int i = rg; i < Z; i += RGe, o += step, rcf += RGe, site += (uint32_t)step)
+            visit(o, (i == 0 ? nsite : 0) - T, (i == Z - 1 ? -nsite : 0) + T, oW, oE, rcf, site);
         }
         __syncthreads();
       }
@@ -464,38 +451,29 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
         if (col_active) {
           if (colour == 1) {
             const int bb = (rg & 1) ? 0 : 1;                               // rows keep their parity: the step is even
-            const int j = 2 * cj + bb;
-            int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
-            asm volatile("" : "+r"(oW), "+r"(oE));
+            const int j = 2 * cj + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
             const int step = RGe * T;
             C* o = psi + rg * T + j;
-            const C* oend = psi + nsite - T;                                // rows 0 .. Z-2
             const RowCoef<R>* rcf = coef + rg;
             uint32_t site = (uint32_t)(rg * T + j);
-            for (; o < oend; o += step, rcf += RGe, site += (uint32_t)step)
-              visit(o, -T, T, oW, oE, rcf, site);
-            if (rg == 0) psi[nsite + j] = psi[j];
+            for (int i = rg; i < Z - 1; i += RGe, o += step, rcf += RGe, site += (uint32_t)step)
+              visit(o, (i == 0 ? nsite : 0) - T, T, oW, oE, rcf, site);
           } else {
             const int bb = colour ? 1 : 0;
-            const int j = 2 * cj + bb;
-            int oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
-            asm volatile("" : "+r"(oW), "+r"(oE));
+            const int j = 2 * cj + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
             const int step = 2 * RGe * T;                                  // even rows in pass 0, odd rows in pass 2
             C* o = psi + (2 * rg + bb) * T + j;
-            const C* oend = psi + nsite - T;                                // rows 2 ii + bb, ii < (Z-1)/2: below the last row
             const RowCoef<R>* rcf = coef + (2 * rg + bb);
             uint32_t site = (uint32_t)((2 * rg + bb) * T + j);
-            for (; o < oend; o += step, rcf += 2 * RGe, site += (uint32_t)step)
-              visit(o, -T, T, oW, oE, rcf, site);
-            if (rg == 0 && bb == 0) psi[nsite + j] = psi[j];
+            for (int ii = rg; ii < half; ii += RGe, o += step, rcf += 2 * RGe, site += (uint32_t)step)
+              visit(o, (ii == 0 && bb == 0 ? nsite : 0) - T, T, oW, oE, rcf, site);
           }
         }
         if (colour != 1 && tid >= SWEEP_NT - Th) {                         // the last row, from the top of the CTA (those
           const int bb = colour ? 0 : 1;                                   // threads have the fewest rows above)
           const int j = 2 * (tid - (SWEEP_NT - Th)) + bb, oW = (j == 0 ? T : 0) - 1, oE = (j == T - 1 ? 1 - T : 1);
           const int row = (Z - 1) * T;
-          visit(psi + row + j, -T, T, oW, oE, coef + (Z - 1), (uint32_t)(row + j));
-          psi[j - T] = psi[row + j];
+          visit(psi + row + j, -T, -row, oW, oE, coef + (Z - 1), (uint32_t)(row + j));
         }
         __syncthreads();
       }
@@ -571,8 +549,13 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
           for (int ib = warp * rows_per_warp; ib < Z; ib += rows_per_round) {   // warp-uniform trip count (shuffles below)
             const int i = ib + (lane >> lg);
             R S[5] = {R(0), R(0), R(0), R(0), R(0)}, sre = R(0), sim = R(0), sabs = R(0);
+            if (i < Z) half_row_moments<R, C, MEAS>(psi + i * T, psi + (i == 0 ? nsite : i * T) - T, p0, p1, T, S, sre, sim, sabs);
+            if (MEAS) e.sa += sabs;
+            if (MEAS && profiles) {
+              sre += __shfl_xor_sync(0xffffffffu, sre, 1); sim += __shfl_xor_sync(0xffffffffu, sim, 1); sabs += __shfl_xor_sync(0xffffffffu, sabs, 1);
+              if (i < Z && part == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sabs; }
+            }
             if (i < Z) {
-              half_row_moments<R, C, MEAS>(psi + i * T, psi + (i == 0 ? nsite : i * T) - T, p0, p1, T, S, sre, sim, sabs);
               const RowWS<R> w = roww[i];
               R ed = (w.nxt[0] - w.cur[0]) * S[0] + (w.nxt[1] - w.cur[1]) * S[1] + (w.nxt[2] - w.cur[2]) * S[2] +
                      (w.nxt[3] - w.cur[3]) * S[3] + (w.nxt[4] - w.cur[4]) * S[4];
@@ -581,12 +564,8 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
               if (MEAS) {
                 R ec = w.cur[0] * S[0] + w.cur[1] * S[1] + w.cur[2] * S[2] + w.cur[3] * S[3] + w.cur[4] * S[4];
                 if (part == 0) ec += w.cst[0];
-                e.ec += ec; e.s2 += S[0]; e.sa += sabs;
+                e.ec += ec; e.s2 += S[0];
               }
-            }
-            if (MEAS && profiles) {
-              sre += __shfl_xor_sync(0xffffffffu, sre, 1); sim += __shfl_xor_sync(0xffffffffu, sim, 1); sabs += __shfl_xor_sync(0xffffffffu, sabs, 1);
-              if (i < Z && part == 0) { prof_s[3 * i] += sre; prof_s[3 * i + 1] += sim; prof_s[3 * i + 2] += sabs; }
             }
           }
         };
@@ -722,7 +701,7 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     // ---- R. metric tables follow the amplitude: the accepted amplitude becomes the metric reference too (rescaled
     //         variants), so the weights are rebuilt rather than taken from the proposal's ----
     if (extras && sc->amp_accept) {
-      rebuild_rows<R>(coef, roww, trig, rc, sc->amp, Z, needs_ref, true);
+      rebuild_rows<R>(coef, roww, trig, &sc->rc, sc->amp, Z, true);
       __syncthreads();
     }
     PHASE_MARK(4);

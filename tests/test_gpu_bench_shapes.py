@@ -207,3 +207,31 @@ def test_f32_smem_bench_shapes_track_oracle(cuda, Z, variant):
         assert o[_abi.OB_E_FIELD] == pytest.approx(acc["e_field"], rel=2e-5)
         assert o[_abi.OB_PSI2] == pytest.approx(acc["psi2"], rel=2e-6)
         np.testing.assert_allclose(prof[0].cpu().numpy()[:, 2], acc["prof"][:, 2], rtol=2e-6)
+
+
+@pytest.mark.parametrize("dtype_name", ["complex64", "complex128"])
+def test_smem_one_launch_equals_many_launches(cuda, dtype_name):
+    """Exact resume on the benchmark's shapes: one launch of n sweeps, n launches of one sweep, and a last sweep taken by the
+    plain-sweep instance (no amplitude machinery, compile-time row length) give bit-identical lattices, replica by replica --
+    every state a launch carries in shared memory (row tables after an accepted amplitude move, widths, draws) is a function
+    of the chain record alone.  Even and odd Z (2 and 3 colours), amplitude moves accepted in the first sweeps."""
+    import sys, os
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from cylinder_b200 import _abi
+    from cylinder_b200.replicas import ReplicaBatch
+    dt = getattr(torch, dtype_name)
+    B, n = 32, 4
+    kw = dict(dims=(50, 50), dtype=dt, device=cuda, seed=11)
+    one = ReplicaBatch(bench.grid_params(B, 0), **kw)
+    one.run(n, measure=False, index_order=True)
+    many = ReplicaBatch(bench.grid_params(B, 0), **kw)
+    for _ in range(n):
+        many.run(1, measure=False, index_order=True)
+    mixed = ReplicaBatch(bench.grid_params(B, 0), **kw)
+    mixed.run(n - 1, measure=False, index_order=True)
+    mixed.run(1, amp_moves=False, measure=False, index_order=True)      # site moves of the last sweep through the plain instance
+    assert one.chain[:, _abi.CH_AMP_ACCEPTED].sum().item() >= B           # the launches did rebuild their tables
+    assert torch.equal(one.psi, many.psi) and torch.equal(one.chain[:, :3], many.chain[:, :3])
+    assert torch.equal(one.psi, mixed.psi)
