@@ -202,11 +202,11 @@ class ReplicaBatch:
             self.chain.copy_(chain_host, non_blocking=non_blocking)
 
     def step_host(self, psi_host, chain_host, psi_out_host, rec_out_host, nsweeps, nchunks=16, amp_moves=True, measure=True,
-                  adapt=True):
+                  adapt=True, wait=True):
         """One step with HOST buffers in and out (pinned tensors): upload lattices + chain state, run nsweeps, download
         lattices + per-replica records.  The batch is cut into `nchunks` slices, each on its own stream, so the H2D copy of
         one slice, the sweeps of another and the D2H copy of a third overlap (PCIe is full duplex; replicas are
-        independent).  Returns after everything has landed in the host buffers."""
+        independent).  Returns after everything has landed in the host buffers (wait=True)."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
         if not hasattr(self, "_streams") or len(self._streams) != nchunks:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(nchunks)]
@@ -227,7 +227,8 @@ class ReplicaBatch:
         for st in self._streams:
             main.wait_stream(st)
         self.sweeps_done += int(nsweeps)
-        main.synchronize()
+        if wait:                                 # wait=False: the caller synchronises before touching the host buffers
+            main.synchronize()
 
     def state_dict(self):
         return dict(psi=self.psi.cpu(), chain=self.chain.cpu(), obs=self.obs.cpu(), prof=self.prof.cpu(), seed=self.seed,
