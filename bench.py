@@ -244,7 +244,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's own stream at high priority: the record gather runs beside the next step's sweeps (a grid of 8192 CTAs), and a
+        # normal-priority kernel behind such a grid is only dispatched when the grid has been dispatched completely
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     _abi.lib()
 
     def barrier():

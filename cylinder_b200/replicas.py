@@ -261,29 +261,40 @@ class RecordExchange:
         self.n, self.w64, self.w32 = n_local, w64, w32
         nmax = max(sh[0] for sh in self.shapes)
         m64, m32 = max(sh[1] for sh in self.shapes), max(sh[2] for sh in self.shapes)
-        self.send64 = torch.zeros(nmax, m64, dtype=torch.float64, device=self.device)
-        self.send32 = torch.zeros(nmax, m32, dtype=torch.float32, device=self.device)
+        # two sets of send buffers, used alternately: the snapshot of one step never waits for the previous step's gather
+        self.send64 = [torch.zeros(nmax, m64, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.send32 = [torch.zeros(nmax, m32, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.turn = 0
         self.recv64 = torch.empty(self.world, nmax, m64, dtype=torch.float64, device=self.device)
         self.recv32 = torch.empty(self.world, nmax, m32, dtype=torch.float32, device=self.device)
         self.cuda = self.device.type == "cuda"
-        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        # high priority: the gather's few CTAs are placed as soon as CTAs of the concurrently running sweeps retire (a normal-
+        # priority kernel launched behind a grid of 8192 CTAs only starts when that grid has been dispatched completely)
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.cuda else None
+        self.done = [None, None]                             # per send-buffer set: event "its last gather has read it"
         self.pending = False
 
     def start(self, rec64, rec32):
         import torch.distributed as dist
+        t = self.turn
+        self.turn ^= 1
+        s64, s32 = self.send64[t], self.send32[t]
         if self.cuda:
             main = torch.cuda.current_stream(self.device)
-            main.wait_stream(self.stream)                    # the previous exchange has read the send buffers (a step ago)
-        self.send64[: self.n, : self.w64].copy_(rec64)
-        self.send32[: self.n, : self.w32].copy_(rec32)
+            if self.done[t] is not None:
+                main.wait_event(self.done[t])                # the gather that last read this set (two steps ago)
+        s64[: self.n, : self.w64].copy_(rec64)
+        s32[: self.n, : self.w32].copy_(rec32)
         if self.cuda:
             self.stream.wait_stream(main)
             with torch.cuda.stream(self.stream):
-                dist.all_gather_into_tensor(self.recv64.view(-1), self.send64.view(-1), group=self.group)
-                dist.all_gather_into_tensor(self.recv32.view(-1), self.send32.view(-1), group=self.group)
+                dist.all_gather_into_tensor(self.recv64.view(-1), s64.view(-1), group=self.group)
+                dist.all_gather_into_tensor(self.recv32.view(-1), s32.view(-1), group=self.group)
+                self.done[t] = torch.cuda.Event()
+                self.done[t].record(self.stream)
         else:
-            dist.all_gather(list(self.recv64.unbind(0)), self.send64, group=self.group)
-            dist.all_gather(list(self.recv32.unbind(0)), self.send32, group=self.group)
+            dist.all_gather(list(self.recv64.unbind(0)), s64, group=self.group)
+            dist.all_gather(list(self.recv32.unbind(0)), s32, group=self.group)
         self.pending = True
 
     def finish(self):

@@ -17,7 +17,8 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=dev)
+    opts = dist.ProcessGroupNCCL.Options(); opts.is_high_priority_stream = True
+    dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 B, nsw = 8192, 200
 batch = ReplicaBatch(bench.grid_params(B, rank * B), dims=(50, 50), dtype=torch.complex64, device=dev, seed=1, replica0=rank * B)
 psi_h, chain_h = batch.psi.cpu().pin_memory(), batch.chain.cpu().pin_memory()
