@@ -246,7 +246,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's own stream at high priority: the record gather runs beside the next step's sweeps (a grid of 8192 CTAs), and a
         # normal-priority kernel behind such a grid is only dispatched when the grid has been dispatched completely
-        opts = dist.ProcessGroupNCCL.Options()
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")     # the gather moves ~12 MB per rank per step: a few CTAs are plenty, and
+        opts = dist.ProcessGroupNCCL.Options()          # every CTA it holds is one the sweeps running beside it do not get
         opts.is_high_priority_stream = True
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     _abi.lib()
