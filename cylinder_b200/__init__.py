@@ -8,7 +8,7 @@ Batched / multi-GPU form of the reference's job farm: replicas.ReplicaBatch, run
 Everything numerical runs in libcylinder_b200.so (CUDA, sm_100a) through the C-ABI of include/cylinder_b200.h;
 importing this package does not need a GPU, using it does.
 """
-__all__ = ["Cylinder", "Cylinder2D", "Lattice", "LatticeRescaled0thOrder", "LatticeRescaled1stOrder", "LatticeDecoupled",
+__all__ = ["Cylinder", "Cylinder1D", "Cylinder2D", "Lattice", "LatticeRescaled0thOrder", "LatticeRescaled1stOrder", "LatticeDecoupled",
            "MetropolisEngine", "ReplicaBatch"]
 
 
@@ -19,6 +19,9 @@ def __getattr__(name):
     if name == "Cylinder2D":
         from .system_cylinder2D import Cylinder2D
         return Cylinder2D
+    if name == "Cylinder1D":
+        from .system_cylinder1D import Cylinder1D
+        return Cylinder1D
     if name in ("Lattice", "LatticeRescaled0thOrder", "LatticeRescaled1stOrder", "LatticeDecoupled"):
         from . import lattice
         return getattr(lattice, name)

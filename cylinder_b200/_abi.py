@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcylinder_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "cylinder_b200.h")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # constants mirrored from the header (checked against it in tests/test_abi_cpu.py)
 VARIANT_SIMPLE, VARIANT_RESCALED_0TH, VARIANT_RESCALED_1ST, VARIANT_DECOUPLED = 0, 1, 2, 3
@@ -72,6 +72,7 @@ _SIGNATURES = {
     "cyl_hbm_row_moments_f64": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "cyl_fourier_energy_f64": [_vp, _i, _i, _vp, _vp, _i, _vp, _vp],
     "cyl_fourier_surface_energy_f64": [_vp, _vp, _i, _vp, _vp],
+    "cyl_fourier_tensor_tables_f64": [_vp, _i, _i, _vp, _i, _vp, _vp, _vp],
     "cyl_fourier_am_state_doubles": [_i, _i],
     "cyl_fourier_am_steps_f64": [_vp, _i, _i, _vp, _vp, _vp, _i, _u64, _i64, _u64, _i, _i, _i, _d, _d, _d, _i, _vp],
 }

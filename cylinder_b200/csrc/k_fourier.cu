@@ -182,6 +182,70 @@ extern "C" int cyl_fourier_surface_energy_f64(const CylParams* params, const dou
 }
 
 // ----------------------------------------------------------------------------------------------------
+// The reference's tensor tables for callers that read them (tests/test_matrixA.py, tests/test_1Dvs2D.py of the reference):
+//   A[d]          = int_0^L e^{i d k z} Gth Gz dz,                    d in [-4 nz, 4 nz]       system_cylinder2D.py:103-109
+//   B[i, j, beta] = int_0^L e^{i (i - j) k z} ( k^2 i j Gz Gth + (beta - n A_theta)^2 Gz / Gth ) dz   :64-100, :134-147
+// one warp per element, 256-node periodic trapezoid (the integrands are analytic and periodic: spectral accuracy; the
+// reference runs scipy.integrate.quad twice per element).  out_A: [B][8 nz + 1] complex, out_B: [B][2nz+1][2nz+1][2nth+1] complex
+// (the diagonal beta' = beta of the reference's 4-index B; its off-diagonal elements are zero by the selection rule).
+// The energies never go through these tables (cyl_fourier_energy_f64 integrates the energy density directly).
+// ----------------------------------------------------------------------------------------------------
+__global__ void fourier_tensor_tables_kernel(const CylParams* __restrict__ params, int nz, int nth, const double* __restrict__ amp, int B,
+                                             double2* __restrict__ out_A, double2* __restrict__ out_B) {
+  const int nA = 8 * nz + 1, lz = 2 * nz + 1, lth = 2 * nth + 1, nB = lz * lz * lth, per = nA + nB;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)B * per) return;
+  const int b = (int)(w / per), e = (int)(w - (long long)b * per), lane = threadIdx.x & 31;
+  const CylParams p = params[b];
+  const double a = amp[b], k = p.wavenumber;
+  const double ra = geo_radius_rescaled(p.radius, a);
+  const double L = 2.0 * 3.14159265358979323846 / k;
+  int d, ii = 0, jj = 0, beta = 0;
+  const bool isA = e < nA;
+  if (isA) d = e - 4 * nz;
+  else {
+    const int q = e - nA;
+    ii = q / (lz * lth) - nz; jj = (q / lth) % lz - nz; beta = q % lth - nth;
+    d = ii - jj;
+  }
+  double sre = 0.0, sim = 0.0;
+  for (int node = lane; node < CYL_QUAD_NODES; node += 32) {
+    const double z = L * node / CYL_QUAD_NODES;
+    double s, c;
+    sincos(k * z, &s, &c);
+    const double gth = ra * (1.0 + a * s);
+    const double t = ra * a * k * c;
+    const double gz = sqrt(1.0 + t * t);
+    double body;
+    if (isA) body = gth * gz;
+    else {
+      const double ath = t / gz, m = (double)beta - p.n * ath;
+      body = k * k * ii * jj * gz * gth + m * m * gz / gth;
+    }
+    double sd, cd;
+    sincospi(2.0 * (double)(((long long)d * node) % CYL_QUAD_NODES) / CYL_QUAD_NODES, &sd, &cd);   // e^{i d k z}, exact phase
+    sre += cd * body; sim += sd * body;
+  }
+  sre = warp_sum(sre) * (L / CYL_QUAD_NODES);
+  sim = warp_sum(sim) * (L / CYL_QUAD_NODES);
+  if (lane == 0) {
+    if (isA) out_A[(size_t)b * nA + e] = make_double2(sre, sim);
+    else out_B[(size_t)b * nB + (e - nA)] = make_double2(sre, sim);
+  }
+}
+
+extern "C" int cyl_fourier_tensor_tables_f64(const CylParams* params, int nz, int nth, const double* amp, int B, double* out_A,
+                                             double* out_B, void* stream) {
+  CYL_CHECK_ARG(params && amp && out_A && out_B && B > 0 && nz >= 0 && nth >= 0, "cyl_fourier_tensor_tables_f64: bad arguments");
+  const long long total = (long long)B * ((8 * nz + 1) + (long long)(2 * nz + 1) * (2 * nz + 1) * (2 * nth + 1));
+  const int warps = 4;
+  fourier_tensor_tables_kernel<<<(unsigned)((total + warps - 1) / warps), warps * 32, 0, as_stream(stream)>>>(
+      params, nz, nth, amp, B, reinterpret_cast<double2*>(out_A), reinterpret_cast<double2*>(out_B));
+  CYL_LAUNCH_CHECK();
+  return CYL_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Batched adaptive Metropolis for the Fourier model: run.py:286-294 (method "sequential") with the engine
 // arithmetic of SURVEY.md Appendix B, one warp per chain, state dimension d = 1 + ncoef <= 33 (one per lane).
 //   per step:  measure_every x [ real-group move ; fieldsteps x complex-group move ] ; measure()

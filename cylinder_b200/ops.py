@@ -234,6 +234,16 @@ def fourier_surface_energy(params, amp):
     return E
 
 
+def fourier_tensor_tables(params, nz, nth, amp):
+    """The reference's A[d] (d = -4nz..4nz) and diagonal B[i, j, beta] tables for B (parameter row, amplitude) pairs:
+    complex128 tensors [B, 8nz+1] and [B, 2nz+1, 2nz+1, 2nth+1] (system_cylinder2D.py:103-147)."""
+    B = amp.numel()
+    A = torch.empty(B, 8 * nz + 1, dtype=torch.complex128, device=amp.device)
+    Bm = torch.empty(B, 2 * nz + 1, 2 * nz + 1, 2 * nth + 1, dtype=torch.complex128, device=amp.device)
+    call("cyl_fourier_tensor_tables_f64", _dev(params), ptr(params), int(nz), int(nth), ptr(amp), B, ptr(A), ptr(Bm), stream())
+    return A, Bm
+
+
 # ------------------------------------------------------------------------------------------------------
 # whole-lattice proposals (cyl_move_*): shift / plane wave / row twist
 # ------------------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CYL_ABI_VERSION 7
+#define CYL_ABI_VERSION 8
 
 /* error codes */
 #define CYL_OK             0
@@ -269,6 +269,13 @@ int cyl_fourier_energy_f64(const CylParams* params /*[B]*/, int nz, int nth, con
 /* Cylinder1D.calc_surface_energy (system_cylinder1D.py:189-194): gamma_eff*int(G_th G_z) + kappa*bending. */
 int cyl_fourier_surface_energy_f64(const CylParams* params, const double* amp, int B, double* E_out,
                                    void* stream);
+
+/* The reference's tensor tables, for callers that read them (Cylinder2D.evaluate_A_integrals, system_cylinder2D.py:103-131: tmp_A_integrals
+ * [8 nz + 1] complex, index d + 4 nz; Cylinder2D.evaluate_B_integrals, :134-147: the beta' = beta diagonal of tmp_B_matrix,
+ * [2nz+1][2nz+1][2nth+1] complex, indices i + nz, j + nz, beta + nth).  B amplitudes / parameter rows per call; 256-node periodic
+ * trapezoid per element in place of two scipy quad calls.  The energy entry points above do not use these tables. */
+int cyl_fourier_tensor_tables_f64(const CylParams* params, int nz, int nth, const double* amp, int B, double* out_A, double* out_B,
+                                  void* stream);
 
 /* The drivers of run.py:286-317 ("method") */
 #define CYL_FOURIER_SEQUENTIAL      0   /* run.py:286-294: amplitude move, then fieldsteps coefficient moves          */

@@ -583,3 +583,68 @@ def test_row_moments_long_rows_match_torch(cuda, T):
         ws = ops.HbmWorkspace(Zs[0], T, torch.complex128, cuda)
         ws.pack(psi[0].contiguous())
         torch.testing.assert_close(ws.row_moments(par[0:1]), expect(psi, 0), rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("tag", FOURIER_CASES)
+def test_fourier_tensor_tables_match_reference(cuda, golden_dir, tag):
+    """Cylinder2D.evaluate_A_integrals / evaluate_B_integrals (system_cylinder2D.py:103-147; the attributes the reference's own
+    tests/test_matrixA.py and tests/test_1Dvs2D.py read): tmp_A_integrals and tmp_B_matrix recorded from the reference (scipy quad)
+    vs the device tables, and the reference's index layout of tmp_A_matrix / tmp_D_matrix; contracted by einsum they reproduce the
+    recorded energies (system_cylinder2D.py:176-198), i.e. the tensor route and the single-integral kernel agree."""
+    import math
+    import cylinder_b200
+    g = np.load(os.path.join(golden_dir, "fourier.npz"))
+    P = dict(zip(FOURIER_NAMES, g[tag + "_params"].tolist()))
+    nz, nth = (int(x) for x in g[tag + "_nfc"])
+    sys2 = cylinder_b200.Cylinder2D(num_field_coeffs=(nz, nth), device=cuda, **P)
+    assert len(sys2.quartic_selection_rule) == sum(1 for a in range(2 * nth + 1) for b in range(2 * nth + 1) for c in range(2 * nth + 1)
+                                                   for d in range(2 * nth + 1) if a + b == c + d)
+    c = g[tag + "_coeffs"]
+    for ia, a in enumerate(g[tag + "_amps"]):
+        sys2.evaluate_A_integrals(float(a))
+        sys2.evaluate_B_integrals(float(a))
+        scale = max(1.0, float(np.abs(g[tag + "_Aint"][ia]).max()))
+        np.testing.assert_allclose(sys2.tmp_A_integrals, g[tag + "_Aint"][ia], rtol=0, atol=1e-10 * scale)
+        np.testing.assert_allclose(sys2.tmp_B_matrix, g[tag + "_B"][ia], rtol=0, atol=1e-10 * max(1.0, float(np.abs(g[tag + "_B"][ia]).max())))
+        A, D, B = sys2.tmp_A_matrix, sys2.tmp_D_matrix, sys2.tmp_B_matrix
+        lz = 2 * nz + 1
+        for i in range(lz):
+            for j in range(lz):
+                assert A[i, j] == sys2.tmp_A_integrals[(i - j) + 4 * nz]           # A[i, j] = A_int[d = i - j]
+        assert D.shape == (lz, lz, lz, lz) and D[0, lz - 1, 0, lz - 1] == sys2.tmp_A_integrals[4 * nz]
+        Ae = sum(np.einsum("ij, i, j -> ", A, c[b], c[b].conjugate()) for b in range(2 * nth + 1))
+        De = sum(np.einsum("ijkl, i, j, k, l -> ", D, c[i1], c[i2], c[i3].conjugate(), c[i4].conjugate())
+                 for (i1, i2, i3, i4) in sys2.quartic_selection_rule)
+        Be = np.einsum("ijab, ai, bj -> ", B, c, c.conjugate())
+        E = P["alpha"] * Ae.real + P["C"] * Be.real + 0.5 * P["u"] * De.real
+        assert E == pytest.approx(float(g[tag + "_E_change"][ia]), rel=1e-9)
+        assert sys2.calc_field_energy_amplitude_change(float(a), c) == pytest.approx(E, rel=1e-9)
+        sys2.save_temporary_matrices()
+        assert sys2.A_matrix is sys2.tmp_A_matrix and sys2.calc_field_energy(c) == pytest.approx(E, rel=1e-9)
+        sys2.evaluate_A_integral_0(float(a))
+        assert sys2.tmp_A_integrals_0 == pytest.approx(complex(sys2.tmp_A_integrals[4 * nz]))
+    sys2.evaluate_A_integrals(0.0)                        # tests/test_matrixA.py: the diff = 0 element at a = 0 is 2 pi r / k
+    assert sys2.tmp_A_integrals[4 * nz] == pytest.approx(2 * math.pi * P["radius"] / P["wavenumber"], rel=1e-12)
+
+
+def test_cylinder1d_matches_reference(cuda, golden_dir):
+    """Cylinder1D (system_cylinder1D.py) = the 2-D model without theta modes: energies recorded from the reference's 1-D class,
+    its attribute names, and 1D == 2D on the (n, 0) slice as in the reference's tests/test_1Dvs2D.py."""
+    import cylinder_b200
+    from cylinder_b200.surfaces_and_fields.system_cylinder1D import Cylinder1D
+    g = np.load(os.path.join(golden_dir, "fourier.npz"))
+    kw = dict(wavenumber=1., radius=1, alpha=-1, C=1, u=1, n=1, kappa=1, gamma=1)
+    s1 = Cylinder1D(num_field_coeffs=1, device=cuda, **kw)
+    s2 = cylinder_b200.Cylinder2D(num_field_coeffs=(1, 0), device=cuda, **kw)
+    co = g["c1d_coeffs"]
+    assert s1.len_arrays == 3 and s1.tmp_A_integrals.shape == (9,)
+    for a, e in zip(g["c1d_amps"], g["c1d_E"]):
+        e1 = s1.calc_field_energy_amplitude_change(float(a), co)
+        assert e1 == pytest.approx(float(e), rel=1e-10)
+        assert s2.calc_field_energy_amplitude_change(float(a), co[None, :]) == pytest.approx(e1, rel=1e-13)
+        s1.evaluate_B_integrals(float(a))
+        assert s1.tmp_B_integrals.shape == (3, 3)
+        s1.save_temporary_matrices()
+        assert s1.calc_field_energy(co) == pytest.approx(e1, rel=1e-13) and s1.B_integrals.shape == (3, 3)
+        s2.evaluate_B_integrals(float(a))
+        np.testing.assert_array_equal(s1.tmp_B_integrals, s2.tmp_B_matrix[:, :, 0, 0])
