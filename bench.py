@@ -390,9 +390,26 @@ def main():
         ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
         h2d = psi_h.numel() * psi_h.element_size() + chain_h.numel() * 8
         d2h = rec_h.numel() * 8 + psi_out_h.numel() * psi_out_h.element_size()
+        # the same with the lattices resident on the device (chain state in, records out): a production run between checkpoints
+        def step_rec():
+            batch.step_host(psi_h, chain_h, psi_out_h, rec_h, nsw, nchunks=args.e2e_chunks, lattices=False)
+            if world > 1:
+                batch.gather_start()
+        step_rec()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step_rec()
+        if world > 1:
+            batch.gather_finish()
+        barrier()
+        ms_rec = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {"value": updates_per_step_all * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K,
-               "api": "ReplicaBatch.step_host: pinned host lattices + chain in, sweeps, lattices + records out, %d-slice stream pipeline, host-synchronised per step" % args.e2e_chunks}
+               "api": "ReplicaBatch.step_host: pinned host lattices + chain in, sweeps, lattices + records out, %d-slice stream pipeline, host-synchronised per step" % args.e2e_chunks,
+               "lattices_resident": {"value": updates_per_step_all * K / (ms_rec * 1e-3), "ms_per_step": ms_rec / K,
+                                     "h2d_bytes_per_step": int(chain_h.numel() * 8), "d2h_bytes_per_step": int(rec_h.numel() * 8),
+                                     "note": "step_host(lattices=False): chain state in, records out, lattices stay on the device (not the headline e2e)"}}
 
     # ---- roofline leg: C4, one large lattice streamed from HBM ----
     roofline = None

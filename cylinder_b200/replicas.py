@@ -202,11 +202,13 @@ class ReplicaBatch:
             self.chain.copy_(chain_host, non_blocking=non_blocking)
 
     def step_host(self, psi_host, chain_host, psi_out_host, rec_out_host, nsweeps, nchunks=16, amp_moves=True, measure=True,
-                  adapt=True, wait=True):
+                  adapt=True, wait=True, lattices=True):
         """One step with HOST buffers in and out (pinned tensors): upload lattices + chain state, run nsweeps, download
         lattices + per-replica records.  The batch is cut into `nchunks` slices, each on its own stream, so the H2D copy of
         one slice, the sweeps of another and the D2H copy of a third overlap (PCIe is full duplex; replicas are
-        independent).  Returns after everything has landed in the host buffers (wait=True)."""
+        independent).  Returns after everything has landed in the host buffers (wait=True).  lattices=False keeps the lattices resident
+        on the device (chain state in, records out): what a production run does between checkpoints -- on a host with several GPUs
+        the pinned copies of the lattices are what limits the step (profiles/r02_e2e_limits.md)."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
         if not hasattr(self, "_streams") or len(self._streams) != nchunks:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(nchunks)]
@@ -217,11 +219,13 @@ class ReplicaBatch:
                 continue
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                self.psi[b0:b1].copy_(psi_host[b0:b1], non_blocking=True)
+                if lattices:
+                    self.psi[b0:b1].copy_(psi_host[b0:b1], non_blocking=True)
                 self.chain[b0:b1].copy_(chain_host[b0:b1], non_blocking=True)
                 ops.sweep_smem(self.psi[b0:b1], self.Z[b0:b1], self.params[b0:b1], self.chain[b0:b1], self.seed, self.sweeps_done,
                                nsweeps, self.variant, flags, self.replica0 + b0, self.obs[b0:b1], self.prof[b0:b1])
-                psi_out_host[b0:b1].copy_(self.psi[b0:b1], non_blocking=True)
+                if lattices:
+                    psi_out_host[b0:b1].copy_(self.psi[b0:b1], non_blocking=True)
                 rec = torch.cat([self.obs[b0:b1], self.chain[b0:b1], self.prof[b0:b1].reshape(b1 - b0, -1)], dim=1)
                 rec_out_host[b0:b1].copy_(rec, non_blocking=True)
         for st in self._streams:
