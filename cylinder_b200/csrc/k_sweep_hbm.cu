@@ -427,8 +427,10 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     static_assert(TW == 128 && HBM_NT % 64 == 0 && ((HBM_NT / 64) & 1) == 0, "thread mapping assumes 64 columns per plane row");
     constexpr int RSTEP = HBM_NT / 64;
     // one site move; `counted` = the site belongs to this tile's interior (not a redundantly recomputed halo site)
-    auto move = [&](auto MEAS, C* own, const C* oth, int r, uint32_t site, bool counted, int c) {
+    // EN = accumulate the energy terms here (border tiles); interior tiles take them in one pass over the finished tile
+    auto move = [&](auto MEAS, auto EN, C* own, const C* oth, int r, uint32_t site, bool counted, int c) {
       constexpr bool meas = decltype(MEAS)::value;                // the measurement terms compiled in or out
+      constexpr bool en = decltype(EN)::value;
       const RowCoef<R> rc = coef[r];
       const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
       const uint2 x = philox2x32_10(site, c1, kc, kr);
@@ -436,7 +438,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const bool acc = site_propose<R, C>(rc, pv, Ln, Rz, W, E, sigma, x, q);
       if (acc) own[0] = q;
       nacc += (acc && counted);
-      if (EXTRAS && HBM_ENERGY_ON && counted) {
+      if (EXTRAS && HBM_ENERGY_ON && en && counted) {
         const RowW<R> rw = roww[r];
         energy_own<R, C>(e, rw, q, meas);
         if (c == 1) {                                             // colour 1 closes every bond: its neighbours are final
@@ -464,16 +466,16 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       if (!border) {
         uint32_t site = site_id(r, q);
         for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH, site += RSTEP * g.T)
-          move(MEAS, own, oth, r, site, c == 1 || (r != 1 && r != SH - 2), c);
+          move(MEAS, std::false_type{}, own, oth, r, site, c == 1 || (r != 1 && r != SH - 2), c);
       } else {
         for (; r < SH - m; r += RSTEP, own += RSTEP * SWH, oth += RSTEP * SWH)
-          move(MEAS, own, oth, r, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T, c);
+          move(MEAS, std::true_type{}, own, oth, r, site_id(r, q), (c == 1 || (r != 1 && r != SH - 2)) && ti0 - 2 + r < g.Z && tj0 - HS + q < g.T, c);
       }
       if (c == 0 && tid >= HBM_NT - (SH - 2)) {
         // the 65th colour-0 site of each row of the grown region: halo column q = HS - 1 (odd rows) or HS + TW (even rows)
         const int r1 = 1 + (tid - (HBM_NT - (SH - 2))), q1 = (r1 & 1) ? HS - 1 : HS + TW;
         const int p1 = q1 & 1;
-        move(MEAS, pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), r1, site_id(r1, q1), false, 0);
+        move(MEAS, std::false_type{}, pl0 + p1 * PS + r1 * SWH + (q1 >> 1), pl0 + (p1 ^ 1) * PS + r1 * SWH + ((q1 - 1) >> 1), r1, site_id(r1, q1), false, 0);
       }
       if (c == 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
       __syncthreads();
@@ -488,7 +490,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
     // are dense.  (Visiting every site of the region in every pass and filtering cost 3.7x the 2-colour sweep.)
     auto col3 = [](int s) { return s >= 3 ? s - 3 : s; };
     // one site of pass c at region coordinates (r, q) = lattice (gi, gj), axis colours (ai, bj)
-    auto site3 = [&](int c, int r, int q, int gi, int gj, int ai, int bj) {
+    auto site3 = [&](auto EN, int c, int r, int q, int gi, int gj, int ai, int bj) {
+      constexpr bool en = decltype(EN)::value;           // energy terms here (border tiles) or in the tile pass below
       const int par = (Q0 + q) & 1;
       C* own = par ? pl1 : pl0;
       C* oth = par ? pl0 : pl1;
@@ -504,7 +507,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const int li = r - NCOL, lj = q - HS;
       const bool counted = (li >= 0 && li < TH && lj >= 0 && lj < TW && ti0 + li < g.Z && tj0 + lj < g.T);
       nacc += (acc && counted);
-      if (EXTRAS && HBM_ENERGY_ON && counted) {
+      if (EXTRAS && HBM_ENERGY_ON && en && counted) {
         const RowW<R> rw = roww[r];
         energy_own<R, C>(e, rw, qv, meas);
         // a bond is added by its later-coloured endpoint: here, when the neighbour's colour is lower than ours
@@ -521,6 +524,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       gj = border ? wrapi(uj, g.T) : uj;                           // interior tiles never leave [0, Z) x [0, T), halo included
       return axis_colour(gj, g.T);
     };
+    auto passes3 = [&](auto EN) {
 #pragma unroll 1
     for (int c = 0; c < NCOL; ++c) {
       const int m = c + 1, mq = m + (HS - NCOL);
@@ -537,8 +541,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         const int ai = axis_colour(gi, g.Z);
         int bj = c - ai;
         if (bj < 0) bj += 3;
-        if (ac0 == bj) site3(c, r, q0, gi, gj0, ai, bj);
-        else if (ac1 == bj) site3(c, r, q0 + 1, gi, gj1, ai, bj);
+        if (ac0 == bj) site3(EN, c, r, q0, gi, gj0, ai, bj);
+        else if (ac1 == bj) site3(EN, c, r, q0 + 1, gi, gj1, ai, bj);
       }
       // the (at most two) pairs beyond the 64 per row, as one flat list over (row, pair)
       const int nextra = npairs - 64;
@@ -552,11 +556,17 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
         if (bj < 0) bj += 3;
         int gja = 0, gjb = 0;
         const int aa = column(qx, qend, gja), ab = column(qx + 1, qend, gjb);
-        if (aa == bj) site3(c, r, qx, gi, gja, ai, bj);
-        else if (ab == bj) site3(c, r, qx + 1, gi, gjb, ai, bj);
+        if (aa == bj) site3(EN, c, r, qx, gi, gja, ai, bj);
+        else if (ab == bj) site3(EN, c, r, qx + 1, gi, gjb, ai, bj);
       }
       if (c == NCOL - 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
       __syncthreads();
+    }
+    };
+    if constexpr (EXTRAS) {
+      if (!border) passes3(std::false_type{}); else passes3(std::true_type{});
+    } else {
+      passes3(std::true_type{});
     }
   }
 
@@ -602,9 +612,122 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
 
   const int warp = tid >> 5, lane = tid & 31;
-  // ---- theta-sums of the profiles (Lattice.measure :121-131) of this tile's rows ----
+  // ---- interior 2-colour tiles with EXTRAS: the field energy (current weights, and proposal - current) and the theta-sums of
+  //      the profiles in ONE read-only pass over the finished tile, as in the batched kernel's energy pass -- a third of the
+  //      instructions of closing the bonds inside the colour passes.  What is final in shared memory: every interior site, and
+  //      the colour-0 sites of the ring around it (recomputed redundantly above); a bond joins a colour-0 and a colour-1 site, so
+  //      the tile in which the colour-1 endpoint is interior sees both ends final and owns the bond -- no bond is missed or taken
+  //      twice across tile boundaries.  Thread = (row, 4 strided column pairs per plane): lane & 7 picks the pair inside a group
+  //      of 16 plane columns, so the 16-byte loads of a quarter-warp cover 128 contiguous bytes (conflict-free); rows are dealt
+  //      warp + 8 k, so the row parity -- which plane holds the colour-1 sites -- is warp-uniform.  Per step a thread loads two
+  //      colour-1 sites with the sites above and below, the two colour-0 sites of the same plane columns and the colour-0
+  //      neighbour beyond the pair: five consecutive columns, four theta-bonds, four z-bonds, four sites' own terms.  The row
+  //      weights are applied once per thread (the z-bonds downwards carry the next row's weight). ----
+  bool tile_pass_done = false;
+  if constexpr (EXTRAS) {
+    if (!border) {
+      static_assert(TH <= 32 && TW == 128 && HBM_NT == 256, "row = warp + 8 k, eight threads per row, 4 x 16 plane columns");
+      tile_pass_done = true;
+      auto tile_pass = [&](auto MEAS) {
+        constexpr bool M = decltype(MEAS)::value;
+        using P = Pk<R>;
+        using V = typename P::T;
+        const int li = warp + 8 * (lane >> 3), seg = lane & 7;
+        R sre = R(0), sim = R(0), sab = R(0);
+        if (li < TH) {
+          const int r = li + NCOL;
+          R s2 = R(0), s4 = R(0), sa = R(0);
+          V zu = P::zero(), zd = P::zero(), dt = P::zero(), im = P::zero(), sp = P::zero();
+          auto own = [&](const C v) {
+            const R p2 = v.x * v.x + v.y * v.y;
+            s2 += p2;
+            s4 += p2 * p2;
+            if (M) { sa += sqrt_fast(p2); sp = P::add(sp, P::make(v)); }
+          };
+          auto tbond = [&](const V hi, const V lo) {                   // as energy_tbond: |dth|^2 and Im(conj(hi) dth)
+            const V t = P::sub(hi, lo);
+            dt = P::fma(t, t, dt);
+            im = P::fma(P::rot(hi), t, im);
+          };
+          if constexpr (NCOL == 2) {
+            const int p1 = (r + 1) & 1;                                // (r + q) & 1 == 1: the plane of this row's colour-1 sites
+            const C* a1 = pl0 + p1 * PS + r * SWH + HS / 2 + 2 * seg;
+            const C* a0 = pl0 + (p1 ^ 1) * PS + r * SWH + HS / 2 + 2 * seg;
+            auto steps = [&](auto PAR) {
+              constexpr int par = decltype(PAR)::value;
+#pragma unroll 2
+              for (int j = 0; j < 4; ++j) {
+                C A0, A1, B0, B1, U0, U1, D0, D1;
+                load_pair(a1 + 16 * j, A0, A1);
+                load_pair(a0 + 16 * j, B0, B1);
+                load_pair(a1 + 16 * j - SWH, U0, U1);
+                load_pair(a1 + 16 * j + SWH, D0, D1);
+                const C X = a0[16 * j + (par ? 2 : -1)];
+                const V vA0 = P::make(A0), vA1 = P::make(A1), vB0 = P::make(B0), vB1 = P::make(B1), vX = P::make(X);
+                if (par) { tbond(vA0, vB0); tbond(vB1, vA0); tbond(vA1, vB1); tbond(vX, vA1); }     // columns B0 A0 B1 A1 X
+                else     { tbond(vA0, vX); tbond(vB0, vA0); tbond(vA1, vB0); tbond(vB1, vA1); }     // columns X A0 B0 A1 B1
+                const V u0 = P::sub(vA0, P::make(U0)), u1 = P::sub(vA1, P::make(U1));
+                zu = P::fma(u0, u0, zu); zu = P::fma(u1, u1, zu);
+                const V d0 = P::sub(P::make(D0), vA0), d1 = P::sub(P::make(D1), vA1);
+                zd = P::fma(d0, d0, zd); zd = P::fma(d1, d1, zd);
+                own(A0); own(A1); own(B0); own(B1);
+              }
+            };
+            if (p1) steps(std::integral_constant<int, 1>{}); else steps(std::integral_constant<int, 0>{});
+          } else {
+            // Three colours, tile away from the lattice edges (so no row or column of axis colour 2 within reach): colour =
+            // (row parity) + (column parity).  Final in shared memory: the interior and the ring sites of colours 0 and 1; the
+            // endpoint of a bond with the ODD coordinate along the bond has the higher colour, and the tile in which that
+            // endpoint is interior owns the bond.  Tiles start on even rows and columns (TH and TW are even), so: every interior
+            // site takes its bond downwards and its bond to the right -- the ring sites these reach are even, hence final.
+            static_assert((TH & 1) == 0 && (TW & 1) == 0, "tile origins must be even");
+            const C* b0 = pl0 + r * SWH + HS / 2 + 2 * seg;           // even columns
+            const C* b1 = b0 + PS;                                    // odd columns
+#pragma unroll 2
+            for (int j = 0; j < 4; ++j) {
+              C E0, E1, O0, O1, F0, F1, G0, G1;                       // columns in order: E0 O0 E1 O1 X
+              load_pair(b0 + 16 * j, E0, E1);
+              load_pair(b1 + 16 * j, O0, O1);
+              load_pair(b0 + 16 * j + SWH, F0, F1);
+              load_pair(b1 + 16 * j + SWH, G0, G1);
+              const C X = b0[16 * j + 2];
+              const V vE0 = P::make(E0), vE1 = P::make(E1), vO0 = P::make(O0), vO1 = P::make(O1);
+              tbond(vO0, vE0); tbond(vE1, vO0); tbond(vO1, vE1); tbond(P::make(X), vO1);
+              const V d0 = P::sub(P::make(F0), vE0), d1 = P::sub(P::make(F1), vE1);
+              const V d2 = P::sub(P::make(G0), vO0), d3 = P::sub(P::make(G1), vO1);
+              zd = P::fma(d0, d0, zd); zd = P::fma(d1, d1, zd); zd = P::fma(d2, d2, zd); zd = P::fma(d3, d3, zd);
+              own(E0); own(E1); own(O0); own(O1);
+            }
+          }
+          if (HBM_ENERGY_ON) {
+            const RowW<R> w = roww[r];
+            const R wnc = roww[r + 1].cur[2], wnd = roww[r + 1].dif[2];
+            const R Szu = P::hsum(zu), Szd = P::hsum(zd), S3 = P::hsum(dt), S4 = P::hsum(im);
+            e.ed += w.dif[0] * s2 + w.dif[1] * s4 + w.dif[2] * Szu + wnd * Szd + w.dif[3] * S3 + w.dif[4] * S4;
+            if (M) {
+              e.ec += w.cur[0] * s2 + w.cur[1] * s4 + w.cur[2] * Szu + wnc * Szd + w.cur[3] * S3 + w.cur[4] * S4;
+              e.s2 += s2;
+              e.sa += sa;
+            }
+          }
+          if (M) { const C spc = P::get(sp); sre = spc.x; sim = spc.y; sab = sa; }
+        }
 #ifndef HBM_ABL_NO_PROF
-  if (EXTRAS && meas && A.rowpart) {
+        if (M && A.rowpart) {                                          // warp-uniform: the shuffles are taken by whole warps
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            sre += __shfl_xor_sync(0xffffffffu, sre, o); sim += __shfl_xor_sync(0xffffffffu, sim, o); sab += __shfl_xor_sync(0xffffffffu, sab, o);
+          }
+          if (li < TH && seg < 3) A.rowpart[((size_t)blockIdx.x * 3 + seg) * g.Z + ti0 + li] = seg == 0 ? sre : seg == 1 ? sim : sab;
+        }
+#endif
+      };
+      if (meas) tile_pass(std::true_type{}); else tile_pass(std::false_type{});
+    }
+  }
+  // ---- theta-sums of the profiles (Lattice.measure :121-131) of this tile's rows: border tiles and 3-colour lattices ----
+#ifndef HBM_ABL_NO_PROF
+  if (EXTRAS && meas && A.rowpart && !tile_pass_done) {
     if (!border) {
       // thread = (row, 16-column segment): 8 consecutive values from each plane, then a 3-step exchange over the 8 segments.
       // The chunk order is rotated by segment so that the 16-byte loads of a quarter-warp hit distinct banks.
@@ -696,32 +819,59 @@ __global__ void hbm_rm_finalize_kernel(HbmAmp* __restrict__ hdr, double* __restr
   chain[CYL_CH_SITE_ACCEPTED] += hdr->acc_total + (double)tot;
 }
 
-template <typename R>
-__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* tot);
-
 // ---- after a sweep: add up the tiles' partial sums (in a fixed order: the result does not depend on scheduling), then the
-// per-sweep decisions.  One CTA; the loads of a thread are independent, so the kernel costs a few memory latencies. ----
-#define HBM_DECIDE_NT 1024
+// per-sweep decisions.  One small CTA (it becomes resident as soon as one tile of the sweep retires).  Everything the decision
+// needs besides the sweep's own sums -- the chain state, the proposal header, the parameters, the accumulators it adds to, the
+// Robbins-Monro logarithms -- is at least two kernels old and is fetched BEFORE the dependency wait, while the sweep is still
+// running; after the wait the kernel costs one round of loads of the partial sums and the decision arithmetic. ----
+#define HBM_DECIDE_NT 256
+template <typename R>
+struct HbmDecidePre {
+  double ch[12];                     // chain state as the previous decision left it (CYL_CH_*)
+  double ob[10];                     // observable sums (CYL_OB_COUNT .. CYL_OB_SIGMA)
+  double a, a_new, u_acc, e_surf_new, lz, lth, temperature, pt;
+  RmLogs<R> rm;
+  int try_move, coef_sel;
+};
+template <typename R>
+__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* tot, const HbmDecidePre<R>& pre);
+
 template <typename R>
 __global__ void __launch_bounds__(HBM_DECIDE_NT)
 hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ HbmGeom g, int ntiles) {
   __shared__ double red[(HBM_DECIDE_NT / 32) * 8];
-  pdl_wait();
-  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool extras = (A.flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
   const int nv = extras ? 5 : 1;
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  __shared__ HbmDecidePre<R> pre;      // written and read by thread 0 only; in shared memory to keep the CTA's registers low
+  if (tid == 0) {
+    const CylParams p = *A.params;
+    const HbmAmp* hdr = A.hdr;
+    const double pi = 3.14159265358979323846;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    if (k < nv) {
-      const double* pk = A.partials + (size_t)k * ntiles;
-#pragma unroll 8
-      for (int t = tid; t < ntiles; t += HBM_DECIDE_NT) v[k] += pk[t];
-    }
+    for (int q = 0; q < 12; ++q) pre.ch[q] = A.chain[q];
+    const bool have_obs = extras && (A.flags & CYL_SWEEP_MEASURE) && A.obs;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) pre.ob[q] = have_obs ? A.obs[q] : 0.0;
+    pre.a = hdr->a; pre.a_new = hdr->a_new; pre.u_acc = hdr->u_acc; pre.e_surf_new = hdr->e_surf_new;
+    pre.try_move = hdr->try_move; pre.coef_sel = hdr->coef_sel;
+    pre.lz = (2 * pi / p.wavenumber) / g.Z; pre.lth = (2 * pi * p.radius) / g.T;
+    pre.temperature = p.temperature;
+    pre.pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
+    pre.rm = rm_logs<R>(pre.ch[CYL_CH_STEP_COUNTER], (double)g.Z * g.T);
   }
   if (extras)
     for (int t = tid; t < A.ncst; t += HBM_DECIDE_NT) { v[5] += A.cstpart[2 * t]; v[6] += A.cstpart[2 * t + 1]; }
+  pdl_wait();
+  pdl_trigger();
+  // a thread's tiles in index order, the five sums side by side: 20 independent loads in flight per round
+#pragma unroll 4
+  for (int t = tid; t < ntiles; t += HBM_DECIDE_NT) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < nv) v[k] += A.partials[(size_t)k * ntiles + t];
+  }
 #pragma unroll
   for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
   if (lane == 0) {
@@ -732,71 +882,68 @@ hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ 
   if (warp != 0) return;
   double tot[7];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) tot[k] = warp_sum(red[lane * 8 + k]);
-  if (lane == 0) hbm_decide<R>(A, g, tot);
+  for (int k = 0; k < 7; ++k) tot[k] = warp_sum(lane < HBM_DECIDE_NT / 32 ? red[lane * 8 + k] : 0.0);
+  if (lane == 0) hbm_decide<R>(A, g, tot, pre);
 }
 
 // Per-sweep decisions, one thread.  tot = {accepted site moves, E(a,a), E(a',a) - E(a,a), sum |psi|^2, sum |psi|, constants of
 // E(a,a), of the difference}, the energies without the pixel-area factor.
 template <typename R>
-__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* v) {
+__device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* v, const HbmDecidePre<R>& pre) {
   double* chain = A.chain;
   const uint32_t flags = A.flags;
   const bool extras = (flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
-  const CylParams p = *A.params;
   const double nsite = (double)g.Z * g.T;
-  const double sigma_used = chain[CYL_CH_SIGMA_SITE];
-  if (flags & CYL_SWEEP_ADAPT_SIGMA)
-    chain[CYL_CH_SIGMA_SITE] = rm_batch_update<R>(sigma_used, chain[CYL_CH_STEP_COUNTER], nsite, v[0]);
-  chain[CYL_CH_STEP_COUNTER] += nsite;
-  chain[CYL_CH_SITE_PROPOSED] += nsite;
-  chain[CYL_CH_SITE_ACCEPTED] += v[0];
+  const double sigma_used = pre.ch[CYL_CH_SIGMA_SITE];
+  if (flags & CYL_SWEEP_ADAPT_SIGMA) chain[CYL_CH_SIGMA_SITE] = rm_apply(sigma_used, pre.rm, nsite, v[0]);
+  chain[CYL_CH_STEP_COUNTER] = pre.ch[CYL_CH_STEP_COUNTER] + nsite;
+  chain[CYL_CH_SITE_PROPOSED] = pre.ch[CYL_CH_SITE_PROPOSED] + nsite;
+  chain[CYL_CH_SITE_ACCEPTED] = pre.ch[CYL_CH_SITE_ACCEPTED] + v[0];
   if (!extras) return;
-  const HbmAmp amp = *A.hdr;
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / g.Z, lth = (2 * pi * p.radius) / g.T;
-  const double a = amp.a;
+  const double lz = pre.lz, lth = pre.lth;
+  const double a = pre.a;
   const double e_dif = (v[2] + v[6]) * lz * lth;
   if (flags & CYL_SWEEP_MEASURE) {
     const double e_cur = (v[1] + v[5]) * lz * lth;                  // :213
     chain[CYL_CH_E_FIELD] = e_cur;
     double* obs = A.obs;
     if (obs) {
-      obs[CYL_OB_COUNT] += 1.0;
-      obs[CYL_OB_ABS_A] += fabs(a);
-      obs[CYL_OB_A] += a;
-      obs[CYL_OB_A2] += a * a;
-      obs[CYL_OB_PSI2] += v[3] / nsite;
-      obs[CYL_OB_ABSPSI] += v[4] / nsite;
-      obs[CYL_OB_E_FIELD] += e_cur;
-      obs[CYL_OB_E_SURF] += chain[CYL_CH_E_SURF];
-      obs[CYL_OB_E_FIELD2] += e_cur * e_cur;
-      obs[CYL_OB_SIGMA] += sigma_used;
+      obs[CYL_OB_COUNT] = pre.ob[CYL_OB_COUNT] + 1.0;
+      obs[CYL_OB_ABS_A] = pre.ob[CYL_OB_ABS_A] + fabs(a);
+      obs[CYL_OB_A] = pre.ob[CYL_OB_A] + a;
+      obs[CYL_OB_A2] = pre.ob[CYL_OB_A2] + a * a;
+      obs[CYL_OB_PSI2] = pre.ob[CYL_OB_PSI2] + v[3] / nsite;
+      obs[CYL_OB_ABSPSI] = pre.ob[CYL_OB_ABSPSI] + v[4] / nsite;
+      obs[CYL_OB_E_FIELD] = pre.ob[CYL_OB_E_FIELD] + e_cur;
+      obs[CYL_OB_E_SURF] = pre.ob[CYL_OB_E_SURF] + pre.ch[CYL_CH_E_SURF];
+      obs[CYL_OB_E_FIELD2] = pre.ob[CYL_OB_E_FIELD2] + e_cur * e_cur;
+      obs[CYL_OB_SIGMA] = pre.ob[CYL_OB_SIGMA] + sigma_used;
     }
   }
   if (!(flags & CYL_SWEEP_AMP_MOVES)) return;
   int accept = 0;
-  if (amp.try_move) {
-    const double dE = (amp.e_surf_new - chain[CYL_CH_E_SURF]) + e_dif;
-    if (!isfinite(dE)) chain[CYL_CH_FLAGS] = (double)((unsigned)chain[CYL_CH_FLAGS] | 1u);
+  if (pre.try_move) {
+    const double dE = (pre.e_surf_new - pre.ch[CYL_CH_E_SURF]) + e_dif;
+    if (!isfinite(dE)) chain[CYL_CH_FLAGS] = (double)((unsigned)pre.ch[CYL_CH_FLAGS] | 1u);
     if (dE <= 0) accept = 1;
-    else if (p.temperature == 0) accept = 0;
-    else accept = (amp.u_acc <= exp(-dE / p.temperature));
+    else if (pre.temperature == 0) accept = 0;
+    else accept = (pre.u_acc <= exp(-dE / pre.temperature));
   }
-  const double pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
+  const double pt = pre.pt;
   const double ratio = 1.0 / (pt * (1.0 - pt));
-  chain[CYL_CH_AMP_COUNTER] += 1;
-  chain[CYL_CH_AMP_PROPOSED] += 1;
-  const double sigma_amp = chain[CYL_CH_SIGMA_AMP];
+  const double amp_counter = pre.ch[CYL_CH_AMP_COUNTER] + 1;
+  chain[CYL_CH_AMP_COUNTER] = amp_counter;
+  chain[CYL_CH_AMP_PROPOSED] = pre.ch[CYL_CH_AMP_PROPOSED] + 1;
+  const double sigma_amp = pre.ch[CYL_CH_SIGMA_AMP];
   if (flags & CYL_SWEEP_ADAPT_SIGMA) {
-    const double cf = sigma_amp * ratio * fast_rcp(fmax(chain[CYL_CH_AMP_COUNTER], 200.0));
+    const double cf = sigma_amp * ratio * fast_rcp(fmax(amp_counter, 200.0));
     chain[CYL_CH_SIGMA_AMP] = accept ? sigma_amp + cf * (1 - pt) : sigma_amp - cf * pt;
   }
   if (accept) {
-    chain[CYL_CH_AMPLITUDE] = amp.a_new;
-    chain[CYL_CH_E_SURF] = amp.e_surf_new;
-    chain[CYL_CH_AMP_ACCEPTED] += 1;
-    A.hdr->coef_sel = amp.coef_sel ^ 1;                             // the table built for a' becomes the current one
+    chain[CYL_CH_AMPLITUDE] = pre.a_new;
+    chain[CYL_CH_E_SURF] = pre.e_surf_new;
+    chain[CYL_CH_AMP_ACCEPTED] = pre.ch[CYL_CH_AMP_ACCEPTED] + 1;
+    A.hdr->coef_sel = pre.coef_sel ^ 1;                             // the table built for a' becomes the current one
   }
 }
 
@@ -831,18 +978,32 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
                 RowW<R>* __restrict__ roww, double* __restrict__ cstpart, const R* __restrict__ rowpart, int ntx,
                 double* __restrict__ prof_flush, int nrb) {
   __shared__ double scr[32];
-  pdl_wait();
-  pdl_trigger();
+  // Before the dependency wait: what does not depend on the preceding decision -- the profile flush (theta-sums of the sweep
+  // before it, three kernels back), the parameters, the amplitude draw, the replica constants and this row's sin / cos (the
+  // fp64 trigonometry is most of this kernel) -- runs while the decision kernel is still summing.
   if ((int)blockIdx.x > nrb) {
     const int i = ((int)blockIdx.x - nrb - 1) * blockDim.x + threadIdx.x;
     if (i < Z) hbm_prof_flush_row<R>(rowpart, ntx, Z, i, prof_flush);
     return;
   }
   const CylParams p = *params;
-  const double a = chain[CYL_CH_AMPLITUDE];
   const uint4 x = philox4x32<10>(0u, rep, (uint32_t)sweep, philox_c3(CYL_TAG_AMP, sweep), (uint32_t)seed, (uint32_t)(seed >> 32));
   double zn, u;
   amp_draw(x, zn, u);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool row = (int)blockIdx.x < nrb && i < Z;
+  const double pi = 3.14159265358979323846;
+  const double lz = (2 * pi / p.wavenumber) / Z;
+  RepConst<R> rc;
+  RowTrig<R> t, tp;
+  if (row) {
+    rc = make_rep_const<R>(p, Z, T, variant);
+    t = row_trig<R>(p.wavenumber, lz, i);
+    tp = row_trig<R>(p.wavenumber, lz, (i + 1 == Z) ? 0 : i + 1);
+  }
+  pdl_wait();
+  pdl_trigger();
+  const double a = chain[CYL_CH_AMPLITUDE];
   double a_new = a + chain[CYL_CH_SIGMA_AMP] * zn;
   const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
   if (!try_move) a_new = a;
@@ -858,17 +1019,12 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
     return;
   }
   const int sel = hdr->coef_sel;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double pi = 3.14159265358979323846;
-  const double lz = (2 * pi / p.wavenumber) / Z;
   double c_cur = 0.0, c_dif = 0.0;
-  if (i < Z) {
+  if (row) {
     // same functions as the shared-memory kernel's tables (cyl_rowtab.cuh, working precision): the current weights are the
     // function of the amplitude the smem kernel stores on accept, the proposal's are evaluated with the current amplitude as
     // metric reference (:75), and dif is the difference of the two -- the chain samples the model with these weights
-    const RepConst<R> rc = make_rep_const<R>(p, Z, T, variant);
     const AmpGeo<R> ar = amp_geo<R>(rc, a), ae = amp_geo<R>(rc, a_new);
-    const RowTrig<R> t = row_trig<R>(p.wavenumber, lz, i);
     const GeoT<R> g0 = geo_sc<R>(ar, t.s0, t.c0), gm = geo_sc<R>(ar, t.sm, t.cm);
     const GeoT<R> h0 = geo_sc<R>(ae, t.s0, t.c0), hm = geo_sc<R>(ae, t.sm, t.cm);
     R wc[6], wn[6];
@@ -882,7 +1038,6 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
     c_cur = (double)wc[5];
     c_dif = (double)(wn[5] - wc[5]);
     if (try_move) {
-      const RowTrig<R> tp = row_trig<R>(p.wavenumber, lz, (i + 1 == Z) ? 0 : i + 1);
       const GeoT<R> hp = geo_sc<R>(ae, tp.sm, tp.cm);
       coef2[(size_t)(sel ^ 1) * Z + i] = coef_row<R>(rc, h0, hm, hp);
     }

@@ -21,6 +21,25 @@ def shard_range(n_total, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def pipeline_slices(n_total, nchunks):
+    """Slice boundaries [(lo, hi)] of a host round trip cut into `nchunks` slices: the first and last slices are a quarter, their
+    neighbours half, of the ones in the middle.  The pipeline's fill is the upload of the first slice (nothing can run before it
+    has landed) and its drain the download of the last one, so those are kept short; the middle slices stay large enough for a
+    launch to fill the GPU."""
+    nchunks = max(1, min(int(nchunks), int(n_total)))
+    if nchunks < 5:
+        return [shard_range(n_total, c, nchunks) for c in range(nchunks)]
+    w = [4] * nchunks
+    w[0] = w[-1] = 1
+    w[1] = w[-2] = 2
+    tot, acc, cuts = sum(w), 0, [0]
+    for x in w[:-1]:
+        acc += x
+        cuts.append(max(cuts[-1], min(n_total, (n_total * acc + tot // 2) // tot)))
+    cuts.append(n_total)
+    return [(cuts[c], cuts[c + 1]) for c in range(nchunks)]
+
+
 def parameter_grid(**axes):
     """Cartesian product of named 1-D axes -> dict of flat arrays (first axis slowest), like the reference's
     varfile.txt written by parallel_preprocessing.py:22-46."""
@@ -210,10 +229,10 @@ class ReplicaBatch:
         on the device (chain state in, records out): what a production run does between checkpoints -- on a host with several GPUs
         the pinned copies of the lattices are what limits the step (profiles/r02_e2e_limits.md)."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
-        if not hasattr(self, "_streams") or len(self._streams) != nchunks:
+        if not hasattr(self, "_streams") or len(self._streams) < nchunks:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(nchunks)]
         main = torch.cuda.current_stream(self.device)
-        bounds = [shard_range(self.B, c, nchunks) for c in range(nchunks)]
+        bounds = pipeline_slices(self.B, nchunks)
         for st, (b0, b1) in zip(self._streams, bounds):
             if b1 <= b0:
                 continue

@@ -17,9 +17,10 @@ ws.pack(psi[0])
 chain = ops.new_chain(1, dev, amplitude=0.3)[0]
 ws.sweep(par, chain, 1, 0, 10, 0, _abi.SWEEP_ADAPT_SIGMA)
 torch.cuda.synchronize()
-for flags, name in ((_abi.SWEEP_ADAPT_SIGMA, "sweeps only"), (7, "sweeps+measure+amp")):
+for flags, name in ((_abi.SWEEP_ADAPT_SIGMA, "sweeps only"), (3, "sweeps+amp"), (7, "sweeps+measure+amp")):
     obs = torch.zeros(16, dtype=torch.float64, device=dev); prof = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+    ws.sweep(par, chain, 1, 10, 5, 0, flags, obs=obs, prof=prof)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); ws.sweep(par, chain, 1, 10, nsw, 0, flags, obs=obs, prof=prof); e1.record(); torch.cuda.synchronize()
+    e0.record(); ws.sweep(par, chain, 1, 15, nsw, 0, flags, obs=obs, prof=prof); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print("%s: %.1f us/sweep, %.3e upd/s, %.1f%% of 6553.9 GB/s at 24 B/upd; acc %.3f" % (name, 1e3 * ms / nsw, n * n * nsw / ms * 1e3, n * n * nsw * 24 / ms / 1e6 / 6553.9 * 100, (chain[7] / chain[6]).item()))
+    print("%d^2 %s: %.1f us/sweep, %.3e upd/s, %.1f%% of 6553.9 GB/s at 24 B/upd; acc %.3f amp acc %.0f/%.0f" % (n, name, 1e3 * ms / nsw, n * n * nsw / ms * 1e3, n * n * nsw * 24 / ms / 1e6 / 6553.9 * 100, (chain[7] / chain[6]).item(), chain[9].item(), chain[8].item()))

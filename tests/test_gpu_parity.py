@@ -406,12 +406,18 @@ def test_hbm_path_with_amplitude_moves_tracks_smem_path(cuda):
     np.testing.assert_allclose(p2.cpu().numpy(), p1.cpu().numpy(), rtol=1e-9, atol=1e-11)
 
 
-@pytest.mark.parametrize("Z,T,variant,temp", [(70, 260, lo.SIMPLE, .3), (71, 131, lo.RESCALED_1ST, .3), (40, 136, lo.RESCALED_0TH, .5),
-                                              (33, 130, lo.DECOUPLED, .3), (64, 256, lo.SIMPLE, 0.0)])
-def test_hbm_sweep_with_amplitude_moves_matches_oracle(cuda, Z, T, variant, temp):
-    """Multi-tile lattices (interior, border and partial tiles, 2 and 3 colours): the energies accumulated tile by tile while
-    the sites are updated, the profile sums and the amplitude decisions of the HBM path equal the oracle's whole-lattice
-    evaluation (fp64, same Philox streams)."""
+@pytest.mark.parametrize("Z,T,variant,temp,tile_rows", [
+    (70, 260, lo.SIMPLE, .3, 0), (71, 131, lo.RESCALED_1ST, .3, 0), (40, 136, lo.RESCALED_0TH, .5, 0),
+    (33, 130, lo.DECOUPLED, .3, 0), (64, 256, lo.SIMPLE, 0.0, 0),
+    # several tiles away from every lattice edge (their energy and profile sums come from the pass over the finished tile;
+    # the tiles on the edges close their bonds inside the colour passes): 2 colours, 3 colours (T odd; Z and T odd), and the
+    # tile heights whose last warp rows stay empty
+    (100, 520, lo.SIMPLE, .3, 24), (96, 516, lo.RESCALED_0TH, .3, 32), (124, 392, lo.RESCALED_1ST, .3, 30),
+    (75, 389, lo.SIMPLE, .3, 24), (90, 391, lo.RESCALED_0TH, .3, 28), (101, 517, lo.SIMPLE, .3, 32)])
+def test_hbm_sweep_with_amplitude_moves_matches_oracle(cuda, Z, T, variant, temp, tile_rows):
+    """Multi-tile lattices (interior, border and partial tiles, 2 and 3 colours): the energies accumulated tile by tile (inside
+    the colour passes on the lattice's edge tiles, in one pass over the finished tile elsewhere), the profile sums and the
+    amplitude decisions of the HBM path equal the oracle's whole-lattice evaluation (fp64, same Philox streams)."""
     import torch
     from cylinder_b200 import ops, _abi
     P = dict(wavenumber=.9, radius=1.1, gamma=1.0, kappa=0.3, intrinsic_curvature=0.2, alpha=-.8, u=1.2, C=.9, n=3, temperature=temp)
@@ -425,7 +431,7 @@ def test_hbm_sweep_with_amplitude_moves_matches_oracle(cuda, Z, T, variant, temp
     chain = ops.new_chain(1, cuda, amplitude=.1, sigma_site=.05, sigma_amp=.004)
     obs, prof = ops.new_obs(1, Z, cuda)
     seed, rep, nsw = 4711, 6, 8
-    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE
+    flags = _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_AMP_MOVES | _abi.SWEEP_MEASURE | (_abi.sweep_tile_rows(tile_rows) if tile_rows else 0)
     ws.sweep(par, chain[0], seed, 3, nsw, variant, flags, replica=rep, obs=obs[0], prof=prof[0])
     sum_abs_a = sum_ef = sum_p2 = 0.0
     prof_o = np.zeros((Z, 3))
