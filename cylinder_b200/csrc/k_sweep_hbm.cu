@@ -563,11 +563,77 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       __syncthreads();
     }
     };
-    if constexpr (EXTRAS) {
-      if (!border) passes3(std::false_type{}); else passes3(std::true_type{});
-    } else {
-      passes3(std::true_type{});
-    }
+    // Tiles away from the lattice edges (the bulk of a large lattice): no row or column of axis colour 2 within reach, tile
+    // origins even, so the colour of region site (r, q) is (parity of r + 1) + (parity of q) and every pass is a regular
+    // sub-lattice: pass 0 = even lattice rows x even columns on the tile grown by 2, pass 1 = (even, odd) and (odd, even) grown
+    // by 1, pass 2 = (odd, odd) on the tile itself.  Thread = (row group tid >> 6, column tid & 63 of the pass's column list):
+    // its plane, its neighbour offsets and the parity of its rows are fixed per pass, and tile address, coefficient row and
+    // Philox counter advance by constants, as in the 2-colour loops; passes 0 and 2 deal the row groups over every other row.
+    // The one or two columns beyond 64 go to the threads at the top of the CTA (fewest rows).  The visited sites, their Philox
+    // counters and the arithmetic are those of the general loops above (which the edge tiles keep): identical results.
+    auto move3 = [&](C* own, const C* oth, int r, uint32_t site, bool counted) {
+      const RowCoef<R> rc = coef[r];
+      const C pv = own[0], Ln = own[-SWH], Rz = own[SWH], W = oth[0], E = oth[1];
+      const uint2 x = philox2x32_10(site, c1, kc, kr);
+      C qv;
+      const bool acc = site_propose<R, C>(rc, pv, Ln, Rz, W, E, sigma, x, qv);
+      if (acc) own[0] = qv;
+      nacc += (acc && counted);
+    };
+    auto passes3_interior = [&]() {
+      static_assert((TH & 1) == 0 && TW == 128 && HBM_NT == 256 && HS == 4, "parity colouring of an interior tile");
+      const int k = tid & 63, g4 = tid >> 6;
+      const uint32_t T32 = (uint32_t)g.T;
+      // site of region (r, q): plane q & 1, plane column q >> 1; its left / right neighbours sit in the other plane
+      auto ptr_own = [&](int r, int q) { return pl0 + (q & 1) * PS + r * SWH + (q >> 1); };
+      auto ptr_oth = [&](int r, int q) { return pl0 + ((q & 1) ^ 1) * PS + r * SWH + (q >> 1) - 1 + (q & 1); };
+      auto site_of = [&](int r, int q) { return (uint32_t)(ti0 - NCOL + r) * T32 + (uint32_t)(tj0 - HS + q); };
+      auto inside = [&](int r, int q) { return r >= NCOL && r < NCOL + TH && q >= HS && q < HS + TW; };
+      // pass 0: rows r odd in [1, SH - 1), columns q even in [2, SW - 2) = 66 columns
+      {
+        const int q = 2 + 2 * k;
+        int r = 1 + 2 * g4;
+        C* own = ptr_own(r, q);
+        const C* oth = ptr_oth(r, q);
+        uint32_t site = site_of(r, q);
+        const bool qin = q >= HS;                                    // q <= 128 < HS + TW
+        for (; r < SH - 1; r += 8, own += 8 * SWH, oth += 8 * SWH, site += 8 * T32) move3(own, oth, r, site, qin && r >= NCOL && r < NCOL + TH);
+        constexpr int nr0 = (SH - 2) / 2;
+        if (tid >= HBM_NT - 2 * nr0) {
+          const int idx = tid - (HBM_NT - 2 * nr0), rx = 1 + 2 * (idx >> 1), qx = 130 + 2 * (idx & 1);
+          move3(ptr_own(rx, qx), ptr_oth(rx, qx), rx, site_of(rx, qx), inside(rx, qx));
+        }
+      }
+      __syncthreads();
+      // pass 1: rows [2, SH - 2); even r (odd lattice row) takes the even columns 4 .. 132, odd r the odd columns 3 .. 131
+      {
+        int r = 2 + g4;
+        const int q = ((r & 1) ? 3 : 4) + 2 * k;
+        C* own = ptr_own(r, q);
+        const C* oth = ptr_oth(r, q);
+        uint32_t site = site_of(r, q);
+        const bool qin = q >= HS;                                    // q <= 130
+        for (; r < SH - 2; r += 4, own += 4 * SWH, oth += 4 * SWH, site += 4 * T32) move3(own, oth, r, site, qin && r >= NCOL && r < NCOL + TH);
+        constexpr int nr1 = SH - 4;
+        if (tid >= HBM_NT - nr1) {
+          const int rx = 2 + (tid - (HBM_NT - nr1)), qx = (rx & 1) ? 131 : 132;
+          move3(ptr_own(rx, qx), ptr_oth(rx, qx), rx, site_of(rx, qx), inside(rx, qx));
+        }
+      }
+      __syncthreads();
+      // pass 2: rows r even in [3, SH - 3), columns q odd in [4, SW - 4) = 64 columns: all of them interior
+      {
+        const int q = 5 + 2 * k;
+        int r = 4 + 2 * g4;
+        C* own = ptr_own(r, q);
+        const C* oth = ptr_oth(r, q);
+        uint32_t site = site_of(r, q);
+        for (; r < SH - 3; r += 8, own += 8 * SWH, oth += 8 * SWH, site += 8 * T32) move3(own, oth, r, site, true);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is final: bulk copies will read it
+      __syncthreads();
+    };
+    if (!border) passes3_interior(); else passes3(std::true_type{});
   }
 
   // ---- write the interior (and its periodic halo copies) to the other buffer ----
