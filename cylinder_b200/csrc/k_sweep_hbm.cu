@@ -637,11 +637,14 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
 
   // ---- write the interior (and its periodic halo copies) to the other buffer ----
-  if (!border) {
-    // interior tile: every (row, plane) is 64 contiguous complex values on both sides, 16-byte aligned: one bulk copy
-    // (cp.async.bulk shared -> global, SASS UBLKCP) per row and plane, issued by 2*TH threads, instead of a load + store
-    // per 16 bytes by everyone.  The shared-memory writes of the colour passes were made visible to the async proxy by the
-    // fence before the last barrier; the issuing threads wait until their sources have been read before the CTA may retire.
+  // A complete tile (all of its TH x TW sites on the lattice): every (row, plane) is 64 contiguous complex values on both sides,
+  // 16-byte aligned: one bulk copy (cp.async.bulk shared -> global, SASS UBLKCP) per row and plane, issued by 2*TH threads,
+  // instead of a load + store per 16 bytes by everyone.  The shared-memory writes of the colour passes were made visible to the
+  // async proxy by the fence before the last barrier; the issuing threads wait until their sources have been read before the
+  // CTA may retire.  Tiles on the lattice's edge add the periodic halo copies of their outermost rows / columns element by
+  // element; tiles cut by the lattice's end store everything that way.
+  const bool bulk_out = !border || ((ti0 + TH <= g.Z) && (tj0 + TW <= g.T));
+  if (bulk_out) {
     static_assert(2 * TH <= HBM_NT, "one thread per (row, plane)");
     if (tid < 2 * TH) {
       const int li = tid >> 1, p = tid & 1;
@@ -652,7 +655,8 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-  } else {
+  }
+  if (border) {
     for (int idx = tid; idx < 2 * TH * (TW / 2); idx += HBM_NT) {
       const int par_slot = idx / (TH * (TW / 2));                    // which smem plane
       const int rem = idx - par_slot * (TH * (TW / 2));
@@ -661,14 +665,15 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const int lj = 2 * cc + ((par_slot - (Q0 + HS)) & 1);
       const int gi = ti0 + li, gj = tj0 + lj;
       if (gi >= g.Z || gj >= g.T) continue;
-      const int r = li + NCOL, q = lj + HS;
-      const C* src = par_slot ? pl1 : pl0;
-      const C v = src[r * SWH + (((Q0 + q) >> 1) - (par_slot ? x1 : x0))];
       const int64_t Rr = gi + g.hr, Q = gj + g.hc;
       int64_t R2 = -1, Q2 = -1;
       if (gi < g.hr) R2 = Rr + g.Z; else if (gi >= g.Z - g.hr) R2 = Rr - g.Z;
       if (gj < g.hc) Q2 = Q + g.T; else if (gj >= g.T - g.hc) Q2 = Q - g.T;
-      out[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)] = v;
+      if (bulk_out && R2 < 0 && Q2 < 0) continue;                    // stored by the bulk copy, no halo copy to make
+      const int r = li + NCOL, q = lj + HS;
+      const C* src = par_slot ? pl1 : pl0;
+      const C v = src[r * SWH + (((Q0 + q) >> 1) - (par_slot ? x1 : x0))];
+      if (!bulk_out) out[(Q & 1) * g.plane_elems + Rr * ph + (Q >> 1)] = v;
       if (R2 >= 0) out[(Q & 1) * g.plane_elems + R2 * ph + (Q >> 1)] = v;
       if (Q2 >= 0) {
         out[(Q2 & 1) * g.plane_elems + Rr * ph + (Q2 >> 1)] = v;
@@ -850,7 +855,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
   __syncthreads();
   // the bulk copies of the write-out must have read their shared-memory sources before the CTA retires
-  if (!border && tid < 2 * TH) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (bulk_out && tid < 2 * TH) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   if (!EXTRAS) {
     if (tid == 0) {
       double t = 0.0;
