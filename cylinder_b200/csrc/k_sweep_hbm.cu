@@ -430,6 +430,11 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // (the last clause: with an odd length the last tile may be thinner than the halo, so its neighbour's halo wraps too)
   const bool border = (bx == 0) | (by == 0) | (bx == gx - 1) | (by == gy - 1) |
                       (ti0 + TH + NCOL > g.Z) | (tj0 + TW + HS > g.T);
+  // complete tile: all of its TH x TW sites are on the lattice (every tile unless a lattice length is no multiple of the tile's)
+  const bool complete = !border || ((ti0 + TH <= g.Z) && (tj0 + TW <= g.T));
+  // EXTRAS: the energy and profile sums of this tile come from one pass over the finished tile (below) instead of being
+  // accumulated inside the colour passes: complete tiles with two colours, tiles away from the edges with three
+  const bool tile_energy = EXTRAS && (NCOL == 2 ? complete : !border);
   constexpr int PS = (int)(L::plane_bytes / sizeof(C));             // plane stride in shared memory (elements)
   C* out = work + (size_t)(cur ^ 1) * g.buffer_elems;
   const int64_t ph = g.pitch / 2;
@@ -452,7 +457,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       const bool acc = site_propose<R, C>(rc, pv, Ln, Rz, W, E, sigma, x, q);
       if (acc) own[0] = q;
       nacc += (acc && counted);
-      if (EXTRAS && HBM_ENERGY_ON && en && counted) {
+      if (EXTRAS && HBM_ENERGY_ON && en && !tile_energy && counted) {
         const RowW<R> rw = roww[r];
         energy_own<R, C>(e, rw, q, meas);
         if (c == 1) {                                             // colour 1 closes every bond: its neighbours are final
@@ -663,7 +668,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // async proxy by the fence before the last barrier; the issuing threads wait until their sources have been read before the
   // CTA may retire.  Tiles on the lattice's edge add the periodic halo copies of their outermost rows / columns element by
   // element; tiles cut by the lattice's end store everything that way.
-  const bool bulk_out = !border || ((ti0 + TH <= g.Z) && (tj0 + TW <= g.T));
+  const bool bulk_out = complete;
   if (bulk_out) {
     static_assert(2 * TH <= HBM_NT, "one thread per (row, plane)");
     if (tid < 2 * TH) {
@@ -745,7 +750,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   //      weights are applied once per thread (the z-bonds downwards carry the next row's weight). ----
   bool tile_pass_done = false;
   if constexpr (EXTRAS) {
-    if (!border) {
+    if (tile_energy) {
       static_assert(TH <= 32 && TW == 128 && HBM_NT == 256, "row = warp + 8 k, eight threads per row, 4 x 16 plane columns");
       tile_pass_done = true;
       auto tile_pass = [&](auto MEAS) {
