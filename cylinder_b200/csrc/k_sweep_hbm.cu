@@ -669,10 +669,15 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   // CTA may retire.  Tiles on the lattice's edge add the periodic halo copies of their outermost rows / columns element by
   // element; tiles cut by the lattice's end store everything that way.
   const bool bulk_out = complete;
+  // The 2 TH copies are issued by lanes 0..7 of all eight warps, not by the first 2 TH threads: a bulk copy is a uniform-datapath
+  // instruction that the compiler serialises over the active lanes of a warp (SASS: R2UR x3 + UBLKCP in a loop), so 32 issuing
+  // lanes of one warp are 32 round trips in a row on the tile's critical path; 8 per warp on 8 warps run side by side.
+  const int bulk_idx = (tid >> 5) + (HBM_NT / 32) * (tid & 31);      // lanes 0..7 of warp w: w, w + 8, ..., w + 56
+  const bool bulk_issuer = bulk_out && (tid & 31) < 8 && bulk_idx < 2 * TH;
   if (bulk_out) {
-    static_assert(2 * TH <= HBM_NT, "one thread per (row, plane)");
-    if (tid < 2 * TH) {
-      const int li = tid >> 1, p = tid & 1;
+    static_assert(2 * TH <= 8 * (HBM_NT / 32), "eight copies per warp");
+    if (bulk_issuer) {
+      const int li = bulk_idx >> 1, p = bulk_idx & 1;
       const C* src = pl0 + p * PS + (li + NCOL) * SWH + HS / 2;
       C* dst = out + p * g.plane_elems + (int64_t)(ti0 + li + g.hr) * ph + ((tj0 + g.hc) >> 1);
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
@@ -909,7 +914,7 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
   __syncthreads();
   // the bulk copies of the write-out must have read their shared-memory sources before the CTA retires
-  if (bulk_out && tid < 2 * TH) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (bulk_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   if (!EXTRAS) {
     if (tid == 0) {
       double t = 0.0;
