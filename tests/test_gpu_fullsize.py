@@ -90,6 +90,45 @@ def test_c4_energy_never_increases_at_zero_temperature(cuda, big):
     assert e[-1] < e[0]
 
 
+@pytest.mark.parametrize("n", [4096, 4095, 2080])
+def test_c4_measured_energy_and_profiles_match_independent_sums(cuda, n):
+    """The fp32 C4 path with CYL_SWEEP_MEASURE at full size: the field energy and the profile sums that the sweep kernel takes
+    from its finished tiles (tiles away from the lattice's end) or inside its colour passes (tiles cut by the end; with three
+    colours all edge tiles) equal an independent evaluation of the swept lattice -- row moments in fp64 + the energy weights, and
+    torch row sums -- sweep by sweep.  4096: two colours, every tile complete; 4095: three colours, last tile row / column cut;
+    2080: two colours with a cut last tile column.  Tolerance: fp32 partial sums of 16 sites per thread and 128 per tile row
+    (2^-24 relative each) under terms of mixed sign: 2e-5 of the energy, 1e-5 of sum |psi|, 2e-3 absolute on the row sums of psi."""
+    import torch
+    from cylinder_b200 import ops, _abi
+    par = ops.make_params(cuda, wavenumber=1.0, radius=1.0, alpha=-1.0, u=1.0, C=1.0, n=6.0, temperature=.01)
+    psi = torch.zeros(1, n, n, dtype=torch.complex64, device=cuda)
+    ops.lattice_init(psi, torch.tensor([n], dtype=torch.int32, device=cuda), .1, 5, 0)
+    ws = ops.HbmWorkspace(n, n, torch.complex64, cuda)
+    ws.pack(psi[0])
+    del psi
+    a = 0.3
+    chain = ops.new_chain(1, cuda, amplitude=a)[0]
+    obs, prof = ops.new_obs(1, n, cuda)
+    e_sum, p2_sum = 0.0, 0.0
+    prof_ref = torch.zeros(n, 3, dtype=torch.float64, device=cuda)
+    nsw = 3
+    for s in range(nsw):
+        ws.sweep(par, chain, 11, s, 1, 0, _abi.SWEEP_ADAPT_SIGMA | _abi.SWEEP_MEASURE, obs=obs[0], prof=prof[0])
+        lat = ws.unpack().to(torch.complex128)
+        e_sum += _energy(ops, ws, par, a)
+        p2_sum += (lat.real ** 2 + lat.imag ** 2).mean().item()
+        prof_ref += torch.stack([lat.real.sum(1), lat.imag.sum(1), lat.abs().sum(1)], 1)
+        del lat
+    o = obs[0].cpu().numpy()
+    assert o[_abi.OB_COUNT] == nsw
+    assert o[_abi.OB_E_FIELD] == pytest.approx(e_sum, rel=2e-5)
+    assert o[_abi.OB_PSI2] == pytest.approx(p2_sum, rel=1e-5)
+    assert chain[_abi.CH_E_FIELD].item() == pytest.approx(_energy(ops, ws, par, a), rel=2e-5)
+    pr, ref = prof[0].cpu().numpy(), prof_ref.cpu().numpy()
+    np.testing.assert_allclose(pr[:, 2], ref[:, 2], rtol=1e-5)
+    np.testing.assert_allclose(pr[:, :2], ref[:, :2], rtol=0, atol=2e-3)
+
+
 def test_c3_batch_is_independent_of_batching(cuda):
     """4096 replicas (C3's grid): replica r gives the same chain whether it runs inside the full batch or inside a
     shard that starts at r0 (replica0 = r0) -- the property multi-GPU sharding relies on; identical parameters with
