@@ -19,9 +19,9 @@
 // Per sweep, plain (site moves + Robbins-Monro): ONE kernel.  The accept count goes to bucketed no-return atomics, and every
 // tile of the next sweep derives the adapted proposal width from the previous sweep's record itself.
 // Per sweep with measurement / amplitude move (EXTRAS): hbm_prep_kernel (proposal, row weights for a and a', coefficient
-// table for a', E_surf(a')) -> sweep kernel (energies for a and a'-a and the profiles' theta-sums accumulated while the sites
-// are finalised; 5 partial sums per tile) -> hbm_decide_kernel (fixed-order sum of the tiles, Robbins-Monro, observables,
-// amplitude decision).  All of them are launched with programmatic stream serialisation (see pdl_wait / pdl_trigger).
+// table for a') -> sweep kernel (energies for a and a'-a and the profiles' theta-sums from one pass over each finished tile;
+// 5 partial sums per tile) -> hbm_decide_kernel (E_surf(a') ahead of its wait; fixed-order sum of the tiles, Robbins-Monro,
+// observables, amplitude decision).  All of them are launched with programmatic stream serialisation (see pdl_wait / pdl_trigger).
 //
 // Reference semantics restated: Lattice.step_lattice_loc (On_lattice_simple.py:598-686) per site,
 // update_sigma (:688-696) batched per sweep, Lattice.measure (:121-131), amplitude move (:544-550).
@@ -221,7 +221,9 @@ __device__ __forceinline__ double ld_early_f64(const double* p) {
 // (returns once the predecessor has completed and its writes are visible) before touching anything the predecessor writes,
 // and lets its own successor start early with pdl_trigger().  Rule used below: a kernel triggers only AFTER its own wait, so
 // a successor never overtakes the kernel two places up the stream; before its wait a kernel reads only data that is at least
-// two kernels old (the sweep kernel: its input tiles, issued by TMA while the decision kernel is still finishing).
+// two kernels old (the sweep kernel: its input tiles, issued by TMA while the decision kernel is still finishing).  One
+// exception, argued where it is made: the preparation kernel triggers at its start -- the kernel two places up from ITS successor
+// is the decision kernel, which writes nothing a sweep tile reads before its wait.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -984,7 +986,7 @@ hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ 
     const bool have_obs = extras && (A.flags & CYL_SWEEP_MEASURE) && A.obs;
 #pragma unroll
     for (int q = 0; q < 10; ++q) pre.ob[q] = have_obs ? A.obs[q] : 0.0;
-    pre.a = hdr->a; pre.a_new = hdr->a_new; pre.u_acc = hdr->u_acc; pre.e_surf_new = hdr->e_surf_new;
+    pre.a = hdr->a; pre.a_new = hdr->a_new; pre.u_acc = hdr->u_acc;               // e_surf_new: warp 1, below
     pre.try_move = hdr->try_move; pre.coef_sel = hdr->coef_sel;
     pre.lz = (2 * pi / p.wavenumber) / g.Z; pre.lth = (2 * pi * p.radius) / g.T;
     pre.temperature = p.temperature;
@@ -993,14 +995,32 @@ hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ 
   }
   if (extras)
     for (int t = tid; t < A.ncst; t += HBM_DECIDE_NT) { v[5] += A.cstpart[2 * t]; v[6] += A.cstpart[2 * t + 1]; }
+  if (extras && warp == 1) {
+    // the proposal's surface energy (an AGM chain of fp64 square roots, ~3 us on one warp): here, under the tail of the sweep,
+    // instead of in the preparation kernel, where the next sweep waited for it
+    const CylParams p = *A.params;
+    const double es = A.hdr->try_move ? surface_energy_warp(p, A.hdr->a_new, nullptr, nullptr, true) : 0.0;
+    if (lane == 0) pre.e_surf_new = es;
+  }
   pdl_wait();
   pdl_trigger();
-  // a thread's tiles in index order, the five sums side by side: 20 independent loads in flight per round
-#pragma unroll 4
-  for (int t = tid; t < ntiles; t += HBM_DECIDE_NT) {
+  // A thread's tiles in index order.  The loads of a round are issued before anything is added (a load of these freshly written
+  // lines takes ~0.5 us, and a loop that adds as it loads pays that once per iteration: 9 us for the 16 iterations of a 4096^2
+  // sweep, measured with %globaltimer stamps): 8 tiles x 5 sums = 40 loads in flight per round.
+  constexpr int DR = 8;
+  for (int t0 = tid; t0 < ntiles; t0 += DR * HBM_DECIDE_NT) {
+    double x[5][DR];
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (k < nv) v[k] += A.partials[(size_t)k * ntiles + t];
+    for (int j = 0; j < DR; ++j) {
+      const int t = t0 + j * HBM_DECIDE_NT;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) x[k][j] = (t < ntiles && k < nv) ? __ldcg(A.partials + (size_t)k * ntiles + t) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < DR; ++j) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[k] += x[k][j];
+    }
   }
 #pragma unroll
   for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
@@ -1080,11 +1100,22 @@ __device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* 
 // Add the per-tile-column theta-sums of one sweep into the profile accumulators: thread i = row i.
 template <typename R>
 __device__ __forceinline__ void hbm_prof_flush_row(const R* __restrict__ rowpart, int ntx, int Z, int i, double* __restrict__ prof) {
+  // the loads of 16 tile columns x 3 sums are issued together (a loop that adds as it loads pays the memory latency per
+  // iteration; inside the preparation kernel this flush would then outlast the decision it is meant to hide behind)
   double s[3] = {0.0, 0.0, 0.0};
-#pragma unroll 8
-  for (int tx = 0; tx < ntx; ++tx) {
+  constexpr int FC = 16;
+  for (int t0 = 0; t0 < ntx; t0 += FC) {
+    R x[FC][3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) s[k] += (double)rowpart[((size_t)tx * 3 + k) * Z + i];
+    for (int j = 0; j < FC; ++j) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) x[j][k] = (t0 + j < ntx) ? rowpart[((size_t)(t0 + j) * 3 + k) * Z + i] : R(0);
+    }
+#pragma unroll
+    for (int j = 0; j < FC; ++j) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s[k] += (double)x[j][k];
+    }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) prof[3 * i + k] += s[k];
@@ -1108,6 +1139,11 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
                 RowW<R>* __restrict__ roww, double* __restrict__ cstpart, const R* __restrict__ rowpart, int ntx,
                 double* __restrict__ prof_flush, int nrb) {
   __shared__ double scr[32];
+  // Let the next sweep's tiles become resident (and issue their loads) right away.  This kernel starts only after the decision
+  // kernel has passed ITS wait, i.e. after the preceding sweep has completed, and before its own wait a sweep tile touches nothing
+  // but its input tile -- so the early trigger exposes no unfinished data, and the first wave's load burst (592 tiles, ~4 us) runs
+  // under the decision and this preparation instead of after them.
+  pdl_trigger();
   // Before the dependency wait: what does not depend on the preceding decision -- the profile flush (theta-sums of the sweep
   // before it, three kernels back), the parameters, the amplitude draw, the replica constants and this row's sin / cos (the
   // fp64 trigonometry is most of this kernel) -- runs while the decision kernel is still summing.
@@ -1132,19 +1168,18 @@ hbm_prep_kernel(const CylParams* __restrict__ params, double* __restrict__ chain
     tp = row_trig<R>(p.wavenumber, lz, (i + 1 == Z) ? 0 : i + 1);
   }
   pdl_wait();
-  pdl_trigger();
   const double a = chain[CYL_CH_AMPLITUDE];
   double a_new = a + chain[CYL_CH_SIGMA_AMP] * zn;
   const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
   if (!try_move) a_new = a;
   if ((int)blockIdx.x == nrb) {
     if (threadIdx.x >= 32) return;
-    double es0 = 0.0, es1 = 0.0;
+    double es0 = 0.0;
     if (init) es0 = surface_energy_warp(p, a, nullptr, nullptr, true);
-    if (try_move) es1 = surface_energy_warp(p, a_new, nullptr, nullptr, true);
     if (threadIdx.x == 0) {
       if (init) chain[CYL_CH_E_SURF] = es0;
-      hdr->a = a; hdr->a_new = a_new; hdr->u_acc = u; hdr->e_surf_new = es1; hdr->try_move = try_move ? 1 : 0;
+      // (the proposal's surface energy is evaluated by the decision kernel, ahead of its dependency wait)
+      hdr->a = a; hdr->a_new = a_new; hdr->u_acc = u; hdr->e_surf_new = 0.0; hdr->try_move = try_move ? 1 : 0;
     }
     return;
   }
