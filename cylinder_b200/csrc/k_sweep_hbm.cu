@@ -313,10 +313,11 @@ struct HbmArgs {
   int ncst;
 };
 
-// EXTRAS: the field energy for the current amplitude and for the proposed one (weights staged per tile row) is
-// accumulated while the sites are updated -- own terms when a site is finalised, a bond by its later-finalised endpoint --
-// and the theta-sums of the profiles are taken from the finished tile, so a sweep with measurement / amplitude move needs
-// no second pass over the lattice.  Each tile leaves its partial sums in scratch for hbm_decide_kernel.
+// EXTRAS: the field energy for the current amplitude and for the proposed one (weights staged per tile row) and the theta-sums of
+// the profiles are taken from the finished tile in shared memory by one read-only pass (complete tiles; with three colours the
+// tiles away from the lattice's edges); the other tiles accumulate them while the sites are updated -- own terms when a site is
+// finalised, a bond by its later-finalised endpoint.  Either way a sweep with measurement / amplitude move needs no second pass
+// over the lattice in HBM.  Each tile leaves its partial sums in scratch for hbm_decide_kernel.
 template <typename R, int NCOL, int TH_, bool EXTRAS>
 __global__ void __launch_bounds__(HBM_NT, sizeof(R) == 4 ? HBM_MINB_F32 : 2)
 sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex_t* __restrict__ work,
@@ -744,17 +745,18 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
   }
 
   const int warp = tid >> 5, lane = tid & 31;
-  // ---- interior 2-colour tiles with EXTRAS: the field energy (current weights, and proposal - current) and the theta-sums of
-  //      the profiles in ONE read-only pass over the finished tile, as in the batched kernel's energy pass -- a third of the
-  //      instructions of closing the bonds inside the colour passes.  What is final in shared memory: every interior site, and
-  //      the colour-0 sites of the ring around it (recomputed redundantly above); a bond joins a colour-0 and a colour-1 site, so
-  //      the tile in which the colour-1 endpoint is interior sees both ends final and owns the bond -- no bond is missed or taken
-  //      twice across tile boundaries.  Thread = (row, 4 strided column pairs per plane): lane & 7 picks the pair inside a group
-  //      of 16 plane columns, so the 16-byte loads of a quarter-warp cover 128 contiguous bytes (conflict-free); rows are dealt
-  //      warp + 8 k, so the row parity -- which plane holds the colour-1 sites -- is warp-uniform.  Per step a thread loads two
-  //      colour-1 sites with the sites above and below, the two colour-0 sites of the same plane columns and the colour-0
-  //      neighbour beyond the pair: five consecutive columns, four theta-bonds, four z-bonds, four sites' own terms.  The row
-  //      weights are applied once per thread (the z-bonds downwards carry the next row's weight). ----
+  // ---- EXTRAS, complete tiles (three colours: tiles away from the lattice's edges): the field energy (current weights, and
+  //      proposal - current) and the theta-sums of the profiles in ONE read-only pass over the finished tile, as in the batched
+  //      kernel's energy pass -- a third of the instructions of closing the bonds inside the colour passes.  Two colours: what is
+  //      final in shared memory is every interior site and the colour-0 sites of the ring around it (recomputed redundantly above,
+  //      on edge tiles from the periodic halo the tile was loaded with); a bond joins a colour-0 and a colour-1 site, so the tile in
+  //      which the colour-1 endpoint is interior sees both ends final and owns the bond -- no bond is missed or taken twice across
+  //      tile boundaries.  Thread = (row, 4 strided column pairs per plane): lane & 7 picks the pair inside a group of 16 plane
+  //      columns, so the 16-byte loads of a quarter-warp cover 128 contiguous bytes (conflict-free); rows are dealt warp + 8 k, so
+  //      the row parity -- which plane holds the colour-1 sites -- is warp-uniform.  Per step a thread loads two colour-1 sites
+  //      with the sites above and below, the two colour-0 sites of the same plane columns and the colour-0 neighbour beyond the
+  //      pair: five consecutive columns, four theta-bonds, four z-bonds, four sites' own terms.  The row weights are applied once
+  //      per thread (the z-bonds downwards carry the next row's weight).  Three colours: see the branch below. ----
   bool tile_pass_done = false;
   if constexpr (EXTRAS) {
     if (tile_energy) {
@@ -857,42 +859,19 @@ sweep_hbm_kernel(const __grid_constant__ HbmMaps maps, typename Real<R>::complex
       if (meas) tile_pass(std::true_type{}); else tile_pass(std::false_type{});
     }
   }
-  // ---- theta-sums of the profiles (Lattice.measure :121-131) of this tile's rows: border tiles and 3-colour lattices ----
+  // ---- theta-sums of the profiles (Lattice.measure :121-131) of the tiles that did not take the pass above (tiles cut by the
+  //      lattice's end; with three colours every edge tile): a warp per row, wrapped plane addressing ----
 #ifndef HBM_ABL_NO_PROF
   if (EXTRAS && meas && A.rowpart && !tile_pass_done) {
-    if (!border) {
-      // thread = (row, 16-column segment): 8 consecutive values from each plane, then a 3-step exchange over the 8 segments.
-      // The chunk order is rotated by segment so that the 16-byte loads of a quarter-warp hit distinct banks.
-      static_assert(TH <= HBM_NT / 8 && TW == 128, "one thread per (row, 16 columns)");
-      const int li = tid >> 3, seg = tid & 7;
+    for (int li = warp; li < TH && ti0 + li < g.Z; li += HBM_NT / 32) {
       R sre = R(0), sim = R(0), sab = R(0);
-      if (li < TH) {
-        const C* rowp = pl0 + (li + NCOL) * SWH + HS / 2 + 8 * seg;
-#pragma unroll
-        for (int pk = 0; pk < 8; ++pk) {
-          const int kk = ((pk & 3) + (seg >> 1)) & 3;
-          C va, vb;
-          load_pair(rowp + (pk >> 2) * PS + 2 * kk, va, vb);
-          sre += va.x + vb.x; sim += va.y + vb.y;
-          sab += sqrt_fast(va.x * va.x + va.y * va.y) + sqrt_fast(vb.x * vb.x + vb.y * vb.y);
-        }
+      for (int lj = lane; lj < TW && tj0 + lj < g.T; lj += 32) {
+        const int q = lj + HS, par = (Q0 + q) & 1;
+        const C v = (par ? pl1 : pl0)[(li + NCOL) * SWH + (((Q0 + q) >> 1) - (par ? x1 : x0))];
+        sre += v.x; sim += v.y; sab += sqrt_fast(v.x * v.x + v.y * v.y);
       }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        sre += __shfl_xor_sync(0xffffffffu, sre, o); sim += __shfl_xor_sync(0xffffffffu, sim, o); sab += __shfl_xor_sync(0xffffffffu, sab, o);
-      }
-      if (li < TH && seg < 3) A.rowpart[((size_t)bx * 3 + seg) * g.Z + ti0 + li] = seg == 0 ? sre : seg == 1 ? sim : sab;
-    } else {
-      for (int li = warp; li < TH && ti0 + li < g.Z; li += HBM_NT / 32) {
-        R sre = R(0), sim = R(0), sab = R(0);
-        for (int lj = lane; lj < TW && tj0 + lj < g.T; lj += 32) {
-          const int q = lj + HS, par = (Q0 + q) & 1;
-          const C v = (par ? pl1 : pl0)[(li + NCOL) * SWH + (((Q0 + q) >> 1) - (par ? x1 : x0))];
-          sre += v.x; sim += v.y; sab += sqrt_fast(v.x * v.x + v.y * v.y);
-        }
-        sre = warp_sum(sre); sim = warp_sum(sim); sab = warp_sum(sab);
-        if (lane < 3) A.rowpart[((size_t)bx * 3 + lane) * g.Z + ti0 + li] = lane == 0 ? sre : lane == 1 ? sim : sab;
-      }
+      sre = warp_sum(sre); sim = warp_sum(sim); sab = warp_sum(sab);
+      if (lane < 3) A.rowpart[((size_t)bx * 3 + lane) * g.Z + ti0 + li] = lane == 0 ? sre : lane == 1 ? sim : sab;
     }
   }
 #endif
