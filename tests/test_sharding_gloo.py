@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cylinder_b200.replicas import RecordExchange, gather_ragged, parameter_grid, shard_range
+from cylinder_b200.replicas import RecordExchange, gather_ragged, parameter_grid, pipeline_slices, shard_range
 
 
 def test_shard_range_partitions():
@@ -19,6 +19,20 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_pipeline_slices_partition_and_taper():
+    """step_host's slices: a contiguous partition of the batch in order, whatever the sizes; with enough replicas the first and
+    last slices are the short ones (a quarter of a middle slice), so the pipeline's fill and drain are short."""
+    for n in (1, 3, 7, 10, 100, 607, 8192, 65536):
+        for nch in (1, 2, 4, 5, 16, 64):
+            b = pipeline_slices(n, nch)
+            assert b[0][0] == 0 and b[-1][1] == n and len(b) == max(1, min(nch, n))
+            assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1)) and all(hi >= lo for lo, hi in b)
+    sizes = [hi - lo for lo, hi in pipeline_slices(8192, 16)]
+    mid = max(sizes)
+    assert sizes[0] <= mid // 3 and sizes[-1] <= mid // 3 and sizes[1] <= mid // 2 + 1 and sizes[-2] <= mid // 2 + 1
+    assert min(sizes[2:-2]) >= mid - 1
 
 
 def test_parameter_grid_order():
