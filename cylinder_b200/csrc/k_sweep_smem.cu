@@ -9,9 +9,10 @@
 // five with three colours, one more when an amplitude move is accepted) and no phase leaves the CTA to one or two threads
 // for long:
 //   T. proposal tables.  a' = a + sigma_amp N(0,1) is known up front (its draws are precomputed, counter-based).  Warps 0..6
-//      build the row weights of the field energy for a' (one row per thread, rows dealt round-robin to the warps) and store
-//      their DIFFERENCE to the current weights; warp 7 evaluates E_surf(a').  No barrier follows: nothing here is read before
-//      the energy pass, so every warp goes straight on to its sites.
+//      build the row weights of the field energy for a' (one row per thread, whole warps counted down from warp 6) and store
+//      them beside the current ones.  No barrier follows: nothing here is read before the energy pass, so every warp goes
+//      straight on to its sites.  (E_surf(a') and the Robbins-Monro logarithms, which only the decision reads, are evaluated by
+//      the last warp during the energy pass, where it holds no rows.)
 //   1. site moves (Lattice.step_lattice_loc, On_lattice_simple.py:598-686) colour by colour, every site once; draws from
 //      Philox2x32-10 at counter (site, sweep) -- stateless, so a sweep can be re-run or resumed bit-identically.  For even T
 //      the loops are column-mapped: a thread keeps its column pair and walks down the rows with an even stride, so colour
@@ -364,19 +365,15 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     const double a_new = extras ? a + sig_amp * ampz[sw & (AMP_CHUNK - 1)] : a;
     const bool try_move = (flags & CYL_SWEEP_AMP_MOVES) && (fabs(a_new) < p.amp_bound);
 
-    // ---- T. tables of the proposal: row weights for a' on whole warps counted down from warp 6, E_surf(a') on warp 7, the
-    //         Robbins-Monro logarithms on one thread.  No barrier: their first reader is the energy pass, two barriers from
-    //         here.  (Running them DURING the first half of the energy pass, on the warps that hold no rows there, with one
-    //         more barrier before the weights are applied, measured 0.7 % slower.) ----
+    // ---- T. tables of the proposal: row weights for a' on whole warps counted down from warp 6.  No barrier: their first
+    //         reader is the energy pass, two barriers from here.  (Running them DURING the first half of the energy pass, on
+    //         the warps that hold no rows there, with one more barrier before the weights are applied, measured 0.7 % slower.
+    //         E_surf(a') used to sit here on warp 7: that warp was then ~1.5k cycles late for the barrier of the first colour
+    //         pass whenever its rows left it no slack; in the energy pass it costs nothing: 33.7 -> 32.9 ms per bench step.) ----
     auto proposal_tables = [&]() {
     if (extras) {
         if (try_move) {
-          if (warp == SWEEP_NWARP - 1) {
-#ifndef SMEM_ABL_NO_ESURF
-            const double es = surface_energy_of(p, a_new);
-            if (lane == 0) sc->e_surf_new = es;
-#endif
-          } else if (SMEM_WEIGHTS_ON) {
+          if (warp != SWEEP_NWARP - 1 && SMEM_WEIGHTS_ON) {
             const AmpGeo<R> ae = amp_geo<R>(rc, a_new), ar = amp_geo<R>(rc, a);
             // row i on thread NT - 33 - i: whole warps, counted down from warp 6 -- the low warps carry the extra row of the
             // site loops when Z is not a multiple of the row groups, so the table chain goes to the others
@@ -393,7 +390,6 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
             }
           }
         }
-        if (tid == 64 && (flags & CYL_SWEEP_ADAPT_SIGMA)) sc->rm = rm_logs<R>(sc->step_counter, (double)nsite);
       }
     };
     proposal_tables();
@@ -536,6 +532,18 @@ sweep_smem_kernel(typename Real<R>::complex_t* __restrict__ psi_g, int B, const 
     //         separate pass costs fewer instructions than closing bonds inside the colour passes, where the bookkeeping of who
     //         closes which bond is per site (and divergent with three colours). ----
     bool has_rows = false;                                                 // warp-uniform: did this warp accumulate anything?
+#ifndef SMEM_ABL_NO_ESURF
+    // E_surf(a') -- an AGM chain of fp64 square roots, ~1.5k cycles of latency on one warp -- on the last warp HERE: with two threads
+    // per row the energy pass leaves that warp without rows up to Z = 112, and its only reader is the decision, one barrier from
+    // here.  (At the top of the sweep it made the last warp late for the barrier of the first colour pass whenever the row count
+    // left that warp no slack: Z a multiple of the row groups, three colours.)
+    if (extras && warp == SWEEP_NWARP - 1 && try_move) {
+      const double es = surface_energy_of(p, a_new);
+      if (lane == 0) sc->e_surf_new = es;
+    }
+#endif
+    // likewise the logarithms of this sweep's Robbins-Monro factors (read by the decision): one lane of the same warp
+    if (extras && tid == SWEEP_NT - 1 && (flags & CYL_SWEEP_ADAPT_SIGMA)) sc->rm = rm_logs<R>(sc->step_counter, (double)nsite);
     if ((extras && SMEM_ENERGY_ON) || profiles) {
       if ((T & 1) == 0) {
         // 2 threads per row; a thread walks its half of the row's column pairs
