@@ -229,7 +229,7 @@ class ReplicaBatch:
         on the device (chain state in, records out): what a production run does between checkpoints -- on a host with several GPUs
         the pinned copies of the lattices are what limits the step (profiles/r02_e2e_limits.md)."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
-        if not hasattr(self, "_streams") or len(self._streams) < nchunks:
+        if not hasattr(self, "_streams") or len(self._streams) != nchunks:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(nchunks)]
         main = torch.cuda.current_stream(self.device)
         bounds = pipeline_slices(self.B, nchunks)
