@@ -66,6 +66,13 @@ __device__ __forceinline__ R site_delta_over_k(const RowCoef<R>& c, C p, C L, C 
 // ------------------------------------------------------------------------------------------------------
 template <typename R> struct Draw;
 
+// u01_f32 never returns a denormal, so the flush-to-zero MUFU form needs no range fix-up
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <> struct Draw<double> {
   static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, double& zre, double& zim) {
     const double rad = sqrt(-2.0 * log(u23_f64(x0)));
@@ -77,16 +84,16 @@ template <> struct Draw<double> {
   // accept iff dE <= 0, or T > 0 and u <= exp(-dE/T); den = dE/K, kacc = K log2(e)/T
   static __device__ __forceinline__ bool accept(uint32_t x1, double den, double kacc) {
     if (den <= 0.0) return true;
-    return log2(u23_f64(x1)) <= -(kacc * den);          // kacc = inf => -inf => false
+    const double thr = -(kacc * den);                    // accept iff log2(u) <= thr; kacc = inf => -inf => false
+    // The fp32 MUFU logarithm of the same uniform (exactly representable in fp32; |error| <= 2^-22 max(1, |lg2 u|) < 6e-6)
+    // decides every case that is not within 1e-4 of the threshold; only the rest evaluate the fp64 logarithm (~50 instructions).
+    // The decisions are those of evaluating it always.
+    const double lf = (double)lg2_fast(u01_f32(x1));
+    if (lf < thr - 1e-4) return true;
+    if (lf > thr + 1e-4) return false;
+    return log2(u23_f64(x1)) <= thr;
   }
 };
-
-// u01_f32 never returns a denormal, so the flush-to-zero MUFU form needs no range fix-up
-__device__ __forceinline__ float lg2_fast(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <> struct Draw<float> {
   static __device__ __forceinline__ void normals(uint32_t x0, uint32_t x1, float& zre, float& zim) {
