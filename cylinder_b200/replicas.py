@@ -223,9 +223,9 @@ class ReplicaBatch:
     def step_host(self, psi_host, chain_host, psi_out_host, rec_out_host, nsweeps, nchunks=16, amp_moves=True, measure=True,
                   adapt=True, wait=True, lattices=True):
         """One step with HOST buffers in and out (pinned tensors): upload lattices + chain state, run nsweeps, download
-        lattices + per-replica records.  The batch is cut into `nchunks` slices, each on its own stream, so the H2D copy of
-        one slice, the sweeps of another and the D2H copy of a third overlap (PCIe is full duplex; replicas are
-        independent).  Returns after everything has landed in the host buffers (wait=True).  lattices=False keeps the lattices resident
+        lattices + per-replica records.  The batch is cut into `nchunks` slices (pipeline_slices: short first and last slices),
+        each on its own stream, so the H2D copy of one slice, the sweeps of another and the D2H copy of a third overlap (PCIe is
+        full duplex; replicas are independent).  Returns after everything has landed in the host buffers (wait=True).  lattices=False keeps the lattices resident
         on the device (chain state in, records out): what a production run does between checkpoints -- on a host with several GPUs
         the pinned copies of the lattices are what limits the step (profiles/r02_e2e_limits.md)."""
         flags = (SWEEP_ADAPT_SIGMA if adapt else 0) | (SWEEP_AMP_MOVES if amp_moves else 0) | (SWEEP_MEASURE if measure else 0)
