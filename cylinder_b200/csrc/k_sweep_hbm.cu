@@ -70,16 +70,18 @@ struct HbmAmp {                      // header: the amplitude proposal of the cu
   double a, a_new, u_acc, e_surf_new;
   int try_move;
   int coef_sel;                      // which of the two RowCoef tables belongs to the current amplitude
-  int pad[2];
+  unsigned int decide_ticket;        // decision kernel: CTAs that have filed their share of the tiles' sums (wraps to 0 by itself)
+  int pad;
   // Robbins-Monro record of the site moves when no decision kernel runs (sweeps without measurement / amplitude move):
   // slot s % 3 of sweep s holds the width it used, the step counter it started from and its accept count, the latter in
   // HBM_NBUCKET buckets so that the no-return atomics of the tiles finishing together do not queue on one address.
   double rm_sigma[3], rm_counter[3];
   double acc_total;                  // accepts of all sweeps of this call but the last
   unsigned int nacc[3][32];
+  double dpart[8][8];                // decision kernel: per-CTA sums of its share of the tiles (HBM_DECIDE_CTAS x 7 used)
 };
 #define HBM_NBUCKET 32
-#define HBM_HDR_BYTES 1024
+#define HBM_HDR_BYTES 2048
 static_assert(sizeof(HbmAmp) <= HBM_HDR_BYTES, "scratch header");
 #ifndef HBM_MINB_F32
 #define HBM_MINB_F32 4             // co-resident CTAs per SM the fp32 sweep kernel is compiled for: with the Philox round keys
@@ -192,7 +194,7 @@ template <typename R>
 __global__ void hbm_coef_kernel(const CylParams* __restrict__ params, const double* __restrict__ chain, int Z, int T, int variant,
                                 RowCoef<R>* __restrict__ coef, HbmAmp* __restrict__ hdr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { hdr->coef_sel = 0; hdr->try_move = 0; hdr->acc_total = 0.0; }       // scratch arrives uninitialised
+  if (i == 0) { hdr->coef_sel = 0; hdr->try_move = 0; hdr->acc_total = 0.0; hdr->decide_ticket = 0u; }   // scratch arrives uninitialised
   if (i < 3 * HBM_NBUCKET) (&hdr->nacc[0][0])[i] = 0u;
   if (i >= Z) return;
   const CylParams p = *params;
@@ -936,6 +938,7 @@ __global__ void hbm_rm_finalize_kernel(HbmAmp* __restrict__ hdr, double* __restr
 // Robbins-Monro logarithms -- is at least two kernels old and is fetched BEFORE the dependency wait, while the sweep is still
 // running; after the wait the kernel costs one round of loads of the partial sums and the decision arithmetic. ----
 #define HBM_DECIDE_NT 256
+#define HBM_DECIDE_CTAS 8
 template <typename R>
 struct HbmDecidePre {
   double ch[12];                     // chain state as the previous decision left it (CYL_CH_*)
@@ -947,11 +950,18 @@ struct HbmDecidePre {
 template <typename R>
 __device__ void hbm_decide(const HbmArgs<R>& A, const HbmGeom& g, const double* tot, const HbmDecidePre<R>& pre);
 
-template <typename R>
-__global__ void __launch_bounds__(HBM_DECIDE_NT)
+// Up to HBM_DECIDE_CTAS CTAs share the tiles' partial sums (one CTA pulls the 160 KB of a 4096^2 sweep at the ~100 GB/s a single
+// SM gets from L2: 3 us of the chain); each files the sums of its contiguous share in the header, and the CTA that files last
+// (a ticket) adds the shares in index order and decides -- the result does not depend on which CTA that is.  Every CTA prepares
+// the decision's inputs ahead of the wait: which one will decide is not known then, and they are idle until the sweep ends.
+// DR = tiles per thread and round: 8 for the single CTA of lattices up to 8192 tiles (two rounds at 4096^2), 2 for the CTAs of a
+// shared sum, which are also held to 64 registers so that each fits the slot one retiring tile frees.
+template <typename R, int DR>
+__global__ void __launch_bounds__(HBM_DECIDE_NT, DR == 2 ? 4 : 1)
 hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ HbmGeom g, int ntiles) {
   __shared__ double red[(HBM_DECIDE_NT / 32) * 8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
   const bool extras = (A.flags & (CYL_SWEEP_AMP_MOVES | CYL_SWEEP_MEASURE)) != 0;
   const int nv = extras ? 5 : 1;
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -972,7 +982,7 @@ hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ 
     pre.pt = (p.amp_target_acceptance > 0) ? p.amp_target_acceptance : 0.3;
     pre.rm = rm_logs<R>(pre.ch[CYL_CH_STEP_COUNTER], (double)g.Z * g.T);
   }
-  if (extras)
+  if (extras && cta == 0)
     for (int t = tid; t < A.ncst; t += HBM_DECIDE_NT) { v[5] += A.cstpart[2 * t]; v[6] += A.cstpart[2 * t + 1]; }
   if (extras && warp == 1) {
     // the proposal's surface energy (an AGM chain of fp64 square roots, ~3 us on one warp): here, under the tail of the sweep,
@@ -983,17 +993,17 @@ hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ 
   }
   pdl_wait();
   pdl_trigger();
-  // A thread's tiles in index order.  The loads of a round are issued before anything is added (a load of these freshly written
-  // lines takes ~0.5 us, and a loop that adds as it loads pays that once per iteration: 9 us for the 16 iterations of a 4096^2
-  // sweep, measured with %globaltimer stamps): 8 tiles x 5 sums = 40 loads in flight per round.
-  constexpr int DR = 8;
-  for (int t0 = tid; t0 < ntiles; t0 += DR * HBM_DECIDE_NT) {
+  // This CTA's share of the tiles, a thread's tiles in index order.  The loads of a round are issued before anything is added (a
+  // loop that adds as it loads pays the ~0.5 us load latency once per iteration: 9 us for a 4096^2 sweep on one CTA, measured with
+  // %globaltimer stamps).
+  const int share = (ntiles + ncta - 1) / ncta, t_lo = cta * share, t_hi = min(ntiles, t_lo + share);
+  for (int t0 = t_lo + tid; t0 < t_hi; t0 += DR * HBM_DECIDE_NT) {
     double x[5][DR];
 #pragma unroll
     for (int j = 0; j < DR; ++j) {
       const int t = t0 + j * HBM_DECIDE_NT;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) x[k][j] = (t < ntiles && k < nv) ? __ldcg(A.partials + (size_t)k * ntiles + t) : 0.0;
+      for (int k = 0; k < 5; ++k) x[k][j] = (t < t_hi && k < nv) ? __ldcg(A.partials + (size_t)k * ntiles + t) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < DR; ++j) {
@@ -1012,6 +1022,25 @@ hbm_decide_kernel(const __grid_constant__ HbmArgs<R> A, const __grid_constant__ 
   double tot[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) tot[k] = warp_sum(lane < HBM_DECIDE_NT / 32 ? red[lane * 8 + k] : 0.0);
+  if (ncta > 1) {
+    int last = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) A.hdr->dpart[cta][k] = tot[k];
+      __threadfence();
+      last = atomicInc(&A.hdr->decide_ticket, (unsigned int)(ncta - 1)) == (unsigned int)(ncta - 1);
+    }
+    if (!__shfl_sync(0xffffffffu, last, 0)) return;
+    if (lane == 0) {
+      __threadfence();
+#pragma unroll
+      for (int k = 0; k < 7; ++k) tot[k] = 0.0;
+      for (int c = 0; c < ncta; ++c) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) tot[k] += __ldcg(&A.hdr->dpart[c][k]);
+      }
+    }
+  }
   if (lane == 0) hbm_decide<R>(A, g, tot, pre);
 }
 
@@ -1324,6 +1353,10 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
   const dim3 grid((g.T + L::TW - 1) / L::TW, (g.Z + L::TH - 1) / L::TH);
   const SiteKeys keys = site_keys_expand(seed, (uint64_t)replica);
   const int nrb = (g.Z + HBM_PREP_NT - 1) / HBM_PREP_NT;
+  const int ntiles = (int)(grid.x * grid.y);
+  // one CTA up to 8192 tiles (at 4096 tiles eight CTAs measured 2 us slower than one: 101.0 against 98.9 us per sweep), eight beyond
+  // (8192^2 = 16384 tiles: 351 against 385 us per sweep)
+  const int ndecide = ntiles > 8192 ? HBM_DECIDE_CTAS : 1;
   hbm_coef_kernel<R><<<nrb, HBM_PREP_NT, 0, st>>>(params, chain, g.Z, g.T, variant, coef2, A.hdr);
   for (int s = 0; s < nsweeps; ++s) {
     const uint64_t sweep = sweep0 + (uint64_t)s;
@@ -1335,7 +1368,10 @@ static int sweep_hbm_impl(const HbmGeom& g, void* work, int32_t* cur, const CylP
     }
     CYL_CUDA(launch_pdl(kern, grid, dim3(HBM_NT), L::total, st, maps, (C*)work, (int)*cur, g, A, keys, sweep, s == 0 ? -1 : s % 3));
     *cur ^= 1;                                                      // host-side ping-pong index
-    if (extras) CYL_CUDA(launch_pdl(hbm_decide_kernel<R>, dim3(1), dim3(HBM_DECIDE_NT), 0, st, A, g, (int)(grid.x * grid.y)));
+    if (extras) {
+      if (ndecide > 1) CYL_CUDA(launch_pdl(hbm_decide_kernel<R, 2>, dim3(ndecide), dim3(HBM_DECIDE_NT), 0, st, A, g, ntiles));
+      else CYL_CUDA(launch_pdl(hbm_decide_kernel<R, 8>, dim3(1), dim3(HBM_DECIDE_NT), 0, st, A, g, ntiles));
+    }
   }
   if (!extras && nsweeps > 0)
     CYL_CUDA(launch_pdl(hbm_rm_finalize_kernel<R>, dim3(1), dim3(32), 0, st, A.hdr, chain, g.Z, g.T, flags, (nsweeps - 1) % 3, nsweeps));

@@ -90,13 +90,14 @@ def test_c4_energy_never_increases_at_zero_temperature(cuda, big):
     assert e[-1] < e[0]
 
 
-@pytest.mark.parametrize("n", [4096, 4095, 2080])
+@pytest.mark.parametrize("n", [4096, 4095, 2080, 6144])
 def test_c4_measured_energy_and_profiles_match_independent_sums(cuda, n):
     """The fp32 C4 path with CYL_SWEEP_MEASURE at full size: the field energy and the profile sums that the sweep kernel takes
     from its finished tiles (tiles away from the lattice's end) or inside its colour passes (tiles cut by the end; with three
     colours all edge tiles) equal an independent evaluation of the swept lattice -- row moments in fp64 + the energy weights, and
     torch row sums -- sweep by sweep.  4096: two colours, every tile complete; 4095: three colours, last tile row / column cut;
-    2080: two colours with a cut last tile column.  Tolerance: fp32 partial sums of 16 sites per thread and 128 per tile row
+    2080: two colours with a cut last tile column; 6144: more than 8192 tiles, where eight CTAs of the decision kernel share the
+    tiles' partial sums and the last one to file its share decides.  Tolerance: fp32 partial sums of 16 sites per thread and 128 per tile row
     (2^-24 relative each) under terms of mixed sign: 2e-5 of the energy, 1e-5 of sum |psi|, 2e-3 absolute on the row sums of psi."""
     import torch
     from cylinder_b200 import ops, _abi
